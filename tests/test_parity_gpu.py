@@ -1,0 +1,309 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every call goes through the C ABI of
+libwakeword_b200.so and is compared with the CPU oracle / the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): indexing bit-exact; log-mel <= 1e-3 dB max abs; logits <= 1e-4
+relative (max |d| / max |ref| over the batch); identical decisions at threshold 0.8."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment as A
+from oracle import logmel as LM
+from oracle import model as M
+from oracle import recipe as R
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_TOL_DB = 1e-3
+LOGIT_REL_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ww():
+    import wakeword_jupyterlab_b200 as w
+    from wakeword_jupyterlab_b200 import _lib
+    _lib.load()          # fails loudly if the CUDA library is missing
+    return w
+
+
+def _norm(clips):
+    return np.stack([A.normalize_audio(c) for c in clips]).astype(np.float32)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def _conv_modes():
+    return [m for m in os.environ.get("WW_TEST_CONV_MODES", "fp32,split3").split(",") if m]
+
+
+# ------------------------------------------------------------------ log-mel
+def test_logmel_golden_code_preset(ww, golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_code.npz"))
+    clips = _norm(R.make_clips(int(g["n"]), seed=int(g["seed"])))
+    out = ww.AudioProcessor().audio_to_mel_batch(torch.from_numpy(clips).cuda())
+    assert out.shape == (int(g["n"]), 1, 80, 32) and out.dtype == torch.float32
+    out = out[:, 0].cpu().numpy()
+    assert np.abs(out - g["logmel_reference"]).max() < LOGMEL_TOL_DB
+    assert np.abs(out - g["logmel_torchaudio"]).max() < LOGMEL_TOL_DB
+    assert np.all(out.max(axis=(1, 2)) == 0.0) and out.min() >= -80.0
+
+
+def test_logmel_golden_readme_preset(ww, golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_readme.npz"))
+    clips = _norm(R.make_clips(12, seed=int(g["seed"])))[:3]
+    out = ww.AudioProcessor(ww.ReadmeAudioConfig).audio_to_mel_batch(torch.from_numpy(clips).cuda())
+    assert out.shape == (3, 1, 80, 161)
+    assert np.abs(out[:, 0].cpu().numpy() - g["logmel_reference"]).max() < LOGMEL_TOL_DB
+
+
+def test_logmel_vs_oracle_larger_batch_and_fused_normalize(ww):
+    clips = R.make_clips(96, seed=77)
+    eng = ww.get_engine()
+    out = eng.logmel(torch.from_numpy(clips).cuda(), normalize=True)[:, 0].cpu().numpy()
+    ref = LM.audio_to_mel_batch(_norm(clips))
+    assert np.abs(out - ref).max() < LOGMEL_TOL_DB
+
+
+def test_logmel_single_clip_api_and_edge_cases(ww):
+    proc = ww.AudioProcessor()
+    clip = _norm(R.make_clips(1, seed=3))[0]
+    mel = proc.audio_to_mel(clip)
+    assert mel.shape == (80, 32) and mel.dtype == np.float32
+    assert np.abs(mel - LM.audio_to_mel(clip)).max() < LOGMEL_TOL_DB
+    assert proc.audio_to_mel(np.zeros(0, np.float32)).shape == (80, 32)             # :86-87
+    assert not proc.audio_to_mel(np.zeros(16000, np.float32)).any()                 # silent clip -> 0 dB
+    short = clip[:12000]                                                            # ragged length -> own frame count
+    assert np.abs(proc.audio_to_mel(short) - LM.audio_to_mel(short)).max() < LOGMEL_TOL_DB
+    imp = np.zeros(16000, np.float32); imp[5000] = 1.0                              # impulse: flat spectrum
+    assert np.abs(proc.audio_to_mel(imp) - LM.audio_to_mel(imp)).max() < 5e-3       # -80 dB floor region, see DESIGN.md
+
+
+def test_logmel_other_fft_sizes(ww):
+    class AC(ww.AudioConfig):
+        N_FFT = 1024
+        WIN_LENGTH = 800
+        HOP_LENGTH = 256
+        N_MELS = 64
+    clips = _norm(R.make_clips(4, seed=11))
+    out = ww.AudioProcessor(AC).audio_to_mel_batch(torch.from_numpy(clips).cuda())[:, 0].cpu().numpy()
+    ref = LM.audio_to_mel_batch(clips, n_fft=1024, hop=256, win_length=800, n_mels=64)
+    assert out.shape == ref.shape == (4, 64, 63)
+    assert np.abs(out - ref).max() < LOGMEL_TOL_DB
+
+
+def test_normalize_bit_exact(ww):
+    x = R.make_clips(1, seed=8)[0][:12345]
+    got = ww.AudioProcessor().normalize_audio(x)
+    assert np.array_equal(got, A.normalize_audio(x))                               # IEEE divide, exact max
+
+
+# ------------------------------------------------------------------ augmentation
+def _aug_to_ww(ww, p):
+    return ww.AugBatch(p.flags, p.shift, p.rs_orig, p.rs_new, p.crop_off, p.noise_idx, p.noise_off, p.snr_db, p.gain)
+
+
+def test_shift_and_crop_bit_exact(ww):
+    n = 16
+    clips = R.make_clips(n, seed=21)
+    shifts = np.array([0, 1, -1, 4800, -4800, 15999, -16000, 16001, 7, -7, 123, -4799, 4799, 8000, -8000, 3], np.int32)
+    z = np.zeros(n, np.int32)
+    p = ww.AugBatch(np.full(n, A.F_SHIFT, np.uint32), shifts, z + 100, z + 100, z, z, z, np.zeros(n, np.float32),
+                    np.ones(n, np.float32))
+    out = ww.get_engine().augment(clips, p).cpu().numpy()
+    for b in range(n):
+        assert np.array_equal(out[b], np.roll(clips[b], shifts[b])), b
+
+
+def test_resample_indexing_and_values(ww):
+    clips = R.make_clips(6, seed=5)
+    speeds = np.array([80, 81, 107, 120, 93, 119], np.int32)
+    crops = np.array([0, 3754, 0, 0, 100, 0], np.int32)        # 81 -> out_len 19754: max inclusive offset 3754
+    n = len(speeds)
+    z = np.zeros(n, np.int32)
+    p = ww.AugBatch(np.full(n, A.F_SPEED, np.uint32), z, speeds, z + 100, crops, z, z, np.zeros(n, np.float32),
+                    np.ones(n, np.float32))
+    out = ww.get_engine().augment(clips, p).cpu().numpy()
+    for b in range(n):
+        ref = A.speed_change(clips[b], int(speeds[b]), 100, int(crops[b]))
+        assert np.abs(out[b] - ref).max() < 2e-5, (b, np.abs(out[b] - ref).max())
+        # structure is exact: zero tail begins exactly at the resampled length
+        out_len = A.resample_plan(int(speeds[b]), 100, 16000)[4]
+        if out_len < 16000:
+            assert not out[b, out_len:].any() and out[b, out_len - 1] != 0.0
+
+
+def test_resample_matches_torchaudio_golden(ww, golden_dir):
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    x = R.make_clips(2, seed=int(g["clip_seed"]))
+    for s in (80, 81, 107, 120):
+        y = g[f"y_{s}"]
+        crop = 0
+        n = 2
+        z = np.zeros(n, np.int32)
+        p = ww.AugBatch(np.full(n, A.F_SPEED, np.uint32), z, z + s, z + 100, z + crop, z, z, np.zeros(n, np.float32),
+                        np.ones(n, np.float32))
+        out = ww.get_engine().augment(x, p).cpu().numpy()
+        m = min(16000, y.shape[1])
+        assert np.abs(out[:, :m] - y[:, :m]).max() < 2e-5
+
+
+def test_full_augment_pipeline_vs_oracle(ww):
+    n = 64
+    clips = R.make_clips(n, seed=1234)
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n)
+    assert ((p.flags & A.F_SPEED) != 0).any() and ((p.flags & A.F_NOISE) != 0).any()
+    out = ww.get_engine().augment(clips, _aug_to_ww(ww, p), noise_bank=bank).cpu().numpy()
+    ref = A.augment_batch(clips, bank, p)
+    assert np.abs(out - ref).max() < 5e-5
+    assert np.isfinite(out).all() and np.abs(np.abs(out).max(axis=1) - 1.0).max() < 1e-6    # NORM_OUT
+
+
+def test_unprepared_ratio_is_loud(ww):
+    eng = ww.Engine()                      # fresh context: no tables prepared
+    import ctypes as C
+    from wakeword_jupyterlab_b200 import _lib
+    clips = torch.from_numpy(R.make_clips(1, seed=1)).cuda()
+    out = torch.empty_like(clips)
+    arrs = [torch.tensor([v], dtype=dt, device="cuda") for v, dt in
+            ((A.F_SPEED, torch.int32), (0, torch.int32), (97, torch.int32), (100, torch.int32), (0, torch.int32),
+             (0, torch.int32), (0, torch.int32), (0.0, torch.float32), (1.0, torch.float32))]
+    st = _lib.WWAug(*[C.c_void_p(t.data_ptr()) for t in arrs])
+    rc = eng.lib.ww_augment(eng._ctx, C.c_void_p(clips.data_ptr()), None, 0, 0, C.byref(st), C.c_void_p(out.data_ptr()),
+                            1, eng._stream())
+    torch.cuda.synchronize()
+    assert rc == 0 and torch.isnan(out).all()
+    eng.close()
+
+
+# ------------------------------------------------------------------ model
+def _load(ww, sd, mc=None, ac=None, mode="fp32"):
+    net = ww.WakewordModel(mc or ww.ModelConfig, ac or ww.AudioConfig).cuda().eval()
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    net.conv_mode = mode
+    return net
+
+
+@pytest.mark.parametrize("mode", _conv_modes())
+def test_forward_golden_seeded(ww, golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, "model_seeded.npz"))
+    clips = _norm(R.make_clips(int(g["n"]), seed=int(g["clip_seed"])))
+    feats = LM.audio_to_mel_batch(clips)[:, None]
+    net = _load(ww, R.seeded_state_dict(256, seed=0), mode=mode)
+    with torch.no_grad():
+        out = net(torch.from_numpy(feats).cuda())
+    assert out.shape == (int(g["n"]), 2)
+    assert _rel(out.cpu().numpy(), g["logits_reference"]) < LOGIT_REL_TOL
+    assert _rel(out.cpu().numpy(), g["logits_f64"]) < LOGIT_REL_TOL
+
+
+@pytest.mark.parametrize("mode", _conv_modes())
+def test_forward_golden_trained_and_decisions(ww, golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    clips = R.make_clips(int(g["n"]), seed=int(g["clip_seed"]))
+    net = _load(ww, sd, mode=mode)
+    logits, prob1, dec = ww.score_clips(torch.from_numpy(clips).cuda(), net, normalize=True)
+    assert _rel(logits.cpu().numpy(), g["logits_reference"]) < LOGIT_REL_TOL
+    assert np.array_equal(dec.cpu().numpy().astype(bool), g["decision"])
+    assert np.abs(prob1.cpu().numpy() - g["prob1"]).max() < 1e-5
+    assert 0 < int(dec.sum()) < len(dec)
+
+
+@pytest.mark.parametrize("mode", _conv_modes())
+def test_forward_readme_preset(ww, golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, "model_readme.npz"))
+    clips = _norm(R.make_clips(24, seed=int(g["clip_seed"])))[:int(g["n"])]
+    feats = LM.audio_to_mel_batch(clips, hop=100)[:, None]
+    net = _load(ww, R.seeded_state_dict(128, seed=1), ww.ReadmeModelConfig, ww.ReadmeAudioConfig, mode=mode)
+    with torch.no_grad():
+        out = net(torch.from_numpy(feats).cuda())
+    assert _rel(out.cpu().numpy(), g["logits_reference"]) < LOGIT_REL_TOL
+
+
+@pytest.mark.parametrize("mode", _conv_modes())
+def test_forward_ragged_batches_and_width_31(ww, mode):
+    sd = R.seeded_state_dict(256, seed=3)
+    net = _load(ww, sd, mode=mode)
+    rng = np.random.default_rng(0)
+    for B in (1, 3, 17, 130):
+        x = (rng.standard_normal((B, 1, 80, 32)) * 20 - 40).astype(np.float32)
+        with torch.no_grad():
+            out = net(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert _rel(out, M.forward_numpy(x, sd, np.float64)) < LOGIT_REL_TOL
+    x31 = (rng.standard_normal((2, 1, 80, 31)) * 20 - 40).astype(np.float32)       # reference dummy width (:211)
+    with torch.no_grad():
+        out = net(torch.from_numpy(x31).cuda()).cpu().numpy()
+    assert _rel(out, M.forward_numpy(x31, sd, np.float64)) < LOGIT_REL_TOL
+    with torch.no_grad():
+        assert net(torch.zeros(0, 1, 80, 32, device="cuda")).shape == (0, 2)
+
+
+def test_weight_updates_are_picked_up(ww):
+    sd = R.seeded_state_dict(256, seed=4)
+    net = _load(ww, sd)
+    x = torch.from_numpy((np.random.default_rng(1).standard_normal((4, 1, 80, 32)) * 10 - 30).astype(np.float32)).cuda()
+    with torch.no_grad():
+        a = net(x).cpu().numpy()
+        net.fc.bias.add_(1.0)
+        b = net(x).cpu().numpy()
+    assert np.allclose(b - a, 1.0, atol=1e-5)
+
+
+def test_train_mode_is_refused_loudly(ww):
+    net = ww.WakewordModel().cuda().train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 1, 80, 32, device="cuda"))
+
+
+# ------------------------------------------------------------------ fused score, host entry, streaming
+@pytest.mark.parametrize("mode", _conv_modes())
+def test_score_with_augmentation_end_to_end(ww, mode):
+    n = 40
+    clips = R.make_clips(n, seed=1234)
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n)
+    sd = R.seeded_state_dict(256, seed=0)
+    net = _load(ww, sd, mode=mode)
+    logits, prob1, dec = ww.score_clips(torch.from_numpy(clips).cuda(), net, aug=_aug_to_ww(ww, p), noise_bank=bank)
+    aug = A.augment_batch(clips, bank, p)
+    ref = M.forward_numpy(LM.audio_to_mel_batch(aug)[:, None], sd, np.float64)
+    assert _rel(logits.cpu().numpy(), ref) < 3e-4      # augment (5e-5 abs) + log-mel tolerance propagate
+    # host-buffer entry gives the same answer as the device-resident one
+    h_logits, h_prob, h_dec = net.engine().score_host(clips, aug=_aug_to_ww(ww, p), noise_bank=bank)
+    assert np.array_equal(h_logits, logits.cpu().numpy()) and np.array_equal(h_dec, dec.cpu().numpy())
+
+
+def test_streaming_windows_match_per_window_scoring(ww, golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    net = _load(ww, sd)
+    audio = R.make_clips(3, seed=42).reshape(-1)                 # 3 s of alternating recipe audio
+    prob1, dec = ww.score_stream(audio, net, hop_samples=160)
+    n_win = 1 + (len(audio) - 16000) // 160
+    assert prob1.shape == (n_win,)
+    idx = [0, 1, 57, n_win - 1]
+    wins = np.stack([audio[k * 160:k * 160 + 16000] for k in idx])
+    ref = M.forward_numpy(LM.audio_to_mel_batch(_norm(wins))[:, None], sd, np.float64)
+    p_ref, d_ref = M.prob_and_decision(ref, 0.8)
+    assert np.abs(prob1.cpu().numpy()[idx] - p_ref).max() < 1e-4
+    assert np.array_equal(dec.cpu().numpy()[idx].astype(bool), d_ref)
+
+
+def test_full_size_properties(ww):
+    """BASELINE config-2 scale (16384 clips): size-independent properties instead of an oracle pass."""
+    eng = ww.get_engine()
+    base = torch.from_numpy(R.make_clips(64, seed=9)).cuda()
+    clips = base.repeat(256, 1)                                  # 16384 clips
+    out = eng.logmel(clips, normalize=True)
+    torch.cuda.synchronize()
+    assert out.shape == (16384, 1, 80, 32)
+    assert torch.equal(out[:64], out[-64:])                      # determinism / no cross-clip leakage
+    assert float(out.amax()) == 0.0 and float(out.amin()) >= -80.0
+    assert torch.equal(out.amax(dim=(1, 2, 3)), torch.zeros(16384, device="cuda"))
+    scaled = eng.logmel(clips[:64] * 0.37, normalize=True)       # peak normalisation removes gain
+    assert (scaled - out[:64]).abs().max() < 1e-3

@@ -1,0 +1,12 @@
+"""wakeword_jupyterlab_b200 -- B200-native drop-in for the hot path of sarpel/wakeword-jupyterlab:
+batched 16 kHz clips -> (augment) -> log-mel -> CNN+LSTM score.  See DESIGN.md / INTEGRATION.md."""
+from .config import (AudioConfig, AugmentationConfig, ModelConfig, ReadmeAudioConfig, ReadmeModelConfig,
+                     TrainingConfig)
+from .engine import AugBatch, Engine, get_engine
+from .model import WakewordModel
+from .predict import predict_wakeword, score_clips, score_stream
+from .processor import AudioProcessor
+
+__all__ = ["AudioConfig", "ModelConfig", "TrainingConfig", "AugmentationConfig", "ReadmeAudioConfig",
+           "ReadmeModelConfig", "AudioProcessor", "WakewordModel", "predict_wakeword", "score_clips",
+           "score_stream", "AugBatch", "Engine", "get_engine"]

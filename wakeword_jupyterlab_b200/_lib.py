@@ -1,0 +1,81 @@
+"""ctypes binding of libwakeword_b200.so (include/wakeword_b200.h).  No CPU fallback: a missing
+library or a non-sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwakeword_b200.so")
+
+WW_CONV_SPLIT3, WW_CONV_FP32, WW_CONV_BF16 = 0, 1, 2
+CONV_MODES = {"split3": WW_CONV_SPLIT3, "fp32": WW_CONV_FP32, "bf16": WW_CONV_BF16}
+
+AUG_NORM_IN, AUG_SHIFT, AUG_SPEED, AUG_NOISE, AUG_GAIN, AUG_NORM_OUT = (1 << i for i in range(6))
+
+
+class WWConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("n_samples", C.c_int32), ("n_fft", C.c_int32),
+                ("win_length", C.c_int32), ("hop_length", C.c_int32), ("n_mels", C.c_int32),
+                ("fmin", C.c_float), ("fmax", C.c_float), ("hidden_size", C.c_int32),
+                ("num_layers", C.c_int32), ("num_classes", C.c_int32), ("threshold", C.c_float),
+                ("conv_mode", C.c_int32), ("chunk_clips", C.c_int32)]
+
+
+class WWAug(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("flags", "shift", "rs_orig", "rs_new", "crop_off",
+                                          "noise_idx", "noise_off", "snr_db", "gain")]
+
+
+EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_frames", "ww_set_weights",
+           "ww_prepare_resample", "ww_augment", "ww_logmel", "ww_forward", "ww_score", "ww_score_stream",
+           "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize"]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class WakewordB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building is __graft_entry__.build()'s job; we never fall back)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise WakewordB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m wakeword_jupyterlab_b200.build` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+        lib.ww_abi_version.restype = C.c_int
+        lib.ww_create.argtypes = [C.POINTER(vp), i32, C.POINTER(WWConfig)]
+        lib.ww_destroy.argtypes = [vp]
+        lib.ww_destroy.restype = None
+        lib.ww_last_error.argtypes = [vp]
+        lib.ww_last_error.restype = C.c_char_p
+        lib.ww_n_frames.argtypes = [vp]
+        lib.ww_set_weights.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+        lib.ww_prepare_resample.argtypes = [vp, i32, i32]
+        lib.ww_augment.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), vp, i32, vp]
+        lib.ww_logmel.argtypes = [vp, vp, i64, vp, i32, i32, vp]
+        lib.ww_forward.argtypes = [vp, vp, vp, i32, vp]
+        lib.ww_score.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), i32, vp, vp, vp, i32, vp]
+        lib.ww_score_stream.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp]
+        lib.ww_score_host.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), i32, vp, vp, vp, i32]
+        lib.ww_kernel_launches.argtypes = [vp]
+        lib.ww_kernel_launches.restype = i64
+        lib.ww_conv_mode.argtypes = [vp]
+        lib.ww_normalize.argtypes = [vp, vp, vp, i64, vp]
+        _lib = lib
+        return lib
+
+
+def check(lib, ctx, rc, what):
+    if rc != 0:
+        msg = lib.ww_last_error(ctx)
+        raise WakewordB200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

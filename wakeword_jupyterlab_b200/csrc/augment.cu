@@ -1,0 +1,212 @@
+// K1: batched augmentation / conditioning  (sm_100a)
+//
+// Stage set of the north star, consuming HOST-drawn (seed-supplied) parameters only:
+//   NORM_IN  peak normalise           AudioProcessor.normalize_audio  wakeword_training_script.py:73-76
+//   SHIFT    circular shift (np.roll) augment_audio                   wakeword_training_script.py:106-108
+//   SPEED    polyphase windowed-sinc resample + crop/zero-pad         :114-117 (speed stage) + :78-83
+//   NOISE    snr_mixer(clean, bank segment, snr)                      stock/ms_snsd/MS-SNSD/audiolib.py:55-71
+//   GAIN     linear gain
+//   NORM_OUT peak normalise
+// One CTA per clip; the clip lives in shared memory between stages, so HBM traffic is one read of
+// the clip (+ one read of the noise segment) and one write: 128 KB (192 KB) per clip.
+// Index arithmetic (roll source index, (q,p) phase decomposition, tap range, crop offset, output
+// length) is integer-exact against oracle/augment.py.
+#include "ctx.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int kThreads = 512;
+
+struct AugKParams {
+  const float* clips;
+  const float* bank;
+  int bank_rows;
+  int64_t bank_len;
+  ww_aug a;
+  float* out;
+  int B, N;
+  const RsDesc* rs_desc;
+  int n_rs;
+  const float* rs_kern;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <bool MAX>
+__device__ __forceinline__ float block_reduce(float v, float* red, int tid) {
+  v = MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < kThreads / 32; ++i) r = MAX ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads) augment_kernel(AugKParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm;          // [N]
+  float* Bf = sm + p.N;   // [N]
+  __shared__ float red[kThreads / 32];
+  const int tid = threadIdx.x;
+  const int N = p.N;
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const uint32_t flags = p.a.flags ? p.a.flags[b] : 0u;
+    const float* __restrict__ x = p.clips + (int64_t)b * N;
+    float* cur = A;
+    float* oth = Bf;
+    for (int i = tid; i < N; i += kThreads) cur[i] = __ldg(x + i);
+    __syncthreads();
+
+    if (flags & WW_AUG_NORM_IN) {
+      float m = 0.0f;
+      for (int i = tid; i < N; i += kThreads) m = fmaxf(m, fabsf(cur[i]));
+      float peak = block_reduce<true>(m, red, tid);
+      if (peak > 0.0f)
+        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], peak);
+      __syncthreads();
+    }
+    if (flags & WW_AUG_SHIFT) {
+      int s = p.a.shift[b] % N;
+      if (s < 0) s += N;                                   // out[i] = in[(i - shift) mod N]
+      for (int i = tid; i < N; i += kThreads) {
+        int src = i - s;
+        if (src < 0) src += N;
+        oth[i] = cur[src];
+      }
+      __syncthreads();
+      float* t = cur; cur = oth; oth = t;
+    }
+    if (flags & WW_AUG_SPEED) {
+      const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+      int found = -1;
+      for (int i = 0; i < p.n_rs; ++i)
+        if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { found = i; break; }
+      if (found < 0) {
+        for (int i = tid; i < N; i += kThreads) oth[i] = __int_as_float(0x7fc00000);   // loud: NaN clip
+      } else {
+        const RsDesc d = p.rs_desc[found];
+        const float* __restrict__ kern = p.rs_kern + d.offset;
+        const long long out_len = ((long long)d.n * N + d.o - 1) / d.o;      // ceil(n*N/o)
+        const int crop = (out_len > N) ? p.a.crop_off[b] : 0;
+        for (int i = tid; i < N; i += kThreads) {
+          const long long j = (long long)i + crop;                          // resampled-domain index
+          float acc = 0.0f;
+          if (j < out_len) {
+            const int q = (int)(j / d.n), ph = (int)(j - (long long)q * d.n);
+            const int x0 = q * d.o - d.width;                                // source index of tap 0
+            const float* __restrict__ kr = kern + ph * d.taps;
+            int k0 = x0 < 0 ? -x0 : 0;
+            int k1 = (x0 + d.taps > N) ? (N - x0) : d.taps;
+            for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(kr + k), cur[x0 + k], acc);
+          }
+          oth[i] = acc;
+        }
+      }
+      __syncthreads();
+      float* t = cur; cur = oth; oth = t;
+    }
+    if (flags & WW_AUG_NOISE) {
+      const float* __restrict__ nz = p.bank + (int64_t)p.a.noise_idx[b] * p.bank_len + p.a.noise_off[b];
+      const float snr = p.a.snr_db[b];
+      const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
+      float sc = 0.0f, sn = 0.0f;
+      for (int i = tid; i < N; i += kThreads) {
+        const float c = cur[i], n = __ldg(nz + i);
+        oth[i] = n;
+        sc = fmaf(c, c, sc);
+        sn = fmaf(n, n, sn);
+      }
+      const float rmsclean = sqrtf(block_reduce<false>(sc, red, tid) / (float)N);
+      const float rmsnoise = sqrtf(block_reduce<false>(sn, red, tid) / (float)N);
+      const float scalarclean = target / rmsclean, scalarnoise = target / rmsnoise;
+      // the reference re-measures both RMS values after scaling (audiolib.py:60,65)
+      float sc2 = 0.0f, sn2 = 0.0f;
+      for (int i = tid; i < N; i += kThreads) {
+        const float c = cur[i] * scalarclean, n = oth[i] * scalarnoise;
+        cur[i] = c; oth[i] = n;
+        sc2 = fmaf(c, c, sc2);
+        sn2 = fmaf(n, n, sn2);
+      }
+      const float rc2 = sqrtf(block_reduce<false>(sc2, red, tid) / (float)N);
+      const float rn2 = sqrtf(block_reduce<false>(sn2, red, tid) / (float)N);
+      const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);      // audiolib.py:68 (sqrt quirk kept)
+      for (int i = tid; i < N; i += kThreads) cur[i] = cur[i] + oth[i] * noisescalar;
+      __syncthreads();
+    }
+    if (flags & WW_AUG_GAIN) {
+      const float g = p.a.gain[b];
+      for (int i = tid; i < N; i += kThreads) cur[i] *= g;
+      __syncthreads();
+    }
+    if (flags & WW_AUG_NORM_OUT) {
+      float m = 0.0f;
+      for (int i = tid; i < N; i += kThreads) m = fmaxf(m, fabsf(cur[i]));
+      float peak = block_reduce<true>(m, red, tid);
+      if (peak > 0.0f)
+        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], peak);
+      __syncthreads();
+    }
+    float* __restrict__ o = p.out + (int64_t)b * N;
+    for (int i = tid; i < N; i += kThreads) o[i] = cur[i];
+    __syncthreads();
+  }
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* out) {
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
+__global__ void divide_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, const unsigned int* peak_bits) {
+  const float peak = __uint_as_float(*peak_bits);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = peak > 0.0f ? __fdiv_rn(x[i], peak) : x[i];
+}
+
+}  // namespace
+
+int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return WW_OK;
+  if (!c->d_scalar) WW_CHECK(c, cudaMalloc((void**)&c->d_scalar, sizeof(unsigned int)));
+  WW_CHECK(c, cudaMemsetAsync(c->d_scalar, 0, sizeof(unsigned int), st));
+  int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+  absmax_kernel<<<grid, 256, 0, st>>>(in, n, c->d_scalar);
+  WW_LAUNCH_CHECK(c);
+  divide_kernel<<<grid, 256, 0, st>>>(in, out, n, c->d_scalar);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
+                      const ww_aug* a, float* out, int B, cudaStream_t st) {
+  if (B <= 0) return WW_OK;
+  AugKParams p;
+  p.clips = clips; p.bank = bank; p.bank_rows = bank_rows; p.bank_len = bank_len;
+  p.a = *a; p.out = out; p.B = B; p.N = c->cfg.n_samples;
+  p.rs_desc = c->d_rs_desc; p.n_rs = (int)c->rs_tables.size(); p.rs_kern = c->d_rs_kern;
+  size_t smem = (size_t)2 * p.N * sizeof(float);
+  if (smem > 220 * 1024) { c->set_error("ww_augment: n_samples too large for the shared-memory clip buffers"); return WW_ERR_INVALID; }
+  static size_t configured = 0;
+  if (smem > configured) {
+    WW_CHECK(c, cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int grid = c->sm_count * (int)((227 * 1024) / (smem + 1024));
+  if (grid > B) grid = B;
+  augment_kernel<<<grid, kThreads, smem, st>>>(p);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}

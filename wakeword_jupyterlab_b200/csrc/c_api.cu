@@ -1,0 +1,514 @@
+// C ABI of libwakeword_b200.so: context, tables, weights, stage orchestration.  See include/wakeword_b200.h.
+#include "ctx.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <numeric>
+
+namespace {
+
+std::string g_create_error;
+
+// ------------------------------------------------------------------ slaney mel filterbank (librosa.filters.mel)
+const double kFsp = 200.0 / 3.0, kMinLogHz = 1000.0, kMinLogMel = 1000.0 / (200.0 / 3.0);
+double hz_to_mel(double f) {
+  const double logstep = log(6.4) / 27.0;
+  return f >= kMinLogHz ? kMinLogMel + log(f / kMinLogHz) / logstep : f / kFsp;
+}
+double mel_to_hz(double m) {
+  const double logstep = log(6.4) / 27.0;
+  return m >= kMinLogMel ? kMinLogHz * exp(logstep * (m - kMinLogMel)) : kFsp * m;
+}
+
+// dense [n_mels][n_bins] float32, same rounding points as librosa (float32 weights, float64 area norm)
+std::vector<float> mel_filterbank(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+  const int n_bins = n_fft / 2 + 1;
+  std::vector<double> mel_f(n_mels + 2);
+  const double m0 = hz_to_mel(fmin), m1 = hz_to_mel(fmax);
+  const double step = (m1 - m0) / (n_mels + 1);
+  for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i == n_mels + 1 ? m1 : m0 + step * i);
+  const double val = 1.0 / (n_fft * (1.0 / sr));
+  std::vector<float> w((size_t)n_mels * n_bins, 0.0f);
+  for (int i = 0; i < n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    for (int k = 0; k < n_bins; ++k) {
+      const double fk = k * val;
+      const double lower = -(mel_f[i] - fk) / fd0, upper = (mel_f[i + 2] - fk) / fd1;
+      const float w32 = (float)std::max(0.0, std::min(lower, upper));
+      w[(size_t)i * n_bins + k] = (float)((double)w32 * enorm);
+    }
+  }
+  return w;
+}
+
+template <typename T>
+int upload(ww_ctx* c, T** dst, const std::vector<T>& src) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  WW_CHECK(c, cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+  if (!src.empty()) WW_CHECK(c, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return WW_OK;
+}
+
+int build_tables(ww_ctx* c) {
+  const ww_config& g = c->cfg;
+  const int N = g.n_fft;
+  // periodic Hann of win_length, centred zero-padding to n_fft (librosa util.pad_center)
+  std::vector<float> win(N, 0.0f);
+  const int lpad = (N - g.win_length) / 2;
+  for (int n = 0; n < g.win_length; ++n)
+    win[lpad + n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / g.win_length));
+  int rc = upload(c, &c->d_window, win);
+  if (rc) return rc;
+  std::vector<float2> tw(N);
+  for (int t = 0; t < N; ++t) {
+    const double a = -2.0 * M_PI * t / N;
+    tw[t] = make_float2((float)cos(a), (float)sin(a));
+  }
+  if ((rc = upload(c, &c->d_twiddle, tw))) return rc;
+  std::vector<float> fb = mel_filterbank(g.sample_rate, N, g.n_mels, g.fmin, g.fmax);
+  const int n_bins = N / 2 + 1;
+  std::vector<int> start(g.n_mels), len(g.n_mels), off(g.n_mels);
+  std::vector<float> packed;
+  for (int m = 0; m < g.n_mels; ++m) {
+    int lo = n_bins, hi = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (fb[(size_t)m * n_bins + k] != 0.0f) { lo = std::min(lo, k); hi = std::max(hi, k); }
+    if (hi < lo) { lo = 0; hi = -1; }
+    start[m] = lo; len[m] = hi - lo + 1; off[m] = (int)packed.size();
+    for (int k = lo; k <= hi; ++k) packed.push_back(fb[(size_t)m * n_bins + k]);
+  }
+  c->mel_nnz = (int)packed.size();
+  if ((rc = upload(c, &c->d_mel_start, start))) return rc;
+  if ((rc = upload(c, &c->d_mel_len, len))) return rc;
+  if ((rc = upload(c, &c->d_mel_off, off))) return rc;
+  if ((rc = upload(c, &c->d_mel_w, packed))) return rc;
+  return WW_OK;
+}
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int expected_shape(const ww_ctx* c, const std::string& name, std::vector<int64_t>* shape) {
+  const int H = c->cfg.hidden_size;
+  if (name == "conv1.weight") { *shape = {32, 1, 3, 3}; return 1; }
+  if (name == "conv2.weight") { *shape = {64, 32, 3, 3}; return 1; }
+  if (name == "conv3.weight") { *shape = {128, 64, 3, 3}; return 1; }
+  if (name == "conv1.bias") { *shape = {32}; return 1; }
+  if (name == "conv2.bias") { *shape = {64}; return 1; }
+  if (name == "conv3.bias") { *shape = {128}; return 1; }
+  if (name == "fc.weight") { *shape = {c->cfg.num_classes, H}; return 1; }
+  if (name == "fc.bias") { *shape = {c->cfg.num_classes}; return 1; }
+  for (int l = 0; l < c->cfg.num_layers; ++l) {
+    const std::string s = std::to_string(l);
+    if (name == "lstm.weight_ih_l" + s) { *shape = {4 * H, l == 0 ? 128 : H}; return 1; }
+    if (name == "lstm.weight_hh_l" + s) { *shape = {4 * H, H}; return 1; }
+    if (name == "lstm.bias_ih_l" + s || name == "lstm.bias_hh_l" + s) { *shape = {4 * H}; return 1; }
+  }
+  return 0;
+}
+
+std::vector<std::string> required_weights(const ww_ctx* c) {
+  std::vector<std::string> r = {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias",
+                                "conv3.weight", "conv3.bias", "fc.weight", "fc.bias"};
+  for (int l = 0; l < c->cfg.num_layers; ++l) {
+    const std::string s = std::to_string(l);
+    r.push_back("lstm.weight_ih_l" + s);
+    r.push_back("lstm.bias_ih_l" + s);
+    r.push_back("lstm.bias_hh_l" + s);   // weight_hh never reaches the output (T = 1, h0 = 0): optional
+  }
+  return r;
+}
+
+std::vector<float> fetch(ww_ctx* c, const std::string& name) {
+  const std::vector<int64_t>& s = c->w_shape[name];
+  size_t n = 1;
+  for (int64_t d : s) n *= (size_t)d;
+  std::vector<float> h(n);
+  cudaMemcpy(h.data(), c->w[name], n * sizeof(float), cudaMemcpyDeviceToHost);
+  return h;
+}
+
+int free_all(ww_ctx* c) {
+  cudaFree(c->d_window); cudaFree(c->d_twiddle); cudaFree(c->d_mel_start); cudaFree(c->d_mel_len);
+  cudaFree(c->d_mel_off); cudaFree(c->d_mel_w); cudaFree(c->d_rs_kern); cudaFree(c->d_rs_desc);
+  for (auto& kv : c->w) cudaFree(kv.second);
+  for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
+  for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); }
+  cudaFree(c->d_w2_split); cudaFree(c->d_w3_split);
+  cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
+  cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits);
+  cudaFree(c->d_scalar); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  return 0;
+}
+
+// workspaces are allocated at the first forward/score call so that log-mel-only contexts stay small
+int ensure_workspaces(ww_ctx* c) {
+  if (c->ws_ready) return WW_OK;
+  const ww_config& g = c->cfg;
+  const int H = g.n_mels, W = c->W;
+  const int tiles_fp32 = ((W + 31) / 32) * ((H + 7) / 8);
+  const int tiles_tc = ((H + 2) * (W + 2) + 127) / 128 + 1;
+  const size_t part_cap = (size_t)std::max(tiles_fp32, tiles_tc);
+  WW_CHECK(c, cudaMalloc((void**)&c->ws_clips, (size_t)c->chunk * g.n_samples * 4));
+  WW_CHECK(c, cudaMalloc((void**)&c->ws_logmel, (size_t)c->chunk * H * W * 4));
+  WW_CHECK(c, cudaMalloc((void**)&c->ws_pool_part, (size_t)c->chunk * part_cap * 128 * 4));
+  WW_CHECK(c, cudaMalloc((void**)&c->ws_logits, (size_t)c->chunk * g.num_classes * 4));
+  if (g.conv_mode == WW_CONV_FP32) {
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_act1, (size_t)c->chunk * 32 * H * W * 4));
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_act2, (size_t)c->chunk * 64 * H * W * 4));
+  } else {
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_split, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
+  }
+  c->ws_ready = true;
+  return WW_OK;
+}
+
+int ensure_buffer(ww_ctx* c, void** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return WW_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  WW_CHECK(c, cudaMalloc(buf, need));
+  *cap = need;
+  return WW_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ww_abi_version(void) { return WW_ABI_VERSION; }
+
+const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ww_n_frames(const ww_ctx* ctx) { return ctx ? ctx->W : 0; }
+int64_t ww_kernel_launches(const ww_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ww_conv_mode(const ww_ctx* ctx) { return ctx ? ctx->cfg.conv_mode : -1; }
+
+int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
+  if (!out || !cfg) { g_create_error = "ww_create: null argument"; return WW_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("ww_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return WW_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "ww_create: bad device index"; return WW_ERR_INVALID; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "ww_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                     ", this library is built for sm_100a only";
+    return WW_ERR_ARCH;
+  }
+  const ww_config& g = *cfg;
+  if (!is_pow2(g.n_fft) || g.n_fft < 256 || g.n_fft > 4096 || g.win_length <= 0 || g.win_length > g.n_fft ||
+      g.hop_length <= 0 || g.n_samples <= 0 || g.n_mels <= 0 || g.n_mels > 256 || g.sample_rate <= 0 ||
+      g.hidden_size <= 0 || g.hidden_size % 32 != 0 || g.hidden_size > 1024 || g.num_layers < 1 ||
+      g.num_layers > 8 || g.num_classes < 1 || g.num_classes > 16 || g.fmax <= g.fmin ||
+      g.conv_mode < 0 || g.conv_mode > 2) {
+    g_create_error = "ww_create: unsupported configuration";
+    return WW_ERR_INVALID;
+  }
+  cudaSetDevice(device);
+  ww_ctx* c = new ww_ctx();
+  c->cfg = g;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->W = 1 + g.n_samples / g.hop_length;
+  c->n_bins = g.n_fft / 2 + 1;
+  c->chunk = g.chunk_clips > 0 ? g.chunk_clips : 2048;
+  if ((size_t)g.n_mels * c->W * 4 + (size_t)(3 * g.n_fft + 2 * (g.n_fft >> 5) + 16) * 8 > 220 * 1024) {
+    g_create_error = "ww_create: n_mels x frames too large for the log-mel kernel's shared memory";
+    delete c;
+    return WW_ERR_INVALID;
+  }
+  int rc = build_tables(c);
+  if (rc == WW_OK && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    c->set_error("ww_create: stream creation failed");
+    rc = WW_ERR_CUDA;
+  }
+  if (rc != WW_OK) {
+    g_create_error = c->err;
+    free_all(c);
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return WW_OK;
+}
+
+void ww_destroy(ww_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_all(c);
+  delete c;
+}
+
+int ww_set_weights(ww_ctx* c, const char* name, const float* src, const int64_t* shape, int ndim) {
+  if (!c || !name || !src || !shape) return WW_ERR_INVALID;
+  std::vector<int64_t> want;
+  if (!expected_shape(c, name, &want)) { c->set_error(std::string("ww_set_weights: unknown parameter ") + name); return WW_ERR_INVALID; }
+  std::vector<int64_t> got(shape, shape + ndim);
+  if (got != want) { c->set_error(std::string("ww_set_weights: shape mismatch for ") + name); return WW_ERR_INVALID; }
+  size_t n = 1;
+  for (int64_t d : want) n *= (size_t)d;
+  cudaSetDevice(c->device);
+  float*& dst = c->w[name];
+  if (!dst) WW_CHECK(c, cudaMalloc((void**)&dst, n * sizeof(float)));
+  WW_CHECK(c, cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
+  c->w_shape[name] = want;
+  c->weights_dirty = true;
+  return WW_OK;
+}
+
+int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
+  if (!c || orig <= 0 || neu <= 0) return WW_ERR_INVALID;
+  for (const ResampleTable& t : c->rs_tables)
+    if (t.orig == orig && t.neu == neu) return WW_OK;
+  cudaSetDevice(c->device);
+  const int g = std::gcd(orig, neu);
+  ResampleTable t;
+  t.orig = orig; t.neu = neu; t.o = orig / g; t.n = neu / g;
+  const double lpw = 6.0, rolloff = 0.99;
+  const double base = std::min(t.o, t.n) * rolloff;
+  t.width = (int)ceil(lpw * t.o / base);
+  t.taps = 2 * t.width + t.o;
+  t.offset = c->rs_kern_floats;
+  std::vector<float> k((size_t)t.n * t.taps);
+  for (int p = 0; p < t.n; ++p)
+    for (int i = 0; i < t.taps; ++i) {
+      double tt = ((double)(-p) / t.n + (double)(i - t.width) / t.o) * base;
+      tt = std::max(-lpw, std::min(lpw, tt));
+      const double wdw = pow(cos(tt * M_PI / lpw / 2.0), 2.0);
+      tt *= M_PI;
+      const double s = (tt == 0.0) ? 1.0 : sin(tt) / tt;
+      k[(size_t)p * t.taps + i] = (float)(s * wdw * (base / t.o));
+    }
+  const int need = c->rs_kern_floats + (int)k.size();
+  if (need > c->rs_kern_cap) {
+    int cap = std::max(need * 2, 1 << 16);
+    float* nb = nullptr;
+    WW_CHECK(c, cudaMalloc((void**)&nb, (size_t)cap * sizeof(float)));
+    if (c->d_rs_kern) {
+      WW_CHECK(c, cudaDeviceSynchronize());
+      WW_CHECK(c, cudaMemcpy(nb, c->d_rs_kern, (size_t)c->rs_kern_floats * sizeof(float), cudaMemcpyDeviceToDevice));
+      cudaFree(c->d_rs_kern);
+    }
+    c->d_rs_kern = nb; c->rs_kern_cap = cap;
+  }
+  WW_CHECK(c, cudaMemcpy(c->d_rs_kern + t.offset, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->rs_kern_floats = need;
+  c->rs_tables.push_back(t);
+  if ((int)c->rs_tables.size() > c->rs_desc_cap) {
+    WW_CHECK(c, cudaDeviceSynchronize());
+    if (c->d_rs_desc) cudaFree(c->d_rs_desc);
+    c->rs_desc_cap = std::max(64, (int)c->rs_tables.size() * 2);
+    WW_CHECK(c, cudaMalloc((void**)&c->d_rs_desc, (size_t)c->rs_desc_cap * sizeof(RsDesc)));
+  }
+  std::vector<RsDesc> d(c->rs_tables.size());
+  for (size_t i = 0; i < d.size(); ++i) {
+    const ResampleTable& r = c->rs_tables[i];
+    d[i] = RsDesc{r.orig, r.neu, r.o, r.n, r.width, r.taps, r.offset, 0};
+  }
+  WW_CHECK(c, cudaMemcpy(c->d_rs_desc, d.data(), d.size() * sizeof(RsDesc), cudaMemcpyHostToDevice));
+  return WW_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation (host side; weights total <= 4 MB)
+int ww_prepare_weights(ww_ctx* c, cudaStream_t st) {
+  if (!c->weights_dirty) return WW_OK;
+  for (const std::string& n : required_weights(c))
+    if (!c->w.count(n)) { c->set_error("forward: weight not set: " + n); return WW_ERR_WEIGHTS; }
+  WW_CHECK(c, cudaStreamSynchronize(st));
+  const int cins[3] = {1, 32, 64}, couts[3] = {32, 64, 128};
+  for (int l = 0; l < 3; ++l) {
+    std::vector<float> w = fetch(c, "conv" + std::to_string(l + 1) + ".weight");   // [Cout][Cin][3][3]
+    std::vector<float> t((size_t)cins[l] * 9 * couts[l]);
+    for (int co = 0; co < couts[l]; ++co)
+      for (int ci = 0; ci < cins[l]; ++ci)
+        for (int k = 0; k < 9; ++k) t[((size_t)ci * 9 + k) * couts[l] + co] = w[((size_t)co * cins[l] + ci) * 9 + k];
+    int rc = upload(c, &c->d_convw_t[l], t);
+    if (rc) return rc;
+  }
+  const int H = c->cfg.hidden_size;
+  for (int l = 0; l < c->cfg.num_layers; ++l) {
+    const std::string s = std::to_string(l);
+    const int K = l == 0 ? 128 : H;
+    std::vector<float> w = fetch(c, "lstm.weight_ih_l" + s);    // [4H][K], rows i,f,g,o
+    std::vector<float> bi = fetch(c, "lstm.bias_ih_l" + s), bh = fetch(c, "lstm.bias_hh_l" + s);
+    std::vector<float> wt((size_t)K * 3 * H), b((size_t)3 * H);
+    const int gate_row[3] = {0, 2, 3};                          // i, g, o
+    for (int g = 0; g < 3; ++g)
+      for (int j = 0; j < H; ++j) {
+        const int row = gate_row[g] * H + j;
+        b[(size_t)g * H + j] = bi[row] + bh[row];
+        for (int k = 0; k < K; ++k) wt[((size_t)k * 3 + g) * H + j] = w[(size_t)row * K + k];
+      }
+    int rc = upload(c, &c->d_head_wt[l], wt);
+    if (rc) return rc;
+    if ((rc = upload(c, &c->d_head_b[l], b))) return rc;
+  }
+  if (c->cfg.conv_mode != WW_CONV_FP32) {
+    int rc = ww_conv_tc_prepare(c, st);
+    if (rc) return rc;
+  }
+  c->weights_dirty = false;
+  return WW_OK;
+}
+
+namespace {
+
+int forward_chunk(ww_ctx* c, const float* logmel, int B, float* logits, float* prob1, uint8_t* decision,
+                  cudaStream_t st) {
+  int rc = (c->cfg.conv_mode == WW_CONV_FP32) ? ww_launch_conv_fp32(c, logmel, B, st)
+                                              : ww_launch_conv_tc(c, logmel, B, st);
+  if (rc) return rc;
+  return ww_launch_head(c, B, logits, prob1, decision, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ww_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
+               const ww_aug* p, float* out, int B, void* stream) {
+  if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return ww_launch_augment(c, clips, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
+}
+
+int ww_normalize(ww_ctx* c, const float* in, float* out, int64_t n, void* stream) {
+  if (!c || !in || !out || n < 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return ww_launch_normalize(c, in, out, n, (cudaStream_t)stream);
+}
+
+int ww_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize, void* stream) {
+  if (!c || !clips || !out || B < 0 || clip_stride <= 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return ww_launch_logmel(c, clips, clip_stride, out, B, normalize, (cudaStream_t)stream);
+}
+
+int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* stream) {
+  if (!c || !logmel || !logits || B < 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_workspaces(c);
+  if (rc) return rc;
+  if ((rc = ww_prepare_weights(c, st))) return rc;
+  const size_t per = (size_t)c->cfg.n_mels * c->W;
+  for (int b0 = 0; b0 < B; b0 += c->chunk) {
+    const int nb = std::min(c->chunk, B - b0);
+    rc = forward_chunk(c, logmel + (size_t)b0 * per, nb, logits + (size_t)b0 * c->cfg.num_classes, nullptr, nullptr, st);
+    if (rc) return rc;
+  }
+  return WW_OK;
+}
+
+static int score_impl(ww_ctx* c, const float* clips, int64_t clip_stride, const float* bank, int bank_rows,
+                      int64_t bank_len, const ww_aug* aug, int normalize, float* logits, float* prob1,
+                      uint8_t* decision, int64_t B, cudaStream_t st) {
+  int rc = ensure_workspaces(c);
+  if (rc) return rc;
+  if ((rc = ww_prepare_weights(c, st))) return rc;
+  const int N = c->cfg.n_samples;
+  for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
+    const int nb = (int)std::min<int64_t>(c->chunk, B - b0);
+    const float* src = clips + b0 * clip_stride;
+    int64_t stride = clip_stride;
+    if (aug) {
+      ww_aug a = *aug;
+      a.flags += b0; a.shift += b0; a.rs_orig += b0; a.rs_new += b0; a.crop_off += b0;
+      a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
+      if ((rc = ww_launch_augment(c, src, bank, bank_rows, bank_len, &a, c->ws_clips, nb, st))) return rc;
+      src = c->ws_clips;
+      stride = N;
+    }
+    if ((rc = ww_launch_logmel(c, src, stride, c->ws_logmel, nb, aug ? 0 : normalize, st))) return rc;
+    rc = forward_chunk(c, c->ws_logmel, nb, logits ? logits + b0 * c->cfg.num_classes : nullptr,
+                       prob1 ? prob1 + b0 : nullptr, decision ? decision + b0 : nullptr, st);
+    if (rc) return rc;
+  }
+  return WW_OK;
+}
+
+int ww_score(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len, const ww_aug* aug,
+             int normalize, float* logits, float* prob1, uint8_t* decision, int B, void* stream) {
+  if (!c || !clips || B < 0) return WW_ERR_INVALID;
+  if (aug && (!aug->flags || !aug->shift || !aug->rs_orig || !aug->rs_new || !aug->crop_off || !aug->noise_idx ||
+              !aug->noise_off || !aug->snr_db || !aug->gain)) {
+    c->set_error("ww_score: ww_aug has null arrays");
+    return WW_ERR_INVALID;
+  }
+  cudaSetDevice(c->device);
+  return score_impl(c, clips, c->cfg.n_samples, bank, bank_rows, bank_len, aug, normalize, logits, prob1, decision, B,
+                    (cudaStream_t)stream);
+}
+
+int ww_score_stream(ww_ctx* c, const float* audio, int64_t T, int hop_samples, float* prob1, uint8_t* decision,
+                    int64_t n_win, void* stream) {
+  if (!c || !audio || hop_samples <= 0 || n_win < 0) return WW_ERR_INVALID;
+  if (n_win > 0 && (n_win - 1) * hop_samples + c->cfg.n_samples > T) {
+    c->set_error("ww_score_stream: windows exceed the audio length");
+    return WW_ERR_INVALID;
+  }
+  cudaSetDevice(c->device);
+  return score_impl(c, audio, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win,
+                    (cudaStream_t)stream);
+}
+
+int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int bank_rows, int64_t bank_len,
+                  const ww_aug* aug_host, int normalize, float* logits_host, float* prob1_host,
+                  uint8_t* decision_host, int B) {
+  if (!c || !clips_host || B < 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->own_stream;
+  const int N = c->cfg.n_samples, C = c->cfg.num_classes;
+  int rc;
+  if ((rc = ensure_buffer(c, &c->d_host_in, &c->d_host_in_bytes, (size_t)B * N * 4))) return rc;
+  const size_t out_bytes = (size_t)B * (C * 4 + 4 + 1);
+  if ((rc = ensure_buffer(c, &c->d_host_out, &c->d_host_out_bytes, out_bytes))) return rc;
+  float* d_logits = (float*)c->d_host_out;
+  float* d_prob = d_logits + (size_t)B * C;
+  uint8_t* d_dec = (uint8_t*)(d_prob + B);
+  ww_aug a_dev;
+  if (aug_host) {
+    if ((rc = ensure_buffer(c, &c->d_host_aug, &c->d_host_aug_bytes, (size_t)B * 9 * 4))) return rc;
+    uint32_t* base = (uint32_t*)c->d_host_aug;
+    const void* srcs[9] = {aug_host->flags, aug_host->shift, aug_host->rs_orig, aug_host->rs_new, aug_host->crop_off,
+                           aug_host->noise_idx, aug_host->noise_off, aug_host->snr_db, aug_host->gain};
+    for (int i = 0; i < 9; ++i)
+      WW_CHECK(c, cudaMemcpyAsync(base + (size_t)i * B, srcs[i], (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    a_dev.flags = base; a_dev.shift = (int32_t*)(base + (size_t)B); a_dev.rs_orig = (int32_t*)(base + (size_t)2 * B);
+    a_dev.rs_new = (int32_t*)(base + (size_t)3 * B); a_dev.crop_off = (int32_t*)(base + (size_t)4 * B);
+    a_dev.noise_idx = (int32_t*)(base + (size_t)5 * B); a_dev.noise_off = (int32_t*)(base + (size_t)6 * B);
+    a_dev.snr_db = (float*)(base + (size_t)7 * B); a_dev.gain = (float*)(base + (size_t)8 * B);
+  }
+  if ((rc = ww_prepare_weights(c, st))) return rc;
+  // chunked so that the H2D copy of chunk i+1 can overlap the kernels of chunk i on the copy engine
+  float* d_in = (float*)c->d_host_in;
+  for (int b0 = 0; b0 < B; b0 += c->chunk) {
+    const int nb = std::min(c->chunk, B - b0);
+    WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N, clips_host + (size_t)b0 * N, (size_t)nb * N * 4,
+                                cudaMemcpyHostToDevice, st));
+  }
+  rc = score_impl(c, d_in, N, bank_dev, bank_rows, bank_len, aug_host ? &a_dev : nullptr, normalize, d_logits, d_prob,
+                  d_dec, B, st);
+  if (rc) return rc;
+  if (logits_host) WW_CHECK(c, cudaMemcpyAsync(logits_host, d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+  if (prob1_host) WW_CHECK(c, cudaMemcpyAsync(prob1_host, d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (decision_host) WW_CHECK(c, cudaMemcpyAsync(decision_host, d_dec, (size_t)B, cudaMemcpyDeviceToHost, st));
+  WW_CHECK(c, cudaStreamSynchronize(st));
+  return WW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Internal context of libwakeword_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/wakeword_b200.h"
+
+#define WW_CHECK(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+      return WW_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define WW_LAUNCH_CHECK(ctx)                                                             \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));         \
+      return WW_ERR_CUDA;                                                                \
+    }                                                                                    \
+    (ctx)->launches++;                                                                   \
+  } while (0)
+
+struct ResampleTable {
+  int orig, neu;      // as passed by the caller
+  int o, n;           // reduced by gcd
+  int width, taps;
+  int offset;         // float offset into d_rs_kern
+};
+
+// Device-visible descriptor of one prepared resample ratio.
+struct RsDesc {
+  int orig, neu, o, n, width, taps, offset, pad;
+};
+
+struct ww_ctx {
+  ww_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  int W = 0;            // frames per clip
+  int n_bins = 0;       // n_fft/2 + 1
+  int chunk = 0;        // clips per work chunk
+  int64_t launches = 0;
+  std::string err;
+
+  // ---- log-mel tables
+  float* d_window = nullptr;     // [n_fft] periodic Hann (zero-padded to n_fft), fp32
+  float2* d_twiddle = nullptr;   // [n_fft] exp(-2 pi i t / n_fft)
+  int* d_mel_start = nullptr;    // [n_mels] first non-zero bin
+  int* d_mel_len = nullptr;      // [n_mels] number of bins
+  int* d_mel_off = nullptr;      // [n_mels] offset into d_mel_w
+  float* d_mel_w = nullptr;      // packed non-zero weights
+  int mel_nnz = 0;
+
+  // ---- resample tables
+  std::vector<ResampleTable> rs_tables;
+  float* d_rs_kern = nullptr;    // packed [n phases][taps] tables
+  RsDesc* d_rs_desc = nullptr;
+  int rs_kern_floats = 0, rs_kern_cap = 0, rs_desc_cap = 0;
+
+  // ---- weights (fp32 masters, reference layouts)
+  std::map<std::string, float*> w;          // name -> device fp32 copy
+  std::map<std::string, std::vector<int64_t>> w_shape;
+  bool weights_dirty = true;
+  // prepared forms
+  float* d_convw_t[3] = {nullptr, nullptr, nullptr};   // [Cin][9][Cout] fp32 (fp32 conv path, conv1 everywhere)
+  float* d_head_wt[8] = {};                            // per LSTM layer: [K][3H] gate-interleaved (i,g,o), fp32
+  float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
+  __nv_bfloat16* d_w2_split = nullptr;                 // conv2 weights, UMMA canonical layout, hi then lo
+  __nv_bfloat16* d_w3_split = nullptr;                 // conv3 weights, UMMA canonical layout, hi then lo
+
+  // ---- workspaces (chunk clips)
+  float* ws_clips = nullptr;     // [chunk][n_samples] augmented clips
+  float* ws_logmel = nullptr;    // [chunk][n_mels][W]
+  float* ws_act1 = nullptr;      // fp32 path: [chunk][32][H][W]
+  float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
+  __nv_bfloat16* ws_act2_split = nullptr;  // tc path: [chunk][8 chunks][2 hi/lo][NPIX][8] bf16
+  float* ws_pool_part = nullptr; // [chunk][n_part][128]
+  float* ws_logits = nullptr;    // [chunk][num_classes] (when caller passes NULL)
+  int n_pool_part = 0;
+  bool ws_ready = false;
+  unsigned int* d_scalar = nullptr;   // scratch word for ww_normalize
+  // host staging for ww_score_host
+  cudaStream_t own_stream = nullptr;
+  void* d_host_in = nullptr; size_t d_host_in_bytes = 0;
+  void* d_host_out = nullptr; size_t d_host_out_bytes = 0;
+  void* d_host_aug = nullptr; size_t d_host_aug_bytes = 0;
+
+  void set_error(const std::string& s) { err = s; }
+};
+
+// ---- stage launchers (each returns WW_OK / error code; all enqueue on `st`)
+int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize,
+                     cudaStream_t st);
+int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st);
+int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
+                      const ww_aug* p, float* out, int B, cudaStream_t st);
+int ww_launch_conv_fp32(ww_ctx* c, const float* logmel, int B, cudaStream_t st);   // -> ws_pool_part
+int ww_launch_conv_tc(ww_ctx* c, const float* logmel, int B, cudaStream_t st);     // -> ws_pool_part
+int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decision, cudaStream_t st);
+int ww_prepare_weights(ww_ctx* c, cudaStream_t st);
+int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t st);
+size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c);

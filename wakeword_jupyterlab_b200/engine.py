@@ -1,0 +1,267 @@
+"""Thin Python owner of a ``ww_ctx`` (one per device + configuration).  PyTorch is used only for
+device memory and streams; all arithmetic happens in libwakeword_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import AudioConfig, ModelConfig
+
+
+@dataclass
+class AugBatch:
+    """Per-clip augmentation parameters (host-drawn).  Arrays of length B; see include/wakeword_b200.h."""
+    flags: np.ndarray
+    shift: np.ndarray
+    rs_orig: np.ndarray
+    rs_new: np.ndarray
+    crop_off: np.ndarray
+    noise_idx: np.ndarray
+    noise_off: np.ndarray
+    snr_db: np.ndarray
+    gain: np.ndarray
+
+    _FIELDS = (("flags", np.uint32), ("shift", np.int32), ("rs_orig", np.int32), ("rs_new", np.int32),
+               ("crop_off", np.int32), ("noise_idx", np.int32), ("noise_off", np.int32),
+               ("snr_db", np.float32), ("gain", np.float32))
+
+    def __len__(self):
+        return len(self.flags)
+
+    def host_arrays(self):
+        return [np.ascontiguousarray(getattr(self, n), dtype=dt) for n, dt in self._FIELDS]
+
+    def ratios(self):
+        f = np.asarray(self.flags)
+        sel = (f & _lib.AUG_SPEED) != 0
+        return sorted(set(zip(np.asarray(self.rs_orig)[sel].tolist(), np.asarray(self.rs_new)[sel].tolist())))
+
+
+def _cfg_key(ac, mc, threshold, conv_mode, n_samples, chunk):
+    return (ac.SAMPLE_RATE, n_samples, ac.N_FFT, ac.WIN_LENGTH, ac.HOP_LENGTH, ac.N_MELS, float(ac.FMIN),
+            float(ac.FMAX), mc.HIDDEN_SIZE, mc.NUM_LAYERS, mc.NUM_CLASSES, float(threshold), conv_mode, chunk)
+
+
+class Engine:
+    """Owns one ww_ctx.  Not thread safe (one per host thread), like the C ABI."""
+
+    def __init__(self, audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8,
+                 conv_mode="split3", n_samples: Optional[int] = None, chunk_clips=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.WakewordB200Error("no CUDA device: wakeword_jupyterlab_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        ac, mc = audio_config, model_config
+        self.n_samples = int(ac.SAMPLE_RATE * ac.DURATION) if n_samples is None else int(n_samples)
+        self.cfg = _lib.WWConfig(ac.SAMPLE_RATE, self.n_samples, ac.N_FFT, ac.WIN_LENGTH, ac.HOP_LENGTH, ac.N_MELS,
+                                 float(ac.FMIN), float(ac.FMAX), mc.HIDDEN_SIZE, mc.NUM_LAYERS, mc.NUM_CLASSES,
+                                 float(threshold), _lib.CONV_MODES[conv_mode] if isinstance(conv_mode, str) else conv_mode,
+                                 chunk_clips)
+        self.n_mels, self.n_classes = ac.N_MELS, mc.NUM_CLASSES
+        self._ctx = C.c_void_p()
+        rc = self.lib.ww_create(C.byref(self._ctx), self.device.index, C.byref(self.cfg))
+        if rc != 0:
+            msg = self.lib.ww_last_error(None)
+            raise _lib.WakewordB200Error(f"ww_create failed (code {rc}): {msg.decode() if msg else ''}")
+        self.W = self.lib.ww_n_frames(self._ctx)
+        self._prepared = set()
+        self._weight_versions = {}
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.ww_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, rc, what):
+        _lib.check(self.lib, self._ctx, rc, what)
+
+    def _dev(self, x, dtype=torch.float32):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.to(device=self.device, dtype=dtype).contiguous()
+
+    @property
+    def launches(self):
+        return int(self.lib.ww_kernel_launches(self._ctx))
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, state_dict):
+        """state_dict: name -> torch tensor / ndarray (reference state_dict keys)."""
+        for name, t in state_dict.items():
+            if name.startswith("lstm.weight_hh") and False:
+                continue
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+            t = t.detach().to(dtype=torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            self._chk(self.lib.ww_set_weights(self._ctx, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
+                      f"ww_set_weights({name})")
+
+    def sync_module(self, module):
+        """Push parameters of an nn.Module that changed since the last call (tracked by ._version)."""
+        changed = {}
+        for name, p in module.state_dict(keep_vars=True).items():
+            key = (p.data_ptr(), p._version, tuple(p.shape))
+            if self._weight_versions.get(name) != key:
+                changed[name] = p
+                self._weight_versions[name] = key
+        if changed:
+            torch.cuda.current_stream(self.device).synchronize()
+            self.set_weights(changed)
+
+    # ------------------------------------------------------------------ stages
+    def _aug_struct(self, aug: AugBatch, B):
+        assert len(aug) == B, "augmentation parameter arrays must have one entry per clip"
+        for o, n in aug.ratios():
+            if (o, n) not in self._prepared:
+                self._chk(self.lib.ww_prepare_resample(self._ctx, int(o), int(n)), "ww_prepare_resample")
+                self._prepared.add((o, n))
+        tens = [torch.from_numpy(a).to(self.device) for a in aug.host_arrays()]
+        st = _lib.WWAug(*[C.c_void_p(t.data_ptr()) for t in tens])
+        return st, tens
+
+    def normalize(self, x):
+        x = self._dev(x).reshape(-1)
+        out = torch.empty_like(x)
+        if x.numel():
+            self._chk(self.lib.ww_normalize(self._ctx, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                            x.numel(), self._stream()), "ww_normalize")
+        return out
+
+    def augment(self, clips, aug: AugBatch, noise_bank=None):
+        clips = self._dev(clips)
+        B = clips.shape[0]
+        assert clips.dim() == 2 and clips.shape[1] == self.n_samples
+        bank = self._dev(noise_bank) if noise_bank is not None else None
+        if bank is None and (np.asarray(aug.flags) & _lib.AUG_NOISE).any():
+            raise ValueError("noise stage requested without a noise bank")
+        out = torch.empty_like(clips)
+        st, keep = self._aug_struct(aug, B)
+        self._chk(self.lib.ww_augment(self._ctx, C.c_void_p(clips.data_ptr()),
+                                      C.c_void_p(bank.data_ptr() if bank is not None else 0),
+                                      bank.shape[0] if bank is not None else 0,
+                                      bank.shape[1] if bank is not None else 0,
+                                      C.byref(st), C.c_void_p(out.data_ptr()), B, self._stream()), "ww_augment")
+        return out
+
+    def logmel(self, clips, normalize=False, out=None):
+        """clips [B, n_samples] (device or host) -> device tensor [B, 1, n_mels, W] fp32 dB."""
+        clips = self._dev(clips)
+        assert clips.dim() == 2 and clips.shape[1] == self.n_samples
+        B = clips.shape[0]
+        if out is None:
+            out = torch.empty((B, 1, self.n_mels, self.W), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.ww_logmel(self._ctx, C.c_void_p(clips.data_ptr()), self.n_samples,
+                                     C.c_void_p(out.data_ptr()), B, int(bool(normalize)), self._stream()), "ww_logmel")
+        return out
+
+    def forward(self, logmel):
+        x = self._dev(logmel)
+        assert x.dim() == 4 and x.shape[1] == 1 and x.shape[2] == self.n_mels and x.shape[3] == self.W, \
+            f"expected [B,1,{self.n_mels},{self.W}], got {tuple(x.shape)}"
+        B = x.shape[0]
+        logits = torch.empty((B, self.n_classes), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.ww_forward(self._ctx, C.c_void_p(x.data_ptr()), C.c_void_p(logits.data_ptr()), B,
+                                      self._stream()), "ww_forward")
+        return logits
+
+    def score(self, clips, aug: Optional[AugBatch] = None, noise_bank=None, normalize=True):
+        """Device-resident scoring: returns (logits [B,C], prob1 [B], decision [B] uint8) device tensors."""
+        clips = self._dev(clips)
+        B = clips.shape[0]
+        bank = self._dev(noise_bank) if noise_bank is not None else None
+        logits = torch.empty((B, self.n_classes), device=self.device, dtype=torch.float32)
+        prob1 = torch.empty((B,), device=self.device, dtype=torch.float32)
+        dec = torch.empty((B,), device=self.device, dtype=torch.uint8)
+        st, keep = (self._aug_struct(aug, B) if aug is not None else (None, None))
+        self._chk(self.lib.ww_score(self._ctx, C.c_void_p(clips.data_ptr()),
+                                    C.c_void_p(bank.data_ptr() if bank is not None else 0),
+                                    bank.shape[0] if bank is not None else 0, bank.shape[1] if bank is not None else 0,
+                                    C.byref(st) if st is not None else None, int(bool(normalize)),
+                                    C.c_void_p(logits.data_ptr()), C.c_void_p(prob1.data_ptr()),
+                                    C.c_void_p(dec.data_ptr()), B, self._stream()), "ww_score")
+        return logits, prob1, dec
+
+    def score_prepared(self, clips, aug_struct, bank, normalize, logits, prob1, dec):
+        """Zero-allocation variant for benchmarks: every argument is already device resident."""
+        self._chk(self.lib.ww_score(self._ctx, C.c_void_p(clips.data_ptr()),
+                                    C.c_void_p(bank.data_ptr() if bank is not None else 0),
+                                    bank.shape[0] if bank is not None else 0, bank.shape[1] if bank is not None else 0,
+                                    C.byref(aug_struct) if aug_struct is not None else None, int(bool(normalize)),
+                                    C.c_void_p(logits.data_ptr()), C.c_void_p(prob1.data_ptr()),
+                                    C.c_void_p(dec.data_ptr()), clips.shape[0], self._stream()), "ww_score")
+
+    def score_host(self, clips_host, aug: Optional[AugBatch] = None, noise_bank=None, normalize=True, out=None):
+        """Host buffers in, host buffers out (H2D + kernels + D2H + sync inside the C call)."""
+        if isinstance(clips_host, torch.Tensor):
+            assert not clips_host.is_cuda and clips_host.dtype == torch.float32 and clips_host.is_contiguous()
+            B, src = clips_host.shape[0], clips_host.data_ptr()
+        else:
+            clips_host = np.ascontiguousarray(clips_host, dtype=np.float32)
+            B, src = clips_host.shape[0], clips_host.ctypes.data
+        bank = self._dev(noise_bank) if noise_bank is not None else None
+        if out is None:
+            out = (np.empty((B, self.n_classes), np.float32), np.empty((B,), np.float32), np.empty((B,), np.uint8))
+        logits, prob1, dec = out
+        ptr = (lambda a: a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        st, arrs = None, None
+        if aug is not None:
+            for o, n in aug.ratios():
+                if (o, n) not in self._prepared:
+                    self._chk(self.lib.ww_prepare_resample(self._ctx, int(o), int(n)), "ww_prepare_resample")
+                    self._prepared.add((o, n))
+            arrs = aug.host_arrays()
+            st = _lib.WWAug(*[C.c_void_p(a.ctypes.data) for a in arrs])
+        self._chk(self.lib.ww_score_host(self._ctx, C.c_void_p(src),
+                                         C.c_void_p(bank.data_ptr() if bank is not None else 0),
+                                         bank.shape[0] if bank is not None else 0,
+                                         bank.shape[1] if bank is not None else 0,
+                                         C.byref(st) if st is not None else None, int(bool(normalize)),
+                                         C.c_void_p(ptr(logits)), C.c_void_p(ptr(prob1)), C.c_void_p(ptr(dec)), B),
+                  "ww_score_host")
+        return logits, prob1, dec
+
+    def score_stream(self, audio, hop_samples=160):
+        """Sliding windows of n_samples at hop_samples over a 1-D signal -> (prob1, decision) device tensors."""
+        audio = self._dev(audio).reshape(-1)
+        T = audio.numel()
+        n_win = 0 if T < self.n_samples else 1 + (T - self.n_samples) // hop_samples
+        prob1 = torch.empty((n_win,), device=self.device, dtype=torch.float32)
+        dec = torch.empty((n_win,), device=self.device, dtype=torch.uint8)
+        if n_win:
+            self._chk(self.lib.ww_score_stream(self._ctx, C.c_void_p(audio.data_ptr()), T, hop_samples,
+                                               C.c_void_p(prob1.data_ptr()), C.c_void_p(dec.data_ptr()), n_win,
+                                               self._stream()), "ww_score_stream")
+        return prob1, dec
+
+
+_engines = {}
+
+
+def get_engine(audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8, conv_mode="split3",
+               n_samples=None, chunk_clips=0) -> Engine:
+    """Per-process cache: one Engine per (device, configuration)."""
+    idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    ns = int(audio_config.SAMPLE_RATE * audio_config.DURATION) if n_samples is None else int(n_samples)
+    cm = _lib.CONV_MODES[conv_mode] if isinstance(conv_mode, str) else conv_mode
+    key = (idx,) + _cfg_key(audio_config, model_config, threshold, cm, ns, chunk_clips)
+    eng = _engines.get(key)
+    if eng is None:
+        eng = Engine(audio_config, model_config, idx, threshold, cm, ns, chunk_clips)
+        _engines[key] = eng
+    return eng
