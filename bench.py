@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path (BASELINE.json): 1 s clips/sec for augment + log-mel + CNN+LSTM score.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload score|logmel|stream]
+
+One "step" = one pass of the fused scoring path over one batch of synthetic clips (config 3 of
+BASELINE.json: full augment (noise mix + shift + gain + 0.8-1.2x speed) + log-mel + CNN+LSTM scoring,
+65,536 clips PER GPU -- weak scaling, clips are batch-sharded with no collective on the scoring path).
+N > 1 is launched by torchrun, one rank per GPU; timing is CUDA events on the launching stream between
+barrier+synchronize pairs, max over ranks.  Rank 0 prints ONE JSON line.
+
+`value`  : device-resident throughput (inputs already in HBM when the timed region starts)
+`e2e`    : same metric through the host-buffer C-ABI entry (ww_score_host): pinned-host H2D of the
+           clips and augmentation parameters and D2H of logits/prob/decision inside the timed region
+`roofline`: the dominant kernel (conv3 + ReLU + global mean) timed live with CUDA events inside the
+           library (ww_profile), algorithmic FLOPs (conv3 = 377.5 MFLOP/clip) / time
+           vs the measured bf16 dense peak in MEASURED_PEAKS.json
+`cpu_baseline`: the oracle port (numpy log-mel per clip, as the reference does, + torch-CPU model)
+           timed on this box's host cores on a bounded sample (rank 0, N = 1 only)
+`--impl reference`: the reference's CPU path (oracle port; the reference is pure Python and cannot
+           travel to the GPU box) with all host threads, same metric/config, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CLIPS_PER_GPU = 65536
+N_SAMPLES = 16000
+FLOP_PER_CLIP = {"conv3": 2 * 2560 * 128 * 576, "conv2": 2 * 2560 * 64 * 288, "conv1": 2 * 2560 * 32 * 9,
+                 "total": 475.5e6}
+METRIC = "clips_per_sec_augment_logmel_cnn_lstm_score"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons, pw = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2]); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs: the reference's create_sample_data recipe (wakeword_training_script.py:350-393)
+def synth_clips_device(n, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.linspace(0, 1, N_SAMPLES, device=device)
+    tone = 0.3 * torch.sin(2 * np.pi * 200 * t) + 0.2 * torch.sin(2 * np.pi * 400 * t)
+    out = torch.empty((n, N_SAMPLES), device=device, dtype=torch.float32)
+    step = 4096
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        z = torch.randn((m, N_SAMPLES), device=device, generator=g)
+        pos = (torch.arange(i, i + m, device=device) % 3 == 0).float()[:, None]
+        out[i:i + m] = pos * (0.1 * z + tone) + (1 - pos) * (0.2 * z)
+    return out
+
+
+def draw_aug(n, seed):
+    """Host draws, reference stage order (oracle.recipe.draw_aug_params restated with numpy for speed)."""
+    from wakeword_jupyterlab_b200 import AugBatch, _lib
+    r = np.random.default_rng(seed)
+    flags = np.full(n, _lib.AUG_NORM_IN | _lib.AUG_NORM_OUT, np.uint32)
+    do_shift, do_speed, do_noise = (r.random(n) < 0.8), (r.random(n) < 0.8), (r.random(n) < 0.8)
+    shift = np.where(do_shift, (r.uniform(-0.3, 0.3, n) * 16000).astype(np.int32), 0).astype(np.int32)
+    speed = r.integers(80, 121, n).astype(np.int32)
+    do_speed &= speed != 100
+    out_len = -(-100 * N_SAMPLES // speed)          # both already reduced by gcd-invariant ceil
+    crop = np.where(do_speed & (out_len > N_SAMPLES), (r.random(n) * (np.maximum(out_len - N_SAMPLES, 0) + 1)).astype(np.int32), 0)
+    flags |= np.where(do_shift, _lib.AUG_SHIFT, 0).astype(np.uint32)
+    flags |= np.where(do_speed, _lib.AUG_SPEED, 0).astype(np.uint32)
+    flags |= np.where(do_noise, _lib.AUG_NOISE, 0).astype(np.uint32)
+    return AugBatch(flags, shift, np.where(do_speed, speed, 100).astype(np.int32), np.full(n, 100, np.int32),
+                    crop.astype(np.int32), r.integers(0, 20, n).astype(np.int32),
+                    r.integers(0, 5 * 16000 - N_SAMPLES + 1, n).astype(np.int32),
+                    r.choice(np.array([0, 10, 20, 30, 40], np.float32), n).astype(np.float32),
+                    np.ones(n, np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_pass(n_clips, threads, seed=1234):
+    """The reference's CPU path on `n_clips` clips (oracle port): returns seconds."""
+    from oracle import augment as A, logmel as LM, model as M, recipe as R
+    clips = R.make_clips(n_clips, seed=seed)
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n_clips)
+    sd = {k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()}
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    aug = A.augment_batch(clips, bank, p)                               # per clip, like augment_audio
+    feats = np.stack([LM.audio_to_mel(c) for c in aug]).astype(np.float32)[:, None]   # per clip, like __getitem__
+    for i in range(0, n_clips, 32):                                     # config 1: batches of 32
+        M.forward_torch_cpu(torch.from_numpy(feats[i:i + 32]), sd)
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    n, seed = args
+    torch.set_num_threads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):      # one BLAS/FFT thread per worker: no oversubscription
+            return cpu_reference_pass(n, 1, seed)
+    except ImportError:
+        return cpu_reference_pass(n, 1, seed)
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per = 16
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(procs) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(per, 1000 + it * procs + i) for i in range(procs)])
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    n = per * procs
+    ms = 1e3 * float(np.mean(times))
+    v = n / (ms / 1e3)
+    sample = f"{n} clips/step ({procs} worker processes x {per} clips, 1 thread each)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config3: augment+logmel+cnn_lstm_score, CPU oracle port of the reference path",
+                   "clips_per_step": n, "preset": "code (80x32, H=256)"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
+    ap.add_argument("--conv-mode", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import wakeword_jupyterlab_b200 as ww
+    from wakeword_jupyterlab_b200 import _lib, processor
+    from oracle import recipe as R
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    conv_mode = args.conv_mode or os.environ.get("WW_CONV_MODE", processor.DEFAULT_CONV_MODE)
+    B = args.clips
+    net = ww.WakewordModel().to(dev).eval()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
+    net.conv_mode = conv_mode
+    eng = net.engine()
+    clips = synth_clips_device(B, dev, seed=1234 + rank)
+    bank = torch.from_numpy(R.make_noise_bank()).to(dev)
+    aug = draw_aug(B, seed=2024 + rank)
+    aug_struct, keep = eng._aug_struct(aug, B)
+    logits = torch.empty((B, 2), device=dev); prob1 = torch.empty((B,), device=dev)
+    dec = torch.empty((B,), device=dev, dtype=torch.uint8)
+
+    def step():
+        eng.score_prepared(clips, aug_struct, bank, True, logits, prob1, dec)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches - l0
+    stages = eng.profile_read(reset=True)
+    eng.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    # ---- e2e through the host-buffer C-ABI entry (pinned host memory in, host memory out)
+    e2e = None
+    if not args.no_e2e:
+        h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+        h_clips.copy_(clips)
+        h_out = (torch.empty((B, 2), dtype=torch.float32, pin_memory=True),
+                 torch.empty((B,), dtype=torch.float32, pin_memory=True),
+                 torch.empty((B,), dtype=torch.uint8, pin_memory=True))
+        for _ in range(2):
+            eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        assert torch.equal(h_out[2].to(dev), dec), "e2e decisions differ from the device-resident run"
+        e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "clips/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(B * N_SAMPLES * 4 + B * 9 * 4), "d2h_bytes_per_step": int(B * (2 * 4 + 4 + 1))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    c3_ms, c3_n = stages["conv3"]
+    per_launch_ms = c3_ms / max(c3_n, 1)
+    clips_per_launch = B * args.steps / max(c3_n, 1)
+    achieved = FLOP_PER_CLIP["conv3"] * clips_per_launch / (per_launch_ms * 1e-3) / 1e12 if c3_n else None
+    peak = peaks["bf16_tflops_sustained"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv3_traffic_bytes_per_launch.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(conv_mode)
+        except Exception:
+            traffic = None
+    roof = {"bound": "tensor", "kernel": "conv3+relu+mean (" + conv_mode + ")", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+            "avg_launch_ms": per_launch_ms, "launches_timed": c3_n, "clips_per_launch": clips_per_launch,
+            "algorithmic_flop_per_clip": FLOP_PER_CLIP["conv3"],
+            "whole_step_frac_of_peak": FLOP_PER_CLIP["total"] * B / (ms_step * 1e-3) / 1e12 / peak}
+    stage_ms = {k: round(v[0] / args.steps, 4) for k, v in stages.items()}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_s = 192
+        cores = os.cpu_count() or 1
+        cpu_reference_pass(16, cores)
+        sec = cpu_reference_pass(n_s, cores)
+        cpu = {"value": n_s / sec, "unit": "clips/s", "cores": cores, "kind": "port",
+               "sample": f"{n_s} clips of the same workload: per-clip numpy augment + log-mel (1 thread, as the "
+                         f"reference does per item) + torch-CPU model forward in batches of 32 ({cores} threads)"}
+
+    out = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": {"fp32": "f32", "split3": "bf16x3 (fp32 accumulate)", "bf16": "bf16"}[conv_mode],
+           "data": "synthetic",
+           "config": {"workload": "config3: augment(noise mix+shift+gain+0.8-1.2x speed)+logmel+cnn_lstm_score",
+                      "clips_per_gpu": B, "global_batch": B * world, "preset": "code (80x32, H=256)",
+                      "conv_mode": conv_mode, "sharding": f"batch-sharded x{world}, no collective",
+                      "l2": "inputs (4.2 GB/GPU) larger than L2; no explicit flush"},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+           "stage_ms_per_step": stage_ms, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

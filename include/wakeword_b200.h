@@ -141,6 +141,17 @@ int ww_score_host(ww_ctx* ctx, const float* clips_host, const float* noise_bank_
                   int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                   float* prob1_host, uint8_t* decision_host, int B);
 
+/* ---- per-stage device timing for benchmarks: CUDA events recorded on the launching stream around
+ *      each stage's kernels while enabled.  ww_profile_read synchronises, returns the summed
+ *      milliseconds and the number of timed launches of `stage`, and (stage < 0) resets the log. */
+#define WW_STAGE_AUGMENT 0
+#define WW_STAGE_LOGMEL 1
+#define WW_STAGE_CONV12 2 /* conv1 + conv2 (+ReLU) */
+#define WW_STAGE_CONV3 3  /* conv3 + ReLU + global mean: the dominant kernel */
+#define WW_STAGE_HEAD 4
+int ww_profile(ww_ctx* ctx, int enable);
+int ww_profile_read(ww_ctx* ctx, int stage, double* total_ms, int64_t* n_launches);
+
 /* ---- introspection for benchmarks / tests */
 int64_t ww_kernel_launches(const ww_ctx* ctx); /* kernels launched by this context so far */
 int ww_conv_mode(const ww_ctx* ctx);

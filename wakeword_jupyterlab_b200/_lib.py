@@ -30,7 +30,7 @@ class WWAug(C.Structure):
 
 EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_frames", "ww_set_weights",
            "ww_prepare_resample", "ww_augment", "ww_logmel", "ww_forward", "ww_score", "ww_score_stream",
-           "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize"]
+           "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize", "ww_profile", "ww_profile_read"]
 
 _lib = None
 _lock = threading.Lock()
@@ -71,6 +71,8 @@ def load():
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]
         lib.ww_normalize.argtypes = [vp, vp, vp, i64, vp]
+        lib.ww_profile.argtypes = [vp, i32]
+        lib.ww_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]
         _lib = lib
         return lib
 

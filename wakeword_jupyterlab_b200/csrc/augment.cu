@@ -206,6 +206,7 @@ int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank
   }
   int grid = c->sm_count * (int)((227 * 1024) / (smem + 1024));
   if (grid > B) grid = B;
+  ProfScope prof(c, WW_STAGE_AUGMENT, st);
   augment_kernel<<<grid, kThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   return WW_OK;

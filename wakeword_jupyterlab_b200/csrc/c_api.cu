@@ -140,6 +140,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits);
   cudaFree(c->d_scalar); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
+  for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   return 0;
 }
@@ -187,6 +188,29 @@ const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 int ww_n_frames(const ww_ctx* ctx) { return ctx ? ctx->W : 0; }
 int64_t ww_kernel_launches(const ww_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int ww_conv_mode(const ww_ctx* ctx) { return ctx ? ctx->cfg.conv_mode : -1; }
+
+int ww_profile(ww_ctx* c, int enable) {
+  if (!c) return WW_ERR_INVALID;
+  c->prof_on = enable != 0;
+  return WW_OK;
+}
+
+int ww_profile_read(ww_ctx* c, int stage, double* total_ms, int64_t* n) {
+  if (!c) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  WW_CHECK(c, cudaDeviceSynchronize());
+  if (stage < 0) { c->prof_used = 0; return WW_OK; }
+  double tot = 0.0; int64_t cnt = 0;
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    if (c->prof_slots[i].stage != stage) continue;
+    float ms = 0.0f;
+    WW_CHECK(c, cudaEventElapsedTime(&ms, c->prof_slots[i].a, c->prof_slots[i].b));
+    tot += ms; ++cnt;
+  }
+  if (total_ms) *total_ms = tot;
+  if (n) *n = cnt;
+  return WW_OK;
+}
 
 int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
   if (!out || !cfg) { g_create_error = "ww_create: null argument"; return WW_ERR_INVALID; }

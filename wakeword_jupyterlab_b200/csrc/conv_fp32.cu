@@ -110,12 +110,16 @@ int ww_launch_conv_fp32(ww_ctx* c, const float* logmel, int B, cudaStream_t st) 
   const int n_tiles = tiles_x * tiles_y;
   c->n_pool_part = n_tiles;
   dim3 block(kThreads);
+  {
+  ProfScope prof(c, WW_STAGE_CONV12, st);
   conv3x3_relu_kernel<1, 32, 32, 1, false><<<dim3(n_tiles, 1, B), block, 0, st>>>(
       logmel, c->d_convw_t[0], c->w["conv1.bias"], c->ws_act1, H, W, tiles_x, n_tiles);
   WW_LAUNCH_CHECK(c);
   conv3x3_relu_kernel<32, 64, 32, 8, false><<<dim3(n_tiles, 2, B), block, 0, st>>>(
       c->ws_act1, c->d_convw_t[1], c->w["conv2.bias"], c->ws_act2, H, W, tiles_x, n_tiles);
   WW_LAUNCH_CHECK(c);
+  }
+  ProfScope prof3(c, WW_STAGE_CONV3, st);
   conv3x3_relu_kernel<64, 128, 32, 8, true><<<dim3(n_tiles, 4, B), block, 0, st>>>(
       c->ws_act2, c->d_convw_t[2], c->w["conv3.bias"], c->ws_pool_part, H, W, tiles_x, n_tiles);
   WW_LAUNCH_CHECK(c);

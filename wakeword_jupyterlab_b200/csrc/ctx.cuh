@@ -41,8 +41,14 @@ struct RsDesc {
   int orig, neu, o, n, width, taps, offset, pad;
 };
 
+struct ProfSlot { cudaEvent_t a, b; int stage; };
+
 struct ww_ctx {
   ww_config cfg;
+  // optional per-stage CUDA-event timing (ww_profile / ww_profile_read)
+  bool prof_on = false;
+  std::vector<ProfSlot> prof_slots;
+  size_t prof_used = 0;
   int device = 0;
   int sm_count = 148;
   int W = 0;            // frames per clip
@@ -95,6 +101,23 @@ struct ww_ctx {
   void* d_host_aug = nullptr; size_t d_host_aug_bytes = 0;
 
   void set_error(const std::string& s) { err = s; }
+};
+
+// RAII: CUDA events around one stage's launches on the launching stream (only when profiling is on).
+struct ProfScope {
+  ww_ctx* c; cudaStream_t st; ProfSlot* slot = nullptr;
+  ProfScope(ww_ctx* c_, int stage, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->prof_on) return;
+    if (c->prof_used == c->prof_slots.size()) {
+      ProfSlot s; s.stage = stage;
+      cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+      c->prof_slots.push_back(s);
+    }
+    slot = &c->prof_slots[c->prof_used++];
+    slot->stage = stage;
+    cudaEventRecord(slot->a, st);
+  }
+  ~ProfScope() { if (slot) cudaEventRecord(slot->b, st); }
 };
 
 // ---- stage launchers (each returns WW_OK / error code; all enqueue on `st`)

@@ -134,6 +134,7 @@ int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decis
   }
   int threads = H < 1024 ? H : 1024;
   if (threads < 64) threads = 64;
+  ProfScope prof(c, WW_STAGE_HEAD, st);
   head_kernel<<<(B + CPB - 1) / CPB, threads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   return WW_OK;

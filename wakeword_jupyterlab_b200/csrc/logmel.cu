@@ -207,10 +207,11 @@ __global__ void __launch_bounds__(kThreads) logmel_kernel(LogmelParams p) {
     float m = 0.0f;
     for (int i = tid; i < total; i += kThreads) m = fmaxf(m, mel_s[i]);
     const float ref = block_max(m, red, tid);
-    const float ref_db = 10.0f * log10f(fmaxf(kAmin, ref));
+    // explicit _rn ops: an FMA contraction here would make the per-clip maximum land at +-1 ulp instead of 0 dB
+    const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(kAmin, ref)));
     float* __restrict__ o = p.out + (int64_t)b * total;
     for (int i = tid; i < total; i += kThreads) {
-      float v = 10.0f * log10f(fmaxf(kAmin, mel_s[i])) - ref_db;
+      float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i]))), ref_db);
       o[i] = fmaxf(v, -kTopDb);
     }
     __syncthreads();
@@ -243,6 +244,7 @@ int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* 
   if (per_sm > 8) per_sm = 8;
   int grid = c->sm_count * per_sm;
   if (grid > B) grid = B;
+  ProfScope prof(c, WW_STAGE_LOGMEL, st);
   logmel_kernel<<<grid, kThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   return WW_OK;

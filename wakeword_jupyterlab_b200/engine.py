@@ -99,6 +99,22 @@ class Engine:
     def launches(self):
         return int(self.lib.ww_kernel_launches(self._ctx))
 
+    STAGES = {"augment": 0, "logmel": 1, "conv12": 2, "conv3": 3, "head": 4}
+
+    def profile(self, enable=True):
+        self._chk(self.lib.ww_profile(self._ctx, int(enable)), "ww_profile")
+
+    def profile_read(self, reset=True):
+        """-> {stage: (total_ms, n_launches)} measured with CUDA events on the launching stream."""
+        out = {}
+        for name, sid in self.STAGES.items():
+            ms, n = C.c_double(), C.c_int64()
+            self._chk(self.lib.ww_profile_read(self._ctx, sid, C.byref(ms), C.byref(n)), "ww_profile_read")
+            out[name] = (ms.value, n.value)
+        if reset:
+            self._chk(self.lib.ww_profile_read(self._ctx, -1, None, None), "ww_profile_read")
+        return out
+
     # ------------------------------------------------------------------ weights
     def set_weights(self, state_dict):
         """state_dict: name -> torch tensor / ndarray (reference state_dict keys)."""
@@ -114,6 +130,10 @@ class Engine:
 
     def sync_module(self, module):
         """Push parameters of an nn.Module that changed since the last call (tracked by ._version)."""
+        uid = getattr(module, "_ww_uid", id(module))
+        if getattr(self, "_owner_uid", None) != uid:      # another module used this engine last: resync all
+            self._owner_uid = uid
+            self._weight_versions = {}
         changed = {}
         for name, p in module.state_dict(keep_vars=True).items():
             key = (p.data_ptr(), p._version, tuple(p.shape))

@@ -3,6 +3,7 @@
 ``load_state_dict``; ``forward`` runs the hand-written sm_100a kernels through the C ABI."""
 from __future__ import annotations
 
+import itertools
 import os
 
 import torch
@@ -13,9 +14,13 @@ from .config import AudioConfig, ModelConfig
 from .engine import get_engine
 
 
+_uid = itertools.count(1)
+
+
 class WakewordModel(nn.Module):
     def __init__(self, config=ModelConfig, audio_config=AudioConfig):
         super().__init__()
+        self._ww_uid = next(_uid)          # identity token for the engine's weight cache
         self.config = config
         self.audio_config = audio_config
         self.mel_height = audio_config.N_MELS
@@ -34,6 +39,10 @@ class WakewordModel(nn.Module):
         self.fc = nn.Linear(config.HIDDEN_SIZE, config.NUM_CLASSES)
         self.threshold = 0.8
         self.conv_mode = None     # None -> WW_CONV_MODE env or package default
+
+    def mark_weights_dirty(self):
+        """Call after modifying parameters through ``.data`` (which does not bump tensor versions)."""
+        self._ww_uid = next(_uid)
 
     def _conv_mode(self):
         return self.conv_mode or os.environ.get("WW_CONV_MODE", _p.DEFAULT_CONV_MODE)
