@@ -196,6 +196,8 @@ class Engine:
             f"expected [B,1,{self.n_mels},{self.W}], got {tuple(x.shape)}"
         B = x.shape[0]
         logits = torch.empty((B, self.n_classes), device=self.device, dtype=torch.float32)
+        if B == 0:
+            return logits
         self._chk(self.lib.ww_forward(self._ctx, C.c_void_p(x.data_ptr()), C.c_void_p(logits.data_ptr()), B,
                                       self._stream()), "ww_forward")
         return logits
