@@ -54,7 +54,7 @@ typedef struct ww_ctx ww_ctx;
 typedef struct ww_config {
   int32_t sample_rate; /* SAMPLE_RATE 16000                      */
   int32_t n_samples;   /* int(SAMPLE_RATE * DURATION) = 16000    */
-  int32_t n_fft;       /* N_FFT 2048 (power of two, 256..4096)   */
+  int32_t n_fft;       /* N_FFT 2048 (power of two, 256..2048)   */
   int32_t win_length;  /* WIN_LENGTH 2048 (<= n_fft)             */
   int32_t hop_length;  /* HOP_LENGTH 512                         */
   int32_t n_mels;      /* N_MELS 80                              */

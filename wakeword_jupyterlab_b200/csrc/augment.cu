@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 1024;
 
 struct AugKParams {
   const float* clips;
@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(kThreads) augment_kernel(AugKParams p) {
             const int q = (int)(j / d.n), ph = (int)(j - (long long)q * d.n);
             const int x0 = q * d.o - d.width;                                // source index of tap 0
             const float* __restrict__ kr = kern + ph * d.taps;
-            int k0 = x0 < 0 ? -x0 : 0;
-            int k1 = (x0 + d.taps > N) ? (N - x0) : d.taps;
+            const int* __restrict__ rng = reinterpret_cast<const int*>(kern + d.n * d.taps);
+            int k0 = max(__ldg(rng + ph), x0 < 0 ? -x0 : 0);                 // non-zero tap range of this phase
+            int k1 = min(__ldg(rng + d.n + ph), (x0 + d.taps > N) ? (N - x0) : d.taps);
             for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(kr + k), cur[x0 + k], acc);
           }
           oth[i] = acc;

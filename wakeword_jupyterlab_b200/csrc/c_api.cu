@@ -139,7 +139,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_w2_split); cudaFree(c->d_w3_split);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits);
-  cudaFree(c->d_scalar); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
+  cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   return 0;
@@ -230,7 +230,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
     return WW_ERR_ARCH;
   }
   const ww_config& g = *cfg;
-  if (!is_pow2(g.n_fft) || g.n_fft < 256 || g.n_fft > 4096 || g.win_length <= 0 || g.win_length > g.n_fft ||
+  if (!is_pow2(g.n_fft) || g.n_fft < 256 || g.n_fft > 2048 || g.win_length <= 0 || g.win_length > g.n_fft ||
       g.hop_length <= 0 || g.n_samples <= 0 || g.n_mels <= 0 || g.n_mels > 256 || g.sample_rate <= 0 ||
       g.hidden_size <= 0 || g.hidden_size % 32 != 0 || g.hidden_size > 1024 || g.num_layers < 1 ||
       g.num_layers > 8 || g.num_classes < 1 || g.num_classes > 16 || g.fmax <= g.fmin ||
@@ -314,6 +314,21 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
       const double s = (tt == 0.0) ? 1.0 : sin(tt) / tt;
       k[(size_t)p * t.taps + i] = (float)(s * wdw * (base / t.o));
     }
+  // Per-phase range of non-zero taps, appended as int bit patterns ([n] first tap, [n] end tap).  Taps outside
+  // the +-6 zero-crossing window are exactly 0.0f (their double value underflows), so skipping them leaves
+  // every output bit-identical while cutting e.g. 111 taps to ~14 for 97 -> 100.
+  {
+    std::vector<float> rng((size_t)2 * t.n);
+    for (int p = 0; p < t.n; ++p) {
+      int lo = t.taps, hi = 0;
+      for (int i = 0; i < t.taps; ++i)
+        if (k[(size_t)p * t.taps + i] != 0.0f) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
+      if (hi <= lo) { lo = 0; hi = 0; }
+      memcpy(&rng[p], &lo, 4);
+      memcpy(&rng[(size_t)t.n + p], &hi, 4);
+    }
+    k.insert(k.end(), rng.begin(), rng.end());
+  }
   const int need = c->rs_kern_floats + (int)k.size();
   if (need > c->rs_kern_cap) {
     int cap = std::max(need * 2, 1 << 16);

@@ -1,0 +1,282 @@
+// K3b (tensor-core path): conv3 (64->128, 3x3) + bias + ReLU + global mean on tcgen05 / TMEM  (sm_100a)
+//
+// Replaces F.relu(self.conv3(x)) and self.pool(x) of WakewordModel.forward
+// (/root/reference/wakeword_training_script.py:172-173): 80 % of the model's FLOPs.
+//
+// Implicit GEMM  D[cout, pixel] += W[cout, (tap, cin)] * Act[pixel + tap_offset, cin]:
+//   * A operand = weights, M = 128 = Cout (TMEM lane = output channel);
+//   * B operand = activations, N = 256 pixels per instruction (two 128-pixel tiles), K = 16 channels.
+//   Activations live in a zero-padded, pixel-linear image (pixel (y,x) at padded index (y+1)*P + (x+1),
+//   pitch P = W+1) stored channel-chunk-major  [chunk of 8 channels][pixel][8 x bf16 = 16 B]  -- exactly the
+//   UMMA K-major SWIZZLE_NONE canonical layout (core matrix = 8 pixels x 16 B contiguous, SBO = 128 B,
+//   LBO = chunk-plane stride).  A 3x3 tap is therefore just a different START ADDRESS of the same shared
+//   memory tile: start += ((ky-1)*P + (kx-1)) * 16 B.  No im2col exists anywhere; each activation byte is
+//   copied to shared memory once per tile group and read by the tensor core 9 taps x 3 passes times.
+//   * fp32 parity (logits <= 1e-4 relative): operands are split bf16 hi + bf16 lo and accumulated in fp32 as
+//   hi*hi + hi*lo + lo*hi (3 passes; SURVEY.md section 7 hard part 1); WW_CONV_BF16 issues hi*hi only.
+//
+// Work item = (clip, group of G <= 4 consecutive 128-pixel tiles) so that every weight stage fetched from L2
+// feeds up to 512 pixels; all 512 TMEM columns hold the group's fp32 accumulators.
+//   warp 0      loader (one thread): activation k-slice planes (4 x 1-D cp.async.bulk per 16-channel slice,
+//               ring of 4 slices = the whole K) and the weight ring (3 stages x 24 KB = (k-slice, 3 taps));
+//   warp 1      MMA issuer (one thread): descriptors are 64-bit adds on precomputed bases;
+//   warps 2-9   epilogue: tcgen05.ld (lane = channel, 32 pixels per load) -> bias + ReLU + padding mask
+//               (precomputed bit masks) -> per-thread sum over pixels -> one deterministic partial per
+//               (clip, group, channel); the head kernel finishes the mean.
+#include "tc_common.cuh"
+
+#include <algorithm>
+
+using namespace tc;
+
+namespace {
+
+constexpr int C3_THREADS = 320;     // warp 0 loader, warp 1 MMA, warps 2-9 epilogue
+
+struct Conv3Params {
+  const __nv_bfloat16* act2;      // [B][16 planes][npix][8]
+  const __nv_bfloat16* w3s;       // [j 4][tap 9][hl][kc 2][cout 128][8]
+  const float* b3;                // [128]
+  const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
+  float* pool_part;               // [B][n_groups][128]
+  int B;
+  Geom g;
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geom g = p.g;
+  const uint32_t plane_bytes = (uint32_t)g.nsl3 * 16u;
+  unsigned char* a_s = smem;                                    // 16 activation planes, index kc*2 + hl
+  unsigned char* w_s = a_s + 16 * plane_bytes;                  // weight ring
+  float* b3s = reinterpret_cast<float*>(w_s + C3_NST * C3_STAGE_BYTES);
+  float* scratch = b3s + 128;                                   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 256);
+  uint64_t* a_full = bars;                 // [4]
+  uint64_t* a_empty = bars + 4;            // [4]
+  uint64_t* w_full = bars + 8;             // [NST]
+  uint64_t* w_empty = bars + 8 + C3_NST;   // [NST]
+  uint64_t* t_full = bars + 8 + 2 * C3_NST;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 128) b3s[tid] = p.b3[tid];
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < C3_NST; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.B * g.n_groups;
+
+  if (warp == 0) {
+    // ===================== loader (one thread)
+    if (lane == 0) {
+      int it = 0;
+      uint32_t ws = 0;        // running weight-stage counter
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int b = item / g.n_groups, grp = item - b * g.n_groups;
+        const int n_t = min(g.G, g.T3 - grp * g.G);
+        const uint32_t nload = (uint32_t)(n_t * 128 + 2 * g.P + 2) * 16u;
+        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) +
+                                    ((size_t)b * 16 * g.npix + (size_t)grp * g.G * 128) * 16;
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
+          mbar_arrive_expect_tx(a_full + j, 4 * nload);
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl)      // planes (kc = 2j, 2j+1) x (hi, lo) are consecutive: index 4j + pl
+            bulk_g2s(a_s + (size_t)(4 * j + pl) * plane_bytes, src0 + (size_t)(4 * j + pl) * g.npix * 16, nload, a_full + j);
+          for (int tt = 0; tt < 3; ++tt, ++ws) {
+            const uint32_t st = ws % C3_NST;
+            mbar_wait(w_empty + st, ((ws / C3_NST) & 1) ^ 1, 41);
+            mbar_arrive_expect_tx(w_full + st, C3_STAGE_BYTES);
+            bulk_g2s(w_s + st * C3_STAGE_BYTES,
+                     reinterpret_cast<const unsigned char*>(p.w3s) + (size_t)(j * 3 + tt) * C3_STAGE_BYTES,
+                     C3_STAGE_BYTES, w_full + st);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
+      const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
+      const uint64_t pdesc0 = make_desc(smem_u32(a_s), 2u * plane_bytes, 128);  // pixels: kc stride = 2 planes
+      const uint32_t plane_u = plane_bytes >> 4;
+      int it = 0;
+      uint32_t ws = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int grp = item % g.n_groups;
+        const int n_t = min(g.G, g.T3 - grp * g.G);
+        // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
+        const uint32_t idA = n_t >= 2 ? idesc256 : idesc128;
+        const uint32_t idB = n_t >= 4 ? idesc256 : idesc128;
+        const bool second = n_t >= 3;
+        mbar_wait(t_empty, (it & 1) ^ 1, 50);
+        uint32_t acc = 0;
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(a_full + j, it & 1, 51);
+          for (int tt = 0; tt < 3; ++tt, ++ws) {
+            const uint32_t st = ws % C3_NST;
+            mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
+            tc_fence_after();
+            const uint64_t wst = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int tl = 0; tl < 3; ++tl) {
+              const int tap = tt * 3 + tl;                       // ky = tt, kx = tl
+              const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));
+#pragma unroll
+              for (int ps = 0; ps < NPASS; ++ps) {
+                const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
+                const uint64_t wd = wst + (uint64_t)(((tl * 2 + hlw) * 4096) >> 4);
+                const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off);
+                umma_bf16(tmem_base, wd, pd, idA, acc);
+                if (second) umma_bf16(tmem_base + 256, wd, pd + 256, idB, acc);
+                acc = 1;
+              }
+              (void)tap;
+            }
+            umma_commit(w_empty + st);
+          }
+          umma_commit(a_empty + j);
+        }
+        umma_commit(t_full);
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps): lane = output channel, columns = pixels
+    const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;       // 0: tiles 0,1   1: tiles 2,3
+    const int ch = q * 32 + lane;
+    const float bias = b3s[ch];
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int b = item / g.n_groups, grp = item - b * g.n_groups;
+      const int n_t = min(g.G, g.T3 - grp * g.G);
+      mbar_wait(t_full, it & 1, 60);
+      tc_fence_after();
+      float sum = 0.0f;
+#pragma unroll
+      for (int ti = 0; ti < 2; ++ti) {
+        const int i = half * 2 + ti;
+        if (i < n_t) {
+          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + (grp * g.G + i));
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + i * 128;
+#pragma unroll
+          for (int cp = 0; cp < 2; ++cp) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32_nowait(taddr + cp * 64, r0);
+            tmem_ld32_nowait(taddr + cp * 64 + 32, r1);
+            tmem_ld_wait();
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float v0 = fmaxf(__uint_as_float(r0[r]) + bias, 0.0f);
+              const float v1 = fmaxf(__uint_as_float(r1[r]) + bias, 0.0f);
+              s0 += (mw[cp * 2] >> r) & 1u ? v0 : 0.0f;
+              s1 += (mw[cp * 2 + 1] >> r) & 1u ? v1 : 0.0f;
+            }
+            sum += s0 + s1;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(t_empty);
+      scratch[half * 128 + ch] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) p.pool_part[((size_t)b * g.n_groups + grp) * 128 + ch] = scratch[ch] + scratch[128 + ch];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {
+  const Geom g = make_geom(c);
+  return (size_t)16 * g.npix * 16;
+}
+
+int ww_conv12_tc_prepare(ww_ctx* c);
+
+// conv3 weights -> bf16 hi/lo in the UMMA canonical layout [j][tap][hl][kc][cout][8]; tile validity masks
+int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
+  int rc = ww_conv12_tc_prepare(c);
+  if (rc) return rc;
+  std::vector<float> w((size_t)128 * 64 * 9);       // [cout][cin][tap]
+  WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv3.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  const size_t blk_elems = 2 * 2 * 128 * 8;         // one (j, tap) block: [hl][kc][cout][8]
+  std::vector<uint16_t> s((size_t)36 * blk_elems);
+  for (int j = 0; j < 4; ++j)
+    for (int tap = 0; tap < 9; ++tap)
+      for (int kc = 0; kc < 2; ++kc)
+        for (int n = 0; n < 128; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const float v = w[((size_t)n * 64 + j * 16 + kc * 8 + e) * 9 + tap];
+            const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+            const size_t blk = ((size_t)j * 9 + tap) * blk_elems;
+            s[blk + (((size_t)0 * 2 + kc) * 128 + n) * 8 + e] = hi;
+            s[blk + (((size_t)1 * 2 + kc) * 128 + n) * 8 + e] = lo;
+          }
+  if (!c->d_w3_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w3_split, s.size() * 2));
+  WW_CHECK(c, cudaMemcpy(c->d_w3_split, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+
+  const Geom g = make_geom(c);
+  std::vector<uint32_t> m((size_t)g.T3 * 4, 0u);
+  for (int t = 0; t < g.T3; ++t)
+    for (int r = 0; r < 128; ++r) {
+      const int pidx = g.P + 128 * t + r;            // padded index of output row r of tile t
+      const int row = pidx / g.P, y = row - 1, x = pidx - row * g.P - 1;
+      if (y >= 0 && y < g.H && x >= 0) m[(size_t)t * 4 + r / 32] |= 1u << (r % 32);
+    }
+  if (c->d_tc_mask) cudaFree(c->d_tc_mask);
+  WW_CHECK(c, cudaMalloc((void**)&c->d_tc_mask, m.size() * 4));
+  WW_CHECK(c, cudaMemcpy(c->d_tc_mask, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+  return WW_OK;
+}
+
+int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
+  const size_t smem = conv3_smem_bytes(g.nsl3);
+  if (smem > 227 * 1024) {
+    c->set_error("conv3_tc: frame count too large for the shared-memory tiles (use WW_CONV_FP32)");
+    return WW_ERR_INVALID;
+  }
+  static size_t conf = 0;
+  if (smem > conf) {
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  Conv3Params p;
+  p.act2 = c->ws_act2_split; p.w3s = c->d_w3_split; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
+  p.pool_part = c->ws_pool_part; p.B = B; p.g = g;
+  const int grid = std::min(c->sm_count, B * g.n_groups);
+  ProfScope prof(c, WW_STAGE_CONV3, st);
+  if (c->cfg.conv_mode == WW_CONV_BF16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
+  else conv3_kernel<3><<<grid, C3_THREADS, smem, st>>>(p);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+int ww_launch_conv_tc(ww_ctx* c, const float* logmel, int B, cudaStream_t st) {
+  if (B <= 0) return WW_OK;
+  const Geom g = make_geom(c);
+  c->n_pool_part = g.n_groups;
+  int rc = ww_launch_conv12_tc(c, logmel, B, g, st);
+  if (rc) return rc;
+  return ww_launch_conv3_tc(c, B, g, st);
+}

@@ -94,6 +94,7 @@ struct ww_ctx {
   int n_pool_part = 0;
   bool ws_ready = false;
   unsigned int* d_scalar = nullptr;   // scratch word for ww_normalize
+  uint32_t* d_tc_mask = nullptr;      // conv3 tile validity masks [T3][4]
   // host staging for ww_score_host
   cudaStream_t own_stream = nullptr;
   void* d_host_in = nullptr; size_t d_host_in_bytes = 0;

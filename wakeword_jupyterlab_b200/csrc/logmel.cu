@@ -4,20 +4,25 @@
 // librosa.feature.melspectrogram(center=True, pad_mode="constant", hann, power=2, slaney mel)
 // followed by librosa.power_to_db(ref=np.max, amin=1e-10, top_db=80).
 //
-// One CTA per clip.  Two real frames are packed into one complex n_fft-point FFT
-// (frame 2p -> real part, frame 2p+1 -> imaginary part) computed by a mixed-radix (8/4/2)
-// Stockham autosort FFT in shared memory; the two spectra are separated by Hermitian symmetry,
-// squared, and projected onto the sparse (banded) slaney filterbank.  The whole n_mels x W mel
-// power of the clip stays in shared memory, so the per-clip max that the dB conversion needs
-// (ref=np.max) never costs a second pass over HBM.
+// One CTA (2 groups of 256 threads, 2 CTAs per SM) per clip; each group owns one in-place n_fft-point complex FFT
+// buffer in shared memory and takes frame PAIRS round-robin: frame 2p is the real part, frame 2p+1 the
+// imaginary part of one complex FFT (mixed radix 8/4/2 Stockham, register-staged so it runs in place);
+// the two spectra are separated by Hermitian symmetry and squared in place ((P_even, P_odd) as one
+// float2 per bin) and projected onto the banded slaney filterbank (2 lanes per mel band, both frames
+// at once).  Twiddles come from compact per-stage tables (no strided shared-memory gathers); window,
+// twiddles and the packed filterbank live in shared memory.  The n_mels x W mel power of the clip stays
+// in shared memory, so the per-clip max that the dB conversion needs (ref=np.max) never costs a second
+// pass over HBM.  Peak normalisation (normalize_audio) is folded in: |X/peak|^2 = |X|^2 / peak^2.
 //
-// HBM traffic per clip: n_samples*4 B in (each sample is re-read n_fft/hop times, from L1/L2)
-// + n_mels*W*4 B out  = 74,240 B at the code preset.
+// HBM traffic per clip: n_samples*4 B in (frame overlap re-reads hit L2) + n_mels*W*4 B out
+// = 74,240 B at the code preset.
 #include "ctx.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kGroups = 2;
+constexpr int kGT = 256;                   // threads per group (one FFT)
+constexpr int kThreads = kGroups * kGT;
 constexpr float kAmin = 1e-10f;
 constexpr float kTopDb = 80.0f;
 
@@ -62,27 +67,51 @@ template <> __device__ __forceinline__ void dftR<2>(float2* v) { dft2(v); }
 template <> __device__ __forceinline__ void dftR<4>(float2* v) { dft4(v); }
 template <> __device__ __forceinline__ void dftR<8>(float2* v) { dft8(v); }
 
-// One Stockham stage: N points, radix R, Ns = product of the radices already applied.
-// v[r] = src[j + r*N/R] * T[r*k*(N/(Ns*R))],  k = j % Ns;  dst[(j/Ns)*Ns*R + k + r*Ns] = DFT_R(v)[r].
-template <int R>
-__device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, float2* __restrict__ dst,
-                                               const float2* __restrict__ tw, int N, int Ns, int tid) {
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGT) : "memory");
+}
+
+// In-place Stockham stage (radix R, Ns = product of the radices already applied) on one group's buffer.
+// Butterfly j: v[r] = z[j + r*N/R] * w^(r),  w = exp(-2 pi i k / (Ns R)), k = j % Ns (compact table `ts[k]`);
+// z[(j - k) * R + k + r * Ns] = DFT_R(v)[r].  Every thread reads its (<= 2) butterflies, the group syncs, then writes.
+template <int R, int ITERS>
+__device__ __forceinline__ void stockham_stage_i(float2* z, const float2* __restrict__ ts, int N, int Ns, int gt, int grp) {
   const int nb = N / R;
-  const int tstep = N / (Ns * R);
-  for (int j = tid; j < nb; j += kThreads) {
-    const int k = j & (Ns - 1);
-    float2 v[R];
+  float2 v[ITERS][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = src[padi(j + r * nb)];
-    if (Ns > 1) {
+  for (int it = 0; it < ITERS; ++it) {
+    const int j = gt + it * kGT;
+    if (j < nb) {
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r * k * tstep]);
+      for (int r = 0; r < R; ++r) v[it][r] = z[padi(j + r * nb)];
+      const float2 w1 = ts[j & (Ns - 1)];
+      float2 w = w1;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        v[it][r] = cmul(v[it][r], w);
+        if (r + 1 < R) w = cmul(w, w1);
+      }
+      dftR<R>(v[it]);
     }
-    dftR<R>(v);
-    const int base = (j - k) * R + k;
-#pragma unroll
-    for (int r = 0; r < R; ++r) dst[padi(base + r * Ns)] = v[r];
   }
+  group_sync(grp);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int j = gt + it * kGT;
+    if (j < nb) {
+      const int k = j & (Ns - 1);
+      const int base = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) z[padi(base + r * Ns)] = v[it][r];
+    }
+  }
+  group_sync(grp);
+}
+template <int R>
+__device__ __forceinline__ void stockham_stage(float2* z, const float2* __restrict__ ts, int N, int Ns, int gt, int grp) {
+  // n_fft <= 2048 (checked in ww_create): a radix-8 stage has <= 256 butterflies, radix 4/2 at most 512
+  if (R < 8 && N / R > kGT) stockham_stage_i<R, (R < 8 ? 2 : 1)>(z, ts, N, Ns, gt, grp);
+  else stockham_stage_i<R, 1>(z, ts, N, Ns, gt, grp);
 }
 
 struct LogmelParams {
@@ -90,7 +119,7 @@ struct LogmelParams {
   int64_t clip_stride;
   float* out;
   int B, normalize;
-  int n_samples, n_fft, log2n, hop, W, n_mels;
+  int n_samples, n_fft, log2n, hop, W, n_mels, mel_nnz;
   const float* window;
   const float2* twiddle;
   const int* mel_start;
@@ -111,97 +140,128 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid) {
   return r;
 }
 
-__global__ void __launch_bounds__(kThreads) logmel_kernel(LogmelParams p) {
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.n_fft;
   const int npad = N + (N >> 5) + 8;
-  float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-  float2* buf1 = buf0 + npad;
-  float2* tw = buf1 + npad;                                  // [N]
-  float* mel_s = reinterpret_cast<float*>(tw + N);           // [n_mels * W]
+  float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][npad]
+  float2* tw = zbuf + kGroups * npad;                          // [N]      exp(-2 pi i t / N)
+  float2* twc = tw + N;                                        // compact tables of the middle stages (< N/8 entries)
+  float* win = reinterpret_cast<float*>(twc + N / 8);          // [N]
+  float* melw = win + N;                                       // [mel_nnz]
+  int* mst = reinterpret_cast<int*>(melw + p.mel_nnz);         // [3][n_mels] start, len, off
+  float* mel_s = reinterpret_cast<float*>(mst + 3 * p.n_mels); // [n_mels * W]
   __shared__ float red[kThreads / 32];
 
   const int tid = threadIdx.x;
+  const int grp = tid / kGT, gt = tid % kGT;
   const int nbins = N / 2 + 1;
-  for (int i = tid; i < N; i += kThreads) tw[i] = p.twiddle[i];
+
+  // ---- tables -> shared memory (once per CTA)
+  for (int i = tid; i < N; i += kThreads) { tw[i] = p.twiddle[i]; win[i] = p.window[i]; }
+  for (int i = tid; i < p.mel_nnz; i += kThreads) melw[i] = p.mel_w[i];
+  for (int i = tid; i < p.n_mels; i += kThreads) {
+    mst[i] = p.mel_start[i]; mst[p.n_mels + i] = p.mel_len[i]; mst[2 * p.n_mels + i] = p.mel_off[i];
+  }
+  {
+    // compact per-stage twiddles: stage with Ns and radix R uses T[k * N/(Ns R)], k < Ns; stages are
+    // (8, 8, ..., last) so Ns = 8, 64, 512, ...; the last stage (tstep == 1) reads `tw` directly.
+    int off = 0, Ns = 8, rem = p.log2n - 3;
+    while (rem > 0) {
+      const int lg = rem >= 3 ? 3 : rem;
+      const int tstep = N / (Ns << lg);
+      if (tstep > 1) {
+        for (int k = tid; k < Ns; k += kThreads) twc[off + k] = p.twiddle[k * tstep];
+        off += Ns;
+      }
+      Ns <<= lg; rem -= lg;
+    }
+  }
+  __syncthreads();
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* __restrict__ x = p.clips + (int64_t)b * p.clip_stride;
-    float peak = 1.0f;
+    float inv_peak = 1.0f;
     if (p.normalize) {
       float m = 0.0f;
       for (int i = tid; i < p.n_samples; i += kThreads) m = fmaxf(m, fabsf(__ldg(x + i)));
-      peak = block_max(m, red, tid);
-      if (!(peak > 0.0f)) peak = 1.0f;     // reference would emit NaN (0/0); guarded, see DESIGN.md
+      const float peak = block_max(m, red, tid);
+      inv_peak = (peak > 0.0f) ? 1.0f / peak : 1.0f;   // silent clip: reference gives NaN (0/0); guarded, see DESIGN.md
     }
-    __syncthreads();
-
+    float2* z = zbuf + grp * npad;
     const int n_pairs = (p.W + 1) >> 1;
-    for (int pr = 0; pr < n_pairs; ++pr) {
+    for (int pr = grp; pr < n_pairs; pr += kGroups) {
       const int t0 = 2 * pr, t1 = 2 * pr + 1;
       const int s0 = p.hop * t0 - (N >> 1);
       const int s1 = (t1 < p.W) ? p.hop * t1 - (N >> 1) : (1 << 30);
-      // ---- first stage: radix 8 straight from global (frame + window), Ns = 1
+      // ---- first stage: radix 8 straight from global (framing + window), Ns = 1
       {
         const int nb = N >> 3;
-        for (int j = tid; j < nb; j += kThreads) {
+        for (int j = gt; j < nb; j += kGT) {
           float2 v[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const int n = j + r * nb;
-            const float w = __ldg(p.window + n);
+            const float w = win[n];
             const int i0 = s0 + n, i1 = s1 + n;
-            float a = (i0 >= 0 && i0 < p.n_samples) ? __ldg(x + i0) : 0.0f;
-            float c = (i1 >= 0 && i1 < p.n_samples) ? __ldg(x + i1) : 0.0f;
-            if (p.normalize) { a = __fdiv_rn(a, peak); c = __fdiv_rn(c, peak); }
+            const float a = (i0 >= 0 && i0 < p.n_samples) ? __ldg(x + i0) : 0.0f;
+            const float c = (i1 >= 0 && i1 < p.n_samples) ? __ldg(x + i1) : 0.0f;
             v[r] = make_float2(w * a, w * c);
           }
           dft8(v);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) buf0[padi(j * 8 + r)] = v[r];
+          for (int r = 0; r < 8; ++r) z[padi(j * 8 + r)] = v[r];
         }
       }
-      __syncthreads();
-      // ---- remaining stages
-      float2* src = buf0;
-      float2* dst = buf1;
-      int Ns = 8, rem = p.log2n - 3;
-      while (rem > 0) {
-        if (rem >= 3) { stockham_stage<8>(src, dst, tw, N, Ns, tid); Ns <<= 3; rem -= 3; }
-        else if (rem == 2) { stockham_stage<4>(src, dst, tw, N, Ns, tid); Ns <<= 2; rem -= 2; }
-        else { stockham_stage<2>(src, dst, tw, N, Ns, tid); Ns <<= 1; rem -= 1; }
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
+      group_sync(grp);
+      // ---- remaining stages (in place)
+      {
+        int Ns = 8, rem = p.log2n - 3, off = 0;
+        while (rem > 0) {
+          const int lg = rem >= 3 ? 3 : rem;
+          const int tstep = N / (Ns << lg);
+          const float2* ts = (tstep > 1) ? (twc + off) : tw;
+          if (lg == 3) stockham_stage<8>(z, ts, N, Ns, gt, grp);
+          else if (lg == 2) stockham_stage<4>(z, ts, N, Ns, gt, grp);
+          else stockham_stage<2>(z, ts, N, Ns, gt, grp);
+          if (tstep > 1) off += Ns;
+          Ns <<= lg; rem -= lg;
+        }
       }
-      // src now holds Z[k] (natural order); dst is free -> power spectra of the two frames
-      float* P0 = reinterpret_cast<float*>(dst);
-      float* P1 = P0 + nbins;
-      for (int k = tid; k < nbins; k += kThreads) {
-        const float2 zk = src[padi(k)];
-        const float2 zn = src[padi((N - k) & (N - 1))];
+      // ---- Hermitian split + power, in place: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2.
+      // Bin k reads z[k] and z[N-k] and is the only reader of both, so no sync is needed before the store.
+      for (int k = gt; k < nbins; k += kGT) {
+        const float2 zk = z[padi(k)];
+        const float2 zn = z[padi((N - k) & (N - 1))];
         const float ar = zk.x + zn.x, ai = zk.y - zn.y;
         const float br = zk.y + zn.y, bi = zk.x - zn.x;
-        P0[k] = 0.25f * (ar * ar + ai * ai);
-        P1[k] = 0.25f * (br * br + bi * bi);
+        z[padi(k)] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
       }
-      __syncthreads();
-      // ---- sparse mel projection: one warp per (frame, mel) pair
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int q = warp; q < 2 * p.n_mels; q += kThreads / 32) {
-        const int f = q >= p.n_mels;
-        const int m = q - f * p.n_mels;
-        const int t = t0 + f;
-        if (t >= p.W) continue;
-        const float* P = f ? P1 : P0;
-        const int st = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m), off = __ldg(p.mel_off + m);
-        float acc = 0.0f;
-        for (int i = lane; i < len; i += 32) acc = fmaf(__ldg(p.mel_w + off + i), P[st + i], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) mel_s[m * p.W + t] = acc;
+      group_sync(grp);
+      // ---- banded mel projection: 2 lanes per band, both frames at once
+      for (int mb = 0; mb < p.n_mels; mb += kGT / 2) {
+        const int m = mb + (gt >> 1), half = gt & 1;
+        float a0 = 0.0f, a1 = 0.0f;
+        if (m < p.n_mels) {
+          const int st = mst[m], len = mst[p.n_mels + m], off = mst[2 * p.n_mels + m];
+#pragma unroll 4
+          for (int i = half; i < len; i += 2) {
+            const float w = melw[off + i];
+            const float2 pw = z[padi(st + i)];
+            a0 = fmaf(w, pw.x, a0);
+            a1 = fmaf(w, pw.y, a1);
+          }
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (m < p.n_mels && half == 0) {
+          mel_s[m * p.W + t0] = a0 * inv_peak * inv_peak;
+          if (t1 < p.W) mel_s[m * p.W + t1] = a1 * inv_peak * inv_peak;
+        }
       }
-      __syncthreads();
+      group_sync(grp);
     }
+    __syncthreads();
     // ---- power_to_db(ref=max, amin, top_db)
     const int total = p.n_mels * p.W;
     float m = 0.0f;
@@ -226,14 +286,17 @@ int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* 
   LogmelParams p;
   p.clips = clips; p.clip_stride = clip_stride; p.out = out; p.B = B; p.normalize = normalize;
   p.n_samples = c->cfg.n_samples; p.n_fft = c->cfg.n_fft; p.hop = c->cfg.hop_length; p.W = c->W;
-  p.n_mels = c->cfg.n_mels;
+  p.n_mels = c->cfg.n_mels; p.mel_nnz = c->mel_nnz;
   int l2 = 0; while ((1 << l2) < p.n_fft) ++l2;
   p.log2n = l2;
   p.window = c->d_window; p.twiddle = c->d_twiddle;
   p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off; p.mel_w = c->d_mel_w;
   const int N = p.n_fft;
   const int npad = N + (N >> 5) + 8;
-  size_t smem = (size_t)(2 * npad + N) * sizeof(float2) + (size_t)p.n_mels * p.W * sizeof(float);
+  size_t smem = (size_t)(kGroups * npad + N + N / 8) * sizeof(float2) + (size_t)N * sizeof(float) +
+                (size_t)p.mel_nnz * sizeof(float) + (size_t)3 * p.n_mels * sizeof(int) +
+                (size_t)p.n_mels * p.W * sizeof(float) + 16;
+  if (smem > 227 * 1024) { c->set_error("ww_logmel: configuration exceeds shared memory"); return WW_ERR_INVALID; }
   static size_t configured = 0;
   if (smem > configured) {
     WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -241,7 +304,7 @@ int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* 
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 2) per_sm = 2;
   int grid = c->sm_count * per_sm;
   if (grid > B) grid = B;
   ProfScope prof(c, WW_STAGE_LOGMEL, st);

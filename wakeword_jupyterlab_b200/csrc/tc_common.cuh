@@ -1,0 +1,186 @@
+// Shared pieces of the tcgen05 convolution kernels: PTX wrappers (mbarrier, bulk copy, TMEM, UMMA),
+// descriptor builders, bf16 hi/lo splitting and the pixel-linear image geometry.  sm_100a only.
+#pragma once
+#include "ctx.cuh"
+
+#include <string.h>
+
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails loudly) instead of hanging the GPU.
+static __device__ __noinline__ void mbar_timeout(int code) {
+  printf("conv_tc watchdog: wait %d timed out (block %d, thread %d)\n", code, blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) mbar_timeout(code);
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread (lane) receives 32 columns of its TMEM lane.  No wait inside.
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (stride between the two 8-element K chunks of one MMA), [32,46) SBO>>4
+// (stride between 8-row groups), [46,48) version = 1, [61,64) layout type = 0 (no swizzle).
+// With no swizzle the start address only needs 16-byte alignment, which is what makes the shifted-view
+// (3x3 tap = pointer offset) trick legal.  Adding (bytes >> 4) to the 64-bit value advances the start.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (kind::f16): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// split 8 floats into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
+    __nv_bfloat162 hh;
+    hh.x = h0; hh.y = h1;
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = pack_bf16(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pixel-linear zero-padded image: pixel (y, x) <-> padded index p = (y+1)*P + (x+1), pitch P = W + 1;
+// activation planes store slot s = p + 1 (one leading slot so that tap offsets never go negative).
+struct Geom {
+  int H, W, P;        // image rows (mels), cols (frames), pitch
+  int npix;           // plane slots per clip (multiple of 128)
+  int T2, T3;         // conv2 tiles (npix / 128), conv3 tiles (ceil(H*P / 128))
+  int G, n_groups;    // conv3: tiles per group (<= 4), groups per clip
+  int nsl2;           // conv12 A-tile slots  = round8(128 + 2P + 2)
+  int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
+};
+
+__device__ __forceinline__ bool pix_valid(int p, const Geom& g, int& y, int& x) {
+  if (p < 0) return false;
+  const int row = p / g.P;
+  y = row - 1;
+  x = p - row * g.P - 1;
+  return (y >= 0) && (y < g.H) && (x >= 0);
+}
+
+// host: bf16 round-to-nearest-even
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+constexpr int C3_NST = 3;                                // conv3 weight ring stages
+constexpr int C3_STAGE_BYTES = 3 * 2 * 2 * 128 * 16;     // [tap 3][hl][kc 2][cout 128][8 bf16] = 24 KB
+
+inline size_t conv3_smem_bytes(int nsl3) {
+  return (size_t)16 * nsl3 * 16 + (size_t)C3_NST * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
+}
+
+inline Geom make_geom(const ww_ctx* c) {
+  Geom g;
+  g.H = c->cfg.n_mels;
+  g.W = c->W;
+  g.P = g.W + 1;
+  g.T3 = (g.H * g.P + 127) / 128;
+  const int need = 2 * g.P + 128 * g.T3 + 2;
+  g.T2 = (need + 127) / 128;
+  g.npix = g.T2 * 128;
+  g.G = 1;
+  for (int G = 4; G >= 1; --G) {      // as many tiles per weight pass as shared memory allows
+    const int nsl3 = (G * 128 + 2 * g.P + 2 + 7) & ~7;
+    if (conv3_smem_bytes(nsl3) <= 227 * 1024) { g.G = G; break; }
+  }
+  g.n_groups = (g.T3 + g.G - 1) / g.G;
+  g.nsl2 = (128 + 2 * g.P + 2 + 7) & ~7;
+  g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
+  return g;
+}
+
+}  // namespace tc
+
+int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const tc::Geom& g, cudaStream_t st);
+int ww_launch_conv3_tc(ww_ctx* c, int B, const tc::Geom& g, cudaStream_t st);
