@@ -7,16 +7,20 @@
 //   NOISE    snr_mixer(clean, bank segment, snr)                      stock/ms_snsd/MS-SNSD/audiolib.py:55-71
 //   GAIN     linear gain
 //   NORM_OUT peak normalise
-// One CTA per clip; the clip lives in shared memory between stages, so HBM traffic is one read of
-// the clip (+ one read of the noise segment) and one write: 128 KB (192 KB) per clip.
-// Index arithmetic (roll source index, (q,p) phase decomposition, tap range, crop offset, output
-// length) is integer-exact against oracle/augment.py.
+// One CTA (1024 threads) per clip.  The clip lives in ONE shared-memory buffer between stages:
+// shift and speed change are a single gather (the resampler reads its taps through the roll index map), whose
+// outputs are held in registers across a barrier and written back in place.  HBM traffic is one read of the clip
+// (+ the noise segment, re-read from L2 for the later passes) and one write: 128 KB (192 KB) per clip.
+// Index arithmetic (roll source index, (q,p) phase decomposition, tap range, crop offset, output length) is
+// integer-exact against oracle/augment.py; only exactly-zero taps of the polyphase table are skipped.
 #include "ctx.cuh"
+
 #include <algorithm>
 
 namespace {
 
 constexpr int kThreads = 1024;
+constexpr int kMaxPerThread = 16;     // n_samples <= kThreads * kMaxPerThread
 
 struct AugKParams {
   const float* clips;
@@ -41,82 +45,103 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// two independent block reductions at once (sum or max); ends with every thread holding both results
 template <bool MAX>
-__device__ __forceinline__ float block_reduce(float v, float* red, int tid) {
-  v = MAX ? warp_max(v) : warp_sum(v);
+__device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, int tid) {
+  a = MAX ? warp_max(a) : warp_sum(a);
+  b = MAX ? warp_max(b) : warp_sum(b);
   __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = v;
+  if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = b; }
   __syncthreads();
-  float r = red[0];
-  for (int i = 1; i < kThreads / 32; ++i) r = MAX ? fmaxf(r, red[i]) : r + red[i];
-  return r;
+  const float ra = red[tid & 31], rb = red[32 + (tid & 31)];       // kThreads / 32 == 32 partials each
+  a = MAX ? warp_max(ra) : warp_sum(ra);
+  b = MAX ? warp_max(rb) : warp_sum(rb);
 }
 
-__global__ void __launch_bounds__(kThreads) augment_kernel(AugKParams p) {
-  extern __shared__ __align__(16) float sm[];
-  float* A = sm;          // [N]
-  float* Bf = sm + p.N;   // [N]
-  __shared__ float red[kThreads / 32];
+__global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
+  extern __shared__ __align__(16) float cur[];   // [N]
+  __shared__ float red[64];
   const int tid = threadIdx.x;
   const int N = p.N;
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    const uint32_t flags = p.a.flags ? p.a.flags[b] : 0u;
+    const uint32_t flags = p.a.flags[b];
     const float* __restrict__ x = p.clips + (int64_t)b * N;
-    float* cur = A;
-    float* oth = Bf;
-    for (int i = tid; i < N; i += kThreads) cur[i] = __ldg(x + i);
+    float m = 0.0f, dummy = 0.0f;
+    for (int i = tid; i < N; i += kThreads) {
+      const float v = __ldg(x + i);
+      cur[i] = v;
+      m = fmaxf(m, fabsf(v));
+    }
+    if (flags & WW_AUG_NORM_IN) {
+      block_reduce2<true>(m, dummy, red, tid);
+      if (m > 0.0f)
+        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], m);     // own elements only: no hazard
+    }
     __syncthreads();
 
-    if (flags & WW_AUG_NORM_IN) {
-      float m = 0.0f;
-      for (int i = tid; i < N; i += kThreads) m = fmaxf(m, fabsf(cur[i]));
-      float peak = block_reduce<true>(m, red, tid);
-      if (peak > 0.0f)
-        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], peak);
-      __syncthreads();
-    }
-    if (flags & WW_AUG_SHIFT) {
-      int s = p.a.shift[b] % N;
-      if (s < 0) s += N;                                   // out[i] = in[(i - shift) mod N]
-      for (int i = tid; i < N; i += kThreads) {
-        int src = i - s;
-        if (src < 0) src += N;
-        oth[i] = cur[src];
-      }
-      __syncthreads();
-      float* t = cur; cur = oth; oth = t;
-    }
-    if (flags & WW_AUG_SPEED) {
-      const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
-      int found = -1;
-      for (int i = 0; i < p.n_rs; ++i)
-        if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { found = i; break; }
-      if (found < 0) {
-        for (int i = tid; i < N; i += kThreads) oth[i] = __int_as_float(0x7fc00000);   // loud: NaN clip
-      } else {
-        const RsDesc d = p.rs_desc[found];
-        const float* __restrict__ kern = p.rs_kern + d.offset;
-        const long long out_len = ((long long)d.n * N + d.o - 1) / d.o;      // ceil(n*N/o)
-        const int crop = (out_len > N) ? p.a.crop_off[b] : 0;
-        for (int i = tid; i < N; i += kThreads) {
-          const long long j = (long long)i + crop;                          // resampled-domain index
-          float acc = 0.0f;
-          if (j < out_len) {
-            const int q = (int)(j / d.n), ph = (int)(j - (long long)q * d.n);
-            const int x0 = q * d.o - d.width;                                // source index of tap 0
-            const float* __restrict__ kr = kern + ph * d.taps;
-            const int* __restrict__ rng = reinterpret_cast<const int*>(kern + d.n * d.taps);
-            int k0 = max(__ldg(rng + ph), x0 < 0 ? -x0 : 0);                 // non-zero tap range of this phase
-            int k1 = min(__ldg(rng + d.n + ph), (x0 + d.taps > N) ? (N - x0) : d.taps);
-            for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(kr + k), cur[x0 + k], acc);
+    if (flags & (WW_AUG_SHIFT | WW_AUG_SPEED)) {
+      // ---- one gather: out[i] = sum_k kern[ph][k] * rolled[x0 + k],  rolled[t] = cur[(t - shift) mod N]
+      int s = (flags & WW_AUG_SHIFT) ? p.a.shift[b] % N : 0;
+      if (s < 0) s += N;
+      float o[kMaxPerThread];
+      if (flags & WW_AUG_SPEED) {
+        const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+        int found = -1;
+        for (int i = 0; i < p.n_rs; ++i)
+          if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { found = i; break; }
+        if (found < 0) {
+#pragma unroll
+          for (int e = 0; e < kMaxPerThread; ++e) o[e] = __int_as_float(0x7fc00000);   // loud: NaN clip
+        } else {
+          const RsDesc d = p.rs_desc[found];
+          const float* __restrict__ kern = p.rs_kern + d.offset;
+          const int* __restrict__ rng = reinterpret_cast<const int*>(kern + d.n * d.taps);
+          const long long out_len = ((long long)d.n * N + d.o - 1) / d.o;          // ceil(n*N/o)
+          const int crop = (out_len > N) ? p.a.crop_off[b] : 0;
+#pragma unroll
+          for (int e = 0; e < kMaxPerThread; ++e) {
+            const int i = tid + e * kThreads;
+            float acc0 = 0.0f, acc1 = 0.0f;
+            const long long j = (long long)i + crop;                                // resampled-domain index
+            if (i < N && j < out_len) {
+              const int q = (int)(j / d.n), ph = (int)(j - (long long)q * d.n);
+              const int x0 = q * d.o - d.width;                                      // source index of tap 0
+              const float* __restrict__ kr = kern + ph * d.taps;
+              const int k0 = max(__ldg(rng + ph), x0 < 0 ? -x0 : 0);                // non-zero taps of this phase
+              const int k1 = min(__ldg(rng + d.n + ph), (x0 + d.taps > N) ? (N - x0) : d.taps);
+              int src = x0 + k0 - s;
+              if (src < 0) src += N;
+              int k = k0;
+              for (; k + 1 < k1; k += 2) {                                           // two independent chains
+                const int s1 = (src + 1 >= N) ? src + 1 - N : src + 1;
+                acc0 = fmaf(__ldg(kr + k), cur[src], acc0);
+                acc1 = fmaf(__ldg(kr + k + 1), cur[s1], acc1);
+                src = (s1 + 1 >= N) ? s1 + 1 - N : s1 + 1;
+              }
+              if (k < k1) acc0 = fmaf(__ldg(kr + k), cur[src], acc0);
+            }
+            o[e] = acc0 + acc1;
           }
-          oth[i] = acc;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < kMaxPerThread; ++e) {
+          const int i = tid + e * kThreads;
+          int src = i - s;
+          if (src < 0) src += N;
+          o[e] = (i < N) ? cur[src] : 0.0f;                                         // bit-exact copy (np.roll)
         }
       }
       __syncthreads();
-      float* t = cur; cur = oth; oth = t;
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) {
+        const int i = tid + e * kThreads;
+        if (i < N) cur[i] = o[e];
+      }
+      __syncthreads();
     }
+
     if (flags & WW_AUG_NOISE) {
       const float* __restrict__ nz = p.bank + (int64_t)p.a.noise_idx[b] * p.bank_len + p.a.noise_off[b];
       const float snr = p.a.snr_db[b];
@@ -124,42 +149,37 @@ __global__ void __launch_bounds__(kThreads) augment_kernel(AugKParams p) {
       float sc = 0.0f, sn = 0.0f;
       for (int i = tid; i < N; i += kThreads) {
         const float c = cur[i], n = __ldg(nz + i);
-        oth[i] = n;
         sc = fmaf(c, c, sc);
         sn = fmaf(n, n, sn);
       }
-      const float rmsclean = sqrtf(block_reduce<false>(sc, red, tid) / (float)N);
-      const float rmsnoise = sqrtf(block_reduce<false>(sn, red, tid) / (float)N);
-      const float scalarclean = target / rmsclean, scalarnoise = target / rmsnoise;
+      block_reduce2<false>(sc, sn, red, tid);
+      const float scalarclean = target / sqrtf(sc / (float)N), scalarnoise = target / sqrtf(sn / (float)N);
       // the reference re-measures both RMS values after scaling (audiolib.py:60,65)
       float sc2 = 0.0f, sn2 = 0.0f;
       for (int i = tid; i < N; i += kThreads) {
-        const float c = cur[i] * scalarclean, n = oth[i] * scalarnoise;
-        cur[i] = c; oth[i] = n;
+        const float c = cur[i] * scalarclean, n = __ldg(nz + i) * scalarnoise;
+        cur[i] = c;
         sc2 = fmaf(c, c, sc2);
         sn2 = fmaf(n, n, sn2);
       }
-      const float rc2 = sqrtf(block_reduce<false>(sc2, red, tid) / (float)N);
-      const float rn2 = sqrtf(block_reduce<false>(sn2, red, tid) / (float)N);
-      const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);      // audiolib.py:68 (sqrt quirk kept)
-      for (int i = tid; i < N; i += kThreads) cur[i] = cur[i] + oth[i] * noisescalar;
-      __syncthreads();
+      block_reduce2<false>(sc2, sn2, red, tid);
+      const float rc2 = sqrtf(sc2 / (float)N), rn2 = sqrtf(sn2 / (float)N);
+      const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);          // audiolib.py:68 (sqrt quirk kept)
+      for (int i = tid; i < N; i += kThreads) cur[i] = cur[i] + (__ldg(nz + i) * scalarnoise) * noisescalar;
     }
     if (flags & WW_AUG_GAIN) {
       const float g = p.a.gain[b];
       for (int i = tid; i < N; i += kThreads) cur[i] *= g;
-      __syncthreads();
-    }
-    if (flags & WW_AUG_NORM_OUT) {
-      float m = 0.0f;
-      for (int i = tid; i < N; i += kThreads) m = fmaxf(m, fabsf(cur[i]));
-      float peak = block_reduce<true>(m, red, tid);
-      if (peak > 0.0f)
-        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], peak);
-      __syncthreads();
     }
     float* __restrict__ o = p.out + (int64_t)b * N;
-    for (int i = tid; i < N; i += kThreads) o[i] = cur[i];
+    if (flags & WW_AUG_NORM_OUT) {
+      float mo = 0.0f;
+      for (int i = tid; i < N; i += kThreads) mo = fmaxf(mo, fabsf(cur[i]));
+      block_reduce2<true>(mo, dummy, red, tid);
+      for (int i = tid; i < N; i += kThreads) o[i] = (mo > 0.0f) ? __fdiv_rn(cur[i], mo) : cur[i];
+    } else {
+      for (int i = tid; i < N; i += kThreads) o[i] = cur[i];
+    }
     __syncthreads();
   }
 }
@@ -198,15 +218,17 @@ int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank
   p.clips = clips; p.bank = bank; p.bank_rows = bank_rows; p.bank_len = bank_len;
   p.a = *a; p.out = out; p.B = B; p.N = c->cfg.n_samples;
   p.rs_desc = c->d_rs_desc; p.n_rs = (int)c->rs_tables.size(); p.rs_kern = c->d_rs_kern;
-  size_t smem = (size_t)2 * p.N * sizeof(float);
-  if (smem > 220 * 1024) { c->set_error("ww_augment: n_samples too large for the shared-memory clip buffers"); return WW_ERR_INVALID; }
+  if (p.N > kThreads * kMaxPerThread) {
+    c->set_error("ww_augment: n_samples too large (max 16384 samples per clip)");
+    return WW_ERR_INVALID;
+  }
+  size_t smem = (size_t)p.N * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     WW_CHECK(c, cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  int grid = c->sm_count * (int)((227 * 1024) / (smem + 1024));
-  if (grid > B) grid = B;
+  int grid = std::min(c->sm_count, B);
   ProfScope prof(c, WW_STAGE_AUGMENT, st);
   augment_kernel<<<grid, kThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);

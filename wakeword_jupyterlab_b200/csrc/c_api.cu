@@ -141,6 +141,8 @@ int free_all(ww_ctx* c) {
   cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits);
   cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   return 0;
 }
@@ -519,7 +521,7 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
   float* d_logits = (float*)c->d_host_out;
   float* d_prob = d_logits + (size_t)B * C;
   uint8_t* d_dec = (uint8_t*)(d_prob + B);
-  ww_aug a_dev;
+  ww_aug a_dev = {};
   if (aug_host) {
     if ((rc = ensure_buffer(c, &c->d_host_aug, &c->d_host_aug_bytes, (size_t)B * 9 * 4))) return rc;
     uint32_t* base = (uint32_t*)c->d_host_aug;
@@ -533,16 +535,33 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
     a_dev.snr_db = (float*)(base + (size_t)7 * B); a_dev.gain = (float*)(base + (size_t)8 * B);
   }
   if ((rc = ww_prepare_weights(c, st))) return rc;
-  // chunked so that the H2D copy of chunk i+1 can overlap the kernels of chunk i on the copy engine
+  // Two streams: the copy engine moves chunk i+1 host->device while the SMs score chunk i.
+  if (!c->copy_stream) WW_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   float* d_in = (float*)c->d_host_in;
-  for (int b0 = 0; b0 < B; b0 += c->chunk) {
-    const int nb = std::min(c->chunk, B - b0);
-    WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N, clips_host + (size_t)b0 * N, (size_t)nb * N * 4,
-                                cudaMemcpyHostToDevice, st));
+  const int n_chunks = (B + c->chunk - 1) / c->chunk;
+  while ((int)c->copy_events.size() < n_chunks) {
+    cudaEvent_t e;
+    WW_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->copy_events.push_back(e);
   }
-  rc = score_impl(c, d_in, N, bank_dev, bank_rows, bank_len, aug_host ? &a_dev : nullptr, normalize, d_logits, d_prob,
-                  d_dec, B, st);
-  if (rc) return rc;
+  for (int i = 0; i < n_chunks; ++i) {
+    const int b0 = i * c->chunk, nb = std::min(c->chunk, B - b0);
+    WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N, clips_host + (size_t)b0 * N, (size_t)nb * N * 4,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+    WW_CHECK(c, cudaEventRecord(c->copy_events[i], c->copy_stream));
+  }
+  for (int i = 0; i < n_chunks; ++i) {
+    const int b0 = i * c->chunk, nb = std::min(c->chunk, B - b0);
+    WW_CHECK(c, cudaStreamWaitEvent(st, c->copy_events[i], 0));
+    ww_aug a = a_dev;
+    if (aug_host) {
+      a.flags += b0; a.shift += b0; a.rs_orig += b0; a.rs_new += b0; a.crop_off += b0;
+      a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
+    }
+    rc = score_impl(c, d_in + (size_t)b0 * N, N, bank_dev, bank_rows, bank_len, aug_host ? &a : nullptr, normalize,
+                    d_logits + (size_t)b0 * C, d_prob + b0, d_dec + b0, nb, st);
+    if (rc) return rc;
+  }
   if (logits_host) WW_CHECK(c, cudaMemcpyAsync(logits_host, d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
   if (prob1_host) WW_CHECK(c, cudaMemcpyAsync(prob1_host, d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (decision_host) WW_CHECK(c, cudaMemcpyAsync(decision_host, d_dec, (size_t)B, cudaMemcpyDeviceToHost, st));

@@ -4,14 +4,14 @@
 // (/root/reference/wakeword_training_script.py:170-171).  See conv3_tc.cu for the layout story.
 //
 // Work item = (clip, 128-pixel tile of the pixel-linear padded image).  Warp roles:
-//   warps 0-3  producers: conv1 + ReLU in fp32 for the tile and its 3x3 halo (128 + 2P + 2 pixels), split to
+//   warps 0-7  producers: conv1 + ReLU in fp32 for the tile and its 3x3 halo (128 + 2P + 2 pixels), split to
 //              bf16 hi/lo and stored as the K-major SWIZZLE_NONE A operand [chunk of 8 ch][pixel][16 B]
 //              (double buffered, overlaps the MMAs of the previous tile);
-//   warp 4     one thread issues the MMAs: per 3x3 tap and 16-channel k-slice
+//   warp 8     one thread issues the MMAs: per 3x3 tap and 16-channel k-slice
 //                 D[:, 0:128] += A_hi x [W_hi ; W_lo]^T   (N = 128: hi*hi and hi*lo in one instruction)
 //                 D[:, 0:64 ] += A_lo x  W_hi^T           (N = 64)
 //              -- the tap is only a start-address offset of the same shared-memory tile;
-//   warps 5-8  epilogue: TMEM -> D1 + D2 + bias, ReLU, zero the padding pixels, split hi/lo, write the conv3
+//   warps 9-16 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM -> D1 + D2 + bias, ReLU, zero the padding pixels, split hi/lo, write the conv3
 //              operand planes to HBM (each warp store is 512 contiguous bytes).
 // conv2 weights (hi and lo stacked along N, 73,728 B) stay resident in shared memory.
 #include "tc_common.cuh"
@@ -22,7 +22,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int C12_THREADS = 288;
+constexpr int C12_THREADS = 544;   // warps 0-7 producers, warp 8 MMA issuer, warps 9-16 epilogue
 constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 bf16]
 
 struct Conv12Params {
@@ -61,14 +61,14 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
   if (tid == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full + i, 128);
+      mbar_init(a_full + i, 256);
       mbar_init(a_empty + i, 1);
       mbar_init(t_full + i, 1);
-      mbar_init(t_empty + i, 128);
+      mbar_init(t_empty + i, 256);
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
   const int n_items = p.B * g.T2;
   const int NL = 128 + 2 * g.P + 2;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== conv1 producers
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
       unsigned char* ab = a_buf0 + buf * a_bytes;
       const float* __restrict__ img = p.logmel + (size_t)b * g.H * g.W;
       const int pbase = 128 * t2 - 1 - g.P - 1;
-      for (int l = tid; l < NL; l += 128) {
+      for (int l = tid; l < NL; l += 256) {
         int y, x;
         float v[32];
         if (pix_valid(pbase + l, g, y, x)) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
       fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(a_full + buf);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== MMA issuer (one thread)
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, W2_BYTES);
@@ -170,28 +170,22 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
     }
   } else {
     // ===================== epilogue
-    const int q = warp & 3;       // TMEM lane quadrant this warp may access
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int hc = (warp - 9) >> 2;       // which 32 of the 64 output channels
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / g.T2, t2 = item - b * g.T2;
       const int buf = it & 1;
       mbar_wait(t_full + buf, (it >> 1) & 1, 30);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + hc * 32;
       uint32_t r0[32], r1[32];
-      float v[64];
+      float v[32];
       tmem_ld32_nowait(taddr, r0);
-      tmem_ld32_nowait(taddr + 32, r1);
+      if (NPASS == 3) tmem_ld32_nowait(taddr + 64, r1);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-      if (NPASS == 3) {
-        tmem_ld32_nowait(taddr + 64, r0);
-        tmem_ld32_nowait(taddr + 96, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] += __uint_as_float(r0[i]); v[32 + i] += __uint_as_float(r1[i]); }
-      }
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + (NPASS == 3 ? __uint_as_float(r1[i]) : 0.0f);
       tc_fence_before();
       mbar_arrive(t_empty + buf);
       const int s = 128 * t2 + q * 32 + lane;
@@ -199,10 +193,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
       const bool ok = pix_valid(s - 1, g, y, x);
       uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 16 * g.npix + s;
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int kc = hc * 4 + k4;
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = ok ? fmaxf(v[kc * 8 + e] + b2s[kc * 8 + e], 0.0f) : 0.0f;
+        for (int e = 0; e < 8; ++e) o[e] = ok ? fmaxf(v[k4 * 8 + e] + b2s[kc * 8 + e], 0.0f) : 0.0f;
         uint4 hi, lo;
         split8(o, hi, lo);
         dst[(size_t)(kc * 2 + 0) * g.npix] = hi;
@@ -212,7 +207,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
 size_t conv12_smem(const Geom& g) { return (size_t)W2_BYTES + 2 * 8 * (size_t)g.nsl2 * 16 + (288 + 32 + 64) * 4 + 16 * 8 + 64; }

@@ -97,6 +97,8 @@ struct ww_ctx {
   uint32_t* d_tc_mask = nullptr;      // conv3 tile validity masks [T3][4]
   // host staging for ww_score_host
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;          // H2D copies of ww_score_host overlap the kernels
+  std::vector<cudaEvent_t> copy_events;
   void* d_host_in = nullptr; size_t d_host_in_bytes = 0;
   void* d_host_out = nullptr; size_t d_host_out_bytes = 0;
   void* d_host_aug = nullptr; size_t d_host_aug_bytes = 0;

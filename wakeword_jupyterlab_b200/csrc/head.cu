@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int CPB = 16;   // clips per CTA
+constexpr int CPB = 8;    // clips per CTA
 
 struct HeadParams {
   const float* pool_part;   // [B][n_part][128] partial sums of relu(conv3)
@@ -62,7 +62,7 @@ __global__ void head_kernel(HeadParams p) {
       const float bi = __ldg(bs + j), bg = __ldg(bs + H + j), bo = __ldg(bs + 2 * H + j);
 #pragma unroll
       for (int c = 0; c < CPB; ++c) { ai[c] = bi; ag[c] = bg; ao[c] = bo; }
-#pragma unroll 2
+#pragma unroll 8
       for (int k = 0; k < K; ++k) {
         const float wi = __ldg(wt + ((size_t)k * 3 + 0) * H + j);
         const float wg = __ldg(wt + ((size_t)k * 3 + 1) * H + j);
