@@ -21,6 +21,7 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kMaxPerThread = 16;     // n_samples <= kThreads * kMaxPerThread
+constexpr int kTblWords = 2560;       // shared-memory room for one ratio's compact polyphase table
 
 struct AugKParams {
   const float* clips;
@@ -59,10 +60,11 @@ __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, in
 }
 
 __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
-  extern __shared__ __align__(16) float cur[];   // [N]
+  extern __shared__ __align__(16) float cur[];   // [N] clip, then [kTblWords] polyphase table
   __shared__ float red[64];
   const int tid = threadIdx.x;
   const int N = p.N;
+  float* tbl = cur + ((N + 3) & ~3);
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const uint32_t flags = p.a.flags[b];
@@ -95,31 +97,39 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
           for (int e = 0; e < kMaxPerThread; ++e) o[e] = __int_as_float(0x7fc00000);   // loud: NaN clip
         } else {
           const RsDesc d = p.rs_desc[found];
-          const float* __restrict__ kern = p.rs_kern + d.offset;
-          const int* __restrict__ rng = reinterpret_cast<const int*>(kern + d.n * d.taps);
-          const long long out_len = ((long long)d.n * N + d.o - 1) / d.o;          // ceil(n*N/o)
+          // compact polyphase table of this ratio -> shared memory ([n][nz] taps, [n] first tap, [n] count)
+          const int tbl_words = d.n * d.nz + 2 * d.n;
+          const bool in_smem = tbl_words <= kTblWords;
+          const float* __restrict__ gk = p.rs_kern + d.offset;
+          if (in_smem)
+            for (int i = tid; i < tbl_words; i += kThreads) tbl[i] = __ldg(gk + i);
+          __syncthreads();
+          const float* kern = in_smem ? tbl : gk;
+          const int* lo_t = reinterpret_cast<const int*>(kern + d.n * d.nz);
+          const int* cnt_t = lo_t + d.n;
+          const int out_len = (d.n * N + d.o - 1) / d.o;                             // ceil(n*N/o), < 2^31
           const int crop = (out_len > N) ? p.a.crop_off[b] : 0;
 #pragma unroll
           for (int e = 0; e < kMaxPerThread; ++e) {
             const int i = tid + e * kThreads;
             float acc0 = 0.0f, acc1 = 0.0f;
-            const long long j = (long long)i + crop;                                // resampled-domain index
+            const int j = i + crop;                                                  // resampled-domain index
             if (i < N && j < out_len) {
-              const int q = (int)(j / d.n), ph = (int)(j - (long long)q * d.n);
-              const int x0 = q * d.o - d.width;                                      // source index of tap 0
-              const float* __restrict__ kr = kern + ph * d.taps;
-              const int k0 = max(__ldg(rng + ph), x0 < 0 ? -x0 : 0);                // non-zero taps of this phase
-              const int k1 = min(__ldg(rng + d.n + ph), (x0 + d.taps > N) ? (N - x0) : d.taps);
+              const int q = j / d.n, ph = j - q * d.n;                               // (q, p) phase decomposition
+              const int x0 = q * d.o - d.width + lo_t[ph];                           // source index of the first non-zero tap
+              const float* kr = kern + ph * d.nz;
+              const int k0 = x0 < 0 ? -x0 : 0;
+              const int k1 = min(cnt_t[ph], N - x0);
               int src = x0 + k0 - s;
               if (src < 0) src += N;
               int k = k0;
               for (; k + 1 < k1; k += 2) {                                           // two independent chains
                 const int s1 = (src + 1 >= N) ? src + 1 - N : src + 1;
-                acc0 = fmaf(__ldg(kr + k), cur[src], acc0);
-                acc1 = fmaf(__ldg(kr + k + 1), cur[s1], acc1);
+                acc0 = fmaf(kr[k], cur[src], acc0);
+                acc1 = fmaf(kr[k + 1], cur[s1], acc1);
                 src = (s1 + 1 >= N) ? s1 + 1 - N : s1 + 1;
               }
-              if (k < k1) acc0 = fmaf(__ldg(kr + k), cur[src], acc0);
+              if (k < k1) acc0 = fmaf(kr[k], cur[src], acc0);
             }
             o[e] = acc0 + acc1;
           }
@@ -222,7 +232,7 @@ int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank
     c->set_error("ww_augment: n_samples too large (max 16384 samples per clip)");
     return WW_ERR_INVALID;
   }
-  size_t smem = (size_t)p.N * sizeof(float);
+  size_t smem = (size_t)(((p.N + 3) & ~3) + kTblWords) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     WW_CHECK(c, cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

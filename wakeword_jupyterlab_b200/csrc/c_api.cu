@@ -319,17 +319,26 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
   // Per-phase range of non-zero taps, appended as int bit patterns ([n] first tap, [n] end tap).  Taps outside
   // the +-6 zero-crossing window are exactly 0.0f (their double value underflows), so skipping them leaves
   // every output bit-identical while cutting e.g. 111 taps to ~14 for 97 -> 100.
+  // Device form: compact [n][nz] table of the non-zero taps + [n] first-tap index + [n] count (int bit patterns).
   {
-    std::vector<float> rng((size_t)2 * t.n);
+    std::vector<int> lo(t.n), cnt(t.n);
+    int nz = 1;
     for (int p = 0; p < t.n; ++p) {
-      int lo = t.taps, hi = 0;
+      int l = t.taps, h = 0;
       for (int i = 0; i < t.taps; ++i)
-        if (k[(size_t)p * t.taps + i] != 0.0f) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
-      if (hi <= lo) { lo = 0; hi = 0; }
-      memcpy(&rng[p], &lo, 4);
-      memcpy(&rng[(size_t)t.n + p], &hi, 4);
+        if (k[(size_t)p * t.taps + i] != 0.0f) { l = std::min(l, i); h = std::max(h, i + 1); }
+      if (h <= l) { l = 0; h = 0; }
+      lo[p] = l; cnt[p] = h - l;
+      nz = std::max(nz, h - l);
     }
-    k.insert(k.end(), rng.begin(), rng.end());
+    std::vector<float> comp((size_t)t.n * nz + 2 * t.n, 0.0f);
+    for (int p = 0; p < t.n; ++p) {
+      for (int i = 0; i < cnt[p]; ++i) comp[(size_t)p * nz + i] = k[(size_t)p * t.taps + lo[p] + i];
+      memcpy(&comp[(size_t)t.n * nz + p], &lo[p], 4);
+      memcpy(&comp[(size_t)t.n * nz + t.n + p], &cnt[p], 4);
+    }
+    t.nz = nz;
+    k.swap(comp);
   }
   const int need = c->rs_kern_floats + (int)k.size();
   if (need > c->rs_kern_cap) {
@@ -355,7 +364,7 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
   std::vector<RsDesc> d(c->rs_tables.size());
   for (size_t i = 0; i < d.size(); ++i) {
     const ResampleTable& r = c->rs_tables[i];
-    d[i] = RsDesc{r.orig, r.neu, r.o, r.n, r.width, r.taps, r.offset, 0};
+    d[i] = RsDesc{r.orig, r.neu, r.o, r.n, r.width, r.taps, r.offset, r.nz};
   }
   WW_CHECK(c, cudaMemcpy(c->d_rs_desc, d.data(), d.size() * sizeof(RsDesc), cudaMemcpyHostToDevice));
   return WW_OK;

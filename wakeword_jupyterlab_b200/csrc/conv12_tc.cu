@@ -79,24 +79,50 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(Conv12Params p) 
 
   if (warp < 8) {
     // ===================== conv1 producers
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int b = item / g.T2, t2 = item - b * g.T2;
-      const int buf = it & 1;
-      mbar_wait(a_empty + buf, ((it >> 1) & 1) ^ 1, 10);
-      unsigned char* ab = a_buf0 + buf * a_bytes;
-      const float* __restrict__ img = p.logmel + (size_t)b * g.H * g.W;
-      const int pbase = 128 * t2 - 1 - g.P - 1;
-      for (int l = tid; l < NL; l += 256) {
-        int y, x;
-        float v[32];
-        if (pix_valid(pbase + l, g, y, x)) {
-          float in[9];
+    // Software pipeline: the 3x3 input patches of the NEXT tile are loaded (global, L2 latency) before the
+    // current tile is computed, so the loads overlap ~600 instructions of conv1 arithmetic.
+    float in_n[2][9];
+    bool ok_n[2] = {false, false};
+    auto load_in = [&](int item_) {
+      const int b_ = item_ / g.T2, t2_ = item_ - b_ * g.T2;
+      const float* __restrict__ img = p.logmel + (size_t)b_ * g.H * g.W;
+      const int pbase = 128 * t2_ - 1 - g.P - 1;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int l = tid + u * 256;
+        int y = 0, x = 0;
+        ok_n[u] = (l < NL) && pix_valid(pbase + l, g, y, x);
+        if (ok_n[u]) {
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
             const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
-            in[k] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(img + yy * g.W + xx) : 0.0f;
+            in_n[u][k] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(img + yy * g.W + xx) : 0.0f;
           }
+        }
+      }
+    };
+    if ((int)blockIdx.x < n_items) load_in(blockIdx.x);
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      float in_c[2][9];
+      bool ok_c[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ok_c[u] = ok_n[u];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) in_c[u][k] = in_n[u][k];
+      }
+      if (item + (int)gridDim.x < n_items) load_in(item + gridDim.x);
+      mbar_wait(a_empty + buf, ((it >> 1) & 1) ^ 1, 10);
+      unsigned char* ab = a_buf0 + buf * a_bytes;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int l = tid + u * 256;
+        if (l >= NL) break;
+        float v[32];
+        if (ok_c[u]) {
+          const float* in = in_c[u];
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = b1s[c];
 #pragma unroll

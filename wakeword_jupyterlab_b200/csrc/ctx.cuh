@@ -34,11 +34,12 @@ struct ResampleTable {
   int o, n;           // reduced by gcd
   int width, taps;
   int offset;         // float offset into d_rs_kern
+  int nz;             // columns of the compact table (max non-zero taps over the phases)
 };
 
 // Device-visible descriptor of one prepared resample ratio.
 struct RsDesc {
-  int orig, neu, o, n, width, taps, offset, pad;
+  int orig, neu, o, n, width, taps, offset, nz;   // device table at `offset`: [n][nz] taps, [n] first tap, [n] count
 };
 
 struct ProfSlot { cudaEvent_t a, b; int stage; };

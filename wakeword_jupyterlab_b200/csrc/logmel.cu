@@ -4,15 +4,16 @@
 // librosa.feature.melspectrogram(center=True, pad_mode="constant", hann, power=2, slaney mel)
 // followed by librosa.power_to_db(ref=np.max, amin=1e-10, top_db=80).
 //
-// One CTA (2 groups of 256 threads, 2 CTAs per SM) per clip; each group owns one in-place n_fft-point complex FFT
-// buffer in shared memory and takes frame PAIRS round-robin: frame 2p is the real part, frame 2p+1 the
-// imaginary part of one complex FFT (mixed radix 8/4/2 Stockham, register-staged so it runs in place);
-// the two spectra are separated by Hermitian symmetry and squared in place ((P_even, P_odd) as one
-// float2 per bin) and projected onto the banded slaney filterbank (2 lanes per mel band, both frames
-// at once).  Twiddles come from compact per-stage tables (no strided shared-memory gathers); window,
-// twiddles and the packed filterbank live in shared memory.  The n_mels x W mel power of the clip stays
-// in shared memory, so the per-clip max that the dB conversion needs (ref=np.max) never costs a second
-// pass over HBM.  Peak normalisation (normalize_audio) is folded in: |X/peak|^2 = |X|^2 / peak^2.
+// One CTA (2 groups of 256 threads, 2 CTAs per SM) per clip; each group owns one in-place n_fft-point
+// complex FFT buffer in shared memory and takes frame PAIRS round-robin: frame 2p is the real part,
+// frame 2p+1 the imaginary part of one complex FFT (mixed radix 8/4/2 Stockham, register-staged so it
+// runs in place; n_fft is a template parameter so every index is a shift/constant); the two spectra are
+// separated by Hermitian symmetry and squared in place ((P_even, P_odd) as one float2 per bin) and
+// projected onto the banded slaney filterbank (2 lanes per mel band, both frames at once).  Twiddles
+// come from compact per-stage tables (no strided shared-memory gathers); window, twiddles and the
+// packed filterbank live in shared memory.  The n_mels x W mel power of the clip stays in shared
+// memory, so the per-clip max that the dB conversion needs (ref=np.max) never costs a second pass over
+// HBM.  Peak normalisation (normalize_audio) is folded in: |X/peak|^2 = |X|^2 / peak^2.
 //
 // HBM traffic per clip: n_samples*4 B in (frame overlap re-reads hit L2) + n_mels*W*4 B out
 // = 74,240 B at the code preset.
@@ -71,20 +72,23 @@ __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGT) : "memory");
 }
 
-// In-place Stockham stage (radix R, Ns = product of the radices already applied) on one group's buffer.
-// Butterfly j: v[r] = z[j + r*N/R] * w^(r),  w = exp(-2 pi i k / (Ns R)), k = j % Ns (compact table `ts[k]`);
-// z[(j - k) * R + k + r * Ns] = DFT_R(v)[r].  Every thread reads its (<= 2) butterflies, the group syncs, then writes.
-template <int R, int ITERS>
-__device__ __forceinline__ void stockham_stage_i(float2* z, const float2* __restrict__ ts, int N, int Ns, int gt, int grp) {
-  const int nb = N / R;
+// In-place Stockham stage (radix R, NS = product of the radices already applied) on one group's buffer.
+// Butterfly j: v[r] = z[j + r*N/R] * w^r,  w = exp(-2 pi i k / (NS R)), k = j % NS (compact table `ts[k]`);
+// z[(j - k) * R + k + r * NS] = DFT_R(v)[r].  Every thread reads its butterflies, the group syncs, then writes.
+template <int N, int R, int NS>
+__device__ __forceinline__ void stockham_stage(float2* z, const float2* __restrict__ ts, int gt, int grp) {
+  constexpr int NB = N / R;                               // butterflies (multiple of 32)
+  constexpr int ITERS = NB > kGT ? NB / kGT : 1;
+  constexpr int RSTEP = NB + NB / 32;                     // padded distance between the R inputs
   float2 v[ITERS][R];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int j = gt + it * kGT;
-    if (j < nb) {
+    if (NB >= kGT || j < NB) {
+      const int rb = padi(j);
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[it][r] = z[padi(j + r * nb)];
-      const float2 w1 = ts[j & (Ns - 1)];
+      for (int r = 0; r < R; ++r) v[it][r] = z[rb + r * RSTEP];
+      const float2 w1 = ts[j & (NS - 1)];
       float2 w = w1;
 #pragma unroll
       for (int r = 1; r < R; ++r) {
@@ -98,20 +102,33 @@ __device__ __forceinline__ void stockham_stage_i(float2* z, const float2* __rest
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int j = gt + it * kGT;
-    if (j < nb) {
-      const int k = j & (Ns - 1);
+    if (NB >= kGT || j < NB) {
+      const int k = j & (NS - 1);
       const int base = (j - k) * R + k;
+      if (NS % 32 == 0) {
+        const int wb = padi(base);
 #pragma unroll
-      for (int r = 0; r < R; ++r) z[padi(base + r * Ns)] = v[it][r];
+        for (int r = 0; r < R; ++r) z[wb + r * (NS + NS / 32)] = v[it][r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[padi(base + r * NS)] = v[it][r];
+      }
     }
   }
   group_sync(grp);
 }
-template <int R>
-__device__ __forceinline__ void stockham_stage(float2* z, const float2* __restrict__ ts, int N, int Ns, int gt, int grp) {
-  // n_fft <= 2048 (checked in ww_create): a radix-8 stage has <= 256 butterflies, radix 4/2 at most 512
-  if (R < 8 && N / R > kGT) stockham_stage_i<R, (R < 8 ? 2 : 1)>(z, ts, N, Ns, gt, grp);
-  else stockham_stage_i<R, 1>(z, ts, N, Ns, gt, grp);
+
+// remaining stages after the first radix-8 one: radices 8, 8, ..., then 4 or 2; compact twiddle tables
+// (stage table k -> T[k * N / (NS R)]) are packed one after the other in `twc`; the last stage (step 1) reads `tw`.
+template <int N, int NS, int REM, int OFF>
+__device__ __forceinline__ void run_stages(float2* z, const float2* tw, const float2* twc, int gt, int grp) {
+  if constexpr (REM > 0) {
+    constexpr int LG = REM >= 3 ? 3 : REM;
+    constexpr int R = 1 << LG;
+    constexpr int TSTEP = N / (NS * R);
+    stockham_stage<N, R, NS>(z, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+    run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0)>(z, tw, twc, gt, grp);
+  }
 }
 
 struct LogmelParams {
@@ -119,7 +136,7 @@ struct LogmelParams {
   int64_t clip_stride;
   float* out;
   int B, normalize;
-  int n_samples, n_fft, log2n, hop, W, n_mels, mel_nnz;
+  int n_samples, hop, W, n_mels, mel_nnz;
   const float* window;
   const float2* twiddle;
   const int* mel_start;
@@ -140,12 +157,14 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid) {
   return r;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
+  constexpr int N = 1 << LOG2N;
+  constexpr int NPAD = N + (N >> 5) + 8;
+  constexpr int NBINS = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = p.n_fft;
-  const int npad = N + (N >> 5) + 8;
-  float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][npad]
-  float2* tw = zbuf + kGroups * npad;                          // [N]      exp(-2 pi i t / N)
+  float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][NPAD]
+  float2* tw = zbuf + kGroups * NPAD;                          // [N]      exp(-2 pi i t / N)
   float2* twc = tw + N;                                        // compact tables of the middle stages (< N/8 entries)
   float* win = reinterpret_cast<float*>(twc + N / 8);          // [N]
   float* melw = win + N;                                       // [mel_nnz]
@@ -155,18 +174,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
 
   const int tid = threadIdx.x;
   const int grp = tid / kGT, gt = tid % kGT;
-  const int nbins = N / 2 + 1;
+  const int n_samples = p.n_samples, hop = p.hop, W = p.W, n_mels = p.n_mels;
 
   // ---- tables -> shared memory (once per CTA)
   for (int i = tid; i < N; i += kThreads) { tw[i] = p.twiddle[i]; win[i] = p.window[i]; }
   for (int i = tid; i < p.mel_nnz; i += kThreads) melw[i] = p.mel_w[i];
-  for (int i = tid; i < p.n_mels; i += kThreads) {
-    mst[i] = p.mel_start[i]; mst[p.n_mels + i] = p.mel_len[i]; mst[2 * p.n_mels + i] = p.mel_off[i];
+  for (int i = tid; i < n_mels; i += kThreads) {
+    mst[i] = p.mel_start[i]; mst[n_mels + i] = p.mel_len[i]; mst[2 * n_mels + i] = p.mel_off[i];
   }
   {
-    // compact per-stage twiddles: stage with Ns and radix R uses T[k * N/(Ns R)], k < Ns; stages are
-    // (8, 8, ..., last) so Ns = 8, 64, 512, ...; the last stage (tstep == 1) reads `tw` directly.
-    int off = 0, Ns = 8, rem = p.log2n - 3;
+    int off = 0, Ns = 8, rem = LOG2N - 3;
     while (rem > 0) {
       const int lg = rem >= 3 ? 3 : rem;
       const int tstep = N / (Ns << lg);
@@ -184,53 +201,43 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
     float inv_peak = 1.0f;
     if (p.normalize) {
       float m = 0.0f;
-      for (int i = tid; i < p.n_samples; i += kThreads) m = fmaxf(m, fabsf(__ldg(x + i)));
+      for (int i = tid; i < n_samples; i += kThreads) m = fmaxf(m, fabsf(__ldg(x + i)));
       const float peak = block_max(m, red, tid);
       inv_peak = (peak > 0.0f) ? 1.0f / peak : 1.0f;   // silent clip: reference gives NaN (0/0); guarded, see DESIGN.md
     }
-    float2* z = zbuf + grp * npad;
-    const int n_pairs = (p.W + 1) >> 1;
+    const float scale = inv_peak * inv_peak;
+    float2* z = zbuf + grp * NPAD;
+    const int n_pairs = (W + 1) >> 1;
     for (int pr = grp; pr < n_pairs; pr += kGroups) {
       const int t0 = 2 * pr, t1 = 2 * pr + 1;
-      const int s0 = p.hop * t0 - (N >> 1);
-      const int s1 = (t1 < p.W) ? p.hop * t1 - (N >> 1) : (1 << 30);
-      // ---- first stage: radix 8 straight from global (framing + window), Ns = 1
+      const int s0 = hop * t0 - (N >> 1);
+      const int s1 = (t1 < W) ? hop * t1 - (N >> 1) : (1 << 30);
+      // ---- first stage: radix 8 straight from global (framing + window), NS = 1
       {
-        const int nb = N >> 3;
-        for (int j = gt; j < nb; j += kGT) {
+        constexpr int NB = N >> 3;
+        if (NB >= kGT || gt < NB) {
           float2 v[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const int n = j + r * nb;
+            const int n = gt + r * NB;
             const float w = win[n];
             const int i0 = s0 + n, i1 = s1 + n;
-            const float a = (i0 >= 0 && i0 < p.n_samples) ? __ldg(x + i0) : 0.0f;
-            const float c = (i1 >= 0 && i1 < p.n_samples) ? __ldg(x + i1) : 0.0f;
+            const float a = ((unsigned)i0 < (unsigned)n_samples) ? __ldg(x + i0) : 0.0f;
+            const float c = ((unsigned)i1 < (unsigned)n_samples) ? __ldg(x + i1) : 0.0f;
             v[r] = make_float2(w * a, w * c);
           }
           dft8(v);
+          const int wb = gt * 8 + (gt >> 2);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) z[padi(j * 8 + r)] = v[r];
+          for (int r = 0; r < 8; ++r) z[wb + r] = v[r];
         }
       }
       group_sync(grp);
-      // ---- remaining stages (in place)
-      {
-        int Ns = 8, rem = p.log2n - 3, off = 0;
-        while (rem > 0) {
-          const int lg = rem >= 3 ? 3 : rem;
-          const int tstep = N / (Ns << lg);
-          const float2* ts = (tstep > 1) ? (twc + off) : tw;
-          if (lg == 3) stockham_stage<8>(z, ts, N, Ns, gt, grp);
-          else if (lg == 2) stockham_stage<4>(z, ts, N, Ns, gt, grp);
-          else stockham_stage<2>(z, ts, N, Ns, gt, grp);
-          if (tstep > 1) off += Ns;
-          Ns <<= lg; rem -= lg;
-        }
-      }
+      run_stages<N, 8, LOG2N - 3, 0>(z, tw, twc, gt, grp);
       // ---- Hermitian split + power, in place: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2.
       // Bin k reads z[k] and z[N-k] and is the only reader of both, so no sync is needed before the store.
-      for (int k = gt; k < nbins; k += kGT) {
+#pragma unroll
+      for (int k = gt; k < NBINS; k += kGT) {
         const float2 zk = z[padi(k)];
         const float2 zn = z[padi((N - k) & (N - 1))];
         const float ar = zk.x + zn.x, ai = zk.y - zn.y;
@@ -239,11 +246,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
       }
       group_sync(grp);
       // ---- banded mel projection: 2 lanes per band, both frames at once
-      for (int mb = 0; mb < p.n_mels; mb += kGT / 2) {
+      for (int mb = 0; mb < n_mels; mb += kGT / 2) {
         const int m = mb + (gt >> 1), half = gt & 1;
         float a0 = 0.0f, a1 = 0.0f;
-        if (m < p.n_mels) {
-          const int st = mst[m], len = mst[p.n_mels + m], off = mst[2 * p.n_mels + m];
+        if (m < n_mels) {
+          const int st = mst[m], len = mst[n_mels + m], off = mst[2 * n_mels + m];
 #pragma unroll 4
           for (int i = half; i < len; i += 2) {
             const float w = melw[off + i];
@@ -254,16 +261,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
         }
         a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-        if (m < p.n_mels && half == 0) {
-          mel_s[m * p.W + t0] = a0 * inv_peak * inv_peak;
-          if (t1 < p.W) mel_s[m * p.W + t1] = a1 * inv_peak * inv_peak;
+        if (m < n_mels && half == 0) {
+          mel_s[m * W + t0] = a0 * scale;
+          if (t1 < W) mel_s[m * W + t1] = a1 * scale;
         }
       }
       group_sync(grp);
     }
     __syncthreads();
     // ---- power_to_db(ref=max, amin, top_db)
-    const int total = p.n_mels * p.W;
+    const int total = n_mels * W;
     float m = 0.0f;
     for (int i = tid; i < total; i += kThreads) m = fmaxf(m, mel_s[i]);
     const float ref = block_max(m, red, tid);
@@ -278,6 +285,19 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(LogmelParams p) {
   }
 }
 
+template <int LOG2N>
+int launch_t(ww_ctx* c, const LogmelParams& p, size_t smem, int grid, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope prof(c, WW_STAGE_LOGMEL, st);
+  logmel_kernel<LOG2N><<<grid, kThreads, smem, st>>>(p);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
 }  // namespace
 
 int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize,
@@ -285,30 +305,25 @@ int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* 
   if (B <= 0) return WW_OK;
   LogmelParams p;
   p.clips = clips; p.clip_stride = clip_stride; p.out = out; p.B = B; p.normalize = normalize;
-  p.n_samples = c->cfg.n_samples; p.n_fft = c->cfg.n_fft; p.hop = c->cfg.hop_length; p.W = c->W;
+  p.n_samples = c->cfg.n_samples; p.hop = c->cfg.hop_length; p.W = c->W;
   p.n_mels = c->cfg.n_mels; p.mel_nnz = c->mel_nnz;
-  int l2 = 0; while ((1 << l2) < p.n_fft) ++l2;
-  p.log2n = l2;
   p.window = c->d_window; p.twiddle = c->d_twiddle;
   p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off; p.mel_w = c->d_mel_w;
-  const int N = p.n_fft;
+  const int N = c->cfg.n_fft;
   const int npad = N + (N >> 5) + 8;
   size_t smem = (size_t)(kGroups * npad + N + N / 8) * sizeof(float2) + (size_t)N * sizeof(float) +
                 (size_t)p.mel_nnz * sizeof(float) + (size_t)3 * p.n_mels * sizeof(int) +
                 (size_t)p.n_mels * p.W * sizeof(float) + 16;
   if (smem > 227 * 1024) { c->set_error("ww_logmel: configuration exceeds shared memory"); return WW_ERR_INVALID; }
-  static size_t configured = 0;
-  if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   int grid = c->sm_count * per_sm;
   if (grid > B) grid = B;
-  ProfScope prof(c, WW_STAGE_LOGMEL, st);
-  logmel_kernel<<<grid, kThreads, smem, st>>>(p);
-  WW_LAUNCH_CHECK(c);
-  return WW_OK;
+  switch (N) {
+    case 256: return launch_t<8>(c, p, smem, grid, st);
+    case 512: return launch_t<9>(c, p, smem, grid, st);
+    case 1024: return launch_t<10>(c, p, smem, grid, st);
+    case 2048: return launch_t<11>(c, p, smem, grid, st);
+    default: c->set_error("ww_logmel: n_fft must be 256, 512, 1024 or 2048"); return WW_ERR_INVALID;
+  }
 }

@@ -107,11 +107,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const float r0 = v[2 * i] - __bfloat162float(h0), r1 = v[2 * i + 1] - __bfloat162float(h1);
-    __nv_bfloat162 hh;
-    hh.x = h0; hh.y = h1;
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    // packed conversions (F2FP, full rate) instead of scalar F2F; bf16 -> f32 is a 16-bit shift / mask
+    h[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+    const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
     l[i] = pack_bf16(r0, r1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
