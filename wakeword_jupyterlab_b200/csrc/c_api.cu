@@ -388,6 +388,7 @@ int ww_prepare_weights(ww_ctx* c, cudaStream_t st) {
         for (int k = 0; k < 9; ++k) t[((size_t)ci * 9 + k) * couts[l] + co] = w[((size_t)co * cins[l] + ci) * 9 + k];
     int rc = upload(c, &c->d_convw_t[l], t);
     if (rc) return rc;
+    if (l == 0) { c->h_w1t = t; c->h_b1 = fetch(c, "conv1.bias"); c->h_b2 = fetch(c, "conv2.bias"); }   // -> kernel parameters (constant bank)
   }
   const int H = c->cfg.hidden_size;
   for (int l = 0; l < c->cfg.num_layers; ++l) {

@@ -26,8 +26,11 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 using namespace tc;
+
+#define C3_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 48 && lane == 0) p.trace[it * 16 + (slot)] = clock64(); } while (0)
 
 namespace {
 
@@ -41,6 +44,7 @@ struct Conv3Params {
   float* pool_part;               // [B][n_groups][128]
   int B;
   Geom g;
+  long long* trace;               // debug (WW_TC_TRACE=1): per-group role timestamps of CTA 0
 };
 
 template <int NPASS>
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
                                     ((size_t)b * 16 * g.npix + (size_t)grp * g.G * 128) * 16;
         for (int j = 0; j < 4; ++j) {
           mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
+          if (j == 0) C3_TRACE(0);
           mbar_arrive_expect_tx(a_full + j, 4 * nload);
 #pragma unroll
           for (int pl = 0; pl < 4; ++pl)      // planes (kc = 2j, 2j+1) x (hi, lo) are consecutive: index 4j + pl
@@ -107,51 +112,56 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
-      const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
-      const uint64_t pdesc0 = make_desc(smem_u32(a_s), 2u * plane_bytes, 128);  // pixels: kc stride = 2 planes
-      const uint32_t plane_u = plane_bytes >> 4;
-      int it = 0;
-      uint32_t ws = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int grp = item % g.n_groups;
-        const int n_t = min(g.G, g.T3 - grp * g.G);
-        // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
-        const uint32_t idA = n_t >= 2 ? idesc256 : idesc128;
-        const uint32_t idB = n_t >= 4 ? idesc256 : idesc128;
-        const bool second = n_t >= 3;
-        mbar_wait(t_empty, (it & 1) ^ 1, 50);
-        uint32_t acc = 0;
-        for (int j = 0; j < 4; ++j) {
-          mbar_wait(a_full + j, it & 1, 51);
-          for (int tt = 0; tt < 3; ++tt, ++ws) {
-            const uint32_t st = ws % C3_NST;
-            mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
-            tc_fence_after();
-            const uint64_t wst = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES) >> 4);
+    // ===================== MMA issuer.  The whole warp runs the loop so that descriptors stay warp-uniform
+    // (uniform registers feed UTCHMMA directly); only the elected lane issues.
+    const bool leader = (lane == 0);
+    constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
+    const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
+    const uint64_t pdesc0 = make_desc(smem_u32(a_s), 2u * plane_bytes, 128);  // pixels: kc stride = 2 planes
+    const uint32_t plane_u = plane_bytes >> 4;
+    int it = 0;
+    uint32_t ws = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int grp = item % g.n_groups;
+      const int n_t = min(g.G, g.T3 - grp * g.G);
+      // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
+      const uint32_t idA = n_t >= 2 ? idesc256 : idesc128;
+      const uint32_t idB = n_t >= 4 ? idesc256 : idesc128;
+      const bool second = n_t >= 3;
+      mbar_wait(t_empty, (it & 1) ^ 1, 50);
+      C3_TRACE(1);
+      uint32_t acc = 0;
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(a_full + j, it & 1, 51);
+        C3_TRACE(2 + j);
+        for (int tt = 0; tt < 3; ++tt, ++ws) {
+          const uint32_t st = ws % C3_NST;
+          mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
+          tc_fence_after();
+          const uint64_t wst = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES) >> 4);
 #pragma unroll
-            for (int tl = 0; tl < 3; ++tl) {
-              const int tap = tt * 3 + tl;                       // ky = tt, kx = tl
-              const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));
+          for (int tl = 0; tl < 3; ++tl) {
+            const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
 #pragma unroll
-              for (int ps = 0; ps < NPASS; ++ps) {
-                const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
-                const uint64_t wd = wst + (uint64_t)(((tl * 2 + hlw) * 4096) >> 4);
-                const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off);
+            for (int ps = 0; ps < NPASS; ++ps) {
+              const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
+              const uint64_t wd = wst + (uint64_t)(((tl * 2 + hlw) * 4096) >> 4);
+              const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off);
+              if (leader) {
                 umma_bf16(tmem_base, wd, pd, idA, acc);
                 if (second) umma_bf16(tmem_base + 256, wd, pd + 256, idB, acc);
-                acc = 1;
               }
-              (void)tap;
+              acc = 1;
             }
-            umma_commit(w_empty + st);
           }
-          umma_commit(a_empty + j);
+          if (leader) umma_commit(w_empty + st);
+          __syncwarp();
         }
-        umma_commit(t_full);
+        if (leader) umma_commit(a_empty + j);
       }
+      if (leader) umma_commit(t_full);
+      __syncwarp();
+      C3_TRACE(6);
     }
   } else {
     // ===================== epilogue (8 warps): lane = output channel, columns = pixels
@@ -163,7 +173,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / g.n_groups, grp = item - b * g.n_groups;
       const int n_t = min(g.G, g.T3 - grp * g.G);
-      mbar_wait(t_full, it & 1, 60);
+      mbar_wait_relaxed(t_full, it & 1, 60);
+      if (warp == 2) C3_TRACE(7);
       tc_fence_after();
       float sum = 0.0f;
 #pragma unroll
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       }
       tc_fence_before();
       mbar_arrive(t_empty);
+      if (warp == 2) C3_TRACE(8);
       scratch[half * 128 + ch] = sum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0) p.pool_part[((size_t)b * g.n_groups + grp) * 128 + ch] = scratch[ch] + scratch[128 + ch];
@@ -264,11 +276,27 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   Conv3Params p;
   p.act2 = c->ws_act2_split; p.w3s = c->d_w3_split; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
   p.pool_part = c->ws_pool_part; p.B = B; p.g = g;
+  static long long* d_trace = nullptr;
+  const bool tracing = getenv("WW_TC_TRACE") != nullptr;
+  if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 16 * 8); }
+  if (tracing) cudaMemset(d_trace, 0, 48 * 16 * 8);
+  p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B * g.n_groups);
   ProfScope prof(c, WW_STAGE_CONV3, st);
   if (c->cfg.conv_mode == WW_CONV_BF16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
   else conv3_kernel<3><<<grid, C3_THREADS, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
+  if (tracing) {
+    long long h[48 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "conv3 trace: ld_start | mma: t_empty a_full0 a_full1 a_full2 a_full3 issued | epi: t_full t_free\n");
+    for (int i = 0; i < 14; ++i) {
+      fprintf(stderr, "grp %2d:", i);
+      for (int k = 0; k < 9; ++k) fprintf(stderr, " %8lld", h[i * 16 + k] ? h[i * 16 + k] - h[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return WW_OK;
 }
 

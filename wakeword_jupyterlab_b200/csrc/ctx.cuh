@@ -96,6 +96,7 @@ struct ww_ctx {
   bool ws_ready = false;
   unsigned int* d_scalar = nullptr;   // scratch word for ww_normalize
   uint32_t* d_tc_mask = nullptr;      // conv3 tile validity masks [T3][4]
+  std::vector<float> h_w1t, h_b1, h_b2;   // host copies of conv1 weights [9][32], conv1/conv2 bias: passed as kernel parameters
   // host staging for ww_score_host
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;          // H2D copies of ww_score_host overlap the kernels

@@ -44,6 +44,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     if (++spins > (1u << 22)) mbar_timeout(code);
   }
 }
+// Same, for roles that are NOT on the critical path (producers / epilogue warps): back off between polls so the
+// spinning warps do not steal issue slots from the MMA-issuing warp that shares their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 22)) mbar_timeout(code);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -127,11 +136,12 @@ struct Geom {
   int G, n_groups;    // conv3: tiles per group (<= 4), groups per clip
   int nsl2;           // conv12 A-tile slots  = round8(128 + 2P + 2)
   int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
+  uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
 };
 
 __device__ __forceinline__ bool pix_valid(int p, const Geom& g, int& y, int& x) {
   if (p < 0) return false;
-  const int row = p / g.P;
+  const int row = (int)__umulhi((uint32_t)p, g.magicP);
   y = row - 1;
   x = p - row * g.P - 1;
   return (y >= 0) && (y < g.H) && (x >= 0);
@@ -176,6 +186,7 @@ inline Geom make_geom(const ww_ctx* c) {
   g.n_groups = (g.T3 + g.G - 1) / g.G;
   g.nsl2 = (128 + 2 * g.P + 2 + 7) & ~7;
   g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
+  g.magicP = (uint32_t)((0x100000000ull + (uint64_t)g.P - 1) / (uint64_t)g.P);
   return g;
 }
 
