@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   const int patch_floats = (((128 + 2 * g.P + 2 + g.P - 1) / g.P + 3) * g.W + 3) & ~3;
   float* patch = reinterpret_cast<float*>(bars + 10);        // [2][patch_floats] log-mel rows of the current / next tile
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so role branches are uniform
+  // branches and the MMA issue loop runs on the uniform datapath (no per-MMA R2UR waterfall)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int n_items = p.B * g.T2;
   const int NL = 128 + 2 * g.P + 2;

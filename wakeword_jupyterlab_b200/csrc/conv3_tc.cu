@@ -61,24 +61,25 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   uint64_t* a_empty = bars + 4;            // [4]
   uint64_t* w_full = bars + 8;             // [NST]
   uint64_t* w_empty = bars + 8 + C3_NST;   // [NST]
-  uint64_t* t_full = bars + 8 + 2 * C3_NST;
-  uint64_t* t_empty = t_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+  uint64_t* t_full = bars + 8 + 2 * C3_NST;   // [2] accumulator halves: tiles (0,1) = TMEM cols 0..255, tiles (2,3) = 256..511
+  uint64_t* t_empty = t_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so role branches are uniform
+  // branches and the MMA issue loop runs on the uniform datapath (no per-MMA R2UR waterfall)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid < 128) b3s[tid] = p.b3[tid];
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < C3_NST; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    mbar_init(t_full, 1);
-    mbar_init(t_empty, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int n_items = p.B * g.n_groups;
 
@@ -119,67 +120,97 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
     const uint64_t pdesc0 = make_desc(smem_u32(a_s), 2u * plane_bytes, 128);  // pixels: kc stride = 2 planes
     const uint32_t plane_u = plane_bytes >> 4;
-    int it = 0;
+    // One (tap, pass) step for accumulator half `h` (0: tiles 0,1   1: tiles 2,3) of k-slice j from weight stage st.
+    auto step = [&](uint32_t st, int j, int tt, int tl, int ps, int h, uint32_t idesc, uint32_t acc) {
+      const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
+      const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
+      const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + hlw) * 4096) >> 4);
+      const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off + h * 256);
+      if (leader) umma_bf16(tmem_base + h * 256, wd, pd, idesc, acc);
+    };
+    int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
     uint32_t ws = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int grp = item % g.n_groups;
       const int n_t = min(g.G, g.T3 - grp * g.G);
       // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
-      const uint32_t idA = n_t >= 2 ? idesc256 : idesc128;
-      const uint32_t idB = n_t >= 4 ? idesc256 : idesc128;
+      const uint32_t id0 = n_t >= 2 ? idesc256 : idesc128;
+      const uint32_t id1 = n_t >= 4 ? idesc256 : idesc128;
       const bool second = n_t >= 3;
-      mbar_wait(t_empty, (it & 1) ^ 1, 50);
-      C3_TRACE(1);
-      uint32_t acc = 0;
+      const uint32_t par = it & 1;
+      // The first and the last k-slice run the two accumulator halves one after the other (the three weight
+      // stages of that slice stay resident for both sweeps), so that the epilogue of half 0 overlaps the last
+      // sweep of half 1, and the epilogue of half 1 overlaps the first sweep of half 0 of the NEXT group.
       for (int j = 0; j < 4; ++j) {
-        mbar_wait(a_full + j, it & 1, 51);
+        mbar_wait(a_full + j, par, 51);
         C3_TRACE(2 + j);
-        for (int tt = 0; tt < 3; ++tt, ++ws) {
-          const uint32_t st = ws % C3_NST;
-          mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
-          tc_fence_after();
-          const uint64_t wst = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES) >> 4);
+        if (j == 0 || j == 3) {
+          if (j == 0) { mbar_wait(t_empty + 0, par ^ 1, 50); C3_TRACE(1); }
+          for (int tt = 0; tt < 3; ++tt) {
+            const uint32_t st = (ws + tt) % C3_NST;
+            mbar_wait(w_full + st, ((ws + tt) / C3_NST) & 1, 52);
+            tc_fence_after();
 #pragma unroll
-          for (int tl = 0; tl < 3; ++tl) {
-            const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
+            for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
-            for (int ps = 0; ps < NPASS; ++ps) {
-              const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
-              const uint64_t wd = wst + (uint64_t)(((tl * 2 + hlw) * 4096) >> 4);
-              const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off);
-              if (leader) {
-                umma_bf16(tmem_base, wd, pd, idA, acc);
-                if (second) umma_bf16(tmem_base + 256, wd, pd + 256, idB, acc);
-              }
-              acc = 1;
-            }
+              for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
           }
-          if (leader) umma_commit(w_empty + st);
-          __syncwarp();
+          if (j == 3) { if (leader) umma_commit(t_full + 0); }
+          if (j == 0 && second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
+          tc_fence_after();
+          for (int tt = 0; tt < 3; ++tt) {
+            const uint32_t st = (ws + tt) % C3_NST;
+            if (second) {
+#pragma unroll
+              for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 1, id1, (j | tt | tl | ps) != 0);
+            }
+            if (leader) umma_commit(w_empty + st);
+            __syncwarp();
+          }
+          ws += 3;
+          if (j == 3 && second) { if (leader) umma_commit(t_full + 1); ++it1; }
+        } else {
+          for (int tt = 0; tt < 3; ++tt, ++ws) {
+            const uint32_t st = ws % C3_NST;
+            mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
+            tc_fence_after();
+#pragma unroll
+            for (int tl = 0; tl < 3; ++tl)
+#pragma unroll
+              for (int ps = 0; ps < NPASS; ++ps) {
+                step(st, j, tt, tl, ps, 0, id0, 1);
+                if (second) step(st, j, tt, tl, ps, 1, id1, 1);
+              }
+            if (leader) umma_commit(w_empty + st);
+            __syncwarp();
+          }
         }
         if (leader) umma_commit(a_empty + j);
+        __syncwarp();
       }
-      if (leader) umma_commit(t_full);
-      __syncwarp();
       C3_TRACE(6);
     }
   } else {
     // ===================== epilogue (8 warps): lane = output channel, columns = pixels
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;       // 0: tiles 0,1   1: tiles 2,3
+    const int sub = (warp - 2) >> 2;        // which tile of each accumulator half this warp drains (the two warps that
+                                            // share a lane quadrant split the half, so all 8 warps work on the ready half)
     const int ch = q * 32 + lane;
     const float bias = b3s[ch];
-    int it = 0;
+    int it = 0, it1 = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / g.n_groups, grp = item - b * g.n_groups;
       const int n_t = min(g.G, g.T3 - grp * g.G);
-      mbar_wait_relaxed(t_full, it & 1, 60);
-      if (warp == 2) C3_TRACE(7);
-      tc_fence_after();
       float sum = 0.0f;
 #pragma unroll
-      for (int ti = 0; ti < 2; ++ti) {
-        const int i = half * 2 + ti;
+      for (int h = 0; h < 2; ++h) {
+        if (h * 2 >= n_t) break;            // half h is unused by this group (no MMAs, no barrier flips)
+        mbar_wait_relaxed(t_full + h, (h ? it1 : it) & 1, 60 + h);
+        if (warp == 2 && h == 0) C3_TRACE(7);
+        tc_fence_after();
+        const int i = h * 2 + sub;
         if (i < n_t) {
           const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + (grp * g.G + i));
           const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
@@ -201,13 +232,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
             sum += s0 + s1;
           }
         }
+        tc_fence_before();
+        mbar_arrive(t_empty + h);
+        if (warp == 2 && h == 0) C3_TRACE(8);
+        if (h) ++it1;
       }
-      tc_fence_before();
-      mbar_arrive(t_empty);
-      if (warp == 2) C3_TRACE(8);
-      scratch[half * 128 + ch] = sum;
+      scratch[sub * 128 + ch] = sum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) p.pool_part[((size_t)b * g.n_groups + grp) * 128 + ch] = scratch[ch] + scratch[128 + ch];
+      if (sub == 0) p.pool_part[((size_t)b * g.n_groups + grp) * 128 + ch] = scratch[ch] + scratch[128 + ch];
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
