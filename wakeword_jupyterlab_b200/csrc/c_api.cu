@@ -138,7 +138,7 @@ int free_all(ww_ctx* c) {
   for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); }
   cudaFree(c->d_w2_split); cudaFree(c->d_w3_split);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
-  cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits);
+  cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
   cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
@@ -152,12 +152,8 @@ int ensure_workspaces(ww_ctx* c) {
   if (c->ws_ready) return WW_OK;
   const ww_config& g = c->cfg;
   const int H = g.n_mels, W = c->W;
-  const int tiles_fp32 = ((W + 31) / 32) * ((H + 7) / 8);
-  const int tiles_tc = ((H + 2) * (W + 2) + 127) / 128 + 1;
-  const size_t part_cap = (size_t)std::max(tiles_fp32, tiles_tc);
   WW_CHECK(c, cudaMalloc((void**)&c->ws_clips, (size_t)c->chunk * g.n_samples * 4));
   WW_CHECK(c, cudaMalloc((void**)&c->ws_logmel, (size_t)c->chunk * H * W * 4));
-  WW_CHECK(c, cudaMalloc((void**)&c->ws_pool_part, (size_t)c->chunk * part_cap * 128 * 4));
   WW_CHECK(c, cudaMalloc((void**)&c->ws_logits, (size_t)c->chunk * g.num_classes * 4));
   if (g.conv_mode == WW_CONV_FP32) {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act1, (size_t)c->chunk * 32 * H * W * 4));
@@ -166,6 +162,28 @@ int ensure_workspaces(ww_ctx* c) {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_split, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
   }
   c->ws_ready = true;
+  return WW_OK;
+}
+
+int ensure_buffer(ww_ctx* c, void** buf, size_t* cap, size_t need);
+
+// pool partials and head activations cover the WHOLE batch of a call (the head runs once per call, not per chunk)
+int ensure_pool(ww_ctx* c, int64_t B) {
+  if (B <= c->pool_cap_clips) return WW_OK;
+  const int H = c->cfg.n_mels, W = c->W;
+  const int tiles_fp32 = ((W + 31) / 32) * ((H + 7) / 8);
+  const int tiles_tc = ((H + 2) * (W + 2) + 127) / 128 + 1;
+  const size_t part_cap = (size_t)std::max(tiles_fp32, tiles_tc);
+  const int64_t cap = std::max<int64_t>(B, c->chunk);
+  size_t dummy = 0;
+  int rc;
+  if ((rc = ensure_buffer(c, (void**)&c->ws_pool_part, &dummy, (size_t)cap * part_cap * 128 * 4))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    dummy = 0;
+    if ((rc = ensure_buffer(c, (void**)&c->ws_h[i], &dummy, (size_t)cap * c->cfg.hidden_size * 4))) return rc;
+  }
+  c->pool_cap_clips = cap;
+  c->pool_part_cap = (int)part_cap;
   return WW_OK;
 }
 
@@ -418,12 +436,15 @@ int ww_prepare_weights(ww_ctx* c, cudaStream_t st) {
 
 namespace {
 
-int forward_chunk(ww_ctx* c, const float* logmel, int B, float* logits, float* prob1, uint8_t* decision,
-                  cudaStream_t st) {
-  int rc = (c->cfg.conv_mode == WW_CONV_FP32) ? ww_launch_conv_fp32(c, logmel, B, st)
-                                              : ww_launch_conv_tc(c, logmel, B, st);
-  if (rc) return rc;
-  return ww_launch_head(c, B, logits, prob1, decision, st);
+int pool_parts(const ww_ctx* c) {
+  if (c->cfg.conv_mode == WW_CONV_FP32) return ((c->W + 31) / 32) * ((c->cfg.n_mels + 7) / 8);
+  return ww_conv_tc_groups(c);
+}
+
+// conv stack of one chunk; its pool partials land at clip offset `pool_off` of the batch-wide buffer
+int conv_chunk(ww_ctx* c, const float* logmel, int B, int64_t pool_off, cudaStream_t st) {
+  c->pool_cur = c->ws_pool_part + (size_t)pool_off * pool_parts(c) * 128;
+  return (c->cfg.conv_mode == WW_CONV_FP32) ? ww_launch_conv_fp32(c, logmel, B, st) : ww_launch_conv_tc(c, logmel, B, st);
 }
 
 }  // namespace
@@ -456,21 +477,24 @@ int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* strea
   int rc = ensure_workspaces(c);
   if (rc) return rc;
   if ((rc = ww_prepare_weights(c, st))) return rc;
+  if ((rc = ensure_pool(c, B))) return rc;
   const size_t per = (size_t)c->cfg.n_mels * c->W;
   for (int b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = std::min(c->chunk, B - b0);
-    rc = forward_chunk(c, logmel + (size_t)b0 * per, nb, logits + (size_t)b0 * c->cfg.num_classes, nullptr, nullptr, st);
-    if (rc) return rc;
+    if ((rc = conv_chunk(c, logmel + (size_t)b0 * per, nb, b0, st))) return rc;
   }
-  return WW_OK;
+  return ww_launch_head(c, B, logits, nullptr, nullptr, st);
 }
 
+// (augment) -> log-mel -> conv stack for clips [0, B) whose pool partials go to clip offset pool_off; the head
+// (whole batch) runs only when run_head is set, over clips [0, pool_off + B).
 static int score_impl(ww_ctx* c, const float* clips, int64_t clip_stride, const float* bank, int bank_rows,
                       int64_t bank_len, const ww_aug* aug, int normalize, float* logits, float* prob1,
-                      uint8_t* decision, int64_t B, cudaStream_t st) {
+                      uint8_t* decision, int64_t B, cudaStream_t st, int64_t pool_off = 0, bool run_head = true) {
   int rc = ensure_workspaces(c);
   if (rc) return rc;
   if ((rc = ww_prepare_weights(c, st))) return rc;
+  if ((rc = ensure_pool(c, pool_off + B))) return rc;
   const int N = c->cfg.n_samples;
   for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = (int)std::min<int64_t>(c->chunk, B - b0);
@@ -485,11 +509,11 @@ static int score_impl(ww_ctx* c, const float* clips, int64_t clip_stride, const 
       stride = N;
     }
     if ((rc = ww_launch_logmel(c, src, stride, c->ws_logmel, nb, aug ? 0 : normalize, st))) return rc;
-    rc = forward_chunk(c, c->ws_logmel, nb, logits ? logits + b0 * c->cfg.num_classes : nullptr,
-                       prob1 ? prob1 + b0 : nullptr, decision ? decision + b0 : nullptr, st);
-    if (rc) return rc;
+    if ((rc = conv_chunk(c, c->ws_logmel, nb, pool_off + b0, st))) return rc;
   }
-  return WW_OK;
+  if (!run_head) return WW_OK;
+  if (pool_off + B > 0x7fffffff) { c->set_error("score: batch too large"); return WW_ERR_INVALID; }
+  return ww_launch_head(c, (int)(pool_off + B), logits, prob1, decision, st);
 }
 
 int ww_score(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len, const ww_aug* aug,
@@ -568,8 +592,9 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
       a.flags += b0; a.shift += b0; a.rs_orig += b0; a.rs_new += b0; a.crop_off += b0;
       a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
     }
+    // the head (whole batch) runs with the last chunk
     rc = score_impl(c, d_in + (size_t)b0 * N, N, bank_dev, bank_rows, bank_len, aug_host ? &a : nullptr, normalize,
-                    d_logits + (size_t)b0 * C, d_prob + b0, d_dec + b0, nb, st);
+                    d_logits, d_prob, d_dec, nb, st, b0, i == n_chunks - 1);
     if (rc) return rc;
   }
   if (logits_host) WW_CHECK(c, cudaMemcpyAsync(logits_host, d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));

@@ -255,6 +255,8 @@ size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {
   return (size_t)16 * g.npix * 16;
 }
 
+int ww_conv_tc_groups(const ww_ctx* c) { return make_geom(c).n_groups; }
+
 int ww_conv12_tc_prepare(ww_ctx* c);
 
 // conv3 weights -> bf16 hi/lo in the UMMA canonical layout [j][tap][hl][kc][cout][8]; tile validity masks
@@ -307,7 +309,7 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   }
   Conv3Params p;
   p.act2 = c->ws_act2_split; p.w3s = c->d_w3_split; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
-  p.pool_part = c->ws_pool_part; p.B = B; p.g = g;
+  p.pool_part = c->pool_cur; p.B = B; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;
   if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 16 * 8); }

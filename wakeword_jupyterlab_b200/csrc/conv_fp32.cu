@@ -121,7 +121,7 @@ int ww_launch_conv_fp32(ww_ctx* c, const float* logmel, int B, cudaStream_t st) 
   }
   ProfScope prof3(c, WW_STAGE_CONV3, st);
   conv3x3_relu_kernel<64, 128, 32, 8, true><<<dim3(n_tiles, 4, B), block, 0, st>>>(
-      c->ws_act2, c->d_convw_t[2], c->w["conv3.bias"], c->ws_pool_part, H, W, tiles_x, n_tiles);
+      c->ws_act2, c->d_convw_t[2], c->w["conv3.bias"], c->pool_cur, H, W, tiles_x, n_tiles);
   WW_LAUNCH_CHECK(c);
   return WW_OK;
 }

@@ -90,7 +90,11 @@ struct ww_ctx {
   float* ws_act1 = nullptr;      // fp32 path: [chunk][32][H][W]
   float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
   __nv_bfloat16* ws_act2_split = nullptr;  // tc path: [chunk][8 chunks][2 hi/lo][NPIX][8] bf16
-  float* ws_pool_part = nullptr; // [chunk][n_part][128]
+  float* ws_pool_part = nullptr; // [pool_cap_clips][n_part][128]: conv3 partial sums of the whole batch of a call
+  float* pool_cur = nullptr;     // where the current chunk's conv launch writes its partials
+  float* ws_h[2] = {nullptr, nullptr};   // [pool_cap_clips][hidden]: head layer outputs (ping-pong)
+  int64_t pool_cap_clips = 0;
+  int pool_part_cap = 0;
   float* ws_logits = nullptr;    // [chunk][num_classes] (when caller passes NULL)
   int n_pool_part = 0;
   bool ws_ready = false;
@@ -137,3 +141,4 @@ int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decis
 int ww_prepare_weights(ww_ctx* c, cudaStream_t st);
 int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t st);
 size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c);
+int ww_conv_tc_groups(const ww_ctx* c);

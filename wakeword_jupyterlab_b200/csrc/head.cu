@@ -5,137 +5,172 @@
 // The reference feeds the LSTM a length-1 sequence with h0 = c0 = 0, so per layer
 //     g = W_ih x + b_ih + b_hh ;  c = sigmoid(g_i) tanh(g_g) ;  h = sigmoid(g_o) tanh(c)
 // (gate rows i,f,g,o; weight_hh and the forget rows never reach the output -- SURVEY.md trap 2);
-// eval-mode dropout is the identity.  Weights are pre-transposed to [K][3][H] (gates i,g,o) so that
-// consecutive threads (hidden units) read consecutive floats; activations of CPB clips sit in shared
-// memory as [K][CPB] and are read as float4 broadcasts: 7 loads per 48 FMAs.
-// Also finishes the global mean: sums the conv kernel's per-tile partial sums in a fixed order.
+// eval-mode dropout is the identity.
+//
+// One launch per layer over the WHOLE batch: a register-tiled fp32 GEMM with the gate nonlinearity as epilogue.
+// CTA tile = 64 clips x 64 hidden units x 3 gates, 256 threads, thread tile 4 clips x 4 units x 3 gates (48 FMAs
+// per 4 LDS.128), K staged through shared memory in chunks of 32 (weights pre-transposed to [K][3][H] so the
+// loads are coalesced).  Layer 0 finishes the global mean on the fly: x = sum of the conv kernel's per-group
+// partial sums (fixed order) / (H*W).  A last small kernel does Linear + softmax + threshold (one warp per clip).
 #include "ctx.cuh"
 
 namespace {
 
-constexpr int CPB = 8;    // clips per CTA
+constexpr int TM = 64, TN = 64, KC = 32, kThreads = 256;
 
-struct HeadParams {
-  const float* pool_part;   // [B][n_part][128] partial sums of relu(conv3)
+struct DenseParams {
+  const float* x;          // [B][K] activations, or pool partials [B][n_part][128] when n_part > 0
   int n_part;
-  float inv_hw;
-  int B, H, layers, n_classes;
-  const float* wt[8];       // [K][3][H]
-  const float* bias[8];     // [3][H]
-  const float* fc_w;        // [n_classes][H]
-  const float* fc_b;
-  float* logits;            // [B][n_classes] or null
-  float* prob1;             // [B] or null
-  uint8_t* decision;        // [B] or null
-  float threshold;
+  float x_scale;
+  const float* wt;         // [K][3][H]
+  const float* bias;       // [3][H]
+  float* out;              // [B][H]
+  int B, K, H;
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void head_kernel(HeadParams p) {
-  extern __shared__ __align__(16) float sm[];
-  const int H = p.H;
-  const int Kmax = H > 128 ? H : 128;
-  float* xs = sm;                   // [Kmax][CPB]
-  float* hs = sm + Kmax * CPB;      // [Kmax][CPB]
-  float* lg = hs + Kmax * CPB;      // [CPB][n_classes]
+__global__ void __launch_bounds__(kThreads) gated_dense_kernel(DenseParams p) {
+  __shared__ __align__(16) float xs[KC][TM];          // [k][clip]
+  __shared__ __align__(16) float ws[KC][3][TN];       // [k][gate][unit]
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * CPB;
+  const int tx = tid & 15, ty = tid >> 4;             // units tx*4.., clips ty*4..
+  const int b0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
 
-  for (int i = tid; i < 128 * CPB; i += blockDim.x) {
-    const int clip = i >> 7, k = i & 127;
-    float s = 0.0f;
-    if (b0 + clip < p.B) {
-      const float* pp = p.pool_part + ((size_t)(b0 + clip) * p.n_part) * 128 + k;
-      for (int t = 0; t < p.n_part; ++t) s += __ldg(pp + (size_t)t * 128);
-    }
-    xs[k * CPB + clip] = s * p.inv_hw;
-  }
-  __syncthreads();
+  float acc[3][4][4];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[g][c][u] = 0.0f;
 
-  int K = 128;
-  for (int l = 0; l < p.layers; ++l) {
-    const float* __restrict__ wt = p.wt[l];
-    const float* __restrict__ bs = p.bias[l];
-    for (int j = tid; j < H; j += blockDim.x) {
-      float ai[CPB], ag[CPB], ao[CPB];
-      const float bi = __ldg(bs + j), bg = __ldg(bs + H + j), bo = __ldg(bs + 2 * H + j);
-#pragma unroll
-      for (int c = 0; c < CPB; ++c) { ai[c] = bi; ag[c] = bg; ao[c] = bo; }
-#pragma unroll 8
-      for (int k = 0; k < K; ++k) {
-        const float wi = __ldg(wt + ((size_t)k * 3 + 0) * H + j);
-        const float wg = __ldg(wt + ((size_t)k * 3 + 1) * H + j);
-        const float wo = __ldg(wt + ((size_t)k * 3 + 2) * H + j);
-        const float4* xr = reinterpret_cast<const float4*>(xs + k * CPB);
-#pragma unroll
-        for (int c4 = 0; c4 < CPB / 4; ++c4) {
-          const float4 x = xr[c4];
-          ai[c4 * 4 + 0] = fmaf(wi, x.x, ai[c4 * 4 + 0]); ag[c4 * 4 + 0] = fmaf(wg, x.x, ag[c4 * 4 + 0]); ao[c4 * 4 + 0] = fmaf(wo, x.x, ao[c4 * 4 + 0]);
-          ai[c4 * 4 + 1] = fmaf(wi, x.y, ai[c4 * 4 + 1]); ag[c4 * 4 + 1] = fmaf(wg, x.y, ag[c4 * 4 + 1]); ao[c4 * 4 + 1] = fmaf(wo, x.y, ao[c4 * 4 + 1]);
-          ai[c4 * 4 + 2] = fmaf(wi, x.z, ai[c4 * 4 + 2]); ag[c4 * 4 + 2] = fmaf(wg, x.z, ag[c4 * 4 + 2]); ao[c4 * 4 + 2] = fmaf(wo, x.z, ao[c4 * 4 + 2]);
-          ai[c4 * 4 + 3] = fmaf(wi, x.w, ai[c4 * 4 + 3]); ag[c4 * 4 + 3] = fmaf(wg, x.w, ag[c4 * 4 + 3]); ao[c4 * 4 + 3] = fmaf(wo, x.w, ao[c4 * 4 + 3]);
+  for (int k0 = 0; k0 < p.K; k0 += KC) {
+    __syncthreads();
+    // ---- x tile: 64 clips x 32 k (global reads coalesced along k), stored transposed
+    for (int i = tid; i < TM * KC; i += kThreads) {
+      const int clip = i / KC, k = i % KC;
+      float v = 0.0f;
+      if (b0 + clip < p.B && k0 + k < p.K) {
+        if (p.n_part > 0) {
+          const float* pp = p.x + ((size_t)(b0 + clip) * p.n_part) * 128 + k0 + k;
+          for (int t = 0; t < p.n_part; ++t) v += __ldg(pp + (size_t)t * 128);
+          v *= p.x_scale;
+        } else {
+          v = __ldg(p.x + (size_t)(b0 + clip) * p.K + k0 + k);
         }
       }
-#pragma unroll
-      for (int c = 0; c < CPB; ++c) {
-        const float cc = sigmoidf_acc(ai[c]) * tanhf(ag[c]);
-        hs[j * CPB + c] = sigmoidf_acc(ao[c]) * tanhf(cc);
-      }
+      xs[k][clip] = v;
+    }
+    // ---- weight tile: 32 k x 3 gates x 64 units (coalesced along units)
+    for (int i = tid; i < KC * 3 * TN; i += kThreads) {
+      const int k = i / (3 * TN), r = i % (3 * TN), g = r / TN, u = r % TN;
+      float v = 0.0f;
+      if (k0 + k < p.K && j0 + u < p.H) v = __ldg(p.wt + ((size_t)(k0 + k) * 3 + g) * p.H + j0 + u);
+      ws[k][g][u] = v;
     }
     __syncthreads();
-    float* t = xs; xs = hs; hs = t;
-    K = H;
+#pragma unroll 8
+    for (int k = 0; k < KC; ++k) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+      const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[k][g][tx * 4]);
+        const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[g][c][u] = fmaf(x[c], w[u], acc[g][c][u]);
+      }
+    }
   }
+  // ---- gate epilogue: h = sigmoid(o) * tanh(sigmoid(i) * tanh(g))
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int b = b0 + ty * 4 + c;
+    if (b >= p.B) continue;
+    float h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + tx * 4 + u;
+      float v = 0.0f;
+      if (j < p.H) {
+        const float gi = acc[0][c][u] + __ldg(p.bias + j);
+        const float gg = acc[1][c][u] + __ldg(p.bias + p.H + j);
+        const float go = acc[2][c][u] + __ldg(p.bias + 2 * p.H + j);
+        v = sigmoidf_acc(go) * tanhf(sigmoidf_acc(gi) * tanhf(gg));
+      }
+      h[u] = v;
+    }
+    const int j = j0 + tx * 4;
+    if (j + 3 < p.H) *reinterpret_cast<float4*>(p.out + (size_t)b * p.H + j) = make_float4(h[0], h[1], h[2], h[3]);
+    else
+      for (int u = 0; u < 4; ++u)
+        if (j + u < p.H) p.out[(size_t)b * p.H + j + u] = h[u];
+  }
+}
 
-  // ---- Linear(H -> n_classes): one warp per (clip, class)
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int q = warp; q < CPB * p.n_classes; q += nwarps) {
-    const int clip = q / p.n_classes, cls = q % p.n_classes;
+struct FcParams {
+  const float* h;          // [B][H]
+  const float* fc_w;       // [n_classes][H]
+  const float* fc_b;
+  float* logits;           // [B][n_classes] or null
+  float* prob1;            // [B] or null
+  uint8_t* decision;       // [B] or null
+  float threshold;
+  int B, H, n_classes;
+};
+
+// Linear(H -> n_classes) + softmax + threshold: one warp per clip
+__global__ void __launch_bounds__(256) fc_softmax_kernel(FcParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B) return;
+  const float* __restrict__ h = p.h + (size_t)warp * p.H;
+  float l[16];
+  for (int cls = 0; cls < p.n_classes; ++cls) {
     float s = 0.0f;
-    for (int j = lane; j < H; j += 32) s = fmaf(xs[j * CPB + clip], __ldg(p.fc_w + (size_t)cls * H + j), s);
+    for (int j = lane; j < p.H; j += 32) s = fmaf(__ldg(h + j), __ldg(p.fc_w + (size_t)cls * p.H + j), s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) lg[q] = s + __ldg(p.fc_b + cls);
+    l[cls] = s + __ldg(p.fc_b + cls);
   }
-  __syncthreads();
-  for (int clip = tid; clip < CPB; clip += blockDim.x) {
-    const int b = b0 + clip;
-    if (b >= p.B) continue;
-    const float* l = lg + clip * p.n_classes;
+  if (lane == 0) {
     float mx = l[0];
     for (int i = 1; i < p.n_classes; ++i) mx = fmaxf(mx, l[i]);
     float den = 0.0f;
     for (int i = 0; i < p.n_classes; ++i) den += expf(l[i] - mx);
     const float p1 = expf(l[p.n_classes > 1 ? 1 : 0] - mx) / den;
-    if (p.logits) for (int i = 0; i < p.n_classes; ++i) p.logits[(size_t)b * p.n_classes + i] = l[i];
-    if (p.prob1) p.prob1[b] = p1;
-    if (p.decision) p.decision[b] = (p1 >= p.threshold) ? 1 : 0;
+    if (p.logits) for (int i = 0; i < p.n_classes; ++i) p.logits[(size_t)warp * p.n_classes + i] = l[i];
+    if (p.prob1) p.prob1[warp] = p1;
+    if (p.decision) p.decision[warp] = (p1 >= p.threshold) ? 1 : 0;
   }
 }
 
 }  // namespace
 
+// pool partials of clips [0, B) at c->ws_pool_part -> logits / prob1 / decision
 int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decision, cudaStream_t st) {
   if (B <= 0) return WW_OK;
-  HeadParams p;
-  p.pool_part = c->ws_pool_part; p.n_part = c->n_pool_part;
-  p.inv_hw = 1.0f / (float)(c->cfg.n_mels * c->W);
-  p.B = B; p.H = c->cfg.hidden_size; p.layers = c->cfg.num_layers; p.n_classes = c->cfg.num_classes;
-  for (int l = 0; l < 8; ++l) { p.wt[l] = c->d_head_wt[l]; p.bias[l] = c->d_head_b[l]; }
-  p.fc_w = c->w["fc.weight"]; p.fc_b = c->w["fc.bias"];
-  p.logits = logits; p.prob1 = prob1; p.decision = decision; p.threshold = c->cfg.threshold;
-  const int H = p.H, Kmax = H > 128 ? H : 128;
-  size_t smem = ((size_t)2 * Kmax * CPB + CPB * p.n_classes) * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  int threads = H < 1024 ? H : 1024;
-  if (threads < 64) threads = 64;
+  const int H = c->cfg.hidden_size;
   ProfScope prof(c, WW_STAGE_HEAD, st);
-  head_kernel<<<(B + CPB - 1) / CPB, threads, smem, st>>>(p);
+  const float* x = c->ws_pool_part;
+  for (int l = 0; l < c->cfg.num_layers; ++l) {
+    DenseParams p;
+    p.x = x; p.n_part = (l == 0) ? c->n_pool_part : 0;
+    p.x_scale = 1.0f / (float)(c->cfg.n_mels * c->W);
+    p.wt = c->d_head_wt[l]; p.bias = c->d_head_b[l];
+    p.out = c->ws_h[l & 1]; p.B = B; p.K = (l == 0) ? 128 : H; p.H = H;
+    dim3 grid((B + TM - 1) / TM, (H + TN - 1) / TN);
+    gated_dense_kernel<<<grid, kThreads, 0, st>>>(p);
+    WW_LAUNCH_CHECK(c);
+    x = p.out;
+  }
+  FcParams f;
+  f.h = x; f.fc_w = c->w["fc.weight"]; f.fc_b = c->w["fc.bias"];
+  f.logits = logits; f.prob1 = prob1; f.decision = decision; f.threshold = c->cfg.threshold;
+  f.B = B; f.H = H; f.n_classes = c->cfg.num_classes;
+  fc_softmax_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(f);
   WW_LAUNCH_CHECK(c);
   return WW_OK;
 }
