@@ -7,9 +7,9 @@
 //   NOISE    snr_mixer(clean, bank segment, snr)                      stock/ms_snsd/MS-SNSD/audiolib.py:55-71
 //   GAIN     linear gain
 //   NORM_OUT peak normalise
-// One CTA (1024 threads) per clip.  The clip lives in ONE shared-memory buffer between stages:
-// shift and speed change are a single gather (the resampler reads its taps through the roll index map), whose
-// outputs are held in registers across a barrier and written back in place.  HBM traffic is one read of the clip
+// One CTA (1024 threads) per clip.  Each thread keeps its 16 samples in REGISTERS through every element-wise stage
+// (normalise, SNR mix, gain); only the gather stage goes through shared memory: shift and speed change are a
+// single gather (the resampler reads its taps through the roll index map).  HBM traffic is one read of the clip
 // (+ the noise segment, re-read from L2 for the later passes) and one write: 128 KB (192 KB) per clip.
 // Index arithmetic (roll source index, (q,p) phase decomposition, tap range, crop offset, output length) is
 // integer-exact against oracle/augment.py; only exactly-zero taps of the polyphase table are skipped.
@@ -69,30 +69,38 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const uint32_t flags = p.a.flags[b];
     const float* __restrict__ x = p.clips + (int64_t)b * N;
+    float o[kMaxPerThread];          // this thread's samples i = tid + e * kThreads, live in registers from here on
     float m = 0.0f, dummy = 0.0f;
-    for (int i = tid; i < N; i += kThreads) {
-      const float v = __ldg(x + i);
-      cur[i] = v;
-      m = fmaxf(m, fabsf(v));
+#pragma unroll
+    for (int e = 0; e < kMaxPerThread; ++e) {
+      const int i = tid + e * kThreads;
+      o[e] = (i < N) ? __ldg(x + i) : 0.0f;
+      m = fmaxf(m, fabsf(o[e]));
     }
     if (flags & WW_AUG_NORM_IN) {
       block_reduce2<true>(m, dummy, red, tid);
-      if (m > 0.0f)
-        for (int i = tid; i < N; i += kThreads) cur[i] = __fdiv_rn(cur[i], m);     // own elements only: no hazard
+      if (m > 0.0f) {
+#pragma unroll
+        for (int e = 0; e < kMaxPerThread; ++e) o[e] = __fdiv_rn(o[e], m);
+      }
     }
-    __syncthreads();
 
     if (flags & (WW_AUG_SHIFT | WW_AUG_SPEED)) {
-      // ---- one gather: out[i] = sum_k kern[ph][k] * rolled[x0 + k],  rolled[t] = cur[(t - shift) mod N]
+      // ---- one gather through shared memory: out[i] = sum_k kern[ph][k] * rolled[x0 + k],  rolled[t] = in[(t - shift) mod N]
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) {
+        const int i = tid + e * kThreads;
+        if (i < N) cur[i] = o[e];
+      }
       int s = (flags & WW_AUG_SHIFT) ? p.a.shift[b] % N : 0;
       if (s < 0) s += N;
-      float o[kMaxPerThread];
       if (flags & WW_AUG_SPEED) {
         const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
         int found = -1;
         for (int i = 0; i < p.n_rs; ++i)
           if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { found = i; break; }
         if (found < 0) {
+          __syncthreads();
 #pragma unroll
           for (int e = 0; e < kMaxPerThread; ++e) o[e] = __int_as_float(0x7fc00000);   // loud: NaN clip
         } else {
@@ -123,18 +131,25 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
               int src = x0 + k0 - s;
               if (src < 0) src += N;
               int k = k0;
-              for (; k + 1 < k1; k += 2) {                                           // two independent chains
-                const int s1 = (src + 1 >= N) ? src + 1 - N : src + 1;
-                acc0 = fmaf(kr[k], cur[src], acc0);
-                acc1 = fmaf(kr[k + 1], cur[s1], acc1);
-                src = (s1 + 1 >= N) ? s1 + 1 - N : s1 + 1;
+              if (src + (k1 - k0) <= N) {                                            // no wrap inside the tap window
+                const float* sp = cur + src - k0;
+                for (; k + 1 < k1; k += 2) {                                         // two independent chains
+                  acc0 = fmaf(kr[k], sp[k], acc0);
+                  acc1 = fmaf(kr[k + 1], sp[k + 1], acc1);
+                }
+                if (k < k1) acc0 = fmaf(kr[k], sp[k], acc0);
+              } else {
+                for (; k < k1; ++k) {
+                  acc0 = fmaf(kr[k], cur[src], acc0);
+                  src = (src + 1 >= N) ? src + 1 - N : src + 1;
+                }
               }
-              if (k < k1) acc0 = fmaf(kr[k], cur[src], acc0);
             }
             o[e] = acc0 + acc1;
           }
         }
       } else {
+        __syncthreads();
 #pragma unroll
         for (int e = 0; e < kMaxPerThread; ++e) {
           const int i = tid + e * kThreads;
@@ -143,54 +158,60 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
           o[e] = (i < N) ? cur[src] : 0.0f;                                         // bit-exact copy (np.roll)
         }
       }
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < kMaxPerThread; ++e) {
-        const int i = tid + e * kThreads;
-        if (i < N) cur[i] = o[e];
-      }
-      __syncthreads();
     }
 
     if (flags & WW_AUG_NOISE) {
       const float* __restrict__ nz = p.bank + (int64_t)p.a.noise_idx[b] * p.bank_len + p.a.noise_off[b];
       const float snr = p.a.snr_db[b];
       const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
+      float n[kMaxPerThread];
       float sc = 0.0f, sn = 0.0f;
-      for (int i = tid; i < N; i += kThreads) {
-        const float c = cur[i], n = __ldg(nz + i);
-        sc = fmaf(c, c, sc);
-        sn = fmaf(n, n, sn);
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) {
+        const int i = tid + e * kThreads;
+        n[e] = (i < N) ? __ldg(nz + i) : 0.0f;
+        sc = fmaf(o[e], o[e], sc);
+        sn = fmaf(n[e], n[e], sn);
       }
       block_reduce2<false>(sc, sn, red, tid);
       const float scalarclean = target / sqrtf(sc / (float)N), scalarnoise = target / sqrtf(sn / (float)N);
       // the reference re-measures both RMS values after scaling (audiolib.py:60,65)
       float sc2 = 0.0f, sn2 = 0.0f;
-      for (int i = tid; i < N; i += kThreads) {
-        const float c = cur[i] * scalarclean, n = __ldg(nz + i) * scalarnoise;
-        cur[i] = c;
-        sc2 = fmaf(c, c, sc2);
-        sn2 = fmaf(n, n, sn2);
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) {
+        o[e] *= scalarclean;
+        n[e] *= scalarnoise;
+        sc2 = fmaf(o[e], o[e], sc2);
+        sn2 = fmaf(n[e], n[e], sn2);
       }
       block_reduce2<false>(sc2, sn2, red, tid);
       const float rc2 = sqrtf(sc2 / (float)N), rn2 = sqrtf(sn2 / (float)N);
       const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);          // audiolib.py:68 (sqrt quirk kept)
-      for (int i = tid; i < N; i += kThreads) cur[i] = cur[i] + (__ldg(nz + i) * scalarnoise) * noisescalar;
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) o[e] = o[e] + n[e] * noisescalar;
     }
     if (flags & WW_AUG_GAIN) {
       const float g = p.a.gain[b];
-      for (int i = tid; i < N; i += kThreads) cur[i] *= g;
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) o[e] *= g;
     }
-    float* __restrict__ o = p.out + (int64_t)b * N;
     if (flags & WW_AUG_NORM_OUT) {
       float mo = 0.0f;
-      for (int i = tid; i < N; i += kThreads) mo = fmaxf(mo, fabsf(cur[i]));
+#pragma unroll
+      for (int e = 0; e < kMaxPerThread; ++e) mo = fmaxf(mo, fabsf(o[e]));
       block_reduce2<true>(mo, dummy, red, tid);
-      for (int i = tid; i < N; i += kThreads) o[i] = (mo > 0.0f) ? __fdiv_rn(cur[i], mo) : cur[i];
-    } else {
-      for (int i = tid; i < N; i += kThreads) o[i] = cur[i];
+      if (mo > 0.0f) {
+#pragma unroll
+        for (int e = 0; e < kMaxPerThread; ++e) o[e] = __fdiv_rn(o[e], mo);
+      }
     }
-    __syncthreads();
+    float* __restrict__ dst = p.out + (int64_t)b * N;
+#pragma unroll
+    for (int e = 0; e < kMaxPerThread; ++e) {
+      const int i = tid + e * kThreads;
+      if (i < N) dst[i] = o[e];
+    }
+    __syncthreads();      // cur / tbl are reused by the next clip
   }
 }
 
