@@ -231,17 +231,17 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             const uint64_t bd = bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 2048) >> 4);
             if (NPASS == 3) {
               const uint64_t a_lo = adesc + (uint64_t)((4 * j + 1) * nsl + row_off);
-              if (leader) {
+              if (elect_one()) {
                 umma_bf16(d, a_hi, bd, idesc128, acc);   // hi*hi -> cols 0..63, hi*lo -> cols 64..127
                 umma_bf16(d, a_lo, bd, idesc64, 1);      // lo*hi -> cols 0..63
               }
             } else {
-              if (leader) umma_bf16(d, a_hi, bd, idesc64, acc);
+              if (elect_one()) umma_bf16(d, a_hi, bd, idesc64, acc);
             }
             acc = 1;
           }
         }
-        if (leader) {
+        if (elect_one()) {
           umma_commit(a_empty + BUF);
           umma_commit(t_full + BUF);
         }

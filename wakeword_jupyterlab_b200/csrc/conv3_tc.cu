@@ -81,19 +81,23 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+  // Every CTA takes a CONTIGUOUS range of (clip, group) items, i.e. whole clips: all CTAs see the same mix of
+  // 4-tile and 3-tile groups (a strided assignment gave even CTAs only the big groups: 25 % imbalance).
   const int n_items = p.B * g.n_groups;
+  const int item_lo = (int)((long long)n_items * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0) {
     // ===================== loader (one thread)
     if (lane == 0) {
       int it = 0;
       uint32_t ws = 0;        // running weight-stage counter
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int item = item_lo; item < item_hi; ++item, ++it) {
         const int b = item / g.n_groups, grp = item - b * g.n_groups;
-        const int n_t = min(g.G, g.T3 - grp * g.G);
+        const int n_t = grp_tiles(g, grp);
         const uint32_t nload = (uint32_t)(n_t * 128 + 2 * g.P + 2) * 16u;
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) +
-                                    ((size_t)b * 16 * g.npix + (size_t)grp * g.G * 128) * 16;
+                                    ((size_t)b * 16 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
         for (int j = 0; j < 4; ++j) {
           mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
           if (j == 0) C3_TRACE(0);
@@ -126,13 +130,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
       const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + hlw) * 4096) >> 4);
       const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off + h * 256);
-      if (leader) umma_bf16(tmem_base + h * 256, wd, pd, idesc, acc);
+      if (elect_one()) umma_bf16(tmem_base + h * 256, wd, pd, idesc, acc);
     };
     int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
     uint32_t ws = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int grp = item % g.n_groups;
-      const int n_t = min(g.G, g.T3 - grp * g.G);
+      const int n_t = grp_tiles(g, grp);
       // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
       const uint32_t id0 = n_t >= 2 ? idesc256 : idesc128;
       const uint32_t id1 = n_t >= 4 ? idesc256 : idesc128;
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
 #pragma unroll
               for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
           }
-          if (j == 3) { if (leader) umma_commit(t_full + 0); }
+          if (j == 3) { if (elect_one()) umma_commit(t_full + 0); }
           if (j == 0 && second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
           tc_fence_after();
           for (int tt = 0; tt < 3; ++tt) {
@@ -166,11 +170,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 1, id1, (j | tt | tl | ps) != 0);
             }
-            if (leader) umma_commit(w_empty + st);
+            if (elect_one()) umma_commit(w_empty + st);
             __syncwarp();
           }
           ws += 3;
-          if (j == 3 && second) { if (leader) umma_commit(t_full + 1); ++it1; }
+          if (j == 3 && second) { if (elect_one()) umma_commit(t_full + 1); ++it1; }
         } else {
           for (int tt = 0; tt < 3; ++tt, ++ws) {
             const uint32_t st = ws % C3_NST;
@@ -183,11 +187,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
                 step(st, j, tt, tl, ps, 0, id0, 1);
                 if (second) step(st, j, tt, tl, ps, 1, id1, 1);
               }
-            if (leader) umma_commit(w_empty + st);
+            if (elect_one()) umma_commit(w_empty + st);
             __syncwarp();
           }
         }
-        if (leader) umma_commit(a_empty + j);
+        if (elect_one()) umma_commit(a_empty + j);
         __syncwarp();
       }
       C3_TRACE(6);
@@ -200,9 +204,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     const int ch = q * 32 + lane;
     const float bias = b3s[ch];
     int it = 0, it1 = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int b = item / g.n_groups, grp = item - b * g.n_groups;
-      const int n_t = min(g.G, g.T3 - grp * g.G);
+      const int n_t = grp_tiles(g, grp);
       float sum = 0.0f;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
         tc_fence_after();
         const int i = h * 2 + sub;
         if (i < n_t) {
-          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + (grp * g.G + i));
+          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + (grp_first(g, grp) + i));
           const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + i * 128;
 #pragma unroll

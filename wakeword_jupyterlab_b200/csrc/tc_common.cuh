@@ -75,6 +75,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// true on exactly one (converged) lane of the warp; ptxas understands elect.sync-guarded regions and keeps the
+// guarded tcgen05 / bulk-copy instructions on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -133,11 +140,15 @@ struct Geom {
   int H, W, P;        // image rows (mels), cols (frames), pitch
   int npix;           // plane slots per clip (multiple of 128)
   int T2, T3;         // conv2 tiles (npix / 128), conv3 tiles (ceil(H*P / 128))
-  int G, n_groups;    // conv3: tiles per group (<= 4), groups per clip
+  int G, n_groups;    // conv3: max tiles per group (<= 4), groups per clip
+  int gbase, grem;    // balanced split of T3 tiles: the first `grem` groups have gbase + 1 tiles, the rest gbase
   int nsl2;           // conv12 A-tile slots  = round8(128 + 2P + 2)
   int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
   uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
 };
+
+__host__ __device__ __forceinline__ int grp_tiles(const Geom& g, int grp) { return g.gbase + (grp < g.grem ? 1 : 0); }
+__host__ __device__ __forceinline__ int grp_first(const Geom& g, int grp) { return grp * g.gbase + (grp < g.grem ? grp : g.grem); }
 
 __device__ __forceinline__ bool pix_valid(int p, const Geom& g, int& y, int& x) {
   if (p < 0) return false;
@@ -184,6 +195,8 @@ inline Geom make_geom(const ww_ctx* c) {
     if (conv3_smem_bytes(nsl3) <= 227 * 1024) { g.G = G; break; }
   }
   g.n_groups = (g.T3 + g.G - 1) / g.G;
+  g.gbase = g.T3 / g.n_groups;
+  g.grem = g.T3 % g.n_groups;
   g.nsl2 = (128 + 2 * g.P + 2 + 7) & ~7;
   g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
   g.magicP = (uint32_t)((0x100000000ull + (uint64_t)g.P - 1) / (uint64_t)g.P);
