@@ -24,12 +24,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass), so
+// waiting warps neither burn issue slots nor hammer the shared-memory pipe with polls.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -41,18 +43,11 @@ static __device__ __noinline__ void mbar_timeout(int code) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) mbar_timeout(code);
+    if (++spins > (1u << 17)) mbar_timeout(code);      // ~2.6 s of 20 us suspensions
   }
 }
-// Same, for roles that are NOT on the critical path (producers / epilogue warps): back off between polls so the
-// spinning warps do not steal issue slots from the MMA-issuing warp that shares their scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if (++spins > (1u << 22)) mbar_timeout(code);
-  }
-}
+// roles off the critical path (producers / epilogue warps) use the same hardware-suspended wait
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) { mbar_wait(bar, parity, code); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
