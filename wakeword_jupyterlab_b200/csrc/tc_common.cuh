@@ -134,10 +134,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 struct Geom {
   int H, W, P;        // image rows (mels), cols (frames), pitch
   int npix;           // plane slots per clip (multiple of 128)
-  int T2, T3;         // conv2 tiles (npix / 128), conv3 tiles (ceil(H*P / 128))
+  int T2, T3;         // conv2 tiles (npix / 128, even), conv3 tiles (ceil(H*P / 128))
   int G, n_groups;    // conv3: max tiles per group (<= 4), groups per clip
   int gbase, grem;    // balanced split of T3 tiles: the first `grem` groups have gbase + 1 tiles, the rest gbase
-  int nsl2;           // conv12 A-tile slots  = round8(128 + 2P + 2)
+  int nsl2;           // conv12 A-buffer slots = round8(256 + 2P + 2) (two tiles + halo)
   int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
   uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
 };
@@ -183,6 +183,7 @@ inline Geom make_geom(const ww_ctx* c) {
   g.T3 = (g.H * g.P + 127) / 128;
   const int need = 2 * g.P + 128 * g.T3 + 2;
   g.T2 = (need + 127) / 128;
+  g.T2 += g.T2 & 1;                   // conv12 works on tile pairs
   g.npix = g.T2 * 128;
   g.G = 1;
   for (int G = 4; G >= 1; --G) {      // as many tiles per weight pass as shared memory allows
@@ -192,7 +193,7 @@ inline Geom make_geom(const ww_ctx* c) {
   g.n_groups = (g.T3 + g.G - 1) / g.G;
   g.gbase = g.T3 / g.n_groups;
   g.grem = g.T3 % g.n_groups;
-  g.nsl2 = (128 + 2 * g.P + 2 + 7) & ~7;
+  g.nsl2 = (256 + 2 * g.P + 2 + 7) & ~7;
   g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
   g.magicP = (uint32_t)((0x100000000ull + (uint64_t)g.P - 1) / (uint64_t)g.P);
   return g;
