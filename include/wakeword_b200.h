@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WW_ABI_VERSION 1
+#define WW_ABI_VERSION 2
 
 /* error codes */
 #define WW_OK 0
@@ -35,10 +35,12 @@ extern "C" {
 #define WW_ERR_WEIGHTS (-3)  /* forward requested before all weights were set */
 #define WW_ERR_ARCH (-4)     /* device is not compute capability 10.x         */
 
-/* conv2/conv3 arithmetic (ww_config.conv_mode) */
-#define WW_CONV_SPLIT3 0 /* tcgen05 bf16 hi/lo split, 3 MMA passes, fp32 accumulate: parity mode (default) */
-#define WW_CONV_FP32 1   /* fp32 CUDA-core direct convolution (exact-arithmetic cross-check path)          */
-#define WW_CONV_BF16 2   /* tcgen05 single bf16 pass: "fast" mode, outside the 1e-4 logit gate             */
+/* conv2/conv3 arithmetic (ww_config.conv_mode).  The tensor-core modes keep activations as one fp16 value
+ * (their rounding errors are independent per pixel and average out in the global mean) and differ in how the
+ * weights -- whose rounding errors do NOT average out -- are represented. */
+#define WW_CONV_SPLIT2 0 /* tcgen05, weights = fp16 hi + fp16 lo (2 MMA passes), fp32 accumulate: parity mode (default) */
+#define WW_CONV_FP32 1   /* fp32 CUDA-core direct convolution (exact-arithmetic cross-check path)                       */
+#define WW_CONV_FP16 2   /* tcgen05, single fp16 pass: "fast" mode (logits ~5e-5 relative on the golden weights)        */
 
 /* augmentation flag bits (ww_aug.flags), applied in this order */
 #define WW_AUG_NORM_IN (1u << 0)  /* peak normalise first: normalize_audio, wakeword_training_script.py:73-76 */

@@ -9,8 +9,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwakeword_b200.so")
 
-WW_CONV_SPLIT3, WW_CONV_FP32, WW_CONV_BF16 = 0, 1, 2
-CONV_MODES = {"split3": WW_CONV_SPLIT3, "fp32": WW_CONV_FP32, "bf16": WW_CONV_BF16}
+WW_CONV_SPLIT2, WW_CONV_FP32, WW_CONV_FP16 = 0, 1, 2
+CONV_MODES = {"split2": WW_CONV_SPLIT2, "fp32": WW_CONV_FP32, "fp16": WW_CONV_FP16}
 
 AUG_NORM_IN, AUG_SHIFT, AUG_SPEED, AUG_NOISE, AUG_GAIN, AUG_NORM_OUT = (1 << i for i in range(6))
 

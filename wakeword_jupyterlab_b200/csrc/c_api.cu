@@ -138,7 +138,7 @@ int free_all(ww_ctx* c) {
   for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); }
   cudaFree(c->d_w2_split); cudaFree(c->d_w3_split);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
-  cudaFree(c->ws_act2_split); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
+  cudaFree(c->ws_act2_h); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
   cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
@@ -159,7 +159,7 @@ int ensure_workspaces(ww_ctx* c) {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act1, (size_t)c->chunk * 32 * H * W * 4));
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2, (size_t)c->chunk * 64 * H * W * 4));
   } else {
-    WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_split, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_h, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
   }
   c->ws_ready = true;
   return WW_OK;
@@ -254,7 +254,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
       g.hop_length <= 0 || g.n_samples <= 0 || g.n_mels <= 0 || g.n_mels > 256 || g.sample_rate <= 0 ||
       g.hidden_size <= 0 || g.hidden_size % 32 != 0 || g.hidden_size > 1024 || g.num_layers < 1 ||
       g.num_layers > 8 || g.num_classes < 1 || g.num_classes > 16 || g.fmax <= g.fmin ||
-      g.conv_mode < 0 || g.conv_mode > 2) {
+      g.conv_mode < WW_CONV_SPLIT2 || g.conv_mode > WW_CONV_FP16) {
     g_create_error = "ww_create: unsupported configuration";
     return WW_ERR_INVALID;
   }

@@ -6,17 +6,17 @@
 // Work item = (clip, PAIR of 128-pixel tiles of the pixel-linear padded image).  Warp roles:
 //   warps 0-15  producers (one pixel x 16 channels per thread): conv1 + ReLU in fp32 (packed FFMA2, weights read
 //               from the constant bank as kernel parameters) for the 256 pixels and their 3x3 halo (2P + 2 more),
-//               split to bf16 hi/lo and stored as the K-major SWIZZLE_NONE A operand [chunk of 8 ch][pixel][16 B];
+//               rounded to fp16 and stored as the K-major SWIZZLE_NONE A operand [chunk of 8 ch][pixel][16 B];
 //               three A buffers so the producers run up to two items ahead of the tensor core; the log-mel rows an
 //               item needs are staged one item ahead with cp.async;
-//   warps 16-23 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM -> D1 + D2 + bias, ReLU,
-//               zero the padding pixels, split hi/lo, write the conv3 operand planes to HBM (512 contiguous bytes
-//               per warp store);
+//   warps 16-23 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM -> (D_hi + D_lo) * 2^-k +
+//               bias, ReLU, zero the padding pixels, round to fp16, write the conv3 operand planes to HBM (512
+//               contiguous bytes per warp store);
 //   warps 24,25 MMA issuers (warp 24: even items / accumulator 0, warp 25: odd items / accumulator 1, so the ~100
 //               cycle issue cost of each small MMA overlaps and the result stays deterministic).  Per 3x3 tap,
 //               16-channel k-slice and tile:
-//                 D[:, 0:128] += A_hi x [W_hi ; W_lo]^T   (N = 128: hi*hi and hi*lo in one instruction)
-//                 D[:, 0:64 ] += A_lo x  W_hi^T           (N = 64)
+//                 D[:, 0:128] += A x [W_hi ; W_lo]^T   (N = 128: both weight halves in one instruction; the
+//               epilogue adds the two column halves; WW_CONV_FP16: N = 64, W_hi only)
 //               -- the tap is only a start-address offset of the same shared-memory tile.
 // conv2 weights (hi and lo stacked along N, 73,728 B) stay resident in shared memory.
 #include "tc_common.cuh"
@@ -32,7 +32,7 @@ using namespace tc;
 namespace {
 
 constexpr int C12_THREADS = 832;
-constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 bf16]
+constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 fp16]
 constexpr int NABUF_MAX = 3;                 // A-operand buffers (3 when shared memory allows, else 2)
 
 struct Conv12Params {
@@ -40,8 +40,9 @@ struct Conv12Params {
   float w1[288];                  // conv1 weights [tap][cout] -- kernel parameters live in the constant bank, so
   float b1[32];                   // the FMAs read them as c[0][..] operands: no shared-memory traffic at all
   float b2[64];                   // conv2 bias, also via the constant bank
-  const __nv_bfloat16* w2s;       // stacked split weights, canonical layout
-  __nv_bfloat16* act2;            // [B][16 planes = chunk*2 + hl][npix][8]
+  const __half* w2s;              // stacked split weights * 2^k, canonical layout
+  __half* act2;                   // [B][8 planes (chunks of 8 channels)][npix][8]
+  float inv_scale;                // 2^-k
   int B, nabuf;
   Geom g;
   long long* trace;               // debug (WW_TC_TRACE=1): per-item role timestamps of CTA 0
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
   unsigned char* w2s = smem;
-  const uint32_t a_bytes = 8u * g.nsl2 * 16u;                  // one act1 buffer: 8 planes (kc*2 + hl)
+  const uint32_t a_bytes = 4u * g.nsl2 * 16u;                  // one act1 buffer: 4 planes (chunks of 8 channels)
   unsigned char* a_buf0 = smem + W2_BYTES;
   const int NABUF = p.nabuf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_buf0 + NABUF * a_bytes);
@@ -174,10 +175,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
 #pragma unroll
           for (int k2 = 0; k2 < 2; ++k2) {
             const int kc = (ch0 >> 3) + k2;
-            uint4 hi, lo;
-            split8(v + k2 * 8, hi, lo);
-            *reinterpret_cast<uint4*>(ab + ((size_t)(kc * 2 + 0) * g.nsl2 + l) * 16) = hi;
-            *reinterpret_cast<uint4*>(ab + ((size_t)(kc * 2 + 1) * g.nsl2 + l) * 16) = lo;
+            *reinterpret_cast<uint4*>(ab + ((size_t)kc * g.nsl2 + l) * 16) = cvt8(v + k2 * 8);
           }
         }
       }
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     mbar_wait(w_full, 0, 20);
     constexpr uint32_t idesc128 = make_idesc(128, 128), idesc64 = make_idesc(128, 64);
     const uint64_t bdesc0 = make_desc(smem_u32(w2s), 2048, 128);
-    const uint32_t lbo_a = 2u * g.nsl2 * 16u;
+    const uint32_t lbo_a = (uint32_t)g.nsl2 * 16u;
     const uint64_t adesc0 = make_desc(smem_u32(a_buf0), lbo_a, 128);
     const uint32_t nsl = (uint32_t)g.nsl2;
     auto issue_items = [&](auto tbc) {
@@ -217,18 +215,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             const uint64_t bd = bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 2048) >> 4);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              const uint64_t a_hi = adesc + (uint64_t)((4 * j + 0) * nsl + row_off + t * 128);
+              const uint64_t ad = adesc + (uint64_t)(2 * j * nsl + row_off + t * 128);
               const uint32_t d = d0 + t * 128;
               const uint32_t acc = (tap | j) != 0;
-              if (NPASS == 3) {
-                const uint64_t a_lo = adesc + (uint64_t)((4 * j + 1) * nsl + row_off + t * 128);
-                if (elect_one()) {
-                  umma_bf16(d, a_hi, bd, idesc128, acc);   // hi*hi -> cols 0..63, hi*lo -> cols 64..127
-                  umma_bf16(d, a_lo, bd, idesc64, 1);      // lo*hi -> cols 0..63
-                }
-              } else {
-                if (elect_one()) umma_bf16(d, a_hi, bd, idesc64, acc);
-              }
+              // NPASS 2: a*W_hi -> cols 0..63 and a*W_lo -> cols 64..127 in one N = 128 instruction
+              if (elect_one()) umma_f16(d, ad, bd, NPASS == 2 ? idesc128 : idesc64, acc);
             }
           }
         }
@@ -260,10 +251,10 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tb * 256 + t * 128 + hc * 32;
           uint32_t r0[32], r1[32];
           tmem_ld32_nowait(taddr, r0);
-          if (NPASS == 3) tmem_ld32_nowait(taddr + 64, r1);
+          if (NPASS == 2) tmem_ld32_nowait(taddr + 64, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + (NPASS == 3 ? __uint_as_float(r1[i]) : 0.0f);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + (NPASS == 2 ? __uint_as_float(r1[i]) : 0.0f);
         }
         if (t == 1) {                       // both tiles are in registers: release the accumulator
           tc_fence_before();
@@ -273,7 +264,8 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         const int s = 256 * tp + t * 128 + q * 32 + lane;
         int y, x;
         const bool ok = pix_valid(s - 1, g, y, x);
-        uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 16 * g.npix + s;
+        uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 8 * g.npix + s;
+        const float inv_s = p.inv_scale;
         auto store_half = [&](auto hcc) {
           constexpr int HC = decltype(hcc)::value;
 #pragma unroll
@@ -281,11 +273,8 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             const int kc = HC * 4 + k4;
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = ok ? fmaxf(v[k4 * 8 + e] + p.b2[kc * 8 + e], 0.0f) : 0.0f;
-            uint4 hi, lo;
-            split8(o, hi, lo);
-            dst[(size_t)(kc * 2 + 0) * g.npix] = hi;
-            dst[(size_t)(kc * 2 + 1) * g.npix] = lo;
+            for (int e = 0; e < 8; ++e) o[e] = ok ? fmaxf(fmaf(v[k4 * 8 + e], inv_s, p.b2[kc * 8 + e]), 0.0f) : 0.0f;
+            dst[(size_t)kc * g.npix] = cvt8(o);
           }
         };
         if (hc == 0) store_half(std::integral_constant<int, 0>{});
@@ -302,22 +291,24 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
 size_t conv12_smem(const Geom& g, int nabuf) {
   const int NL = 256 + 2 * g.P + 2;
   const size_t patch_floats = (((NL + g.P - 1) / g.P + 3) * g.W + 3) & ~3;
-  return (size_t)W2_BYTES + (size_t)nabuf * 8 * g.nsl2 * 16 + 16 * 8 + 2 * patch_floats * 4 + 64;
+  return (size_t)W2_BYTES + (size_t)nabuf * 4 * g.nsl2 * 16 + 16 * 8 + 2 * patch_floats * 4 + 64;
 }
 
 }  // namespace
 
-// conv2 weights -> bf16 hi/lo, stacked along N, UMMA canonical layout [tap][kc][n' = 64 hi + 64 lo][8]
+// conv2 weights -> scaled fp16 hi/lo, stacked along N, UMMA canonical layout [tap][kc][n' = 64 hi + 64 lo][8]
 int ww_conv12_tc_prepare(ww_ctx* c) {
   std::vector<float> w((size_t)64 * 32 * 9);       // [n][cin][tap]
   WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv2.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
   std::vector<uint16_t> s((size_t)W2_BYTES / 2);
+  const float sc = weight_scale(w);
+  c->w2_inv_scale = 1.0f / sc;
   for (int tap = 0; tap < 9; ++tap)
     for (int kc = 0; kc < 4; ++kc)
       for (int n = 0; n < 64; ++n)
         for (int e = 0; e < 8; ++e) {
-          const float v = w[((size_t)n * 32 + kc * 8 + e) * 9 + tap];
-          const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+          const float v = w[((size_t)n * 32 + kc * 8 + e) * 9 + tap] * sc;
+          const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
           s[(((size_t)tap * 4 + kc) * 128 + n) * 8 + e] = hi;
           s[(((size_t)tap * 4 + kc) * 128 + 64 + n) * 8 + e] = lo;
         }
@@ -336,9 +327,9 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const Geom& g, cu
   }
   static size_t conf = 0;
   if (smem > conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
@@ -347,7 +338,7 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const Geom& g, cu
   memcpy(p.w1, c->h_w1t.data(), sizeof(p.w1));
   memcpy(p.b1, c->h_b1.data(), sizeof(p.b1));
   memcpy(p.b2, c->h_b2.data(), sizeof(p.b2));
-  p.act2 = c->ws_act2_split; p.B = B; p.nabuf = nabuf; p.g = g;
+  p.act2 = c->ws_act2_h; p.inv_scale = c->w2_inv_scale; p.B = B; p.nabuf = nabuf; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;
   if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 8 * 8); }
@@ -355,13 +346,13 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const Geom& g, cu
   p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
   ProfScope prof(c, WW_STAGE_CONV12, st);
-  const bool fast = c->cfg.conv_mode == WW_CONV_BF16;
+  const bool fast = c->cfg.conv_mode == WW_CONV_FP16;
   if (slots <= 2) {
     if (fast) conv12_kernel<1, 2><<<grid, C12_THREADS, smem, st>>>(p);
-    else conv12_kernel<3, 2><<<grid, C12_THREADS, smem, st>>>(p);
+    else conv12_kernel<2, 2><<<grid, C12_THREADS, smem, st>>>(p);
   } else {
     if (fast) conv12_kernel<1, 3><<<grid, C12_THREADS, smem, st>>>(p);
-    else conv12_kernel<3, 3><<<grid, C12_THREADS, smem, st>>>(p);
+    else conv12_kernel<2, 3><<<grid, C12_THREADS, smem, st>>>(p);
   }
   WW_LAUNCH_CHECK(c);
   if (tracing) {

@@ -7,18 +7,21 @@
 //   * A operand = weights, M = 128 = Cout (TMEM lane = output channel);
 //   * B operand = activations, N = 256 pixels per instruction (two 128-pixel tiles), K = 16 channels.
 //   Activations live in a zero-padded, pixel-linear image (pixel (y,x) at padded index (y+1)*P + (x+1),
-//   pitch P = W+1) stored channel-chunk-major  [chunk of 8 channels][pixel][8 x bf16 = 16 B]  -- exactly the
+//   pitch P = W+1) stored channel-chunk-major  [chunk of 8 channels][pixel][8 x fp16 = 16 B]  -- exactly the
 //   UMMA K-major SWIZZLE_NONE canonical layout (core matrix = 8 pixels x 16 B contiguous, SBO = 128 B,
 //   LBO = chunk-plane stride).  A 3x3 tap is therefore just a different START ADDRESS of the same shared
 //   memory tile: start += ((ky-1)*P + (kx-1)) * 16 B.  No im2col exists anywhere; each activation byte is
-//   copied to shared memory once per tile group and read by the tensor core 9 taps x 3 passes times.
-//   * fp32 parity (logits <= 1e-4 relative): operands are split bf16 hi + bf16 lo and accumulated in fp32 as
-//   hi*hi + hi*lo + lo*hi (3 passes; SURVEY.md section 7 hard part 1); WW_CONV_BF16 issues hi*hi only.
+//   copied to shared memory once per tile group and read by the tensor core 9 taps x NPASS passes times.
+//   * fp32 parity (logits <= 1e-4 relative; SURVEY.md section 7 hard part 1).  Rounding errors of the ACTIVATIONS
+//   are independent from pixel to pixel and average out in the global mean; rounding errors of the WEIGHTS are the
+//   same at every pixel and do not.  So activations are a single fp16 value (11-bit significand) and only the
+//   weights are split: W * 2^k = fp16 hi + fp16 lo, accumulated in fp32 as W_hi*a + W_lo*a (2 passes,
+//   WW_CONV_SPLIT2: logits 1e-6 .. 7e-6 relative on the golden weights).  WW_CONV_FP16 issues W_hi*a only (5e-5).
 //
 // Work item = (clip, group of G <= 4 consecutive 128-pixel tiles) so that every weight stage fetched from L2
 // feeds up to 512 pixels; all 512 TMEM columns hold the group's fp32 accumulators.
-//   warp 0      loader (one thread): activation k-slice planes (4 x 1-D cp.async.bulk per 16-channel slice,
-//               ring of 4 slices = the whole K) and the weight ring (3 stages x 24 KB = (k-slice, 3 taps));
+//   warp 0      loader (one thread): activation k-slice planes (2 x 1-D cp.async.bulk per 16-channel slice,
+//               ring of 4 slices = the whole K) and the weight ring (3-6 stages x 24 KB = (k-slice, 3 taps));
 //   warp 1      MMA issuer (one thread): descriptors are 64-bit adds on precomputed bases;
 //   warps 2-9   epilogue: tcgen05.ld (lane = channel, 32 pixels per load) -> bias + ReLU + padding mask
 //               (precomputed bit masks) -> per-thread sum over pixels -> one deterministic partial per
@@ -37,8 +40,9 @@ namespace {
 constexpr int C3_THREADS = 320;     // warp 0 loader, warp 1 MMA, warps 2-9 epilogue
 
 struct Conv3Params {
-  const __nv_bfloat16* act2;      // [B][16 planes][npix][8]
-  const __nv_bfloat16* w3s;       // [j 4][tap 9][hl][kc 2][cout 128][8]
+  const __half* act2;             // [B][8 planes][npix][8]
+  const __half* w3s;              // [j 4][tap 9][hl][kc 2][cout 128][8], scaled by 2^k
+  float inv_scale;                // 2^-k
   const float* b3;                // [128]
   const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
   float* pool_part;               // [B][n_groups][128]
@@ -52,16 +56,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
   const uint32_t plane_bytes = (uint32_t)g.nsl3 * 16u;
-  unsigned char* a_s = smem;                                    // 16 activation planes, index kc*2 + hl
-  unsigned char* w_s = a_s + 16 * plane_bytes;                  // weight ring
-  float* b3s = reinterpret_cast<float*>(w_s + C3_NST * C3_STAGE_BYTES);
+  const int NST = g.nst3;
+  unsigned char* a_s = smem;                                    // 8 activation planes (chunks of 8 channels)
+  unsigned char* w_s = a_s + 8 * plane_bytes;                   // weight ring
+  float* b3s = reinterpret_cast<float*>(w_s + NST * C3_STAGE_BYTES);
   float* scratch = b3s + 128;                                   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 256);
   uint64_t* a_full = bars;                 // [4]
   uint64_t* a_empty = bars + 4;            // [4]
-  uint64_t* w_full = bars + 8;             // [NST]
-  uint64_t* w_empty = bars + 8 + C3_NST;   // [NST]
-  uint64_t* t_full = bars + 8 + 2 * C3_NST;   // [2] accumulator halves: tiles (0,1) = TMEM cols 0..255, tiles (2,3) = 256..511
+  uint64_t* w_full = bars + 8;             // [NST_MAX]
+  uint64_t* w_empty = bars + 8 + C3_NST_MAX;   // [NST_MAX]
+  uint64_t* t_full = bars + 8 + 2 * C3_NST_MAX;   // [2] accumulator halves: tiles (0,1) = TMEM cols 0..255, tiles (2,3) = 256..511
   uint64_t* t_empty = t_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   if (tid < 128) b3s[tid] = p.b3[tid];
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < C3_NST; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < C3_NST_MAX; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
     fence_barrier_init();
   }
@@ -91,27 +96,27 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     // ===================== loader (one thread)
     if (lane == 0) {
       int it = 0;
-      uint32_t ws = 0;        // running weight-stage counter
+      uint32_t st = 0, wpar = 1;        // weight ring position and the parity to wait for on w_empty
       for (int item = item_lo; item < item_hi; ++item, ++it) {
         const int b = item / g.n_groups, grp = item - b * g.n_groups;
         const int n_t = grp_tiles(g, grp);
         const uint32_t nload = (uint32_t)(n_t * 128 + 2 * g.P + 2) * 16u;
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) +
-                                    ((size_t)b * 16 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
+                                    ((size_t)b * 8 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
         for (int j = 0; j < 4; ++j) {
           mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
           if (j == 0) C3_TRACE(0);
-          mbar_arrive_expect_tx(a_full + j, 4 * nload);
+          mbar_arrive_expect_tx(a_full + j, 2 * nload);
 #pragma unroll
-          for (int pl = 0; pl < 4; ++pl)      // planes (kc = 2j, 2j+1) x (hi, lo) are consecutive: index 4j + pl
-            bulk_g2s(a_s + (size_t)(4 * j + pl) * plane_bytes, src0 + (size_t)(4 * j + pl) * g.npix * 16, nload, a_full + j);
-          for (int tt = 0; tt < 3; ++tt, ++ws) {
-            const uint32_t st = ws % C3_NST;
-            mbar_wait(w_empty + st, ((ws / C3_NST) & 1) ^ 1, 41);
+          for (int pl = 0; pl < 2; ++pl)      // planes kc = 2j, 2j+1
+            bulk_g2s(a_s + (size_t)(2 * j + pl) * plane_bytes, src0 + (size_t)(2 * j + pl) * g.npix * 16, nload, a_full + j);
+          for (int tt = 0; tt < 3; ++tt) {
+            mbar_wait(w_empty + st, wpar, 41);
             mbar_arrive_expect_tx(w_full + st, C3_STAGE_BYTES);
             bulk_g2s(w_s + st * C3_STAGE_BYTES,
                      reinterpret_cast<const unsigned char*>(p.w3s) + (size_t)(j * 3 + tt) * C3_STAGE_BYTES,
                      C3_STAGE_BYTES, w_full + st);
+            if (++st == (uint32_t)NST) { st = 0; wpar ^= 1; }
           }
         }
       }
@@ -122,18 +127,19 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     const bool leader = (lane == 0);
     constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
     const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
-    const uint64_t pdesc0 = make_desc(smem_u32(a_s), 2u * plane_bytes, 128);  // pixels: kc stride = 2 planes
+    const uint64_t pdesc0 = make_desc(smem_u32(a_s), plane_bytes, 128);       // pixels: kc stride = 1 plane
     const uint32_t plane_u = plane_bytes >> 4;
     // One (tap, pass) step for accumulator half `h` (0: tiles 0,1   1: tiles 2,3) of k-slice j from weight stage st.
     auto step = [&](uint32_t st, int j, int tt, int tl, int ps, int h, uint32_t idesc, uint32_t acc) {
       const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
-      const int hla = (ps == 2), hlw = (ps == 1);      // (act, weight) halves: hi*hi, hi*lo(w), lo(a)*hi
-      const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + hlw) * 4096) >> 4);
-      const uint64_t pd = pdesc0 + (uint64_t)((4 * j + hla) * plane_u + row_off + h * 256);
-      if (elect_one()) umma_bf16(tmem_base + h * 256, wd, pd, idesc, acc);
+      // pass 0: W_hi * a, pass 1: W_lo * a
+      const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + ps) * 4096) >> 4);
+      const uint64_t pd = pdesc0 + (uint64_t)(2 * j * plane_u + row_off + h * 256);
+      if (elect_one()) umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);
     };
     int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
-    uint32_t ws = 0;
+    uint32_t st = 0, wpar = 0;        // weight ring position and the parity to wait for on w_full
+    auto ring_next = [&](uint32_t s_, uint32_t& par_) { if (++s_ == (uint32_t)NST) { s_ = 0; par_ ^= 1; } return s_; };
     for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int grp = item % g.n_groups;
       const int n_t = grp_tiles(g, grp);
@@ -150,20 +156,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
         C3_TRACE(2 + j);
         if (j == 0 || j == 3) {
           if (j == 0) { mbar_wait(t_empty + 0, par ^ 1, 50); C3_TRACE(1); }
+          uint32_t s1 = st, p1 = wpar;
           for (int tt = 0; tt < 3; ++tt) {
-            const uint32_t st = (ws + tt) % C3_NST;
-            mbar_wait(w_full + st, ((ws + tt) / C3_NST) & 1, 52);
+            mbar_wait(w_full + s1, p1, 52);
             tc_fence_after();
 #pragma unroll
             for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
-              for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
+              for (int ps = 0; ps < NPASS; ++ps) step(s1, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
+            s1 = ring_next(s1, p1);
           }
           if (j == 3) { if (elect_one()) umma_commit(t_full + 0); }
           if (j == 0 && second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
           tc_fence_after();
           for (int tt = 0; tt < 3; ++tt) {
-            const uint32_t st = (ws + tt) % C3_NST;
             if (second) {
 #pragma unroll
               for (int tl = 0; tl < 3; ++tl)
@@ -172,13 +178,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
             }
             if (elect_one()) umma_commit(w_empty + st);
             __syncwarp();
+            st = ring_next(st, wpar);
           }
-          ws += 3;
           if (j == 3 && second) { if (elect_one()) umma_commit(t_full + 1); ++it1; }
         } else {
-          for (int tt = 0; tt < 3; ++tt, ++ws) {
-            const uint32_t st = ws % C3_NST;
-            mbar_wait(w_full + st, (ws / C3_NST) & 1, 52);
+          for (int tt = 0; tt < 3; ++tt) {
+            mbar_wait(w_full + st, wpar, 52);
             tc_fence_after();
 #pragma unroll
             for (int tl = 0; tl < 3; ++tl)
@@ -189,6 +194,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
               }
             if (elect_one()) umma_commit(w_empty + st);
             __syncwarp();
+            st = ring_next(st, wpar);
           }
         }
         if (elect_one()) umma_commit(a_empty + j);
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     const int sub = (warp - 2) >> 2;        // which tile of each accumulator half this warp drains (the two warps that
                                             // share a lane quadrant split the half, so all 8 warps work on the ready half)
     const int ch = q * 32 + lane;
-    const float bias = b3s[ch];
+    const float bias = b3s[ch], inv_s = p.inv_scale;
     int it = 0, it1 = 0;
     for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int b = item / g.n_groups, grp = item - b * g.n_groups;
@@ -228,8 +234,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              const float v0 = fmaxf(__uint_as_float(r0[r]) + bias, 0.0f);
-              const float v1 = fmaxf(__uint_as_float(r1[r]) + bias, 0.0f);
+              const float v0 = fmaxf(fmaf(__uint_as_float(r0[r]), inv_s, bias), 0.0f);
+              const float v1 = fmaxf(fmaf(__uint_as_float(r1[r]), inv_s, bias), 0.0f);
               s0 += (mw[cp * 2] >> r) & 1u ? v0 : 0.0f;
               s1 += (mw[cp * 2 + 1] >> r) & 1u ? v1 : 0.0f;
             }
@@ -256,14 +262,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
 
 size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {
   const Geom g = make_geom(c);
-  return (size_t)16 * g.npix * 16;
+  return (size_t)8 * g.npix * 16;
 }
 
 int ww_conv_tc_groups(const ww_ctx* c) { return make_geom(c).n_groups; }
 
 int ww_conv12_tc_prepare(ww_ctx* c);
 
-// conv3 weights -> bf16 hi/lo in the UMMA canonical layout [j][tap][hl][kc][cout][8]; tile validity masks
+// conv3 weights -> scaled fp16 hi/lo in the UMMA canonical layout [j][tap][hl][kc][cout][8]; tile validity masks
 int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
   int rc = ww_conv12_tc_prepare(c);
   if (rc) return rc;
@@ -271,13 +277,15 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
   WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv3.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
   const size_t blk_elems = 2 * 2 * 128 * 8;         // one (j, tap) block: [hl][kc][cout][8]
   std::vector<uint16_t> s((size_t)36 * blk_elems);
+  const float sc = weight_scale(w);
+  c->w3_inv_scale = 1.0f / sc;
   for (int j = 0; j < 4; ++j)
     for (int tap = 0; tap < 9; ++tap)
       for (int kc = 0; kc < 2; ++kc)
         for (int n = 0; n < 128; ++n)
           for (int e = 0; e < 8; ++e) {
-            const float v = w[((size_t)n * 64 + j * 16 + kc * 8 + e) * 9 + tap];
-            const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+            const float v = w[((size_t)n * 64 + j * 16 + kc * 8 + e) * 9 + tap] * sc;
+            const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
             const size_t blk = ((size_t)j * 9 + tap) * blk_elems;
             s[blk + (((size_t)0 * 2 + kc) * 128 + n) * 8 + e] = hi;
             s[blk + (((size_t)1 * 2 + kc) * 128 + n) * 8 + e] = lo;
@@ -300,19 +308,19 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
 }
 
 int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
-  const size_t smem = conv3_smem_bytes(g.nsl3);
+  const size_t smem = conv3_smem_bytes(g.nsl3, g.nst3);
   if (smem > 227 * 1024) {
     c->set_error("conv3_tc: frame count too large for the shared-memory tiles (use WW_CONV_FP32)");
     return WW_ERR_INVALID;
   }
   static size_t conf = 0;
   if (smem > conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
   Conv3Params p;
-  p.act2 = c->ws_act2_split; p.w3s = c->d_w3_split; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
+  p.act2 = c->ws_act2_h; p.w3s = c->d_w3_split; p.inv_scale = c->w3_inv_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
   p.pool_part = c->pool_cur; p.B = B; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;
@@ -321,8 +329,8 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B * g.n_groups);
   ProfScope prof(c, WW_STAGE_CONV3, st);
-  if (c->cfg.conv_mode == WW_CONV_BF16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
-  else conv3_kernel<3><<<grid, C3_THREADS, smem, st>>>(p);
+  if (c->cfg.conv_mode == WW_CONV_FP16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
+  else conv3_kernel<2><<<grid, C3_THREADS, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   if (tracing) {
     long long h[48 * 16];

@@ -1,7 +1,7 @@
 // Internal context of libwakeword_b200.so (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -81,15 +81,16 @@ struct ww_ctx {
   float* d_convw_t[3] = {nullptr, nullptr, nullptr};   // [Cin][9][Cout] fp32 (fp32 conv path, conv1 everywhere)
   float* d_head_wt[8] = {};                            // per LSTM layer: [K][3H] gate-interleaved (i,g,o), fp32
   float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
-  __nv_bfloat16* d_w2_split = nullptr;                 // conv2 weights, UMMA canonical layout, hi then lo
-  __nv_bfloat16* d_w3_split = nullptr;                 // conv3 weights, UMMA canonical layout, hi then lo
+  __half* d_w2_split = nullptr;                        // conv2 weights * 2^k, fp16 hi/lo, UMMA canonical layout
+  __half* d_w3_split = nullptr;                        // conv3 weights * 2^k, fp16 hi/lo, UMMA canonical layout
+  float w2_inv_scale = 1.0f, w3_inv_scale = 1.0f;      // 2^-k of the two layers
 
   // ---- workspaces (chunk clips)
   float* ws_clips = nullptr;     // [chunk][n_samples] augmented clips
   float* ws_logmel = nullptr;    // [chunk][n_mels][W]
   float* ws_act1 = nullptr;      // fp32 path: [chunk][32][H][W]
   float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
-  __nv_bfloat16* ws_act2_split = nullptr;  // tc path: [chunk][8 chunks][2 hi/lo][NPIX][8] bf16
+  __half* ws_act2_h = nullptr;   // tc path: [chunk][8 channel chunks][NPIX][8] fp16
   float* ws_pool_part = nullptr; // [pool_cap_clips][n_part][128]: conv3 partial sums of the whole batch of a call
   float* pool_cur = nullptr;     // where the current chunk's conv launch writes its partials
   float* ws_h[2] = {nullptr, nullptr};   // [pool_cap_clips][hidden]: head layer outputs (ping-pong)

@@ -1,9 +1,13 @@
 // Shared pieces of the tcgen05 convolution kernels: PTX wrappers (mbarrier, bulk copy, TMEM, UMMA),
-// descriptor builders, bf16 hi/lo splitting and the pixel-linear image geometry.  sm_100a only.
+// descriptor builders, fp16 packing / hi-lo weight splitting and the pixel-linear image geometry.  sm_100a only.
 #pragma once
 #include "ctx.cuh"
 
+#include <cuda_fp16.h>
+#include <math.h>
+
 #include <string.h>
+#include <algorithm>
 
 namespace tc {
 
@@ -64,7 +68,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
@@ -104,28 +108,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// instruction descriptor (kind::f16): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
+// instruction descriptor (kind::f16): D = f32 (bit 4), A = B = fp16 (format fields at bits 7 and 10 = 0), both
+// K-major, N>>3 at 17, M>>4 at 24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+// two floats -> packed fp16x2 (round to nearest even, saturating to +-65504 instead of inf): `lo` in bits 0..15
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
-// split 8 floats into bf16 hi (round-to-nearest) and bf16 lo = bf16(x - hi)
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    // packed conversions (F2FP, full rate) instead of scalar F2F; bf16 -> f32 is a 16-bit shift / mask
-    h[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-    const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
-    const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
-    l[i] = pack_bf16(r0, r1);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+// 8 floats -> one 16-byte core-matrix row of fp16
+__device__ __forceinline__ uint4 cvt8(const float* v) {
+  return make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +136,7 @@ struct Geom {
   int gbase, grem;    // balanced split of T3 tiles: the first `grem` groups have gbase + 1 tiles, the rest gbase
   int nsl2;           // conv12 A-buffer slots = round8(256 + 2P + 2) (two tiles + halo)
   int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
+  int nst3;           // conv3 weight ring stages
   uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
 };
 
@@ -153,26 +151,37 @@ __device__ __forceinline__ bool pix_valid(int p, const Geom& g, int& y, int& x) 
   return (y >= 0) && (y < g.H) && (x >= 0);
 }
 
-// host: bf16 round-to-nearest-even
-inline uint16_t f2bf(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
+// host: fp16 round-to-nearest-even (bit pattern) and back
+inline uint16_t f2h(float f) {
+  const __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
 }
-inline float bf2f(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
+inline float h2f(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+// Weight scale: the tensor-core operands are w * 2^k as fp16 hi + fp16 lo with k chosen so the largest |w| lands
+// near 2^13.  hi is then far from fp16's subnormal range and lo (~2^-11 of hi) stays a normal number for every
+// weight that matters; the epilogues multiply the fp32 accumulator by 2^-k (exact).
+inline float weight_scale(const std::vector<float>& w) {
+  float m = 0.0f;
+  for (float v : w) m = std::max(m, fabsf(v));
+  if (!(m > 0.0f) || !std::isfinite(m)) return 1.0f;
+  int e;
+  frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+  const int k = std::min(std::max(13 - e, -24), 24);
+  return ldexpf(1.0f, k);
 }
 
-constexpr int C3_NST = 3;                                // conv3 weight ring stages
-constexpr int C3_STAGE_BYTES = 3 * 2 * 2 * 128 * 16;     // [tap 3][hl][kc 2][cout 128][8 bf16] = 24 KB
+constexpr int C3_NST_MAX = 6;                            // conv3 weight ring stages (as many as shared memory allows)
+constexpr int C3_NST_MIN = 3;
+constexpr int C3_STAGE_BYTES = 3 * 2 * 2 * 128 * 16;     // [tap 3][hl][kc 2][cout 128][8 fp16] = 24 KB
 
-inline size_t conv3_smem_bytes(int nsl3) {
-  return (size_t)16 * nsl3 * 16 + (size_t)C3_NST * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
+inline size_t conv3_smem_bytes(int nsl3, int nst) {
+  return (size_t)8 * nsl3 * 16 + (size_t)nst * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
 }
 
 inline Geom make_geom(const ww_ctx* c) {
@@ -188,13 +197,15 @@ inline Geom make_geom(const ww_ctx* c) {
   g.G = 1;
   for (int G = 4; G >= 1; --G) {      // as many tiles per weight pass as shared memory allows
     const int nsl3 = (G * 128 + 2 * g.P + 2 + 7) & ~7;
-    if (conv3_smem_bytes(nsl3) <= 227 * 1024) { g.G = G; break; }
+    if (conv3_smem_bytes(nsl3, C3_NST_MIN) <= 227 * 1024) { g.G = G; break; }
   }
   g.n_groups = (g.T3 + g.G - 1) / g.G;
   g.gbase = g.T3 / g.n_groups;
   g.grem = g.T3 % g.n_groups;
   g.nsl2 = (256 + 2 * g.P + 2 + 7) & ~7;
   g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
+  g.nst3 = C3_NST_MIN;
+  while (g.nst3 < C3_NST_MAX && conv3_smem_bytes(g.nsl3, g.nst3 + 1) <= 227 * 1024) ++g.nst3;
   g.magicP = (uint32_t)((0x100000000ull + (uint64_t)g.P - 1) / (uint64_t)g.P);
   return g;
 }

@@ -51,7 +51,7 @@ class Engine:
     """Owns one ww_ctx.  Not thread safe (one per host thread), like the C ABI."""
 
     def __init__(self, audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8,
-                 conv_mode="split3", n_samples: Optional[int] = None, chunk_clips=0):
+                 conv_mode="split2", n_samples: Optional[int] = None, chunk_clips=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.WakewordB200Error("no CUDA device: wakeword_jupyterlab_b200 has no CPU fallback")
@@ -275,7 +275,7 @@ class Engine:
 _engines = {}
 
 
-def get_engine(audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8, conv_mode="split3",
+def get_engine(audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8, conv_mode="split2",
                n_samples=None, chunk_clips=0) -> Engine:
     """Per-process cache: one Engine per (device, configuration)."""
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)

@@ -130,4 +130,4 @@ class AudioProcessor:
         return self._engine(n_samples=clips.shape[1]).augment(clips, params, self.noise_bank)
 
 
-DEFAULT_CONV_MODE = "split3"
+DEFAULT_CONV_MODE = "split2"
