@@ -104,7 +104,11 @@ def synth_clips_device(n, device, seed):
         z = torch.randn((m, N_SAMPLES), device=device, generator=g)
         pos = (torch.arange(i, i + m, device=device) % 3 == 0).float()[:, None]
         out[i:i + m] = pos * (0.1 * z + tone) + (1 - pos) * (0.2 * z)
-    return out
+    # The reference's recipe stores its clips as 16-bit WAV (sf.write, wakeword_training_script.py:371,380) and
+    # reads them back with librosa.load (s / 32768): quantise the same way, so the fp32 device-resident arm and the
+    # int16-PCM host arm score bit-identical samples.
+    pcm = torch.clamp(torch.round(out * 32768.0), -32768, 32767).to(torch.int16)
+    return pcm.to(torch.float32) / 32768.0, pcm
 
 
 def draw_aug(n, seed):
@@ -197,7 +201,7 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
     if args.workload == "logmel":
         B = 16384 if args.clips == CLIPS_PER_GPU else args.clips
         eng = ww.get_engine(device=dev.index)
-        clips = synth_clips_device(B, dev, seed=1234 + rank)
+        clips, _ = synth_clips_device(B, dev, seed=1234 + rank)
         out = torch.empty((B, 1, 80, eng.W), device=dev)
         for _ in range(args.warmup):
             eng.logmel(clips, normalize=False, out=out)
@@ -223,7 +227,7 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
     net = ww.WakewordModel().to(dev).eval()
     net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
     net.conv_mode = conv_mode
-    base = synth_clips_device(64, dev, seed=1234).reshape(-1)                  # recipe audio, tiled over the hour
+    base = synth_clips_device(64, dev, seed=1234)[0].reshape(-1)                  # recipe audio, tiled over the hour
     audio = base.repeat((n_audio + base.numel() - 1) // base.numel())[:n_audio].contiguous()
     eng = net.engine()
     for _ in range(max(1, args.warmup - 2)):
@@ -256,6 +260,7 @@ def main():
                     help="score = BASELINE config 3 (default, the contract line); logmel = config 2; stream = config 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg with fp32 host buffers instead of int16 PCM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -300,7 +305,7 @@ def main():
     net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
     net.conv_mode = conv_mode
     eng = net.engine()
-    clips = synth_clips_device(B, dev, seed=1234 + rank)
+    clips, clips_pcm = synth_clips_device(B, dev, seed=1234 + rank)
     bank = torch.from_numpy(R.make_noise_bank()).to(dev)
     aug = draw_aug(B, seed=2024 + rank)
     aug_struct, keep = eng._aug_struct(aug, B)
@@ -337,8 +342,9 @@ def main():
     # ---- e2e through the host-buffer C-ABI entry (pinned host memory in, host memory out)
     e2e = None
     if not args.no_e2e:
-        h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32, pin_memory=True)
-        h_clips.copy_(clips)
+        # host buffers hold the clips as they are on disk: int16 PCM (ww_score_host_pcm16; --e2e-fp32 for fp32 buffers)
+        h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32 if args.e2e_fp32 else torch.int16, pin_memory=True)
+        h_clips.copy_(clips if args.e2e_fp32 else clips_pcm)
         h_out = (torch.empty((B, 2), dtype=torch.float32, pin_memory=True),
                  torch.empty((B,), dtype=torch.float32, pin_memory=True),
                  torch.empty((B,), dtype=torch.uint8, pin_memory=True))
@@ -352,7 +358,9 @@ def main():
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
         assert torch.equal(h_out[2].to(dev), dec), "e2e decisions differ from the device-resident run"
         e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "clips/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(B * N_SAMPLES * 4 + B * 9 * 4), "d2h_bytes_per_step": int(B * (2 * 4 + 4 + 1))}
+               "h2d_bytes_per_step": int(B * N_SAMPLES * h_clips.element_size() + B * 9 * 4),
+               "d2h_bytes_per_step": int(B * (2 * 4 + 4 + 1)),
+               "host_input": "fp32 clips" if args.e2e_fp32 else "int16 PCM clips (as stored in the reference's WAV files)"}
 
     if rank != 0:
         if world > 1:

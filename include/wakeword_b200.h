@@ -143,6 +143,24 @@ int ww_score_host(ww_ctx* ctx, const float* clips_host, const float* noise_bank_
                   int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                   float* prob1_host, uint8_t* decision_host, int B);
 
+/* ---- int16 PCM inputs.  The reference's clips are 16-bit WAV files that
+ *      librosa.load turns into float32 as s / 32768 (AudioProcessor.load_audio, wakeword_training_script.py:65-71;
+ *      the synthetic recipe writes them with sf.write, :359-388).  These entries take the int16 samples as they are
+ *      on disk and apply exactly that scaling on the device: results are bit-identical to the fp32 entries fed
+ *      with s / 32768, at half the host->device and HBM input bytes.  n_samples must be even. */
+int ww_augment_pcm16(ww_ctx* ctx, const int16_t* clips, const float* noise_bank, int bank_rows, int64_t bank_len,
+                     const ww_aug* p, float* out, int B, void* stream);
+int ww_logmel_pcm16(ww_ctx* ctx, const int16_t* clips, int64_t clip_stride, float* out, int B, int normalize,
+                    void* stream);
+int ww_score_pcm16(ww_ctx* ctx, const int16_t* clips, const float* noise_bank, int bank_rows, int64_t bank_len,
+                   const ww_aug* aug, int normalize, float* logits, float* prob1, uint8_t* decision, int B,
+                   void* stream);
+int ww_score_stream_pcm16(ww_ctx* ctx, const int16_t* audio, int64_t T, int hop_samples, float* prob1,
+                          uint8_t* decision, int64_t n_win, void* stream);
+int ww_score_host_pcm16(ww_ctx* ctx, const int16_t* clips_host, const float* noise_bank_dev, int bank_rows,
+                        int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
+                        float* prob1_host, uint8_t* decision_host, int B);
+
 /* ---- per-stage device timing for benchmarks: CUDA events recorded on the launching stream around
  *      each stage's kernels while enabled.  ww_profile_read synchronises, returns the summed
  *      milliseconds and the number of timed launches of `stage`, and (stage < 0) resets the log. */

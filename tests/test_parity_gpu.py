@@ -163,6 +163,51 @@ def test_full_augment_pipeline_vs_oracle(ww):
     assert np.isfinite(out).all() and np.abs(np.abs(out).max(axis=1) - 1.0).max() < 1e-6    # NORM_OUT
 
 
+def test_augment_pipelined_over_many_clips(ww):
+    """More clips than SMs: every CTA walks several clips through its double-buffered cp.async stage."""
+    n = 700
+    clips = np.tile(R.make_clips(70, seed=99), (10, 1))
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n, seed=77)
+    eng = ww.get_engine()
+    out = eng.augment(clips, _aug_to_ww(ww, p), noise_bank=bank).cpu().numpy()
+    idx = np.r_[0:8, 147:156, 290:300, 692:700]
+    sub = A.AugParams(*[getattr(p, f)[idx] for f in ("flags", "shift", "rs_orig", "rs_new", "crop_off", "noise_idx",
+                                                     "noise_off", "snr_db", "gain")])
+    ref = A.augment_batch(clips[idx], bank, sub)
+    assert np.abs(out[idx] - ref).max() < 5e-5
+    # one-iteration-per-CTA launches (64 clips) give bit-identical results to the pipelined launch
+    for lo in (0, 320, 636):
+        sl = slice(lo, lo + 64)
+        ps = ww.AugBatch(*[getattr(p, f)[sl] for f in ("flags", "shift", "rs_orig", "rs_new", "crop_off", "noise_idx",
+                                                       "noise_off", "snr_db", "gain")])
+        assert np.array_equal(eng.augment(clips[sl], ps, noise_bank=bank).cpu().numpy(), out[sl])
+
+
+def test_int16_pcm_inputs_match_fp32_of_the_same_samples(ww):
+    """int16 PCM in = the fp32 entries fed with s / 32768 (what librosa.load returns)."""
+    n = 200
+    pcm = np.clip(np.round(R.make_clips(n, seed=5) * 32768.0), -32768, 32767).astype(np.int16)
+    f32 = pcm.astype(np.float32) / 32768.0
+    bank = R.make_noise_bank()
+    p = _aug_to_ww(ww, R.draw_aug_params(n, seed=3))
+    eng = ww.get_engine()
+    assert torch.equal(eng.logmel(pcm, normalize=True), eng.logmel(f32, normalize=True))
+    assert torch.equal(eng.augment(pcm, p, noise_bank=bank), eng.augment(f32, p, noise_bank=bank))
+    sd = R.seeded_state_dict(256, seed=0)
+    net = _load(ww, sd, mode="split2")
+    a = ww.score_clips(torch.from_numpy(pcm).cuda(), net, aug=p, noise_bank=bank)
+    b = ww.score_clips(torch.from_numpy(f32).cuda(), net, aug=p, noise_bank=bank)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    h = net.engine().score_host(pcm, aug=p, noise_bank=bank)
+    assert np.array_equal(h[0], a[0].cpu().numpy()) and np.array_equal(h[2], a[2].cpu().numpy())
+    # streaming entry
+    audio16 = pcm[:3].reshape(-1)
+    p16, d16 = ww.score_stream(audio16, net, hop_samples=1600)
+    p32, d32 = ww.score_stream(audio16.astype(np.float32) / 32768.0, net, hop_samples=1600)
+    assert torch.equal(p16, p32) and torch.equal(d16, d32)
+
+
 def test_unprepared_ratio_is_loud(ww):
     eng = ww.Engine()                      # fresh context: no tables prepared
     import ctypes as C

@@ -30,7 +30,8 @@ class WWAug(C.Structure):
 
 EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_frames", "ww_set_weights",
            "ww_prepare_resample", "ww_augment", "ww_logmel", "ww_forward", "ww_score", "ww_score_stream",
-           "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize", "ww_profile", "ww_profile_read"]
+           "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize", "ww_profile", "ww_profile_read",
+           "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
 _lock = threading.Lock()
@@ -67,6 +68,8 @@ def load():
         lib.ww_score.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), i32, vp, vp, vp, i32, vp]
         lib.ww_score_stream.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp]
         lib.ww_score_host.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), i32, vp, vp, vp, i32]
+        for base in ("ww_augment", "ww_logmel", "ww_score", "ww_score_stream", "ww_score_host"):
+            getattr(lib, base + "_pcm16").argtypes = getattr(lib, base).argtypes
         lib.ww_kernel_launches.argtypes = [vp]
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]

@@ -7,12 +7,21 @@
 //   NOISE    snr_mixer(clean, bank segment, snr)                      stock/ms_snsd/MS-SNSD/audiolib.py:55-71
 //   GAIN     linear gain
 //   NORM_OUT peak normalise
-// One CTA (1024 threads) per clip.  Each thread keeps its 16 samples in REGISTERS through every element-wise stage
-// (normalise, SNR mix, gain); only the gather stage goes through shared memory: shift and speed change are a
-// single gather (the resampler reads its taps through the roll index map).  HBM traffic is one read of the clip
-// (+ the noise segment, re-read from L2 for the later passes) and one write: 128 KB (192 KB) per clip.
+// Input clips are fp32 or int16 PCM (x = s / 32768, the value librosa.load returns for a 16-bit WAV).
+//
+// Persistent kernel, one CTA (1024 threads) per SM, software-pipelined over clips with cp.async:
+//   * while clip b is processed, the raw samples of clip b + grid stream into the other half of a double-buffered
+//     shared-memory stage, and its scalar parameters / resample-table lookup are fetched by a few threads;
+//   * the polyphase table and the noise segment of clip b are requested at the top of the iteration and waited for
+//     only where they are consumed (after the normalise pass / after the gather), so no global latency is exposed.
+// Each thread owns samples tid + 1024 e and keeps them in REGISTERS through every element-wise stage; only the
+// gather goes through shared memory: shift and speed change are a single gather (the resampler reads its taps through
+// the roll index map) whose taps come as 128-bit rows of a compact, zero-padded per-phase table (row pitch = 4 mod 8
+// words, so the 128-bit row loads of consecutive phases are bank-conflict free; the sample loads of a warp fall into
+// one or two 128-byte lines and are broadcast).  HBM traffic is one read of the clip and one write (the noise bank stays in L2): 128 KB per clip
+// (96 KB from int16 PCM).
 // Index arithmetic (roll source index, (q,p) phase decomposition, tap range, crop offset, output length) is
-// integer-exact against oracle/augment.py; only exactly-zero taps of the polyphase table are skipped.
+// integer-exact against oracle/augment.py; only exactly-zero taps of the polyphase table are skipped or added.
 #include "ctx.cuh"
 
 #include <algorithm>
@@ -24,7 +33,7 @@ constexpr int kMaxPerThread = 16;     // n_samples <= kThreads * kMaxPerThread
 constexpr int kTblWords = 2560;       // shared-memory room for one ratio's compact polyphase table
 
 struct AugKParams {
-  const float* clips;
+  const void* clips;                  // fp32 or int16
   const float* bank;
   int bank_rows;
   int64_t bank_len;
@@ -34,6 +43,15 @@ struct AugKParams {
   const RsDesc* rs_desc;
   int n_rs;
   const float* rs_kern;
+};
+
+// per-clip scalars, fetched one iteration ahead into shared memory
+struct ClipPrm {
+  uint32_t flags;
+  int shift, crop, noise_idx, noise_off;
+  float snr, gain;
+  int rs;                             // index into rs_desc, -1 = ratio not prepared
+  RsDesc d;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -59,22 +77,105 @@ __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, in
   b = MAX ? warp_max(rb) : warp_sum(rb);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
-  extern __shared__ __align__(16) float cur[];   // [N] clip, then [kTblWords] polyphase table
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// `bytes` (multiple of 4) from global to shared, 16-byte chunks when both sides allow it; all threads take part
+__device__ __forceinline__ void stage_bytes(void* dst, const void* src, int bytes, int tid) {
+  if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)bytes) & 15) == 0) {
+    for (int i = tid * 16; i < bytes; i += kThreads * 16)
+      cp_async16(static_cast<char*>(dst) + i, static_cast<const char*>(src) + i);
+  } else {
+    for (int i = tid * 4; i < bytes; i += kThreads * 4)
+      cp_async4(static_cast<char*>(dst) + i, static_cast<const char*>(src) + i);
+  }
+}
+
+__device__ __forceinline__ float cvt_in(float v) { return v; }
+__device__ __forceinline__ float cvt_in(int16_t v) { return (float)v * (1.0f / 32768.0f); }
+
+// Sample index of register slot e (0..15) of thread tid.
+__device__ __forceinline__ int slot_index(int tid, int e) { return tid + e * kThreads; }
+
+// Scalars of clip b -> shared memory; called by threads 0..63 (warp 0: the plain fields; warp 1: parallel search of
+// the prepared resample ratios).
+__device__ __forceinline__ void fetch_prm(const AugKParams& p, ClipPrm& q, int b, int tid) {
+  const uint32_t flags = p.a.flags[b];
+  if (tid == 0) {
+    q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
+    q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b];
+  }
+  if (tid == 32) q.rs = -1;
+  asm volatile("bar.sync 3, 64;" ::: "memory");         // the default lands before a match overwrites it
+  if ((flags & WW_AUG_SPEED) && tid >= 32) {
+    const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+    for (int i = tid - 32; i < p.n_rs; i += 32)
+      if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
+  }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[64];
+  __shared__ ClipPrm prm[2];
   const int tid = threadIdx.x;
   const int N = p.N;
-  float* tbl = cur + ((N + 3) & ~3);
+  const int NP = (N + 3) & ~3;                      // every buffer is padded to whole float4 / short4 groups
+  constexpr bool kInPlace = sizeof(TIn) == 4;        // fp32 input: the stage buffer doubles as the gather source
+  TIn* stage0 = reinterpret_cast<TIn*>(smem_raw);
+  TIn* stage1 = stage0 + NP;
+  float* curf = kInPlace ? nullptr : reinterpret_cast<float*>(stage1 + NP);
+  float* noise_s = kInPlace ? reinterpret_cast<float*>(stage1 + NP) : curf + NP;
+  float* tbl = noise_s + NP;
 
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    const uint32_t flags = p.a.flags[b];
-    const float* __restrict__ x = p.clips + (int64_t)b * N;
-    float o[kMaxPerThread];          // this thread's samples i = tid + e * kThreads, live in registers from here on
+  int it = 0;
+  // prologue: parameters and raw samples of the first clip
+  if ((int)blockIdx.x < p.B) {
+    if (tid < 64) fetch_prm(p, prm[0], blockIdx.x, tid);
+    stage_bytes(stage0, static_cast<const TIn*>(p.clips) + (int64_t)blockIdx.x * N, N * (int)sizeof(TIn), tid);
+  }
+  cp_commit();
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
+    cp_wait<0>();
+    __syncthreads();                                  // stage[it&1] and prm[it&1] are complete and visible
+    const ClipPrm& q = prm[it & 1];
+    const uint32_t flags = q.flags;
+    TIn* st = (it & 1) ? stage1 : stage0;
+    float* cur = kInPlace ? reinterpret_cast<float*>(st) : curf;
+    const bool do_speed = (flags & WW_AUG_SPEED) != 0;
+    const bool rs_ok = do_speed && q.rs >= 0;
+    const RsDesc d = q.d;
+    const int pitch = d.nz + ((d.nz & 4) ? 0 : 4);    // table row pitch in words: 4 mod 8 (see ww_prepare_resample)
+    const int tbl_words = rs_ok ? d.n * pitch + 2 * d.n : 0;
+    const bool in_smem = tbl_words <= kTblWords;
+    // ---- async requests: G1 = polyphase table of this clip, G2 = its noise segment, G3 = next clip's samples
+    if (rs_ok && in_smem) stage_bytes(tbl, p.rs_kern + d.offset, ((tbl_words + 3) & ~3) * 4, tid);
+    cp_commit();
+    if (flags & WW_AUG_NOISE)
+      stage_bytes(noise_s, p.bank + (int64_t)q.noise_idx * p.bank_len + q.noise_off, N * 4, tid);
+    cp_commit();
+    const int bn = b + gridDim.x;
+    if (bn < p.B) stage_bytes((it & 1) ? stage0 : stage1, static_cast<const TIn*>(p.clips) + (int64_t)bn * N, N * (int)sizeof(TIn), tid);
+    cp_commit();
+    // ---- scalars of the next clip (64 threads; consumed after the __syncthreads at the top of the next iteration)
+    if (tid < 64 && bn < p.B) fetch_prm(p, prm[(it + 1) & 1], bn, tid);
+
+    // ---- load own samples from the stage, peak normalise
+    float o[kMaxPerThread];
     float m = 0.0f, dummy = 0.0f;
 #pragma unroll
     for (int e = 0; e < kMaxPerThread; ++e) {
-      const int i = tid + e * kThreads;
-      o[e] = (i < N) ? __ldg(x + i) : 0.0f;
+      const int i = slot_index(tid, e);
+      o[e] = (i < N) ? cvt_in(st[i]) : 0.0f;
       m = fmaxf(m, fabsf(o[e]));
     }
     if (flags & WW_AUG_NORM_IN) {
@@ -87,59 +188,58 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
 
     if (flags & (WW_AUG_SHIFT | WW_AUG_SPEED)) {
       // ---- one gather through shared memory: out[i] = sum_k kern[ph][k] * rolled[x0 + k],  rolled[t] = in[(t - shift) mod N]
+      if (!kInPlace || (flags & WW_AUG_NORM_IN)) {
 #pragma unroll
-      for (int e = 0; e < kMaxPerThread; ++e) {
-        const int i = tid + e * kThreads;
-        if (i < N) cur[i] = o[e];
+        for (int e = 0; e < kMaxPerThread; ++e) {
+          const int i = slot_index(tid, e);
+          if (i < N) cur[i] = o[e];
+        }
       }
-      int s = (flags & WW_AUG_SHIFT) ? p.a.shift[b] % N : 0;
+      int s = (flags & WW_AUG_SHIFT) ? q.shift % N : 0;
       if (s < 0) s += N;
-      if (flags & WW_AUG_SPEED) {
-        const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
-        int found = -1;
-        for (int i = 0; i < p.n_rs; ++i)
-          if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { found = i; break; }
-        if (found < 0) {
-          __syncthreads();
+      cp_wait<2>();                                    // G1 (table) landed; G2 / G3 may still be in flight
+      __syncthreads();
+      if (do_speed) {
+        if (!rs_ok) {
 #pragma unroll
           for (int e = 0; e < kMaxPerThread; ++e) o[e] = __int_as_float(0x7fc00000);   // loud: NaN clip
         } else {
-          const RsDesc d = p.rs_desc[found];
-          // compact polyphase table of this ratio -> shared memory ([n][nz] taps, [n] first tap, [n] count)
-          const int tbl_words = d.n * d.nz + 2 * d.n;
-          const bool in_smem = tbl_words <= kTblWords;
-          const float* __restrict__ gk = p.rs_kern + d.offset;
-          if (in_smem)
-            for (int i = tid; i < tbl_words; i += kThreads) tbl[i] = __ldg(gk + i);
-          __syncthreads();
-          const float* kern = in_smem ? tbl : gk;
-          const int* lo_t = reinterpret_cast<const int*>(kern + d.n * d.nz);
+          const float* kern = in_smem ? tbl : p.rs_kern + d.offset;
+          const int* lo_t = reinterpret_cast<const int*>(kern + d.n * pitch);
           const int* cnt_t = lo_t + d.n;
           const int out_len = (d.n * N + d.o - 1) / d.o;                             // ceil(n*N/o), < 2^31
-          const int crop = (out_len > N) ? p.a.crop_off[b] : 0;
+          const int crop = (out_len > N) ? q.crop : 0;
+          const uint32_t magic = 0xffffffffu / (uint32_t)d.n + 1u;                   // j / n == umulhi(j, magic) for j, n < 2^16
+          const int nz4 = d.nz >> 2;                                                 // table rows are zero-padded to x4 taps
 #pragma unroll
           for (int e = 0; e < kMaxPerThread; ++e) {
-            const int i = tid + e * kThreads;
+            const int i = slot_index(tid, e);
             float acc0 = 0.0f, acc1 = 0.0f;
             const int j = i + crop;                                                  // resampled-domain index
             if (i < N && j < out_len) {
-              const int q = j / d.n, ph = j - q * d.n;                               // (q, p) phase decomposition
-              const int x0 = q * d.o - d.width + lo_t[ph];                           // source index of the first non-zero tap
-              const float* kr = kern + ph * d.nz;
-              const int k0 = x0 < 0 ? -x0 : 0;
-              const int k1 = min(cnt_t[ph], N - x0);
-              int src = x0 + k0 - s;
+              const int qq = (int)__umulhi((uint32_t)j, magic), ph = j - qq * d.n;   // (q, p) phase decomposition
+              const int x0 = qq * d.o - d.width + lo_t[ph];                          // source index of the first non-zero tap
+              const float* kr = kern + ph * pitch;
+              int src = x0 - s;
               if (src < 0) src += N;
-              int k = k0;
-              if (src + (k1 - k0) <= N) {                                            // no wrap inside the tap window
-                const float* sp = cur + src - k0;
-                for (; k + 1 < k1; k += 2) {                                         // two independent chains
-                  acc0 = fmaf(kr[k], sp[k], acc0);
-                  acc1 = fmaf(kr[k + 1], sp[k + 1], acc1);
+              if (x0 >= 0 && x0 + d.nz <= N && src >= 0 && src + d.nz <= N) {
+                // interior: no edge clipping, no wrap inside the (padded) tap window
+                const float4* kr4 = reinterpret_cast<const float4*>(kr);
+                const float* sp = cur + src;
+                for (int k4 = 0; k4 < nz4; ++k4) {
+                  const float4 w = kr4[k4];
+                  acc0 = fmaf(w.x, sp[4 * k4], acc0);
+                  acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
+                  acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
+                  acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
                 }
-                if (k < k1) acc0 = fmaf(kr[k], sp[k], acc0);
               } else {
-                for (; k < k1; ++k) {
+                const int k0 = x0 < 0 ? -x0 : 0;
+                const int k1 = min(cnt_t[ph], N - x0);
+                src = x0 + k0 - s;
+                if (src < 0) src += N;
+                if (src < 0) src += N;
+                for (int k = k0; k < k1; ++k) {
                   acc0 = fmaf(kr[k], cur[src], acc0);
                   src = (src + 1 >= N) ? src + 1 - N : src + 1;
                 }
@@ -149,10 +249,9 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
           }
         }
       } else {
-        __syncthreads();
 #pragma unroll
         for (int e = 0; e < kMaxPerThread; ++e) {
-          const int i = tid + e * kThreads;
+          const int i = slot_index(tid, e);
           int src = i - s;
           if (src < 0) src += N;
           o[e] = (i < N) ? cur[src] : 0.0f;                                         // bit-exact copy (np.roll)
@@ -161,15 +260,16 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
     }
 
     if (flags & WW_AUG_NOISE) {
-      const float* __restrict__ nz = p.bank + (int64_t)p.a.noise_idx[b] * p.bank_len + p.a.noise_off[b];
-      const float snr = p.a.snr_db[b];
+      cp_wait<1>();                                    // G2 (noise segment) landed
+      __syncthreads();
+      const float snr = q.snr;
       const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
       float n[kMaxPerThread];
       float sc = 0.0f, sn = 0.0f;
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) {
-        const int i = tid + e * kThreads;
-        n[e] = (i < N) ? __ldg(nz + i) : 0.0f;
+        const int i = slot_index(tid, e);
+        n[e] = (i < N) ? noise_s[i] : 0.0f;
         sc = fmaf(o[e], o[e], sc);
         sn = fmaf(n[e], n[e], sn);
       }
@@ -191,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
       for (int e = 0; e < kMaxPerThread; ++e) o[e] = o[e] + n[e] * noisescalar;
     }
     if (flags & WW_AUG_GAIN) {
-      const float g = p.a.gain[b];
+      const float g = q.gain;
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) o[e] *= g;
     }
@@ -208,11 +308,13 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(AugKParams p) {
     float* __restrict__ dst = p.out + (int64_t)b * N;
 #pragma unroll
     for (int e = 0; e < kMaxPerThread; ++e) {
-      const int i = tid + e * kThreads;
+      const int i = slot_index(tid, e);
       if (i < N) dst[i] = o[e];
     }
-    __syncthreads();      // cur / tbl are reused by the next clip
+    // the __syncthreads at the top of the next iteration orders this clip's shared-memory reads (cur, tbl, noise)
+    // before the next clip's cp.async writes and in-place normalise
   }
+  cp_wait<0>();
 }
 
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* out) {
@@ -242,7 +344,24 @@ int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaS
   return WW_OK;
 }
 
-int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
+template <typename TIn>
+static int launch_augment_t(ww_ctx* c, const AugKParams& p, cudaStream_t st) {
+  const int NP = (p.N + 3) & ~3;
+  const size_t smem = (size_t)2 * NP * sizeof(TIn) + (sizeof(TIn) == 4 ? 0 : (size_t)NP * 4) + (size_t)NP * 4 +
+                      (size_t)kTblWords * 4;
+  static size_t configured = 0;
+  if (smem > configured) {
+    WW_CHECK(c, cudaFuncSetAttribute(augment_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = std::min(c->sm_count, p.B);
+  ProfScope prof(c, WW_STAGE_AUGMENT, st);
+  augment_kernel<TIn><<<grid, kThreads, smem, st>>>(p);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+int ww_launch_augment(ww_ctx* c, const void* clips, int pcm16, const float* bank, int bank_rows, int64_t bank_len,
                       const ww_aug* a, float* out, int B, cudaStream_t st) {
   if (B <= 0) return WW_OK;
   AugKParams p;
@@ -253,15 +372,9 @@ int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank
     c->set_error("ww_augment: n_samples too large (max 16384 samples per clip)");
     return WW_ERR_INVALID;
   }
-  size_t smem = (size_t)(((p.N + 3) & ~3) + kTblWords) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  if ((reinterpret_cast<uintptr_t>(clips) & 3) || (pcm16 && (p.N & 1))) {
+    c->set_error("ww_augment: clips must be 4-byte aligned (and n_samples even for int16 PCM)");
+    return WW_ERR_INVALID;
   }
-  int grid = std::min(c->sm_count, B);
-  ProfScope prof(c, WW_STAGE_AUGMENT, st);
-  augment_kernel<<<grid, kThreads, smem, st>>>(p);
-  WW_LAUNCH_CHECK(c);
-  return WW_OK;
+  return pcm16 ? launch_augment_t<int16_t>(c, p, st) : launch_augment_t<float>(c, p, st);
 }

@@ -136,7 +136,7 @@ int free_all(ww_ctx* c) {
   for (auto& kv : c->w) cudaFree(kv.second);
   for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
   for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); }
-  cudaFree(c->d_w2_split); cudaFree(c->d_w3_split);
+  cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_h); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
   cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
@@ -160,6 +160,9 @@ int ensure_workspaces(ww_ctx* c) {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2, (size_t)c->chunk * 64 * H * W * 4));
   } else {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_h, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
+    const size_t pad_bytes = (size_t)c->chunk * ww_conv_tc_inpad_floats_per_clip(c) * 4;
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_logmel_pad, pad_bytes));
+    WW_CHECK(c, cudaMemset(c->ws_logmel_pad, 0, pad_bytes));      // the padding stays zero: kernels only write pixels
   }
   c->ws_ready = true;
   return WW_OK;
@@ -323,7 +326,7 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
   const double base = std::min(t.o, t.n) * rolloff;
   t.width = (int)ceil(lpw * t.o / base);
   t.taps = 2 * t.width + t.o;
-  t.offset = c->rs_kern_floats;
+  t.offset = (c->rs_kern_floats + 3) & ~3;             // table rows are read as float4: 16-byte aligned base
   std::vector<float> k((size_t)t.n * t.taps);
   for (int p = 0; p < t.n; ++p)
     for (int i = 0; i < t.taps; ++i) {
@@ -349,16 +352,19 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
       lo[p] = l; cnt[p] = h - l;
       nz = std::max(nz, h - l);
     }
-    std::vector<float> comp((size_t)t.n * nz + 2 * t.n, 0.0f);
+    nz = (nz + 3) & ~3;                                  // rows zero-padded to whole float4 groups
+    // row pitch = 4 (mod 8) words: the 128-bit row loads of 8 consecutive phases then hit 8 different bank groups
+    const int pitch = nz + ((nz & 4) ? 0 : 4);
+    std::vector<float> comp((((size_t)t.n * pitch + 2 * t.n) + 3) & ~(size_t)3, 0.0f);
     for (int p = 0; p < t.n; ++p) {
-      for (int i = 0; i < cnt[p]; ++i) comp[(size_t)p * nz + i] = k[(size_t)p * t.taps + lo[p] + i];
-      memcpy(&comp[(size_t)t.n * nz + p], &lo[p], 4);
-      memcpy(&comp[(size_t)t.n * nz + t.n + p], &cnt[p], 4);
+      for (int i = 0; i < cnt[p]; ++i) comp[(size_t)p * pitch + i] = k[(size_t)p * t.taps + lo[p] + i];
+      memcpy(&comp[(size_t)t.n * pitch + p], &lo[p], 4);
+      memcpy(&comp[(size_t)t.n * pitch + t.n + p], &cnt[p], 4);
     }
     t.nz = nz;
     k.swap(comp);
   }
-  const int need = c->rs_kern_floats + (int)k.size();
+  const int need = t.offset + (int)k.size();
   if (need > c->rs_kern_cap) {
     int cap = std::max(need * 2, 1 << 16);
     float* nb = nullptr;
@@ -441,7 +447,8 @@ int pool_parts(const ww_ctx* c) {
   return ww_conv_tc_groups(c);
 }
 
-// conv stack of one chunk; its pool partials land at clip offset `pool_off` of the batch-wide buffer
+// conv stack of one chunk; its pool partials land at clip offset `pool_off` of the batch-wide buffer.
+// fp32 mode: `logmel` is the plain [B][H][W] image; tensor-core modes: the padded image in ws_logmel_pad.
 int conv_chunk(ww_ctx* c, const float* logmel, int B, int64_t pool_off, cudaStream_t st) {
   c->pool_cur = c->ws_pool_part + (size_t)pool_off * pool_parts(c) * 128;
   return (c->cfg.conv_mode == WW_CONV_FP32) ? ww_launch_conv_fp32(c, logmel, B, st) : ww_launch_conv_tc(c, logmel, B, st);
@@ -455,7 +462,14 @@ int ww_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, 
                const ww_aug* p, float* out, int B, void* stream) {
   if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
   cudaSetDevice(c->device);
-  return ww_launch_augment(c, clips, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
+  return ww_launch_augment(c, clips, 0, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
+}
+
+int ww_augment_pcm16(ww_ctx* c, const int16_t* clips, const float* bank, int bank_rows, int64_t bank_len,
+                     const ww_aug* p, float* out, int B, void* stream) {
+  if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return ww_launch_augment(c, clips, 1, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
 }
 
 int ww_normalize(ww_ctx* c, const float* in, float* out, int64_t n, void* stream) {
@@ -467,7 +481,13 @@ int ww_normalize(ww_ctx* c, const float* in, float* out, int64_t n, void* stream
 int ww_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize, void* stream) {
   if (!c || !clips || !out || B < 0 || clip_stride <= 0) return WW_ERR_INVALID;
   cudaSetDevice(c->device);
-  return ww_launch_logmel(c, clips, clip_stride, out, B, normalize, (cudaStream_t)stream);
+  return ww_launch_logmel(c, clips, 0, clip_stride, out, B, normalize, (cudaStream_t)stream);
+}
+
+int ww_logmel_pcm16(ww_ctx* c, const int16_t* clips, int64_t clip_stride, float* out, int B, int normalize, void* stream) {
+  if (!c || !clips || !out || B < 0 || clip_stride <= 0) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return ww_launch_logmel(c, clips, 1, clip_stride, out, B, normalize, (cudaStream_t)stream);
 }
 
 int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* stream) {
@@ -481,14 +501,19 @@ int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* strea
   const size_t per = (size_t)c->cfg.n_mels * c->W;
   for (int b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = std::min(c->chunk, B - b0);
-    if ((rc = conv_chunk(c, logmel + (size_t)b0 * per, nb, b0, st))) return rc;
+    const float* src = logmel + (size_t)b0 * per;
+    if (c->cfg.conv_mode != WW_CONV_FP32) {
+      if ((rc = ww_launch_pad_logmel(c, src, c->ws_logmel_pad, nb, st))) return rc;
+      src = c->ws_logmel_pad;
+    }
+    if ((rc = conv_chunk(c, src, nb, b0, st))) return rc;
   }
   return ww_launch_head(c, B, logits, nullptr, nullptr, st);
 }
 
 // (augment) -> log-mel -> conv stack for clips [0, B) whose pool partials go to clip offset pool_off; the head
 // (whole batch) runs only when run_head is set, over clips [0, pool_off + B).
-static int score_impl(ww_ctx* c, const float* clips, int64_t clip_stride, const float* bank, int bank_rows,
+static int score_impl(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, const float* bank, int bank_rows,
                       int64_t bank_len, const ww_aug* aug, int normalize, float* logits, float* prob1,
                       uint8_t* decision, int64_t B, cudaStream_t st, int64_t pool_off = 0, bool run_head = true) {
   int rc = ensure_workspaces(c);
@@ -498,26 +523,32 @@ static int score_impl(ww_ctx* c, const float* clips, int64_t clip_stride, const 
   const int N = c->cfg.n_samples;
   for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = (int)std::min<int64_t>(c->chunk, B - b0);
-    const float* src = clips + b0 * clip_stride;
+    const void* src = static_cast<const char*>(clips) + b0 * clip_stride * (pcm16 ? 2 : 4);
     int64_t stride = clip_stride;
+    int in16 = pcm16;
     if (aug) {
       ww_aug a = *aug;
       a.flags += b0; a.shift += b0; a.rs_orig += b0; a.rs_new += b0; a.crop_off += b0;
       a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
-      if ((rc = ww_launch_augment(c, src, bank, bank_rows, bank_len, &a, c->ws_clips, nb, st))) return rc;
+      if ((rc = ww_launch_augment(c, src, in16, bank, bank_rows, bank_len, &a, c->ws_clips, nb, st))) return rc;
       src = c->ws_clips;
       stride = N;
+      in16 = 0;
     }
-    if ((rc = ww_launch_logmel(c, src, stride, c->ws_logmel, nb, aug ? 0 : normalize, st))) return rc;
-    if ((rc = conv_chunk(c, c->ws_logmel, nb, pool_off + b0, st))) return rc;
+    const bool tc = c->cfg.conv_mode != WW_CONV_FP32;
+    const LogmelOut lo = tc ? ww_conv_tc_logmel_out(c, c->ws_logmel_pad)
+                            : LogmelOut{c->ws_logmel, c->W, 0, (int64_t)c->cfg.n_mels * c->W};
+    if ((rc = ww_launch_logmel_ex(c, src, in16, stride, lo, nb, aug ? 0 : normalize, st))) return rc;
+    if ((rc = conv_chunk(c, tc ? c->ws_logmel_pad : c->ws_logmel, nb, pool_off + b0, st))) return rc;
   }
   if (!run_head) return WW_OK;
   if (pool_off + B > 0x7fffffff) { c->set_error("score: batch too large"); return WW_ERR_INVALID; }
   return ww_launch_head(c, (int)(pool_off + B), logits, prob1, decision, st);
 }
 
-int ww_score(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len, const ww_aug* aug,
-             int normalize, float* logits, float* prob1, uint8_t* decision, int B, void* stream) {
+static int score_entry(ww_ctx* c, const void* clips, int pcm16, const float* bank, int bank_rows, int64_t bank_len,
+                       const ww_aug* aug, int normalize, float* logits, float* prob1, uint8_t* decision, int B,
+                       void* stream) {
   if (!c || !clips || B < 0) return WW_ERR_INVALID;
   if (aug && (!aug->flags || !aug->shift || !aug->rs_orig || !aug->rs_new || !aug->crop_off || !aug->noise_idx ||
               !aug->noise_off || !aug->snr_db || !aug->gain)) {
@@ -525,31 +556,53 @@ int ww_score(ww_ctx* c, const float* clips, const float* bank, int bank_rows, in
     return WW_ERR_INVALID;
   }
   cudaSetDevice(c->device);
-  return score_impl(c, clips, c->cfg.n_samples, bank, bank_rows, bank_len, aug, normalize, logits, prob1, decision, B,
-                    (cudaStream_t)stream);
+  return score_impl(c, clips, pcm16, c->cfg.n_samples, bank, bank_rows, bank_len, aug, normalize, logits, prob1,
+                    decision, B, (cudaStream_t)stream);
 }
 
-int ww_score_stream(ww_ctx* c, const float* audio, int64_t T, int hop_samples, float* prob1, uint8_t* decision,
-                    int64_t n_win, void* stream) {
+int ww_score(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len, const ww_aug* aug,
+             int normalize, float* logits, float* prob1, uint8_t* decision, int B, void* stream) {
+  return score_entry(c, clips, 0, bank, bank_rows, bank_len, aug, normalize, logits, prob1, decision, B, stream);
+}
+
+int ww_score_pcm16(ww_ctx* c, const int16_t* clips, const float* bank, int bank_rows, int64_t bank_len,
+                   const ww_aug* aug, int normalize, float* logits, float* prob1, uint8_t* decision, int B,
+                   void* stream) {
+  return score_entry(c, clips, 1, bank, bank_rows, bank_len, aug, normalize, logits, prob1, decision, B, stream);
+}
+
+static int stream_entry(ww_ctx* c, const void* audio, int pcm16, int64_t T, int hop_samples, float* prob1,
+                        uint8_t* decision, int64_t n_win, void* stream) {
   if (!c || !audio || hop_samples <= 0 || n_win < 0) return WW_ERR_INVALID;
   if (n_win > 0 && (n_win - 1) * hop_samples + c->cfg.n_samples > T) {
     c->set_error("ww_score_stream: windows exceed the audio length");
     return WW_ERR_INVALID;
   }
   cudaSetDevice(c->device);
-  return score_impl(c, audio, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win,
+  return score_impl(c, audio, pcm16, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win,
                     (cudaStream_t)stream);
 }
 
-int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int bank_rows, int64_t bank_len,
-                  const ww_aug* aug_host, int normalize, float* logits_host, float* prob1_host,
-                  uint8_t* decision_host, int B) {
+int ww_score_stream(ww_ctx* c, const float* audio, int64_t T, int hop_samples, float* prob1, uint8_t* decision,
+                    int64_t n_win, void* stream) {
+  return stream_entry(c, audio, 0, T, hop_samples, prob1, decision, n_win, stream);
+}
+
+int ww_score_stream_pcm16(ww_ctx* c, const int16_t* audio, int64_t T, int hop_samples, float* prob1,
+                          uint8_t* decision, int64_t n_win, void* stream) {
+  return stream_entry(c, audio, 1, T, hop_samples, prob1, decision, n_win, stream);
+}
+
+static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const float* bank_dev, int bank_rows,
+                           int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
+                           float* prob1_host, uint8_t* decision_host, int B) {
   if (!c || !clips_host || B < 0) return WW_ERR_INVALID;
   cudaSetDevice(c->device);
   cudaStream_t st = c->own_stream;
   const int N = c->cfg.n_samples, C = c->cfg.num_classes;
+  const size_t esz = pcm16 ? 2 : 4;
   int rc;
-  if ((rc = ensure_buffer(c, &c->d_host_in, &c->d_host_in_bytes, (size_t)B * N * 4))) return rc;
+  if ((rc = ensure_buffer(c, &c->d_host_in, &c->d_host_in_bytes, (size_t)B * N * esz))) return rc;
   const size_t out_bytes = (size_t)B * (C * 4 + 4 + 1);
   if ((rc = ensure_buffer(c, &c->d_host_out, &c->d_host_out_bytes, out_bytes))) return rc;
   float* d_logits = (float*)c->d_host_out;
@@ -571,7 +624,8 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
   if ((rc = ww_prepare_weights(c, st))) return rc;
   // Two streams: the copy engine moves chunk i+1 host->device while the SMs score chunk i.
   if (!c->copy_stream) WW_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  float* d_in = (float*)c->d_host_in;
+  char* d_in = (char*)c->d_host_in;
+  const char* h_in = (const char*)clips_host;
   const int n_chunks = (B + c->chunk - 1) / c->chunk;
   while ((int)c->copy_events.size() < n_chunks) {
     cudaEvent_t e;
@@ -580,7 +634,7 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
   }
   for (int i = 0; i < n_chunks; ++i) {
     const int b0 = i * c->chunk, nb = std::min(c->chunk, B - b0);
-    WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N, clips_host + (size_t)b0 * N, (size_t)nb * N * 4,
+    WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N * esz, h_in + (size_t)b0 * N * esz, (size_t)nb * N * esz,
                                 cudaMemcpyHostToDevice, c->copy_stream));
     WW_CHECK(c, cudaEventRecord(c->copy_events[i], c->copy_stream));
   }
@@ -593,8 +647,8 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
       a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
     }
     // the head (whole batch) runs with the last chunk
-    rc = score_impl(c, d_in + (size_t)b0 * N, N, bank_dev, bank_rows, bank_len, aug_host ? &a : nullptr, normalize,
-                    d_logits, d_prob, d_dec, nb, st, b0, i == n_chunks - 1);
+    rc = score_impl(c, d_in + (size_t)b0 * N * esz, pcm16, N, bank_dev, bank_rows, bank_len, aug_host ? &a : nullptr,
+                    normalize, d_logits, d_prob, d_dec, nb, st, b0, i == n_chunks - 1);
     if (rc) return rc;
   }
   if (logits_host) WW_CHECK(c, cudaMemcpyAsync(logits_host, d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
@@ -602,6 +656,20 @@ int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int
   if (decision_host) WW_CHECK(c, cudaMemcpyAsync(decision_host, d_dec, (size_t)B, cudaMemcpyDeviceToHost, st));
   WW_CHECK(c, cudaStreamSynchronize(st));
   return WW_OK;
+}
+
+int ww_score_host(ww_ctx* c, const float* clips_host, const float* bank_dev, int bank_rows, int64_t bank_len,
+                  const ww_aug* aug_host, int normalize, float* logits_host, float* prob1_host,
+                  uint8_t* decision_host, int B) {
+  return score_host_impl(c, clips_host, 0, bank_dev, bank_rows, bank_len, aug_host, normalize, logits_host, prob1_host,
+                         decision_host, B);
+}
+
+int ww_score_host_pcm16(ww_ctx* c, const int16_t* clips_host, const float* bank_dev, int bank_rows, int64_t bank_len,
+                        const ww_aug* aug_host, int normalize, float* logits_host, float* prob1_host,
+                        uint8_t* decision_host, int B) {
+  return score_host_impl(c, clips_host, 1, bank_dev, bank_rows, bank_len, aug_host, normalize, logits_host, prob1_host,
+                         decision_host, B);
 }
 
 }  // extern "C"

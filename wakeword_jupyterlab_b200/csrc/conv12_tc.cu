@@ -1,96 +1,114 @@
-// K3a (tensor-core path): conv1 (CUDA cores, fp32) fused into conv2 (tcgen05 implicit GEMM) + bias + ReLU  (sm_100a)
+// K3a (tensor-core path): conv1 + ReLU and conv2 + ReLU, both as tcgen05 implicit GEMMs, chained through shared memory
+// (sm_100a).
 //
 // Replaces F.relu(self.conv1(x)) and F.relu(self.conv2(x)) of WakewordModel.forward
 // (/root/reference/wakeword_training_script.py:170-171).  See conv3_tc.cu for the layout story.
 //
-// Work item = (clip, PAIR of 128-pixel tiles of the pixel-linear padded image).  Warp roles:
-//   warps 0-15  producers (one pixel x 16 channels per thread): conv1 + ReLU in fp32 (packed FFMA2, weights read
-//               from the constant bank as kernel parameters) for the 256 pixels and their 3x3 halo (2P + 2 more),
-//               rounded to fp16 and stored as the K-major SWIZZLE_NONE A operand [chunk of 8 ch][pixel][16 B];
-//               three A buffers so the producers run up to two items ahead of the tensor core; the log-mel rows an
-//               item needs are staged one item ahead with cp.async;
-//   warps 16-23 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM -> (D_hi + D_lo) * 2^-k +
-//               bias, ReLU, zero the padding pixels, round to fp16, write the conv3 operand planes to HBM (512
-//               contiguous bytes per warp store);
-//   warps 24,25 MMA issuers (warp 24: even items / accumulator 0, warp 25: odd items / accumulator 1, so the ~100
-//               cycle issue cost of each small MMA overlaps and the result stays deterministic).  Per 3x3 tap,
-//               16-channel k-slice and tile:
-//                 D[:, 0:128] += A x [W_hi ; W_lo]^T   (N = 128: both weight halves in one instruction; the
-//               epilogue adds the two column halves; WW_CONV_FP16: N = 64, W_hi only)
-//               -- the tap is only a start-address offset of the same shared-memory tile.
-// conv2 weights (hi and lo stacked along N, 73,728 B) stay resident in shared memory.
+// Input: the log-mel image in the zero-padded pixel-linear layout (pixel (y,x) at padded index (y+1)*P + (x+1),
+// pitch P = W+1, fp32, `lead` zero floats in front), so that the rows an item needs are ONE contiguous range.
+// Work item = (clip, PAIR of 128-pixel conv2 tiles) = 256 output pixels, which need conv1 on NL = 256 + 2P + 2
+// pixels (3x3 halo), i.e. NM = ceil(NL / 128) conv1 M-tiles.  Warp roles (19 warps):
+//   warp 0      loader: conv1/conv2 weights once (resident, 76 KB), then one 1-D bulk copy per item (3-stage ring);
+//   warp 1      conv1 MMA issuer: per M-tile two K = 16 steps,  D1[128 px, 64] = A1[128 px, 32] x [W1_hi ; W1_lo]^T
+//               with A1 row = (9 taps as fp16 hi | 9 taps as fp16 lo)  -- K = 9 padded to 16, twice;
+//   warps 2,19  conv2 MMA issuers (one per tile of the pair: a small MMA costs ~100 cycles to issue but only 64 to
+//               execute, so two issuers keep the tensor pipe fed): per 3x3 tap and 16-channel k-slice
+//                 D2[:, 0:128] += A2 x [W2_hi ; W2_lo]^T   (N = 128; WW_CONV_FP16: N = 64, W2_hi only)
+//               -- the tap is only a start-address offset of the same shared-memory tile;
+//   warps 3-6   im2col: 9 shared-memory loads per pixel -> fp16 hi/lo split -> four 16-byte rows of A1 (ring of 4 M-tiles);
+//   warps 7-10  conv1 epilogue: TMEM D1 -> (hi + lo) * 2^-k + bias, ReLU fused into the fp16 conversion, zero the padding
+//               pixels -> conv2's A operand A2 [chunk of 8 ch][pixel][16 B] (double-buffered);
+//   warps 11-18 conv2 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM D2 -> (hi + lo) * 2^-k +
+//               bias, ReLU+fp16, zero the padding pixels -> conv3's operand planes in HBM (512 contiguous bytes per
+//               warp store).
+// Every CUDA-core stage touches each activation once; all multiply-adds run on the tensor core.
 #include "tc_common.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
-#include <type_traits>
 
 using namespace tc;
 
-#define C12_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 48 && lane == 0) p.trace[it * 8 + (slot)] = clock64(); } while (0)
-
 namespace {
 
-constexpr int C12_THREADS = 832;
+constexpr int C12_THREADS = 20 * 32;
 constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 fp16]
-constexpr int NABUF_MAX = 3;                 // A-operand buffers (3 when shared memory allows, else 2)
+constexpr int W1_BYTES = 4 * 64 * 16;        // [kc 4][n' 64 = 32 hi + 32 lo][8 fp16]; kc 2,3 repeat kc 0,1 (for the lo taps)
+constexpr int A1_SLOT_BYTES = 4 * 128 * 16;  // one conv1 M-tile: [kc 4][row 128][8 fp16]
+constexpr int A1_SLOTS = 4;
+constexpr int P_STAGES = 3;
 
 struct Conv12Params {
-  const float* logmel;            // [B][H][W]
-  float w1[288];                  // conv1 weights [tap][cout] -- kernel parameters live in the constant bank, so
-  float b1[32];                   // the FMAs read them as c[0][..] operands: no shared-memory traffic at all
-  float b2[64];                   // conv2 bias, also via the constant bank
-  const __half* w2s;              // stacked split weights * 2^k, canonical layout
+  const float* in_pad;            // [B][npix_in] zero-padded pixel-linear log-mel
+  float b1[32];                   // biases via the constant bank
+  float b2[64];
+  const __half* w1s;              // conv1 weights * 2^k1, stacked hi/lo
+  const __half* w2s;              // conv2 weights * 2^k2, stacked hi/lo
   __half* act2;                   // [B][8 planes (chunks of 8 channels)][npix][8]
-  float inv_scale;                // 2^-k
-  int B, nabuf;
+  float inv_s1, inv_s2;           // 2^-k1, 2^-k2
+  int B;
+  int spin;                       // WW_C12_SPIN: poll the mbarriers instead of suspending (experiment switch)
   Geom g;
-  long long* trace;               // debug (WW_TC_TRACE=1): per-item role timestamps of CTA 0
 };
 
-// packed fp32x2 FMA (Blackwell): d = a * b + d on two lanes of a 64-bit register pair
-__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+#define C12_WAIT(bar, par, code) do { if (p.spin) mbar_wait_spin(bar, par, code); else mbar_wait(bar, par, code); } while (0)
+
+// two floats -> packed fp16x2 with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_f16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+__device__ __forceinline__ uint4 cvt8_relu(const float* v, bool ok) {
+  uint4 u = make_uint4(pack_f16_relu(v[0], v[1]), pack_f16_relu(v[2], v[3]), pack_f16_relu(v[4], v[5]),
+                       pack_f16_relu(v[6], v[7]));
+  if (!ok) u = make_uint4(0u, 0u, 0u, 0u);
+  return u;
 }
+__device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
+__device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
 
-// SLOTS = ceil((256 + 2P + 2) / 256): halo'd pixels per producer thread (2 at the code preset, 3 at W = 161)
-template <int NPASS, int SLOTS>
+template <int NPASS>
 __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_constant__ Conv12Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
+  const uint32_t a2_bytes = 4u * g.nsl2 * 16u;                  // one conv2 A buffer: 4 planes (chunks of 8 channels)
+  const uint32_t patch_bytes = (uint32_t)g.patch_f * 4u;
   unsigned char* w2s = smem;
-  const uint32_t a_bytes = 4u * g.nsl2 * 16u;                  // one act1 buffer: 4 planes (chunks of 8 channels)
-  unsigned char* a_buf0 = smem + W2_BYTES;
-  const int NABUF = p.nabuf;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_buf0 + NABUF * a_bytes);
-  uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;      // [3]
-  uint64_t* a_empty = bars + 4;     // [3]
-  uint64_t* t_full = bars + 7;      // [2]
-  uint64_t* t_empty = bars + 9;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-  const int NL = 256 + 2 * g.P + 2;                            // pixels of an item incl. halo
-  const int patch_rows = (NL + g.P - 1) / g.P + 3;
-  const int patch_floats = (patch_rows * g.W + 3) & ~3;
-  float* patch = reinterpret_cast<float*>(bars + 12);          // [2][patch_floats] log-mel rows of the current / next item
+  unsigned char* w1s = w2s + W2_BYTES;
+  unsigned char* a1 = w1s + W1_BYTES;                           // [A1_SLOTS][A1_SLOT_BYTES]
+  unsigned char* a2 = a1 + A1_SLOTS * A1_SLOT_BYTES;            // [2][a2_bytes]
+  float* patch = reinterpret_cast<float*>(a2 + 2 * a2_bytes);   // [P_STAGES][patch_f]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + P_STAGES * patch_bytes);
+  uint64_t* w_full = bars;                       // [1]
+  uint64_t* p_full = bars + 1;                   // [3]
+  uint64_t* p_empty = bars + 4;                  // [3]
+  uint64_t* a1_full = bars + 7;                  // [4]
+  uint64_t* a1_empty = bars + 11;                // [4]
+  uint64_t* d1_full = bars + 15;                 // [4]
+  uint64_t* d1_empty = bars + 19;                // [4]
+  uint64_t* a2_full = bars + 23;                 // [2]
+  uint64_t* a2_empty = bars + 25;                // [2]
+  uint64_t* t_full = bars + 27;                  // [2]
+  uint64_t* t_empty = bars + 29;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, so role branches are uniform branches
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < NABUF_MAX; ++i) { mbar_init(a_full + i, 512); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
+    for (int i = 0; i < P_STAGES; ++i) { mbar_init(p_full + i, 1); mbar_init(p_empty + i, 128); }
+    for (int i = 0; i < A1_SLOTS; ++i) {
+      mbar_init(a1_full + i, 128); mbar_init(a1_empty + i, 1);
+      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a2_full + i, 128); mbar_init(a2_empty + i, 2);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256);
+    }
     fence_barrier_init();
   }
-  if (warp == 24) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);      // D1 ring: columns 64 s (s < 4); D2 tiles: columns 256 + 128 t
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,273 +116,290 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
 
   const int items_per_clip = g.T2 >> 1;
   const int n_items = p.B * items_per_clip;
+  const int NM = g.NM, NL = g.NL;
 
-  if (warp < 16) {
-    // ===================== conv1 producers
-    const int ch0 = (tid >> 8) * 16;      // this thread's 16 of the 32 conv1 output channels
-    auto stage_patch = [&](int item_, float* dst) {
-      const int b_ = item_ / items_per_clip, tp_ = item_ - b_ * items_per_clip;
-      const int pbase = 256 * tp_ - 1 - g.P - 1;
-      const int r0 = (pbase >= 0 ? (int)__umulhi((uint32_t)pbase, g.magicP) : -1) - 2;   // image row of the first patch row
-      const float* __restrict__ img = p.logmel + (size_t)b_ * g.H * g.W;
-      for (int i = tid; i < patch_rows * g.W; i += 512) {
-        const int pr = i / g.W;
-        const int yy = r0 + pr;
-        if (yy >= 0 && yy < g.H) {
-          const uint32_t d = smem_u32(dst + i);
-          const float* src = img + (size_t)yy * g.W + (i - pr * g.W);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
-        }
+  if (warp == 0) {
+    // ===================== loader (one thread)
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, W2_BYTES + W1_BYTES);
+      bulk_g2s(w2s, p.w2s, W2_BYTES, w_full);
+      bulk_g2s(w1s, p.w1s, W1_BYTES, w_full);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int b = item / items_per_clip, tp = item - b * items_per_clip;
+        const int st = it % P_STAGES;
+        C12_WAIT(p_empty + st, ((it / P_STAGES) & 1) ^ 1, 10);
+        mbar_arrive_expect_tx(p_full + st, patch_bytes);
+        bulk_g2s(patch + (size_t)st * g.patch_f, p.in_pad + (size_t)b * g.npix_in + 256 * tp, patch_bytes, p_full + st);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if ((int)blockIdx.x < n_items) stage_patch(blockIdx.x, patch);
+    }
+  } else if (warp == 1) {
+    // ===================== conv1 MMA issuer (whole warp runs the loop; tcgen05 instructions guarded by elect.sync)
+    C12_WAIT(w_full, 0, 20);
+    constexpr uint32_t idesc64 = make_idesc(128, 64);
+    const uint64_t adesc0 = make_desc(smem_u32(a1), 128 * 16, 128);      // K-chunk stride = 128 rows x 16 B
+    const uint64_t bdesc0 = make_desc(smem_u32(w1s), 64 * 16, 128);      // K-chunk stride = 64 rows x 16 B
+    uint32_t g1 = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int m = 0; m < NM; ++m, ++g1) {
+        const uint32_t s = g1 & (A1_SLOTS - 1), par = (g1 / A1_SLOTS) & 1;
+        C12_WAIT(a1_full + s, par, 21);
+        C12_WAIT(d1_empty + s, par ^ 1, 22);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((s * A1_SLOT_BYTES) >> 4);
+          umma_f16(tmem_base + s * 64, ad, bdesc0, idesc64, 0);                                // taps as fp16 hi
+          umma_f16(tmem_base + s * 64, ad + (2 * 128 * 16 >> 4), bdesc0 + (2 * 64 * 16 >> 4), idesc64, 1);   // taps as fp16 lo
+          umma_commit(a1_empty + s);
+          umma_commit(d1_full + s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2 || warp == 19) {
+    // ===================== conv2 MMA issuers: warp 2 -> tile 0, warp 19 -> tile 1 of every item
+    const int t = warp == 2 ? 0 : 1;
+    C12_WAIT(w_full, 0, 30);
+    constexpr uint32_t idesc = NPASS == 2 ? make_idesc(128, 128) : make_idesc(128, 64);
+    const uint64_t bdesc0 = make_desc(smem_u32(w2s), 2048, 128);
+    const uint64_t adesc0 = make_desc(smem_u32(a2), (uint32_t)g.nsl2 * 16u, 128);
+    const uint32_t nsl = (uint32_t)g.nsl2;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int buf = it % NABUF;
-      mbar_wait_relaxed(a_empty + buf, ((it / NABUF) & 1) ^ 1, 10);
-      if (warp == 0) C12_TRACE(0);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 2, 512;" ::: "memory");                    // patch(it) visible; patch(it-1) no longer read
-      if (item + (int)gridDim.x < n_items) stage_patch(item + gridDim.x, patch + ((it + 1) & 1) * patch_floats);
-      const float* pt = patch + (it & 1) * patch_floats;
-      const int tp = item % items_per_clip;
-      const int pbase = 256 * tp - 1 - g.P - 1;
-      const int r0 = (pbase >= 0 ? (int)__umulhi((uint32_t)pbase, g.magicP) : -1) - 2;
-      unsigned char* ab = a_buf0 + buf * a_bytes;
-#pragma unroll 1      // keep one copy of the conv1 body: the warp-specialised roles must share the instruction cache
-      for (int u = 0; u < SLOTS; ++u) {
-        const int l = (tid & 255) + u * 256;
-        if (l < NL) {                                                    // warp-uniform except in one warp
-          int y = 0, x = 0;
-          const bool ok = pix_valid(pbase + l, g, y, x);
-          float v[16];
-          if (ok) {
-            float in[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
-              in[k] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? pt[(yy - r0) * g.W + xx] : 0.0f;
-            }
-            // 16 channels as 8 packed fp32x2 accumulators: 72 FFMA2 instead of 144 FFMA
-            unsigned long long acc[8];
-            auto conv1 = [&](auto ch0c) {
-              constexpr int CH0 = decltype(ch0c)::value;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) acc[c] = pack2(p.b1[CH0 + 2 * c], p.b1[CH0 + 2 * c + 1]);
-#pragma unroll
-              for (int k = 0; k < 9; ++k) {
-                const unsigned long long in2 = pack2(in[k], in[k]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                  ffma2(acc[c], in2, pack2(p.w1[k * 32 + CH0 + 2 * c], p.w1[k * 32 + CH0 + 2 * c + 1]));
-              }
-            };
-            if (ch0 == 0) conv1(std::integral_constant<int, 0>{});
-            else conv1(std::integral_constant<int, 16>{});
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              unpack2(acc[c], v[2 * c], v[2 * c + 1]);
-              v[2 * c] = fmaxf(v[2 * c], 0.0f);
-              v[2 * c + 1] = fmaxf(v[2 * c + 1], 0.0f);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = 0.0f;
-          }
-#pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2) {
-            const int kc = (ch0 >> 3) + k2;
-            *reinterpret_cast<uint4*>(ab + ((size_t)kc * g.nsl2 + l) * 16) = cvt8(v + k2 * 8);
-          }
-        }
-      }
-      fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(a_full + buf);
-      if (warp == 0) C12_TRACE(1);
-    }
-  } else if (warp >= 24) {
-    // ===================== MMA issuers.  The whole warp runs the loop (descriptor math stays warp-uniform); the
-    // tcgen05 instructions are guarded by elect.sync.
-    if (warp == 24 && elect_one()) {
-      mbar_arrive_expect_tx(w_full, W2_BYTES);
-      bulk_g2s(w2s, p.w2s, W2_BYTES, w_full);
-    }
-    mbar_wait(w_full, 0, 20);
-    constexpr uint32_t idesc128 = make_idesc(128, 128), idesc64 = make_idesc(128, 64);
-    const uint64_t bdesc0 = make_desc(smem_u32(w2s), 2048, 128);
-    const uint32_t lbo_a = (uint32_t)g.nsl2 * 16u;
-    const uint64_t adesc0 = make_desc(smem_u32(a_buf0), lbo_a, 128);
-    const uint32_t nsl = (uint32_t)g.nsl2;
-    auto issue_items = [&](auto tbc) {
-      constexpr int TB = decltype(tbc)::value;                           // accumulator buffer of this issuer
-      const uint32_t d0 = tmem_base + TB * 256;
-      int it = TB;
-      for (int item = blockIdx.x + TB * gridDim.x; item < n_items; item += 2 * gridDim.x, it += 2) {
-        const int buf = it % NABUF;
-        mbar_wait(a_full + buf, (it / NABUF) & 1, 21);
-        C12_TRACE(2);
-        mbar_wait(t_empty + TB, ((it >> 1) & 1) ^ 1, 22);
+      const int buf = it & 1;
+      C12_WAIT(a2_full + buf, (it >> 1) & 1, 31);
+      const uint64_t adesc = adesc0 + (uint64_t)((buf * a2_bytes) >> 4);
+      {
+        C12_WAIT(t_empty + t, (it & 1) ^ 1, 32);
         tc_fence_after();
-        const uint64_t adesc = adesc0 + (uint64_t)((buf * a_bytes) >> 4);
+        const uint32_t d = tmem_base + 256 + t * 128;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const uint32_t row_off = (uint32_t)((g.P + 1) + (tap / 3 - 1) * g.P + (tap % 3 - 1));
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint64_t bd = bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 2048) >> 4);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint64_t ad = adesc + (uint64_t)(2 * j * nsl + row_off + t * 128);
-              const uint32_t d = d0 + t * 128;
-              const uint32_t acc = (tap | j) != 0;
-              // NPASS 2: a*W_hi -> cols 0..63 and a*W_lo -> cols 64..127 in one N = 128 instruction
-              if (elect_one()) umma_f16(d, ad, bd, NPASS == 2 ? idesc128 : idesc64, acc);
-            }
+            const uint64_t ad = adesc + (uint64_t)(2 * j * nsl + row_off + t * 128);
+            // NPASS 2: a*W_hi -> cols 0..63 and a*W_lo -> cols 64..127 in one N = 128 instruction
+            if (elect_one()) umma_f16(d, ad, bd, idesc, (tap | j) != 0);
           }
         }
-        if (elect_one()) {
-          umma_commit(a_empty + buf);
-          umma_commit(t_full + TB);
-        }
+        if (elect_one()) umma_commit(t_full + t);
         __syncwarp();
-        C12_TRACE(3);
       }
-    };
-    if (warp == 24) issue_items(std::integral_constant<int, 0>{});
-    else issue_items(std::integral_constant<int, 1>{});
-  } else {
-    // ===================== epilogue
+      if (elect_one()) umma_commit(a2_empty + buf);
+      __syncwarp();
+    }
+  } else if (warp < 7) {
+    // ===================== im2col producers: thread = one row (pixel) of the current conv1 M-tile
+    const int r = (warp - 3) * 32 + lane;
+    uint32_t g1 = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int st = it % P_STAGES;
+      C12_WAIT(p_full + st, (it / P_STAGES) & 1, 40);
+      const float* pt = patch + (size_t)st * g.patch_f;
+      for (int m = 0; m < NM; ++m, ++g1) {
+        const uint32_t s = g1 & (A1_SLOTS - 1);
+        C12_WAIT(a1_empty + s, ((g1 / A1_SLOTS) & 1) ^ 1, 41);
+        // act1 pixel l of the item sits at padded index pbase + l; its 3x3 neighbourhood starts at patch[l]
+        const float* c0 = pt + 128 * m + r;
+        uint32_t hi[5], lo[5];
+        float v[10];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = c0[(k / 3) * g.P + (k % 3)];
+        v[9] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          hi[k] = pack_f16(v[2 * k], v[2 * k + 1]);
+          lo[k] = pack_f16(v[2 * k] - h_lo(hi[k]), v[2 * k + 1] - h_hi(hi[k]));
+        }
+        unsigned char* dst = a1 + s * A1_SLOT_BYTES + r * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + 128 * 16) = make_uint4(hi[4], 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + 2 * 128 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(dst + 3 * 128 * 16) = make_uint4(lo[4], 0u, 0u, 0u);
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(a1_full + s);
+      }
+      mbar_arrive(p_empty + st);
+    }
+  } else if (warp < 11) {
+    // ===================== conv1 epilogue: D1 -> act1 (fp16) = conv2's A operand
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
-    const int hc = (warp - 16) >> 2;      // which 32 of the 64 output channels
+    const int r = q * 32 + lane;
+    const float inv_s = p.inv_s1;
+    uint32_t g1 = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int tp = item % items_per_clip;
+      const int pbase = 256 * tp - 1 - g.P - 1;
+      const int buf = it & 1;
+      C12_WAIT(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
+      unsigned char* ab = a2 + buf * a2_bytes;
+      for (int m = 0; m < NM; ++m, ++g1) {
+        const uint32_t s = g1 & (A1_SLOTS - 1);
+        C12_WAIT(d1_full + s, (g1 / A1_SLOTS) & 1, 51);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64;
+        tmem_ld32_nowait(taddr, r0);
+        tmem_ld32_nowait(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(d1_empty + s);
+        const int l = 128 * m + r;
+        if (l < NL) {
+          int y, x;
+          const bool ok = pix_valid(pbase + l, g, y, x);
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = fmaf(__uint_as_float(r0[kc * 8 + e]) + __uint_as_float(r1[kc * 8 + e]), inv_s, p.b1[kc * 8 + e]);
+            *reinterpret_cast<uint4*>(ab + ((size_t)kc * g.nsl2 + l) * 16) = cvt8_relu(o, ok);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(a2_full + buf);
+    }
+  } else {
+    // ===================== conv2 epilogue
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int hc = (warp - 11) >> 2;      // which 32 of the 64 output channels
+    const float inv_s = p.inv_s2;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / items_per_clip, tp = item - b * items_per_clip;
-      const int tb = it & 1;
-      mbar_wait_relaxed(t_full + tb, (it >> 1) & 1, 30);
-      if (warp == 16) C12_TRACE(4);
-      tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
-        float v[32];
-        {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tb * 256 + t * 128 + hc * 32;
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(taddr, r0);
-          if (NPASS == 2) tmem_ld32_nowait(taddr + 64, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + (NPASS == 2 ? __uint_as_float(r1[i]) : 0.0f);
-        }
-        if (t == 1) {                       // both tiles are in registers: release the accumulator
-          tc_fence_before();
-          mbar_arrive(t_empty + tb);
-          if (warp == 16) C12_TRACE(5);
-        }
+        C12_WAIT(t_full + t, it & 1, 60);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + t * 128 + hc * 32;
+        tmem_ld32_nowait(taddr, r0);
+        if (NPASS == 2) tmem_ld32_nowait(taddr + 64, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(t_empty + t);
         const int s = 256 * tp + t * 128 + q * 32 + lane;
         int y, x;
         const bool ok = pix_valid(s - 1, g, y, x);
         uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 8 * g.npix + s;
-        const float inv_s = p.inv_scale;
-        auto store_half = [&](auto hcc) {
-          constexpr int HC = decltype(hcc)::value;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const int kc = HC * 4 + k4;
-            float o[8];
+        for (int k4 = 0; k4 < 4; ++k4) {
+          float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = ok ? fmaxf(fmaf(v[k4 * 8 + e], inv_s, p.b2[kc * 8 + e]), 0.0f) : 0.0f;
-            dst[(size_t)kc * g.npix] = cvt8(o);
+          for (int e = 0; e < 8; ++e) {
+            const float acc = __uint_as_float(r0[k4 * 8 + e]) + (NPASS == 2 ? __uint_as_float(r1[k4 * 8 + e]) : 0.0f);
+            o[e] = fmaf(acc, inv_s, hc ? p.b2[32 + k4 * 8 + e] : p.b2[k4 * 8 + e]);
           }
-        };
-        if (hc == 0) store_half(std::integral_constant<int, 0>{});
-        else store_half(std::integral_constant<int, 1>{});
+          dst[(size_t)(hc * 4 + k4) * g.npix] = cvt8_relu(o, ok);
+        }
       }
-      if (warp == 16) C12_TRACE(6);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 24) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-size_t conv12_smem(const Geom& g, int nabuf) {
-  const int NL = 256 + 2 * g.P + 2;
-  const size_t patch_floats = (((NL + g.P - 1) / g.P + 3) * g.W + 3) & ~3;
-  return (size_t)W2_BYTES + (size_t)nabuf * 4 * g.nsl2 * 16 + 16 * 8 + 2 * patch_floats * 4 + 64;
+size_t conv12_smem(const Geom& g) {
+  return (size_t)W2_BYTES + W1_BYTES + A1_SLOTS * A1_SLOT_BYTES + (size_t)2 * 4 * g.nsl2 * 16 +
+         (size_t)P_STAGES * g.patch_f * 4 + 32 * 8 + 64;
+}
+
+// plain [B][H][W] log-mel -> the zero-padded pixel-linear layout (padding is zero from the allocation's memset)
+__global__ void pad_logmel_kernel(const float* __restrict__ in, float* __restrict__ out, int B, Geom g) {
+  const int per = g.H * g.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)B * per; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), rr = (int)(i - (int64_t)b * per);
+    const int y = rr / g.W, x = rr - y * g.W;
+    out[(size_t)b * g.npix_in + g.lead + (y + 1) * g.P + (x + 1)] = in[i];
+  }
 }
 
 }  // namespace
 
-// conv2 weights -> scaled fp16 hi/lo, stacked along N, UMMA canonical layout [tap][kc][n' = 64 hi + 64 lo][8]
+// conv1 / conv2 weights -> scaled fp16 hi/lo, stacked along N, UMMA canonical layouts
 int ww_conv12_tc_prepare(ww_ctx* c) {
-  std::vector<float> w((size_t)64 * 32 * 9);       // [n][cin][tap]
-  WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv2.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  std::vector<uint16_t> s((size_t)W2_BYTES / 2);
-  const float sc = weight_scale(w);
-  c->w2_inv_scale = 1.0f / sc;
-  for (int tap = 0; tap < 9; ++tap)
-    for (int kc = 0; kc < 4; ++kc)
-      for (int n = 0; n < 64; ++n)
+  {
+    std::vector<float> w((size_t)64 * 32 * 9);       // [n][cin][tap]
+    WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv2.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> s((size_t)W2_BYTES / 2);
+    const float sc = weight_scale(w);
+    c->w2_inv_scale = 1.0f / sc;
+    for (int tap = 0; tap < 9; ++tap)
+      for (int kc = 0; kc < 4; ++kc)
+        for (int n = 0; n < 64; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const float v = w[((size_t)n * 32 + kc * 8 + e) * 9 + tap] * sc;
+            const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
+            s[(((size_t)tap * 4 + kc) * 128 + n) * 8 + e] = hi;
+            s[(((size_t)tap * 4 + kc) * 128 + 64 + n) * 8 + e] = lo;
+          }
+    if (!c->d_w2_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w2_split, W2_BYTES));
+    WW_CHECK(c, cudaMemcpy(c->d_w2_split, s.data(), W2_BYTES, cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<float> w((size_t)32 * 9);            // [n][tap]
+    WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv1.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> s((size_t)W1_BYTES / 2, 0);
+    const float sc = weight_scale(w);
+    c->w1_inv_scale = 1.0f / sc;
+    for (int kc = 0; kc < 4; ++kc)                   // K = [taps 0..7 | tap 8, 0 x7] for the hi taps, again for the lo taps
+      for (int n = 0; n < 32; ++n)
         for (int e = 0; e < 8; ++e) {
-          const float v = w[((size_t)n * 32 + kc * 8 + e) * 9 + tap] * sc;
+          const int tap = (kc & 1) * 8 + e;
+          if (tap >= 9) continue;
+          const float v = w[(size_t)n * 9 + tap] * sc;
           const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
-          s[(((size_t)tap * 4 + kc) * 128 + n) * 8 + e] = hi;
-          s[(((size_t)tap * 4 + kc) * 128 + 64 + n) * 8 + e] = lo;
+          s[((size_t)kc * 64 + n) * 8 + e] = hi;
+          s[((size_t)kc * 64 + 32 + n) * 8 + e] = lo;
         }
-  if (!c->d_w2_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w2_split, W2_BYTES));
-  WW_CHECK(c, cudaMemcpy(c->d_w2_split, s.data(), W2_BYTES, cudaMemcpyHostToDevice));
+    if (!c->d_w1_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w1_split, W1_BYTES));
+    WW_CHECK(c, cudaMemcpy(c->d_w1_split, s.data(), W1_BYTES, cudaMemcpyHostToDevice));
+  }
   return WW_OK;
 }
 
-int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const Geom& g, cudaStream_t st) {
-  const int nabuf = conv12_smem(g, 3) <= 227 * 1024 ? 3 : 2;
-  const size_t smem = conv12_smem(g, nabuf);
-  const int slots = (256 + 2 * g.P + 2 + 255) / 256;
-  if (smem > 227 * 1024 || slots > 3) {
+size_t ww_conv_tc_inpad_floats_per_clip(const ww_ctx* c) { return (size_t)make_geom(c).npix_in; }
+
+// plain log-mel [B][H][W] -> padded layout in the context's workspace
+int ww_launch_pad_logmel(ww_ctx* c, const float* logmel, float* in_pad, int B, cudaStream_t st) {
+  const Geom g = make_geom(c);
+  const int64_t total = (int64_t)B * g.H * g.W;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 16);
+  ProfScope prof(c, WW_STAGE_CONV12, st);
+  pad_logmel_kernel<<<grid, 256, 0, st>>>(logmel, in_pad, B, g);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cudaStream_t st) {
+  const size_t smem = conv12_smem(g);
+  if (smem > 227 * 1024) {
     c->set_error("conv12_tc: frame count too large for the shared-memory tiles (use WW_CONV_FP32)");
     return WW_ERR_INVALID;
   }
   static size_t conf = 0;
   if (smem > conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
   Conv12Params p;
-  p.logmel = logmel; p.w2s = c->d_w2_split;
-  memcpy(p.w1, c->h_w1t.data(), sizeof(p.w1));
+  p.in_pad = in_pad; p.w1s = c->d_w1_split; p.w2s = c->d_w2_split;
   memcpy(p.b1, c->h_b1.data(), sizeof(p.b1));
   memcpy(p.b2, c->h_b2.data(), sizeof(p.b2));
-  p.act2 = c->ws_act2_h; p.inv_scale = c->w2_inv_scale; p.B = B; p.nabuf = nabuf; p.g = g;
-  static long long* d_trace = nullptr;
-  const bool tracing = getenv("WW_TC_TRACE") != nullptr;
-  if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 8 * 8); }
-  if (tracing) cudaMemset(d_trace, 0, 48 * 8 * 8);
-  p.trace = tracing ? d_trace : nullptr;
+  p.spin = getenv("WW_C12_SPIN") != nullptr;
+  p.act2 = c->ws_act2_h; p.inv_s1 = c->w1_inv_scale; p.inv_s2 = c->w2_inv_scale; p.B = B; p.g = g;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
   ProfScope prof(c, WW_STAGE_CONV12, st);
-  const bool fast = c->cfg.conv_mode == WW_CONV_FP16;
-  if (slots <= 2) {
-    if (fast) conv12_kernel<1, 2><<<grid, C12_THREADS, smem, st>>>(p);
-    else conv12_kernel<2, 2><<<grid, C12_THREADS, smem, st>>>(p);
-  } else {
-    if (fast) conv12_kernel<1, 3><<<grid, C12_THREADS, smem, st>>>(p);
-    else conv12_kernel<2, 3><<<grid, C12_THREADS, smem, st>>>(p);
-  }
+  if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
+  else conv12_kernel<2><<<grid, C12_THREADS, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
-  if (tracing) {
-    long long h[48 * 8];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "conv12 trace (cycles rel. to item 0 producer start): prod_start prod_end mma_start mma_issued epi_start epi_tmem_free epi_end\n");
-    for (int i = 30; i < 48; ++i) {
-      fprintf(stderr, "item %2d:", i);
-      for (int k = 0; k < 7; ++k) fprintf(stderr, " %8lld", h[i * 8 + k] ? h[i * 8 + k] - h[0] : -1);
-      fprintf(stderr, "\n");
-    }
-  }
   return WW_OK;
 }

@@ -267,6 +267,13 @@ size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {
 
 int ww_conv_tc_groups(const ww_ctx* c) { return make_geom(c).n_groups; }
 
+// where the log-mel kernel writes pixel (mel m, frame t) of clip b for the tensor-core path:
+// ptr[b * stride + off + m * pitch + t]
+LogmelOut ww_conv_tc_logmel_out(const ww_ctx* c, float* in_pad) {
+  const Geom g = make_geom(c);
+  return LogmelOut{in_pad, g.P, g.lead + g.P + 1, (int64_t)g.npix_in};
+}
+
 int ww_conv12_tc_prepare(ww_ctx* c);
 
 // conv3 weights -> scaled fp16 hi/lo in the UMMA canonical layout [j][tap][hl][kc][cout][8]; tile validity masks
@@ -346,11 +353,12 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   return WW_OK;
 }
 
-int ww_launch_conv_tc(ww_ctx* c, const float* logmel, int B, cudaStream_t st) {
+// in_pad: the chunk's log-mel images in the zero-padded pixel-linear layout (ww_conv_tc_logmel_out / ww_launch_pad_logmel)
+int ww_launch_conv_tc(ww_ctx* c, const float* in_pad, int B, cudaStream_t st) {
   if (B <= 0) return WW_OK;
   const Geom g = make_geom(c);
   c->n_pool_part = g.n_groups;
-  int rc = ww_launch_conv12_tc(c, logmel, B, g, st);
+  int rc = ww_launch_conv12_tc(c, in_pad, B, g, st);
   if (rc) return rc;
   return ww_launch_conv3_tc(c, B, g, st);
 }

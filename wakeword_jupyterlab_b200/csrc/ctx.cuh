@@ -83,11 +83,13 @@ struct ww_ctx {
   float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
   __half* d_w2_split = nullptr;                        // conv2 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w3_split = nullptr;                        // conv3 weights * 2^k, fp16 hi/lo, UMMA canonical layout
-  float w2_inv_scale = 1.0f, w3_inv_scale = 1.0f;      // 2^-k of the two layers
+  __half* d_w1_split = nullptr;                        // conv1 weights * 2^k, fp16 hi/lo, K = 9 padded to 16, twice
+  float w1_inv_scale = 1.0f, w2_inv_scale = 1.0f, w3_inv_scale = 1.0f;      // 2^-k per layer
 
   // ---- workspaces (chunk clips)
   float* ws_clips = nullptr;     // [chunk][n_samples] augmented clips
   float* ws_logmel = nullptr;    // [chunk][n_mels][W]
+  float* ws_logmel_pad = nullptr;   // tc path: [chunk][npix_in] zero-padded pixel-linear log-mel (padding zeroed once)
   float* ws_act1 = nullptr;      // fp32 path: [chunk][32][H][W]
   float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
   __half* ws_act2_h = nullptr;   // tc path: [chunk][8 channel chunks][NPIX][8] fp16
@@ -130,14 +132,23 @@ struct ProfScope {
   ~ProfScope() { if (slot) cudaEventRecord(slot->b, st); }
 };
 
+// Output addressing of the log-mel kernel: pixel (mel m, frame t) of clip b -> ptr[b * stride + off + m * pitch + t]
+struct LogmelOut { float* ptr; int pitch; int off; int64_t stride; };
+
 // ---- stage launchers (each returns WW_OK / error code; all enqueue on `st`)
-int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize,
-                     cudaStream_t st);
+// `clips` is fp32, or int16 PCM (x = s / 32768) when pcm16 != 0; strides are in samples
+int ww_launch_logmel(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, float* out, int B, int normalize,
+                     cudaStream_t st);                        // out: plain [B][1][n_mels][W]
+int ww_launch_logmel_ex(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
+                        int normalize, cudaStream_t st);
 int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st);
-int ww_launch_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
+int ww_launch_augment(ww_ctx* c, const void* clips, int pcm16, const float* bank, int bank_rows, int64_t bank_len,
                       const ww_aug* p, float* out, int B, cudaStream_t st);
 int ww_launch_conv_fp32(ww_ctx* c, const float* logmel, int B, cudaStream_t st);   // -> ws_pool_part
-int ww_launch_conv_tc(ww_ctx* c, const float* logmel, int B, cudaStream_t st);     // -> ws_pool_part
+int ww_launch_conv_tc(ww_ctx* c, const float* in_pad, int B, cudaStream_t st);     // padded log-mel -> ws_pool_part
+int ww_launch_pad_logmel(ww_ctx* c, const float* logmel, float* in_pad, int B, cudaStream_t st);
+LogmelOut ww_conv_tc_logmel_out(const ww_ctx* c, float* in_pad);
+size_t ww_conv_tc_inpad_floats_per_clip(const ww_ctx* c);
 int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decision, cudaStream_t st);
 int ww_prepare_weights(ww_ctx* c, cudaStream_t st);
 int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t st);

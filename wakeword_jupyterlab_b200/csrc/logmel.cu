@@ -131,10 +131,14 @@ __device__ __forceinline__ void run_stages(float2* z, const float2* tw, const fl
   }
 }
 
+// input sample -> float: fp32 as is, int16 PCM as s / 32768 (what librosa.load returns for a 16-bit WAV)
+__device__ __forceinline__ float ldin(const float* x, int i) { return __ldg(x + i); }
+__device__ __forceinline__ float ldin(const int16_t* x, int i) { return (float)__ldg(x + i) * (1.0f / 32768.0f); }
+
 struct LogmelParams {
-  const float* clips;
+  const void* clips;
   int64_t clip_stride;
-  float* out;
+  LogmelOut out;
   int B, normalize;
   int n_samples, hop, W, n_mels, mel_nnz;
   const float* window;
@@ -157,7 +161,7 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid) {
   return r;
 }
 
-template <int LOG2N>
+template <int LOG2N, typename TIn>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   constexpr int N = 1 << LOG2N;
   constexpr int NPAD = N + (N >> 5) + 8;
@@ -197,11 +201,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   __syncthreads();
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    const float* __restrict__ x = p.clips + (int64_t)b * p.clip_stride;
+    const TIn* __restrict__ x = static_cast<const TIn*>(p.clips) + (int64_t)b * p.clip_stride;
     float inv_peak = 1.0f;
     if (p.normalize) {
       float m = 0.0f;
-      for (int i = tid; i < n_samples; i += kThreads) m = fmaxf(m, fabsf(__ldg(x + i)));
+      for (int i = tid; i < n_samples; i += kThreads) m = fmaxf(m, fabsf(ldin(x, i)));
       const float peak = block_max(m, red, tid);
       inv_peak = (peak > 0.0f) ? 1.0f / peak : 1.0f;   // silent clip: reference gives NaN (0/0); guarded, see DESIGN.md
     }
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             const int n = gt + r * NB;
             const float w = win[n];
             const int i0 = s0 + n, i1 = s1 + n;
-            const float a = ((unsigned)i0 < (unsigned)n_samples) ? __ldg(x + i0) : 0.0f;
-            const float c = ((unsigned)i1 < (unsigned)n_samples) ? __ldg(x + i1) : 0.0f;
+            const float a = ((unsigned)i0 < (unsigned)n_samples) ? ldin(x, i0) : 0.0f;
+            const float c = ((unsigned)i1 < (unsigned)n_samples) ? ldin(x, i1) : 0.0f;
             v[r] = make_float2(w * a, w * c);
           }
           dft8(v);
@@ -276,32 +280,44 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     const float ref = block_max(m, red, tid);
     // explicit _rn ops: an FMA contraction here would make the per-clip maximum land at +-1 ulp instead of 0 dB
     const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(kAmin, ref)));
-    float* __restrict__ o = p.out + (int64_t)b * total;
+    float* __restrict__ o = p.out.ptr + (int64_t)b * p.out.stride + p.out.off;
+    const uint32_t magicW = 0xffffffffu / (uint32_t)W + 1u;             // i / W == umulhi(i, magicW) for i, W < 2^16
     for (int i = tid; i < total; i += kThreads) {
       float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i]))), ref_db);
-      o[i] = fmaxf(v, -kTopDb);
+      const int m = (int)__umulhi((uint32_t)i, magicW);
+      o[m * p.out.pitch + (i - m * W)] = fmaxf(v, -kTopDb);
     }
     __syncthreads();
   }
 }
 
-template <int LOG2N>
-int launch_t(ww_ctx* c, const LogmelParams& p, size_t smem, int grid, cudaStream_t st) {
+template <int LOG2N, typename TIn>
+int launch_tt(ww_ctx* c, const LogmelParams& p, size_t smem, int grid, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel<LOG2N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   ProfScope prof(c, WW_STAGE_LOGMEL, st);
-  logmel_kernel<LOG2N><<<grid, kThreads, smem, st>>>(p);
+  logmel_kernel<LOG2N, TIn><<<grid, kThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   return WW_OK;
+}
+template <int LOG2N>
+int launch_t(ww_ctx* c, const LogmelParams& p, int pcm16, size_t smem, int grid, cudaStream_t st) {
+  return pcm16 ? launch_tt<LOG2N, int16_t>(c, p, smem, grid, st) : launch_tt<LOG2N, float>(c, p, smem, grid, st);
 }
 
 }  // namespace
 
-int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize,
+int ww_launch_logmel(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, float* out, int B, int normalize,
                      cudaStream_t st) {
+  return ww_launch_logmel_ex(c, clips, pcm16, clip_stride, LogmelOut{out, c->W, 0, (int64_t)c->cfg.n_mels * c->W}, B,
+                             normalize, st);
+}
+
+int ww_launch_logmel_ex(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
+                        int normalize, cudaStream_t st) {
   if (B <= 0) return WW_OK;
   LogmelParams p;
   p.clips = clips; p.clip_stride = clip_stride; p.out = out; p.B = B; p.normalize = normalize;
@@ -320,10 +336,10 @@ int ww_launch_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* 
   int grid = c->sm_count * per_sm;
   if (grid > B) grid = B;
   switch (N) {
-    case 256: return launch_t<8>(c, p, smem, grid, st);
-    case 512: return launch_t<9>(c, p, smem, grid, st);
-    case 1024: return launch_t<10>(c, p, smem, grid, st);
-    case 2048: return launch_t<11>(c, p, smem, grid, st);
+    case 256: return launch_t<8>(c, p, pcm16, smem, grid, st);
+    case 512: return launch_t<9>(c, p, pcm16, smem, grid, st);
+    case 1024: return launch_t<10>(c, p, pcm16, smem, grid, st);
+    case 2048: return launch_t<11>(c, p, pcm16, smem, grid, st);
     default: c->set_error("ww_logmel: n_fft must be 256, 512, 1024 or 2048"); return WW_ERR_INVALID;
   }
 }

@@ -50,6 +50,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     if (++spins > (1u << 17)) mbar_timeout(code);      // ~2.6 s of 20 us suspensions
   }
 }
+// Latency-critical waits (fine-grained producer/consumer hops): plain try_wait polling, no suspension, so the waiter
+// resumes within a few cycles of the phase flip.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, int code) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 28)) mbar_timeout(code);
+  } while (!ok);
+}
 // roles off the critical path (producers / epilogue warps) use the same hardware-suspended wait
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) { mbar_wait(bar, parity, code); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -135,6 +148,10 @@ struct Geom {
   int G, n_groups;    // conv3: max tiles per group (<= 4), groups per clip
   int gbase, grem;    // balanced split of T3 tiles: the first `grem` groups have gbase + 1 tiles, the rest gbase
   int nsl2;           // conv12 A-buffer slots = round8(256 + 2P + 2) (two tiles + halo)
+  int NL, NM;         // conv1 pixels per item (256 + 2P + 2) and conv1 M-tiles per item (ceil(NL / 128))
+  int lead;           // zero floats in front of padded index 0 of the padded log-mel image (2P + 3)
+  int npix_in;        // floats per clip of the padded log-mel image
+  int patch_f;        // floats of one item's input patch = round4(NM*128 + 2P + 2)
   int nsl3;           // conv3 plane slots    = round8(G*128 + 2P + 2)
   int nst3;           // conv3 weight ring stages
   uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
@@ -203,6 +220,11 @@ inline Geom make_geom(const ww_ctx* c) {
   g.gbase = g.T3 / g.n_groups;
   g.grem = g.T3 % g.n_groups;
   g.nsl2 = (256 + 2 * g.P + 2 + 7) & ~7;
+  g.NL = 256 + 2 * g.P + 2;
+  g.NM = (g.NL + 127) / 128;
+  g.lead = 2 * g.P + 3;
+  g.patch_f = (g.NM * 128 + 2 * g.P + 2 + 3) & ~3;
+  g.npix_in = (128 * g.T2 + g.patch_f + 3) & ~3;     // last item starts at 128*T2 - 256 and reads patch_f floats
   g.nsl3 = (g.G * 128 + 2 * g.P + 2 + 7) & ~7;
   g.nst3 = C3_NST_MIN;
   while (g.nst3 < C3_NST_MAX && conv3_smem_bytes(g.nsl3, g.nst3 + 1) <= 227 * 1024) ++g.nst3;
@@ -212,5 +234,5 @@ inline Geom make_geom(const ww_ctx* c) {
 
 }  // namespace tc
 
-int ww_launch_conv12_tc(ww_ctx* c, const float* logmel, int B, const tc::Geom& g, cudaStream_t st);
+int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const tc::Geom& g, cudaStream_t st);
 int ww_launch_conv3_tc(ww_ctx* c, int B, const tc::Geom& g, cudaStream_t st);

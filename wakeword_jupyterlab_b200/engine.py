@@ -95,6 +95,14 @@ class Engine:
             x = torch.from_numpy(np.ascontiguousarray(x))
         return x.to(device=self.device, dtype=dtype).contiguous()
 
+    def _dev_audio(self, x):
+        """Audio stays int16 PCM when it arrives as int16 (x = s / 32768 is applied by the kernels), else fp32."""
+        is16 = (x.dtype == np.int16) if isinstance(x, np.ndarray) else (x.dtype == torch.int16)
+        return self._dev(x, torch.int16 if is16 else torch.float32), is16
+
+    def _fn(self, name, pcm16):
+        return getattr(self.lib, name + "_pcm16" if pcm16 else name)
+
     @property
     def launches(self):
         return int(self.lib.ww_kernel_launches(self._ctx))
@@ -164,15 +172,15 @@ class Engine:
         return out
 
     def augment(self, clips, aug: AugBatch, noise_bank=None):
-        clips = self._dev(clips)
+        clips, pcm16 = self._dev_audio(clips)
         B = clips.shape[0]
         assert clips.dim() == 2 and clips.shape[1] == self.n_samples
         bank = self._dev(noise_bank) if noise_bank is not None else None
         if bank is None and (np.asarray(aug.flags) & _lib.AUG_NOISE).any():
             raise ValueError("noise stage requested without a noise bank")
-        out = torch.empty_like(clips)
+        out = torch.empty(clips.shape, device=self.device, dtype=torch.float32)
         st, keep = self._aug_struct(aug, B)
-        self._chk(self.lib.ww_augment(self._ctx, C.c_void_p(clips.data_ptr()),
+        self._chk(self._fn("ww_augment", pcm16)(self._ctx, C.c_void_p(clips.data_ptr()),
                                       C.c_void_p(bank.data_ptr() if bank is not None else 0),
                                       bank.shape[0] if bank is not None else 0,
                                       bank.shape[1] if bank is not None else 0,
@@ -181,12 +189,12 @@ class Engine:
 
     def logmel(self, clips, normalize=False, out=None):
         """clips [B, n_samples] (device or host) -> device tensor [B, 1, n_mels, W] fp32 dB."""
-        clips = self._dev(clips)
+        clips, pcm16 = self._dev_audio(clips)
         assert clips.dim() == 2 and clips.shape[1] == self.n_samples
         B = clips.shape[0]
         if out is None:
             out = torch.empty((B, 1, self.n_mels, self.W), device=self.device, dtype=torch.float32)
-        self._chk(self.lib.ww_logmel(self._ctx, C.c_void_p(clips.data_ptr()), self.n_samples,
+        self._chk(self._fn("ww_logmel", pcm16)(self._ctx, C.c_void_p(clips.data_ptr()), self.n_samples,
                                      C.c_void_p(out.data_ptr()), B, int(bool(normalize)), self._stream()), "ww_logmel")
         return out
 
@@ -204,14 +212,14 @@ class Engine:
 
     def score(self, clips, aug: Optional[AugBatch] = None, noise_bank=None, normalize=True):
         """Device-resident scoring: returns (logits [B,C], prob1 [B], decision [B] uint8) device tensors."""
-        clips = self._dev(clips)
+        clips, pcm16 = self._dev_audio(clips)
         B = clips.shape[0]
         bank = self._dev(noise_bank) if noise_bank is not None else None
         logits = torch.empty((B, self.n_classes), device=self.device, dtype=torch.float32)
         prob1 = torch.empty((B,), device=self.device, dtype=torch.float32)
         dec = torch.empty((B,), device=self.device, dtype=torch.uint8)
         st, keep = (self._aug_struct(aug, B) if aug is not None else (None, None))
-        self._chk(self.lib.ww_score(self._ctx, C.c_void_p(clips.data_ptr()),
+        self._chk(self._fn("ww_score", pcm16)(self._ctx, C.c_void_p(clips.data_ptr()),
                                     C.c_void_p(bank.data_ptr() if bank is not None else 0),
                                     bank.shape[0] if bank is not None else 0, bank.shape[1] if bank is not None else 0,
                                     C.byref(st) if st is not None else None, int(bool(normalize)),
@@ -221,7 +229,7 @@ class Engine:
 
     def score_prepared(self, clips, aug_struct, bank, normalize, logits, prob1, dec):
         """Zero-allocation variant for benchmarks: every argument is already device resident."""
-        self._chk(self.lib.ww_score(self._ctx, C.c_void_p(clips.data_ptr()),
+        self._chk(self._fn("ww_score", clips.dtype == torch.int16)(self._ctx, C.c_void_p(clips.data_ptr()),
                                     C.c_void_p(bank.data_ptr() if bank is not None else 0),
                                     bank.shape[0] if bank is not None else 0, bank.shape[1] if bank is not None else 0,
                                     C.byref(aug_struct) if aug_struct is not None else None, int(bool(normalize)),
@@ -231,10 +239,11 @@ class Engine:
     def score_host(self, clips_host, aug: Optional[AugBatch] = None, noise_bank=None, normalize=True, out=None):
         """Host buffers in, host buffers out (H2D + kernels + D2H + sync inside the C call)."""
         if isinstance(clips_host, torch.Tensor):
-            assert not clips_host.is_cuda and clips_host.dtype == torch.float32 and clips_host.is_contiguous()
-            B, src = clips_host.shape[0], clips_host.data_ptr()
+            assert not clips_host.is_cuda and clips_host.dtype in (torch.float32, torch.int16) and clips_host.is_contiguous()
+            B, src, pcm16 = clips_host.shape[0], clips_host.data_ptr(), clips_host.dtype == torch.int16
         else:
-            clips_host = np.ascontiguousarray(clips_host, dtype=np.float32)
+            pcm16 = np.asarray(clips_host).dtype == np.int16
+            clips_host = np.ascontiguousarray(clips_host, dtype=np.int16 if pcm16 else np.float32)
             B, src = clips_host.shape[0], clips_host.ctypes.data
         bank = self._dev(noise_bank) if noise_bank is not None else None
         if out is None:
@@ -249,7 +258,7 @@ class Engine:
                     self._prepared.add((o, n))
             arrs = aug.host_arrays()
             st = _lib.WWAug(*[C.c_void_p(a.ctypes.data) for a in arrs])
-        self._chk(self.lib.ww_score_host(self._ctx, C.c_void_p(src),
+        self._chk(self._fn("ww_score_host", pcm16)(self._ctx, C.c_void_p(src),
                                          C.c_void_p(bank.data_ptr() if bank is not None else 0),
                                          bank.shape[0] if bank is not None else 0,
                                          bank.shape[1] if bank is not None else 0,
@@ -260,13 +269,14 @@ class Engine:
 
     def score_stream(self, audio, hop_samples=160):
         """Sliding windows of n_samples at hop_samples over a 1-D signal -> (prob1, decision) device tensors."""
-        audio = self._dev(audio).reshape(-1)
+        audio, pcm16 = self._dev_audio(audio)
+        audio = audio.reshape(-1)
         T = audio.numel()
         n_win = 0 if T < self.n_samples else 1 + (T - self.n_samples) // hop_samples
         prob1 = torch.empty((n_win,), device=self.device, dtype=torch.float32)
         dec = torch.empty((n_win,), device=self.device, dtype=torch.uint8)
         if n_win:
-            self._chk(self.lib.ww_score_stream(self._ctx, C.c_void_p(audio.data_ptr()), T, hop_samples,
+            self._chk(self._fn("ww_score_stream", pcm16)(self._ctx, C.c_void_p(audio.data_ptr()), T, hop_samples,
                                                C.c_void_p(prob1.data_ptr()), C.c_void_p(dec.data_ptr()), n_win,
                                                self._stream()), "ww_score_stream")
         return prob1, dec
