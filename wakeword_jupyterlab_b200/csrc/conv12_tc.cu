@@ -7,18 +7,18 @@
 // Input: the log-mel image in the zero-padded pixel-linear layout (pixel (y,x) at padded index (y+1)*P + (x+1),
 // pitch P = W+1, fp32, `lead` zero floats in front), so that the rows an item needs are ONE contiguous range.
 // Work item = (clip, PAIR of 128-pixel conv2 tiles) = 256 output pixels, which need conv1 on NL = 256 + 2P + 2
-// pixels (3x3 halo), i.e. NM = ceil(NL / 128) conv1 M-tiles.  Warp roles (19 warps):
+// pixels (3x3 halo), i.e. NM = ceil(NL / 128) conv1 M-tiles.  Warp roles (23 warps):
 //   warp 0      loader: conv1/conv2 weights once (resident, 76 KB), then one 1-D bulk copy per item (3-stage ring);
 //   warp 1      conv1 MMA issuer: per M-tile two K = 16 steps,  D1[128 px, 64] = A1[128 px, 32] x [W1_hi ; W1_lo]^T
 //               with A1 row = (9 taps as fp16 hi | 9 taps as fp16 lo)  -- K = 9 padded to 16, twice;
-//   warps 2,19  conv2 MMA issuers (one per tile of the pair: a small MMA costs ~100 cycles to issue but only 64 to
-//               execute, so two issuers keep the tensor pipe fed): per 3x3 tap and 16-channel k-slice
+//   warp 2      conv2 MMA issuer (tile 0, then tile 1: the epilogue of one tile overlaps the MMAs of the other; the 18
+//               MMAs of a tile are straight-line code inside one elect.sync region): per 3x3 tap and 16-channel k-slice
 //                 D2[:, 0:128] += A2 x [W2_hi ; W2_lo]^T   (N = 128; WW_CONV_FP16: N = 64, W2_hi only)
 //               -- the tap is only a start-address offset of the same shared-memory tile;
 //   warps 3-6   im2col: 9 shared-memory loads per pixel -> fp16 hi/lo split -> four 16-byte rows of A1 (ring of 4 M-tiles);
-//   warps 7-10  conv1 epilogue: TMEM D1 -> (hi + lo) * 2^-k + bias, ReLU fused into the fp16 conversion, zero the padding
+//   warps 7-14  conv1 epilogue (two warps per TMEM lane quadrant, 16 channels each): TMEM D1 -> (hi + lo) * 2^-k + bias, ReLU fused into the fp16 conversion, zero the padding
 //               pixels -> conv2's A operand A2 [chunk of 8 ch][pixel][16 B] (double-buffered);
-//   warps 11-18 conv2 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM D2 -> (hi + lo) * 2^-k +
+//   warps 15-22 conv2 epilogue (two warps per TMEM lane quadrant, 32 output channels each): TMEM D2 -> (hi + lo) * 2^-k +
 //               bias, ReLU+fp16, zero the padding pixels -> conv3's operand planes in HBM (512 contiguous bytes per
 //               warp store).
 // Every CUDA-core stage touches each activation once; all multiply-adds run on the tensor core.
@@ -31,7 +31,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int C12_THREADS = 20 * 32;
+constexpr int C12_THREADS = 23 * 32;
 constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 fp16]
 constexpr int W1_BYTES = 4 * 64 * 16;        // [kc 4][n' 64 = 32 hi + 32 lo][8 fp16]; kc 2,3 repeat kc 0,1 (for the lo taps)
 constexpr int A1_SLOT_BYTES = 4 * 128 * 16;  // one conv1 M-tile: [kc 4][row 128][8 fp16]
@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     for (int i = 0; i < P_STAGES; ++i) { mbar_init(p_full + i, 1); mbar_init(p_empty + i, 128); }
     for (int i = 0; i < A1_SLOTS; ++i) {
       mbar_init(a1_full + i, 128); mbar_init(a1_empty + i, 1);
-      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 128);
+      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 256);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a2_full + i, 128); mbar_init(a2_empty + i, 2);
+      mbar_init(a2_full + i, 256); mbar_init(a2_empty + i, 1);
       mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256);
     }
     fence_barrier_init();
@@ -156,39 +156,42 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         __syncwarp();
       }
     }
-  } else if (warp == 2 || warp == 19) {
-    // ===================== conv2 MMA issuers: warp 2 -> tile 0, warp 19 -> tile 1 of every item
-    const int t = warp == 2 ? 0 : 1;
+  } else if (warp == 2) {
+    // ===================== conv2 MMA issuer: tile 0 then tile 1 of every item, 18 MMAs each, issued from one
+    // elect.sync region of straight-line code (descriptor = loop-invariant base + precomputed offset)
     C12_WAIT(w_full, 0, 30);
     constexpr uint32_t idesc = NPASS == 2 ? make_idesc(128, 128) : make_idesc(128, 64);
     const uint64_t bdesc0 = make_desc(smem_u32(w2s), 2048, 128);
     const uint64_t adesc0 = make_desc(smem_u32(a2), (uint32_t)g.nsl2 * 16u, 128);
     const uint32_t nsl = (uint32_t)g.nsl2;
+    uint32_t aoff[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) aoff[tap] = (uint32_t)((g.P + 1) + (tap / 3 - 1) * g.P + (tap % 3 - 1));
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       C12_WAIT(a2_full + buf, (it >> 1) & 1, 31);
       const uint64_t adesc = adesc0 + (uint64_t)((buf * a2_bytes) >> 4);
-      {
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
         C12_WAIT(t_empty + t, (it & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t d = tmem_base + 256 + t * 128;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t row_off = (uint32_t)((g.P + 1) + (tap / 3 - 1) * g.P + (tap % 3 - 1));
+        const uint64_t ad_t = adesc + (uint64_t)(t * 128);
+        if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t bd = bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 2048) >> 4);
-            const uint64_t ad = adesc + (uint64_t)(2 * j * nsl + row_off + t * 128);
-            // NPASS 2: a*W_hi -> cols 0..63 and a*W_lo -> cols 64..127 in one N = 128 instruction
-            if (elect_one()) umma_f16(d, ad, bd, idesc, (tap | j) != 0);
-          }
+          for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              // NPASS 2: a*W_hi -> cols 0..63 and a*W_lo -> cols 64..127 in one N = 128 instruction
+              umma_f16(d, ad_t + (uint64_t)(2 * j * nsl + aoff[tap]), bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 2048) >> 4),
+                       idesc, (tap | j) != 0);
+            }
+          umma_commit(t_full + t);
+          if (t == 1) umma_commit(a2_empty + buf);
         }
-        if (elect_one()) umma_commit(t_full + t);
         __syncwarp();
       }
-      if (elect_one()) umma_commit(a2_empty + buf);
-      __syncwarp();
     }
   } else if (warp < 7) {
     // ===================== im2col producers: thread = one row (pixel) of the current conv1 M-tile
@@ -224,9 +227,10 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
       }
       mbar_arrive(p_empty + st);
     }
-  } else if (warp < 11) {
+  } else if (warp < 15) {
     // ===================== conv1 epilogue: D1 -> act1 (fp16) = conv2's A operand
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 7) >> 2;     // which 16 of the 32 conv1 channels
     const int r = q * 32 + lane;
     const float inv_s = p.inv_s1;
     uint32_t g1 = 0;
@@ -241,10 +245,10 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         const uint32_t s = g1 & (A1_SLOTS - 1);
         C12_WAIT(d1_full + s, (g1 / A1_SLOTS) & 1, 51);
         tc_fence_after();
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64;
-        tmem_ld32_nowait(taddr, r0);
-        tmem_ld32_nowait(taddr + 32, r1);
+        uint32_t r0[16], r1[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64 + half * 16;
+        tmem_ld16_nowait(taddr, r0);
+        tmem_ld16_nowait(taddr + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(d1_empty + s);
@@ -253,12 +257,13 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
           int y, x;
           const bool ok = pix_valid(pbase + l, g, y, x);
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
+          for (int k2 = 0; k2 < 2; ++k2) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              o[e] = fmaf(__uint_as_float(r0[kc * 8 + e]) + __uint_as_float(r1[kc * 8 + e]), inv_s, p.b1[kc * 8 + e]);
-            *reinterpret_cast<uint4*>(ab + ((size_t)kc * g.nsl2 + l) * 16) = cvt8_relu(o, ok);
+              o[e] = fmaf(__uint_as_float(r0[k2 * 8 + e]) + __uint_as_float(r1[k2 * 8 + e]), inv_s,
+                          half ? p.b1[16 + k2 * 8 + e] : p.b1[k2 * 8 + e]);
+            *reinterpret_cast<uint4*>(ab + ((size_t)(half * 2 + k2) * g.nsl2 + l) * 16) = cvt8_relu(o, ok);
           }
         }
       }
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   } else {
     // ===================== conv2 epilogue
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
-    const int hc = (warp - 11) >> 2;      // which 32 of the 64 output channels
+    const int hc = (warp - 15) >> 2;      // which 32 of the 64 output channels
     const float inv_s = p.inv_s2;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       // pass 0: W_hi * a, pass 1: W_lo * a
       const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + ps) * 4096) >> 4);
       const uint64_t pd = pdesc0 + (uint64_t)(2 * j * plane_u + row_off + h * 256);
-      if (elect_one()) umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);
+      umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);      // caller holds the elect.sync guard
     };
     int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
     uint32_t st = 0, wpar = 0;        // weight ring position and the parity to wait for on w_full
@@ -160,23 +160,28 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
           for (int tt = 0; tt < 3; ++tt) {
             mbar_wait(w_full + s1, p1, 52);
             tc_fence_after();
+            if (elect_one()) {          // one guarded straight-line region per weight stage: descriptors stay uniform
 #pragma unroll
-            for (int tl = 0; tl < 3; ++tl)
+              for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
-              for (int ps = 0; ps < NPASS; ++ps) step(s1, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
+                for (int ps = 0; ps < NPASS; ++ps) step(s1, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
+            }
+            __syncwarp();
             s1 = ring_next(s1, p1);
           }
           if (j == 3) { if (elect_one()) umma_commit(t_full + 0); }
           if (j == 0 && second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
           tc_fence_after();
           for (int tt = 0; tt < 3; ++tt) {
-            if (second) {
+            if (elect_one()) {
+              if (second) {
 #pragma unroll
-              for (int tl = 0; tl < 3; ++tl)
+                for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 1, id1, (j | tt | tl | ps) != 0);
+                  for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 1, id1, (j | tt | tl | ps) != 0);
+              }
+              umma_commit(w_empty + st);
             }
-            if (elect_one()) umma_commit(w_empty + st);
             __syncwarp();
             st = ring_next(st, wpar);
           }
@@ -185,14 +190,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
           for (int tt = 0; tt < 3; ++tt) {
             mbar_wait(w_full + st, wpar, 52);
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int tl = 0; tl < 3; ++tl)
+              for (int tl = 0; tl < 3; ++tl)
 #pragma unroll
-              for (int ps = 0; ps < NPASS; ++ps) {
-                step(st, j, tt, tl, ps, 0, id0, 1);
-                if (second) step(st, j, tt, tl, ps, 1, id1, 1);
-              }
-            if (elect_one()) umma_commit(w_empty + st);
+                for (int ps = 0; ps < NPASS; ++ps) {
+                  step(st, j, tt, tl, ps, 0, id0, 1);
+                  if (second) step(st, j, tt, tl, ps, 1, id1, 1);
+                }
+              umma_commit(w_empty + st);
+            }
             __syncwarp();
             st = ring_next(st, wpar);
           }
