@@ -161,6 +161,32 @@ int ww_score_host_pcm16(ww_ctx* ctx, const int16_t* clips_host, const float* noi
                         int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                         float* prob1_host, uint8_t* decision_host, int B);
 
+/* ---- training step (BASELINE config 5).  Replaces the body of the batch loop of
+ *      WakewordTrainer.train_epoch (wakeword_training_script.py:247-257) with the optimiser of
+ *      WakewordTrainer.__init__ (:225-226): CrossEntropyLoss (mean), backward, Adam with coupled weight decay.
+ *      The context owns the fp32 master weights (ww_set_weights / ww_get_weights), one flat fp32 gradient buffer in
+ *      state_dict order (conv1.weight, conv1.bias, ..., lstm.weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, ...,
+ *      fc.weight, fc.bias; every entry padded to a multiple of 4 floats) and the Adam moments.
+ *      ww_train_backward: logmel[B][1][n_mels][W] (device), labels int64[B] (device); drop_lstm [layers-1][B][hidden]
+ *      and drop_out [B][hidden] are optional multiplicative dropout masks (values 0 or 1/(1-p), host-seeded like the
+ *      augmentation parameters; NULL = no dropout); writes the mean loss (device or host float*) and optionally the
+ *      train-mode logits, and leaves the gradients in the flat buffer.
+ *      Data parallelism = one sum all-reduce of ww_train_grad_buffer()[0 .. ww_train_n_params()) between
+ *      ww_train_backward and ww_train_apply(grad_scale = 1 / world_size).
+ *      ww_train_step = backward + (ncclAllReduce on `nccl_comm` when it is not NULL) + Adam(lr, 0.9, 0.999, 1e-8,
+ *      weight_decay 1e-5), the reference's optimiser settings. */
+int ww_train_backward(ww_ctx* ctx, const float* logmel, const int64_t* labels, int B, const float* drop_lstm,
+                      const float* drop_out, float* loss, float* logits_out, void* stream);
+int ww_train_apply(ww_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   void* stream);
+int ww_train_step(ww_ctx* ctx, const float* logmel, const int64_t* labels, int B, float* loss, float lr,
+                  void* nccl_comm, int world_size, void* stream);
+int ww_train_reset(ww_ctx* ctx);                       /* zero the Adam moments and the step counter */
+int64_t ww_train_n_params(ww_ctx* ctx);                /* floats in the flat gradient buffer (with padding) */
+float* ww_train_grad_buffer(ww_ctx* ctx);              /* device pointer of the flat gradient buffer */
+int ww_train_param_range(ww_ctx* ctx, const char* name, int64_t* offset, int64_t* count);
+int ww_get_weights(ww_ctx* ctx, const char* name, float* dst); /* dst: device or host pointer */
+
 /* ---- per-stage device timing for benchmarks: CUDA events recorded on the launching stream around
  *      each stage's kernels while enabled.  ww_profile_read synchronises, returns the summed
  *      milliseconds and the number of timed launches of `stage`, and (stage < 0) resets the log. */

@@ -1,0 +1,146 @@
+"""GPU parity tests of the training step (BASELINE config 5) through the C ABI
+(ww_train_backward / ww_train_apply) against (i) golden vectors recorded from the UNMODIFIED reference
+``WakewordTrainer.train_epoch`` (tests/golden/make_golden_train.py) and (ii) torch autograd of the restated forward.
+
+Tolerances: loss 1e-5 relative; gradients 1e-4 relative per tensor (max |d| / max |ref|); parameters after three Adam
+steps 2e-5 absolute worst element / 1e-7 mean (each step moves a weight by about lr = 1e-4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import recipe as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ww():
+    import wakeword_jupyterlab_b200 as w
+    from wakeword_jupyterlab_b200 import _lib
+    _lib.load()
+    return w
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _model(ww, hidden, dropout, sd):
+    class MC(ww.ModelConfig):
+        HIDDEN_SIZE = hidden
+        DROPOUT = dropout
+    net = ww.WakewordModel(MC, ww.AudioConfig).cuda().train()
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return net
+
+
+def test_train_steps_match_the_unmodified_reference_trainer(ww, golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_ref.npz"))
+    hidden, B, steps, seed = int(g["hidden"]), int(g["batch"]), int(g["steps"]), int(g["seed"])
+    rng = np.random.default_rng(seed)
+    xs = (rng.standard_normal((steps, B, 1, 80, 32)) * 15.0 - 40.0).astype(np.float32)
+    ys = rng.integers(0, 2, size=(steps, B, 1)).astype(np.int64)
+    net = _model(ww, hidden, 0.0, R.seeded_state_dict(hidden, seed=int(g["weight_seed"])))
+    tr = ww.WakewordTrainer(net, "cuda")
+    for s in range(steps):
+        loss, logits = tr.train_step(torch.from_numpy(xs[s]).cuda(), torch.from_numpy(ys[s]).cuda().squeeze())
+        assert abs(loss.item() - g["losses"][s]) < 1e-5 * abs(g["losses"][s]), (s, loss.item(), g["losses"][s])
+        assert logits.shape == (B, 2)
+        if s == 0:
+            grads = tr.gradients(net.engine())
+            for name in net.state_dict():
+                ref = g["grad1/" + name]
+                got = grads[name].cpu().numpy()
+                if np.abs(ref).max() == 0.0:
+                    assert not got.any(), name                      # weight_hh: no data gradient (T = 1, h0 = 0)
+                else:
+                    assert _rel(got, ref) < 1e-4, (name, _rel(got, ref))
+    for name, p in net.state_dict().items():
+        ref = g["param3/" + name]
+        d = np.abs(p.cpu().numpy() - ref)
+        # Adam divides by sqrt(v): where a gradient element is ~eps-sized its update amplifies fp32 summation-order
+        # noise, so the bound is 20 % of ONE step's movement for the worst element and 1e-7 on average
+        assert d.max() < 2e-5 and d.mean() < 1e-7, (name, d.max(), d.mean())
+    # weight decay moves the parameters that never see a data gradient, exactly as in the reference
+    w0 = R.seeded_state_dict(hidden, seed=int(g["weight_seed"]))["lstm.weight_hh_l0"]
+    assert np.abs(net.state_dict()["lstm.weight_hh_l0"].cpu().numpy() - w0).max() > 1e-4
+    # the scoring path picks the updated weights up
+    net.eval()
+    with torch.no_grad():
+        out = net(torch.from_numpy(xs[0]).cuda())
+    assert torch.isfinite(out).all()
+
+
+def _autograd_reference(sd, x, y, m_lstm=None, m_out=None):
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        p = {k: torch.from_numpy(np.asarray(v)).cuda().double().requires_grad_(True) for k, v in sd.items()}
+        h = x.double()
+        for n in ("conv1", "conv2", "conv3"):
+            h = F.relu(F.conv2d(h, p[n + ".weight"], p[n + ".bias"], padding=1))
+        h = h.mean(dim=(2, 3))
+        layer = 0
+        while f"lstm.weight_ih_l{layer}" in p:
+            gt = F.linear(h, p[f"lstm.weight_ih_l{layer}"], p[f"lstm.bias_ih_l{layer}"] + p[f"lstm.bias_hh_l{layer}"])
+            H = gt.shape[1] // 4
+            c = torch.sigmoid(gt[:, :H]) * torch.tanh(gt[:, 2 * H:3 * H])
+            h = torch.sigmoid(gt[:, 3 * H:]) * torch.tanh(c)
+            last = f"lstm.weight_ih_l{layer + 1}" not in p
+            mask = m_out if last else (m_lstm[layer] if m_lstm is not None else None)
+            if mask is not None:
+                h = h * mask.double()
+            layer += 1
+        logits = F.linear(h, p["fc.weight"], p["fc.bias"])
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        return loss.item(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)).float().cpu().numpy() for k, v in p.items()}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("B", [5, 70])
+def test_gradients_default_config_vs_autograd(ww, B):
+    sd = R.seeded_state_dict(256, seed=2)
+    rng = np.random.default_rng(B)
+    x = torch.from_numpy((rng.standard_normal((B, 1, 80, 32)) * 15 - 40).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.integers(0, 2, B).astype(np.int64)).cuda()
+    net = _model(ww, 256, 0.0, sd)
+    tr = ww.WakewordTrainer(net, "cuda")
+    loss, _ = tr.train_step(x, y)
+    ref_loss, ref = _autograd_reference(sd, x, y)
+    assert abs(loss.item() - ref_loss) < 1e-5 * abs(ref_loss)
+    grads = tr.gradients(net.engine())
+    for name, r in ref.items():
+        got = grads[name].cpu().numpy()
+        if np.abs(r).max() == 0.0:
+            assert not got.any(), name
+        else:
+            # conv1.weight sums B x 2560 products of dB-valued inputs (all around -40) that largely cancel: against
+            # this float64 reference the fp32 accumulation itself is only good to a few 1e-4 of the result
+            assert _rel(got, r) < (3e-4 if name == "conv1.weight" else 1e-4), (name, _rel(got, r))
+
+
+def test_dropout_masks_are_applied_like_torch(ww):
+    """Seed-supplied masks: the kernels consume them, torch autograd with the same masks is the check."""
+    sd = R.seeded_state_dict(64, seed=9)
+    B, H, p = 12, 64, 0.6
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy((rng.standard_normal((B, 1, 80, 32)) * 15 - 40).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.integers(0, 2, B).astype(np.int64)).cuda()
+    net = _model(ww, H, p, sd)
+    tr = ww.WakewordTrainer(net, "cuda")
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    loss, _ = tr.train_step(x, y, generator=gen)
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    m_lstm, m_out = tr._dropout_masks(B, gen)
+    assert set(np.unique(m_out.cpu().numpy()).round(4)) <= {0.0, round(1 / (1 - p), 4)}
+    ref_loss, ref = _autograd_reference(sd, x, y, m_lstm, m_out)
+    assert abs(loss.item() - ref_loss) < 1e-5 * abs(ref_loss)
+    grads = tr.gradients(net.engine())
+    for name in ("conv1.weight", "conv3.weight", "lstm.weight_ih_l0", "lstm.weight_ih_l1", "fc.weight"):
+        assert _rel(grads[name].cpu().numpy(), ref[name]) < 1e-4, name

@@ -6,7 +6,8 @@ from .engine import AugBatch, Engine, get_engine
 from .model import WakewordModel
 from .predict import predict_wakeword, score_clips, score_stream
 from .processor import AudioProcessor
+from .trainer import WakewordTrainer
 
 __all__ = ["AudioConfig", "ModelConfig", "TrainingConfig", "AugmentationConfig", "ReadmeAudioConfig",
            "ReadmeModelConfig", "AudioProcessor", "WakewordModel", "predict_wakeword", "score_clips",
-           "score_stream", "AugBatch", "Engine", "get_engine"]
+           "score_stream", "AugBatch", "Engine", "get_engine", "WakewordTrainer"]

@@ -31,6 +31,8 @@ class WWAug(C.Structure):
 EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_frames", "ww_set_weights",
            "ww_prepare_resample", "ww_augment", "ww_logmel", "ww_forward", "ww_score", "ww_score_stream",
            "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize", "ww_profile", "ww_profile_read",
+           "ww_train_backward", "ww_train_apply", "ww_train_step", "ww_train_reset", "ww_train_n_params",
+           "ww_train_grad_buffer", "ww_train_param_range", "ww_get_weights",
            "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
@@ -70,6 +72,17 @@ def load():
         lib.ww_score_host.argtypes = [vp, vp, vp, i32, i64, C.POINTER(WWAug), i32, vp, vp, vp, i32]
         for base in ("ww_augment", "ww_logmel", "ww_score", "ww_score_stream", "ww_score_host"):
             getattr(lib, base + "_pcm16").argtypes = getattr(lib, base).argtypes
+        f32 = C.c_float
+        lib.ww_train_backward.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+        lib.ww_train_apply.argtypes = [vp, f32, f32, f32, f32, f32, f32, vp]
+        lib.ww_train_step.argtypes = [vp, vp, vp, i32, vp, f32, vp, i32, vp]
+        lib.ww_train_reset.argtypes = [vp]
+        lib.ww_train_n_params.argtypes = [vp]
+        lib.ww_train_n_params.restype = i64
+        lib.ww_train_grad_buffer.argtypes = [vp]
+        lib.ww_train_grad_buffer.restype = vp
+        lib.ww_train_param_range.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
+        lib.ww_get_weights.argtypes = [vp, C.c_char_p, vp]
         lib.ww_kernel_launches.argtypes = [vp]
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]

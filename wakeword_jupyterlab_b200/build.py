@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwakeword_b200.so")
-SOURCES = ["c_api.cu", "logmel.cu", "augment.cu", "conv_fp32.cu", "conv12_tc.cu", "conv3_tc.cu", "head.cu"]
+SOURCES = ["c_api.cu", "logmel.cu", "augment.cu", "conv_fp32.cu", "conv12_tc.cu", "conv3_tc.cu", "head.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas=-v"]
 
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(r.stdout)
     if r.returncode != 0:

@@ -135,7 +135,13 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_mel_off); cudaFree(c->d_mel_w); cudaFree(c->d_rs_kern); cudaFree(c->d_rs_desc);
   for (auto& kv : c->w) cudaFree(kv.second);
   for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
-  for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); }
+  for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); cudaFree(c->d_bias_sum[i]); }
+  {
+    TrainState& t = c->train;
+    float* bufs[] = {t.grad, t.m, t.v, t.wflip3, t.wflip2, t.part, t.loss, t.act1, t.act2, t.act3, t.dact2, t.dact1, t.pooled,
+                     t.dpooled, t.gates, t.hbuf, t.dh, t.logits, t.dlogits, t.loss_row};
+    for (float* b : bufs) cudaFree(b);
+  }
   cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_h); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
@@ -431,6 +437,9 @@ int ww_prepare_weights(ww_ctx* c, cudaStream_t st) {
     int rc = upload(c, &c->d_head_wt[l], wt);
     if (rc) return rc;
     if ((rc = upload(c, &c->d_head_b[l], b))) return rc;
+    std::vector<float> bs((size_t)4 * H);
+    for (int r = 0; r < 4 * H; ++r) bs[r] = bi[r] + bh[r];
+    if ((rc = upload(c, &c->d_bias_sum[l], bs))) return rc;
   }
   if (c->cfg.conv_mode != WW_CONV_FP32) {
     int rc = ww_conv_tc_prepare(c, st);

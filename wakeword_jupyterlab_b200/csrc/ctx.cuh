@@ -44,6 +44,19 @@ struct RsDesc {
 
 struct ProfSlot { cudaEvent_t a, b; int stage; };
 
+// training-step state (train.cu): flat gradient / Adam buffers in state_dict order + saved activations
+struct TrainState {
+  std::vector<std::string> names;
+  std::map<std::string, int64_t> offset, count;
+  int64_t n_flat = 0, step = 0;
+  float *grad = nullptr, *m = nullptr, *v = nullptr;
+  float *wflip3 = nullptr, *wflip2 = nullptr, *part = nullptr, *loss = nullptr;
+  int cap = 0;
+  float *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *dact2 = nullptr, *dact1 = nullptr;
+  float *pooled = nullptr, *dpooled = nullptr, *gates = nullptr, *hbuf = nullptr, *dh = nullptr;
+  float *logits = nullptr, *dlogits = nullptr, *loss_row = nullptr;
+};
+
 struct ww_ctx {
   ww_config cfg;
   // optional per-stage CUDA-event timing (ww_profile / ww_profile_read)
@@ -81,6 +94,8 @@ struct ww_ctx {
   float* d_convw_t[3] = {nullptr, nullptr, nullptr};   // [Cin][9][Cout] fp32 (fp32 conv path, conv1 everywhere)
   float* d_head_wt[8] = {};                            // per LSTM layer: [K][3H] gate-interleaved (i,g,o), fp32
   float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
+  float* d_bias_sum[8] = {};                           // per layer: [4H] b_ih + b_hh in reference row order (training)
+  TrainState train;
   __half* d_w2_split = nullptr;                        // conv2 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w3_split = nullptr;                        // conv3 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w1_split = nullptr;                        // conv1 weights * 2^k, fp16 hi/lo, K = 9 padded to 16, twice

@@ -65,8 +65,8 @@ class WakewordModel(nn.Module):
         """x [B, 1, N_MELS, W] float32 CUDA tensor -> logits [B, NUM_CLASSES]."""
         if self.training and (self.config.DROPOUT > 0):
             raise NotImplementedError(
-                "train-mode forward (dropout + autograd) is the config-5 training step, not built yet; "
-                "call model.eval() for scoring")
+                "train-mode forward with dropout runs inside WakewordTrainer.train_step (forward + backward + Adam in "
+                "one C-ABI call, no autograd graph); call model.eval() for scoring")
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (there is no CPU fallback)")
         eng = self.engine(x.device, width=x.shape[-1])

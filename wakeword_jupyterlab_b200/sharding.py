@@ -44,3 +44,28 @@ def gather_to_rank0(local: torch.Tensor, total: int):
     if rank != 0:
         return None
     return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data-parallel training (config 5): the flat gradient buffer of the C ABI and its all-reduce
+def flat_layout(shapes) -> Tuple[dict, int]:
+    """Offsets of the parameters inside the flat fp32 gradient buffer of ``ww_train_grad_buffer``: state_dict order,
+    every entry padded to a multiple of 4 floats.  shapes: ordered mapping name -> shape.  Returns ({name: (offset,
+    count)}, total floats)."""
+    out, off = {}, 0
+    for name, shape in shapes.items():
+        cnt = 1
+        for d in shape:
+            cnt *= int(d)
+        out[name] = (off, cnt)
+        off += (cnt + 3) & ~3
+    return out, off
+
+
+def allreduce_mean_(flat: torch.Tensor) -> float:
+    """Sum-all-reduce the flat gradient buffer in place and return the scale (1 / world_size) the optimiser applies
+    (``ww_train_apply(grad_scale=...)``).  The package's only collective; a no-op without a process group."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return 1.0 / dist.get_world_size()
