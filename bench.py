@@ -221,6 +221,40 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
                                            "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                                            "algorithmic_bytes_per_clip": 74240}}))
         return
+    if args.workload == "train":
+        # ---- config 5: CNN+LSTM training step (fwd + bwd + Adam) on on-GPU features, batch 4096 per GPU, gradient
+        # all-reduce over NCCL when world > 1 (dropout off: its masks are inputs of the kernels, not work)
+        B = 4096 if args.clips == CLIPS_PER_GPU else args.clips
+
+        class MC(ww.ModelConfig):
+            DROPOUT = 0.0
+        net = ww.WakewordModel(MC).to(dev).train()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
+        tr = ww.WakewordTrainer(net, dev)
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        x = torch.randn((B, 1, 80, 32), device=dev, generator=g) * 15.0 - 40.0
+        y = torch.randint(0, 2, (B,), device=dev, generator=g)
+        for _ in range(args.warmup):
+            tr.train_step(x, y)
+        barrier(); e0.record()
+        for _ in range(args.steps):
+            loss, _ = tr.train_step(x, y)
+        e1.record(); barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        flop = 1.419e9 * B
+        if rank == 0:
+            print(json.dumps({"metric": "clips_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "clips/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic",
+                              "config": {"workload": "config5: CNN+LSTM training step (fwd+bwd+Adam), on-GPU features",
+                                         "clips_per_gpu": B, "allreduce": "nccl sum of the flat fp32 gradient buffer" if world > 1 else "none",
+                                         "loss": float(loss.item())},
+                              "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
+                                           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                           "frac": flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+                                           "note": "round-1 arithmetic is fp32 on CUDA cores (exact); tcgen05 dgrad/wgrad is next"}}))
+        return
     # ---- streaming: 1 h of 16 kHz audio, 1 s windows every 10 ms, each scored like predict_wakeword
     T, N, hop = 57_600_000, N_SAMPLES, 160
     w0, n_win, s0, n_audio = window_shards(T, N, hop, world)[rank]
@@ -256,8 +290,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--conv-mode", default=None)
-    ap.add_argument("--workload", default="score", choices=["score", "logmel", "stream"],
-                    help="score = BASELINE config 3 (default, the contract line); logmel = config 2; stream = config 4")
+    ap.add_argument("--workload", default="score", choices=["score", "logmel", "stream", "train"],
+                    help="score = BASELINE config 3 (default, the contract line); logmel = config 2; stream = config 4; "
+                         "train = config 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg with fp32 host buffers instead of int16 PCM")

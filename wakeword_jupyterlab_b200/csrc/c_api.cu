@@ -144,7 +144,7 @@ int free_all(ww_ctx* c) {
   }
   cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
-  cudaFree(c->ws_act2_h); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
+  cudaFree(c->ws_act2_h); cudaFree(c->ws_act2_8); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
   cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
@@ -166,6 +166,7 @@ int ensure_workspaces(ww_ctx* c) {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2, (size_t)c->chunk * 64 * H * W * 4));
   } else {
     WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_h, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c)));
+    WW_CHECK(c, cudaMalloc((void**)&c->ws_act2_8, (size_t)c->chunk * ww_conv_tc_act2_bytes_per_clip(c) / 2));
     const size_t pad_bytes = (size_t)c->chunk * ww_conv_tc_inpad_floats_per_clip(c) * 4;
     WW_CHECK(c, cudaMalloc((void**)&c->ws_logmel_pad, pad_bytes));
     WW_CHECK(c, cudaMemset(c->ws_logmel_pad, 0, pad_bytes));      // the padding stays zero: kernels only write pixels
@@ -274,7 +275,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
   c->sm_count = prop.multiProcessorCount;
   c->W = 1 + g.n_samples / g.hop_length;
   c->n_bins = g.n_fft / 2 + 1;
-  c->chunk = g.chunk_clips > 0 ? g.chunk_clips : 2048;
+  c->chunk = g.chunk_clips > 0 ? g.chunk_clips : 4096;
   if ((size_t)g.n_mels * c->W * 4 + (size_t)(3 * g.n_fft + 2 * (g.n_fft >> 5) + 16) * 8 > 220 * 1024) {
     g_create_error = "ww_create: n_mels x frames too large for the log-mel kernel's shared memory";
     delete c;

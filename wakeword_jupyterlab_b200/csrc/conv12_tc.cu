@@ -44,7 +44,8 @@ struct Conv12Params {
   float b2[64];
   const __half* w1s;              // conv1 weights * 2^k1, stacked hi/lo
   const __half* w2s;              // conv2 weights * 2^k2, stacked hi/lo
-  __half* act2;                   // [B][8 planes (chunks of 8 channels)][npix][8]
+  __half* act2;                   // [B][8 planes (chunks of 8 channels)][npix][8 fp16]
+  uint8_t* act2_8;                // [B][4 planes (chunks of 16 channels)][npix][16 e4m3]: operand of conv3's W_lo pass
   float inv_s1, inv_s2;           // 2^-k1, 2^-k2
   int B;
   int spin;                       // WW_C12_SPIN: poll the mbarriers instead of suspending (experiment switch)
@@ -293,15 +294,22 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         int y, x;
         const bool ok = pix_valid(s - 1, g, y, x);
         uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 8 * g.npix + s;
+        uint4* dst8 = reinterpret_cast<uint4*>(p.act2_8) + (size_t)b * 4 * g.npix + s;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          float o[8];
+        for (int k2 = 0; k2 < 2; ++k2) {
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float acc = __uint_as_float(r0[k4 * 8 + e]) + (NPASS == 2 ? __uint_as_float(r1[k4 * 8 + e]) : 0.0f);
-            o[e] = fmaf(acc, inv_s, hc ? p.b2[32 + k4 * 8 + e] : p.b2[k4 * 8 + e]);
+          for (int e = 0; e < 16; ++e) {
+            const float acc = __uint_as_float(r0[k2 * 16 + e]) + (NPASS == 2 ? __uint_as_float(r1[k2 * 16 + e]) : 0.0f);
+            o[e] = fmaf(acc, inv_s, hc ? p.b2[32 + k2 * 16 + e] : p.b2[k2 * 16 + e]);
           }
-          dst[(size_t)(hc * 4 + k4) * g.npix] = cvt8_relu(o, ok);
+          dst[(size_t)(hc * 4 + 2 * k2) * g.npix] = cvt8_relu(o, ok);
+          dst[(size_t)(hc * 4 + 2 * k2 + 1) * g.npix] = cvt8_relu(o + 8, ok);
+          if (NPASS == 2) {
+            uint4 u8 = cvt16_e4m3<true>(o);
+            if (!ok) u8 = make_uint4(0u, 0u, 0u, 0u);
+            dst8[(size_t)(hc * 2 + k2) * g.npix] = u8;
+          }
         }
       }
     }
@@ -400,7 +408,7 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   memcpy(p.b1, c->h_b1.data(), sizeof(p.b1));
   memcpy(p.b2, c->h_b2.data(), sizeof(p.b2));
   p.spin = getenv("WW_C12_SPIN") != nullptr;
-  p.act2 = c->ws_act2_h; p.inv_s1 = c->w1_inv_scale; p.inv_s2 = c->w2_inv_scale; p.B = B; p.g = g;
+  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.inv_s1 = c->w1_inv_scale; p.inv_s2 = c->w2_inv_scale; p.B = B; p.g = g;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
   ProfScope prof(c, WW_STAGE_CONV12, st);
   if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);

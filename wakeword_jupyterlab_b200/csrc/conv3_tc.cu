@@ -15,8 +15,10 @@
 //   * fp32 parity (logits <= 1e-4 relative; SURVEY.md section 7 hard part 1).  Rounding errors of the ACTIVATIONS
 //   are independent from pixel to pixel and average out in the global mean; rounding errors of the WEIGHTS are the
 //   same at every pixel and do not.  So activations are a single fp16 value (11-bit significand) and only the
-//   weights are split: W * 2^k = fp16 hi + fp16 lo, accumulated in fp32 as W_hi*a + W_lo*a (2 passes,
-//   WW_CONV_SPLIT2: logits 1e-6 .. 7e-6 relative on the golden weights).  WW_CONV_FP16 issues W_hi*a only (5e-5).
+//   weights are split: W * 2^k = fp16 hi + lo, accumulated in fp32 as W_hi*a + W_lo*a.  The correction term only
+//   needs a few bits, so W_lo and a second copy of the activations are e4m3 and that pass runs as kind::f8f6f4
+//   (K = 32 per instruction at the cost of a K = 16 fp16 one): 1.5 passes instead of 2 (WW_CONV_SPLIT2: logits
+//   1e-6 .. 8e-6 relative on the golden weights, same as an fp16 lo).  WW_CONV_FP16 issues W_hi*a only (5e-5).
 //
 // Work item = (clip, group of G <= 4 consecutive 128-pixel tiles) so that every weight stage fetched from L2
 // feeds up to 512 pixels; all 512 TMEM columns hold the group's fp32 accumulators.
@@ -40,8 +42,9 @@ namespace {
 constexpr int C3_THREADS = 320;     // warp 0 loader, warp 1 MMA, warps 2-9 epilogue
 
 struct Conv3Params {
-  const __half* act2;             // [B][8 planes][npix][8]
-  const __half* w3s;              // [j 4][tap 9][hl][kc 2][cout 128][8], scaled by 2^k
+  const __half* act2;             // [B][8 planes][npix][8 fp16]
+  const uint8_t* act2_8;          // [B][4 planes][npix][16 e4m3]
+  const unsigned char* w3s;       // [j 4][tap row 3] stages of {hi fp16 [tap 3][kc 2][cout 128][8], lo e4m3 [tap 3][kc 2][cout 128][16]}
   float inv_scale;                // 2^-k
   const float* b3;                // [128]
   const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
@@ -57,8 +60,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   const Geom g = p.g;
   const uint32_t plane_bytes = (uint32_t)g.nsl3 * 16u;
   const int NST = g.nst3;
-  unsigned char* a_s = smem;                                    // 8 activation planes (chunks of 8 channels)
-  unsigned char* w_s = a_s + 8 * plane_bytes;                   // weight ring
+  unsigned char* a_s = smem;                                    // 8 fp16 activation planes (chunks of 8 channels)
+  unsigned char* a8_s = a_s + 8 * plane_bytes;                  // 4 e4m3 activation planes (chunks of 16 channels)
+  unsigned char* w_s = a8_s + 4 * plane_bytes;                  // weight ring
   float* b3s = reinterpret_cast<float*>(w_s + NST * C3_STAGE_BYTES);
   float* scratch = b3s + 128;                                   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 256);
@@ -106,16 +110,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
         for (int j = 0; j < 4; ++j) {
           mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
           if (j == 0) C3_TRACE(0);
-          mbar_arrive_expect_tx(a_full + j, 2 * nload);
+          const bool lo_pass = NPASS == 2 && (j & 1);         // the e4m3 planes of channels 32 (j >> 1) .. + 31 ride with odd j
+          mbar_arrive_expect_tx(a_full + j, (lo_pass ? 4 : 2) * nload);
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl)      // planes kc = 2j, 2j+1
             bulk_g2s(a_s + (size_t)(2 * j + pl) * plane_bytes, src0 + (size_t)(2 * j + pl) * g.npix * 16, nload, a_full + j);
+          if (lo_pass) {
+            const unsigned char* src8 = p.act2_8 + ((size_t)b * 4 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              bulk_g2s(a8_s + (size_t)(j - 1 + pl) * plane_bytes, src8 + (size_t)(j - 1 + pl) * g.npix * 16, nload, a_full + j);
+          }
           for (int tt = 0; tt < 3; ++tt) {
             mbar_wait(w_empty + st, wpar, 41);
-            mbar_arrive_expect_tx(w_full + st, C3_STAGE_BYTES);
-            bulk_g2s(w_s + st * C3_STAGE_BYTES,
-                     reinterpret_cast<const unsigned char*>(p.w3s) + (size_t)(j * 3 + tt) * C3_STAGE_BYTES,
-                     C3_STAGE_BYTES, w_full + st);
+            const uint32_t wbytes = lo_pass ? C3_STAGE_BYTES : C3_HALF_BYTES;
+            mbar_arrive_expect_tx(w_full + st, wbytes);
+            bulk_g2s(w_s + st * C3_STAGE_BYTES, p.w3s + (size_t)(j * 3 + tt) * C3_STAGE_BYTES, wbytes, w_full + st);
             if (++st == (uint32_t)NST) { st = 0; wpar ^= 1; }
           }
         }
@@ -128,14 +138,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
     const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
     const uint64_t pdesc0 = make_desc(smem_u32(a_s), plane_bytes, 128);       // pixels: kc stride = 1 plane
+    const uint64_t p8desc0 = make_desc(smem_u32(a8_s), plane_bytes, 128);     // e4m3 pixels: 16-channel chunk stride = 1 plane
     const uint32_t plane_u = plane_bytes >> 4;
     // One (tap, pass) step for accumulator half `h` (0: tiles 0,1   1: tiles 2,3) of k-slice j from weight stage st.
+    // pass 0: fp16 W_hi * a over the 16 channels of slice j; pass 1 (odd j only): e4m3 W_lo * a over the 32 channels
+    // of slices j-1 and j.  The caller holds the elect.sync guard.
     auto step = [&](uint32_t st, int j, int tt, int tl, int ps, int h, uint32_t idesc, uint32_t acc) {
       const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
-      // pass 0: W_hi * a, pass 1: W_lo * a
-      const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + (tl * 2 + ps) * 4096) >> 4);
-      const uint64_t pd = pdesc0 + (uint64_t)(2 * j * plane_u + row_off + h * 256);
-      umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);      // caller holds the elect.sync guard
+      if (ps == 0) {
+        const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + tl * 4096) >> 4);
+        const uint64_t pd = pdesc0 + (uint64_t)(2 * j * plane_u + row_off + h * 256);
+        umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);
+      } else if (j & 1) {
+        const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + C3_HALF_BYTES + tl * 4096) >> 4);
+        const uint64_t pd = p8desc0 + (uint64_t)((j - 1) * plane_u + row_off + h * 256);
+        umma_f8(tmem_base + h * 256, wd, pd, idesc, acc);
+      }
     };
     int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
     uint32_t st = 0, wpar = 0;        // weight ring position and the parity to wait for on w_full
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
 
 }  // namespace
 
-size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {
+size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {      // fp16 planes; the e4m3 copy is half of this
   const Geom g = make_geom(c);
   return (size_t)8 * g.npix * 16;
 }
@@ -289,8 +307,7 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
   if (rc) return rc;
   std::vector<float> w((size_t)128 * 64 * 9);       // [cout][cin][tap]
   WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv3.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  const size_t blk_elems = 2 * 2 * 128 * 8;         // one (j, tap) block: [hl][kc][cout][8]
-  std::vector<uint16_t> s((size_t)36 * blk_elems);
+  std::vector<unsigned char> s((size_t)12 * C3_STAGE_BYTES, 0);      // 12 stages (slice j, tap row)
   const float sc = weight_scale(w);
   c->w3_inv_scale = 1.0f / sc;
   for (int j = 0; j < 4; ++j)
@@ -298,14 +315,20 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
       for (int kc = 0; kc < 2; ++kc)
         for (int n = 0; n < 128; ++n)
           for (int e = 0; e < 8; ++e) {
-            const float v = w[((size_t)n * 64 + j * 16 + kc * 8 + e) * 9 + tap] * sc;
-            const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
-            const size_t blk = ((size_t)j * 9 + tap) * blk_elems;
-            s[blk + (((size_t)0 * 2 + kc) * 128 + n) * 8 + e] = hi;
-            s[blk + (((size_t)1 * 2 + kc) * 128 + n) * 8 + e] = lo;
+            const int ci = j * 16 + kc * 8 + e;
+            const float v = w[((size_t)n * 64 + ci) * 9 + tap] * sc;
+            const uint16_t hi = f2h(v);
+            const int tt = tap / 3, tl = tap % 3;
+            // stage (j, tt): hi half [tl][kc][cout][8 fp16]
+            unsigned char* stg = s.data() + ((size_t)j * 3 + tt) * C3_STAGE_BYTES;
+            memcpy(stg + (((size_t)tl * 2 + kc) * 128 + n) * 16 + e * 2, &hi, 2);
+            // lo half lives in the stage of the ODD slice of the pair: [tl][kc8][cout][16 e4m3], kc8 = 16-channel chunk
+            const int jo = j | 1, c32 = ci & 31;
+            unsigned char* stg_lo = s.data() + ((size_t)jo * 3 + tt) * C3_STAGE_BYTES + C3_HALF_BYTES;
+            stg_lo[(((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] = f2e4m3(v - h2f(hi));
           }
-  if (!c->d_w3_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w3_split, s.size() * 2));
-  WW_CHECK(c, cudaMemcpy(c->d_w3_split, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+  if (!c->d_w3_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w3_split, s.size()));
+  WW_CHECK(c, cudaMemcpy(c->d_w3_split, s.data(), s.size(), cudaMemcpyHostToDevice));
 
   const Geom g = make_geom(c);
   std::vector<uint32_t> m((size_t)g.T3 * 4, 0u);
@@ -334,7 +357,7 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
     conf = smem;
   }
   Conv3Params p;
-  p.act2 = c->ws_act2_h; p.w3s = c->d_w3_split; p.inv_scale = c->w3_inv_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
+  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.w3s = reinterpret_cast<const unsigned char*>(c->d_w3_split); p.inv_scale = c->w3_inv_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
   p.pool_part = c->pool_cur; p.B = B; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;

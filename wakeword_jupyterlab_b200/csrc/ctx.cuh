@@ -108,6 +108,7 @@ struct ww_ctx {
   float* ws_act1 = nullptr;      // fp32 path: [chunk][32][H][W]
   float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
   __half* ws_act2_h = nullptr;   // tc path: [chunk][8 channel chunks][NPIX][8] fp16
+  uint8_t* ws_act2_8 = nullptr;  // tc path: [chunk][4 channel chunks][NPIX][16] e4m3 (operand of the W_lo pass)
   float* ws_pool_part = nullptr; // [pool_cap_clips][n_part][128]: conv3 partial sums of the whole batch of a call
   float* pool_cur = nullptr;     // where the current chunk's conv launch writes its partials
   float* ws_h[2] = {nullptr, nullptr};   // [pool_cap_clips][hidden]: head layer outputs (ping-pong)

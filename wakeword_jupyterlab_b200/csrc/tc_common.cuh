@@ -4,6 +4,7 @@
 #include "ctx.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 
 #include <string.h>
@@ -87,6 +88,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// same instruction with 8-bit operands (kind::f8f6f4, here e4m3 x e4m3 -> fp32): K = 32 per instruction at the cycle
+// count of a K = 16 fp16 instruction.  The instruction descriptor has the same bit layout (format 0 = e4m3).
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // true on exactly one (converged) lane of the warp; ptxas understands elect.sync-guarded regions and keeps the
 // guarded tcgen05 / bulk-copy instructions on the uniform datapath
 __device__ __forceinline__ bool elect_one() {
@@ -143,6 +152,23 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// two floats -> packed e4m3x2 (round to nearest, saturating to +-448), optionally with ReLU: `lo` in bits 0..7
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_e4m3(float lo, float hi) {
+  unsigned short r;
+  if (RELU) asm("cvt.rn.satfinite.relu.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return (uint32_t)r;
+}
+// 16 floats -> one 16-byte core-matrix row of e4m3
+template <bool RELU>
+__device__ __forceinline__ uint4 cvt16_e4m3(const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = pack_e4m3<RELU>(v[4 * i], v[4 * i + 1]) | (pack_e4m3<RELU>(v[4 * i + 2], v[4 * i + 3]) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
 // 8 floats -> one 16-byte core-matrix row of fp16
 __device__ __forceinline__ uint4 cvt8(const float* v) {
   return make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
@@ -190,6 +216,9 @@ inline float h2f(uint16_t u) {
   memcpy(&h, &u, 2);
   return __half2float(h);
 }
+// host: e4m3 round-to-nearest, saturating (bit pattern) -- the lo half of the conv3 weights
+inline uint8_t f2e4m3(float f) { return (uint8_t)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3); }
+
 // Weight scale: the tensor-core operands are w * 2^k as fp16 hi + fp16 lo with k chosen so the largest |w| lands
 // near 2^13.  hi is then far from fp16's subnormal range and lo (~2^-11 of hi) stays a normal number for every
 // weight that matters; the epilogues multiply the fp32 accumulator by 2^-k (exact).
@@ -205,10 +234,12 @@ inline float weight_scale(const std::vector<float>& w) {
 
 constexpr int C3_NST_MAX = 6;                            // conv3 weight ring stages (as many as shared memory allows)
 constexpr int C3_NST_MIN = 3;
-constexpr int C3_STAGE_BYTES = 3 * 2 * 2 * 128 * 16;     // [tap 3][hl][kc 2][cout 128][8 fp16] = 24 KB
+constexpr int C3_HALF_BYTES = 3 * 2 * 128 * 16;          // [tap 3][kc 2][cout 128][16 B] = 12 KB
+constexpr int C3_STAGE_BYTES = 2 * C3_HALF_BYTES;        // fp16 hi weights of (16-channel slice j, tap row); for odd j also
+                                                         // the e4m3 lo weights of the 32-channel slice pair (j-1, j)
 
 inline size_t conv3_smem_bytes(int nsl3, int nst) {
-  return (size_t)8 * nsl3 * 16 + (size_t)nst * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
+  return (size_t)12 * nsl3 * 16 + (size_t)nst * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
 }
 
 inline Geom make_geom(const ww_ctx* c) {

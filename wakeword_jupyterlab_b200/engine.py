@@ -3,6 +3,7 @@ device memory and streams; all arithmetic happens in libwakeword_b200.so."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -58,6 +59,7 @@ class Engine:
         self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
         ac, mc = audio_config, model_config
         self.n_samples = int(ac.SAMPLE_RATE * ac.DURATION) if n_samples is None else int(n_samples)
+        chunk_clips = int(chunk_clips or os.environ.get("WW_CHUNK_CLIPS", 0))
         self.cfg = _lib.WWConfig(ac.SAMPLE_RATE, self.n_samples, ac.N_FFT, ac.WIN_LENGTH, ac.HOP_LENGTH, ac.N_MELS,
                                  float(ac.FMIN), float(ac.FMAX), mc.HIDDEN_SIZE, mc.NUM_LAYERS, mc.NUM_CLASSES,
                                  float(threshold), _lib.CONV_MODES[conv_mode] if isinstance(conv_mode, str) else conv_mode,
