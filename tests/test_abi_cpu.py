@@ -80,3 +80,27 @@ def test_reference_checkpoint_loads(golden_dir):
     g = np.load(os.path.join(golden_dir, "model_trained.npz"))
     sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
     ww.WakewordModel().load_state_dict(sd, strict=True)
+
+
+def test_reference_checkpoint_formats_round_trip(tmp_path):
+    """the reference's checkpoint dictionaries load into the mirror module (CPU tensors only)."""
+    import torch
+    import wakeword_jupyterlab_b200 as ww
+    net = ww.WakewordModel()
+    ref_keys = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias",
+                "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+                "lstm.weight_ih_l1", "lstm.weight_hh_l1", "lstm.bias_ih_l1", "lstm.bias_hh_l1", "fc.weight", "fc.bias"]
+    assert list(net.state_dict().keys()) == ref_keys                               # SURVEY.md appendix C
+    assert sum(p.numel() for p in net.parameters()) == 1_014_786                   # model_architecture.txt:10
+    best, final = tmp_path / "best_wakeword_model.pth", tmp_path / "final_wakeword_model.pth"
+    ww.save_best_checkpoint(best, net, epoch=3, val_acc=91.0, train_acc=95.0, train_loss=0.1, val_loss=0.2)
+    ww.save_final_checkpoint(final, net, best_val_acc=91.0, device="cuda")
+    assert set(torch.load(best, weights_only=False)) == {"epoch", "model_state_dict", "optimizer_state_dict", "val_acc",
+                                                         "train_acc", "train_loss", "val_loss"}
+    assert set(torch.load(final, weights_only=False)) == {"model_state_dict", "config", "best_val_acc", "device"}
+    for path in (best, final):
+        other = ww.WakewordModel()
+        meta = ww.load_checkpoint(path, other)
+        assert "model_state_dict" in meta
+        for k, v in net.state_dict().items():
+            assert torch.equal(other.state_dict()[k], v)

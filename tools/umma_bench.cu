@@ -1,4 +1,4 @@
-// Micro-benchmark: tcgen05.mma (kind::f16, bf16, M=128, cta_group::1, SS, K-major SWIZZLE_NONE) throughput
+// Micro-benchmark: tcgen05.mma (kind::f16, fp16, M=128, cta_group::1, SS, K-major SWIZZLE_NONE) throughput
 // as a function of N, accumulator rotation and operand start alignment.  One CTA per SM, unrolled issue loop.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/umma_bench tools/umma_bench.cu
 #include <cstdio>
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long* out) {
     long long t0 = clock64();
     for (int i = 0; i < c.iters; i += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) umma_bf16(tm + (u % NACC) * (512 / NACC), x + u * 3, y + u * 3, idesc, 1);
+      for (int u = 0; u < 8; ++u) umma_f16(tm + (u % NACC) * (512 / NACC), x + u * 3, y + u * 3, idesc, 1);
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0, 1);

@@ -7,7 +7,9 @@ from .model import WakewordModel
 from .predict import predict_wakeword, score_clips, score_stream
 from .processor import AudioProcessor
 from .trainer import WakewordTrainer
+from .checkpoint import load_checkpoint, save_best_checkpoint, save_final_checkpoint
 
 __all__ = ["AudioConfig", "ModelConfig", "TrainingConfig", "AugmentationConfig", "ReadmeAudioConfig",
            "ReadmeModelConfig", "AudioProcessor", "WakewordModel", "predict_wakeword", "score_clips",
-           "score_stream", "AugBatch", "Engine", "get_engine", "WakewordTrainer"]
+           "score_stream", "AugBatch", "Engine", "get_engine", "WakewordTrainer", "load_checkpoint", "save_best_checkpoint",
+           "save_final_checkpoint"]
