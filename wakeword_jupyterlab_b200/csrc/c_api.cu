@@ -276,7 +276,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
   c->W = 1 + g.n_samples / g.hop_length;
   c->n_bins = g.n_fft / 2 + 1;
   c->chunk = g.chunk_clips > 0 ? g.chunk_clips : 4096;
-  if ((size_t)g.n_mels * c->W * 4 + (size_t)(3 * g.n_fft + 2 * (g.n_fft >> 5) + 16) * 8 > 220 * 1024) {
+  if ((size_t)g.n_mels * c->W * 4 + (size_t)(5 * g.n_fft + g.n_fft / 4 + 4 * (g.n_fft >> 5) + 48) * 8 > 216 * 1024) {
     g_create_error = "ww_create: n_mels x frames too large for the log-mel kernel's shared memory";
     delete c;
     return WW_ERR_INVALID;

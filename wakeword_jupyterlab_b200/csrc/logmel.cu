@@ -72,11 +72,12 @@ __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGT) : "memory");
 }
 
-// In-place Stockham stage (radix R, NS = product of the radices already applied) on one group's buffer.
-// Butterfly j: v[r] = z[j + r*N/R] * w^r,  w = exp(-2 pi i k / (NS R)), k = j % NS (compact table `ts[k]`);
-// z[(j - k) * R + k + r * NS] = DFT_R(v)[r].  Every thread reads its butterflies, the group syncs, then writes.
+// Stockham stage (radix R, NS = product of the radices already applied) from one buffer of the group into the other
+// (ping-pong: one barrier per stage).
+// Butterfly j: v[r] = zin[j + r*N/R] * w^r,  w = exp(-2 pi i k / (NS R)), k = j % NS (compact table `ts[k]`);
+// zout[(j - k) * R + k + r * NS] = DFT_R(v)[r].
 template <int N, int R, int NS>
-__device__ __forceinline__ void stockham_stage(float2* z, const float2* __restrict__ ts, int gt, int grp) {
+__device__ __forceinline__ void stockham_stage(const float2* zin, float2* zout, const float2* __restrict__ ts, int gt, int grp) {
   constexpr int NB = N / R;                               // butterflies (multiple of 32)
   constexpr int ITERS = NB > kGT ? NB / kGT : 1;
   constexpr int RSTEP = NB + NB / 32;                     // padded distance between the R inputs
@@ -87,7 +88,7 @@ __device__ __forceinline__ void stockham_stage(float2* z, const float2* __restri
     if (NB >= kGT || j < NB) {
       const int rb = padi(j);
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[it][r] = z[rb + r * RSTEP];
+      for (int r = 0; r < R; ++r) v[it][r] = zin[rb + r * RSTEP];
       const float2 w1 = ts[j & (NS - 1)];
       float2 w = w1;
 #pragma unroll
@@ -98,7 +99,6 @@ __device__ __forceinline__ void stockham_stage(float2* z, const float2* __restri
       dftR<R>(v[it]);
     }
   }
-  group_sync(grp);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int j = gt + it * kGT;
@@ -108,10 +108,10 @@ __device__ __forceinline__ void stockham_stage(float2* z, const float2* __restri
       if (NS % 32 == 0) {
         const int wb = padi(base);
 #pragma unroll
-        for (int r = 0; r < R; ++r) z[wb + r * (NS + NS / 32)] = v[it][r];
+        for (int r = 0; r < R; ++r) zout[wb + r * (NS + NS / 32)] = v[it][r];
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) z[padi(base + r * NS)] = v[it][r];
+        for (int r = 0; r < R; ++r) zout[padi(base + r * NS)] = v[it][r];
       }
     }
   }
@@ -120,14 +120,17 @@ __device__ __forceinline__ void stockham_stage(float2* z, const float2* __restri
 
 // remaining stages after the first radix-8 one: radices 8, 8, ..., then 4 or 2; compact twiddle tables
 // (stage table k -> T[k * N / (NS R)]) are packed one after the other in `twc`; the last stage (step 1) reads `tw`.
+// returns the buffer that holds the spectrum
 template <int N, int NS, int REM, int OFF>
-__device__ __forceinline__ void run_stages(float2* z, const float2* tw, const float2* twc, int gt, int grp) {
+__device__ __forceinline__ float2* run_stages(float2* zin, float2* zout, const float2* tw, const float2* twc, int gt, int grp) {
   if constexpr (REM > 0) {
     constexpr int LG = REM >= 3 ? 3 : REM;
     constexpr int R = 1 << LG;
     constexpr int TSTEP = N / (NS * R);
-    stockham_stage<N, R, NS>(z, TSTEP > 1 ? twc + OFF : tw, gt, grp);
-    run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0)>(z, tw, twc, gt, grp);
+    stockham_stage<N, R, NS>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+    return run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0)>(zout, zin, tw, twc, gt, grp);
+  } else {
+    return zin;
   }
 }
 
@@ -167,11 +170,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   constexpr int NPAD = N + (N >> 5) + 8;
   constexpr int NBINS = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][NPAD]
-  float2* tw = zbuf + kGroups * NPAD;                          // [N]      exp(-2 pi i t / N)
+  float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][2][NPAD]: ping-pong FFT buffers
+  float2* tw = zbuf + kGroups * 2 * NPAD;                      // [N]      exp(-2 pi i t / N)
   float2* twc = tw + N;                                        // compact tables of the middle stages (< N/8 entries)
-  float* win = reinterpret_cast<float*>(twc + N / 8);          // [N]
-  float* melw = win + N;                                       // [mel_nnz]
+  const float* __restrict__ win = p.window;                    // [N] read once per frame pair through L1
+  float* melw = reinterpret_cast<float*>(twc + N / 8);         // [mel_nnz]
   int* mst = reinterpret_cast<int*>(melw + p.mel_nnz);         // [3][n_mels] start, len, off
   float* mel_s = reinterpret_cast<float*>(mst + 3 * p.n_mels); // [n_mels * W]
   __shared__ float red[kThreads / 32];
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   const int n_samples = p.n_samples, hop = p.hop, W = p.W, n_mels = p.n_mels;
 
   // ---- tables -> shared memory (once per CTA)
-  for (int i = tid; i < N; i += kThreads) { tw[i] = p.twiddle[i]; win[i] = p.window[i]; }
+  for (int i = tid; i < N; i += kThreads) tw[i] = p.twiddle[i];
   for (int i = tid; i < p.mel_nnz; i += kThreads) melw[i] = p.mel_w[i];
   for (int i = tid; i < n_mels; i += kThreads) {
     mst[i] = p.mel_start[i]; mst[n_mels + i] = p.mel_len[i]; mst[2 * n_mels + i] = p.mel_off[i];
@@ -210,7 +213,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       inv_peak = (peak > 0.0f) ? 1.0f / peak : 1.0f;   // silent clip: reference gives NaN (0/0); guarded, see DESIGN.md
     }
     const float scale = inv_peak * inv_peak;
-    float2* z = zbuf + grp * NPAD;
+    float2* za = zbuf + grp * 2 * NPAD;
+    float2* zb = za + NPAD;
     const int n_pairs = (W + 1) >> 1;
     for (int pr = grp; pr < n_pairs; pr += kGroups) {
       const int t0 = 2 * pr, t1 = 2 * pr + 1;
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             const int n = gt + r * NB;
-            const float w = win[n];
+            const float w = __ldg(win + n);
             const int i0 = s0 + n, i1 = s1 + n;
             const float a = ((unsigned)i0 < (unsigned)n_samples) ? ldin(x, i0) : 0.0f;
             const float c = ((unsigned)i1 < (unsigned)n_samples) ? ldin(x, i1) : 0.0f;
@@ -233,11 +237,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           dft8(v);
           const int wb = gt * 8 + (gt >> 2);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) z[wb + r] = v[r];
+          for (int r = 0; r < 8; ++r) za[wb + r] = v[r];
         }
       }
       group_sync(grp);
-      run_stages<N, 8, LOG2N - 3, 0>(z, tw, twc, gt, grp);
+      // Each stage reads one buffer and writes the other.  The mel projection of the previous pair read the buffer the
+      // spectrum ends in; it is next written two barriers from here at the earliest, so no barrier is needed after it.
+      float2* z = run_stages<N, 8, LOG2N - 3, 0>(za, zb, tw, twc, gt, grp);
       // ---- Hermitian split + power, in place: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2.
       // Bin k reads z[k] and z[N-k] and is the only reader of both, so no sync is needed before the store.
 #pragma unroll
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
           if (t1 < W) mel_s[m * W + t1] = a1 * scale;
         }
       }
-      group_sync(grp);
+      if (((LOG2N - 3 + 2) / 3) < 2) group_sync(grp);      // fewer than two ping-pong stages: the next pair would overwrite z
     }
     __syncthreads();
     // ---- power_to_db(ref=max, amin, top_db)
@@ -327,7 +333,7 @@ int ww_launch_logmel_ex(ww_ctx* c, const void* clips, int pcm16, int64_t clip_st
   p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off; p.mel_w = c->d_mel_w;
   const int N = c->cfg.n_fft;
   const int npad = N + (N >> 5) + 8;
-  size_t smem = (size_t)(kGroups * npad + N + N / 8) * sizeof(float2) + (size_t)N * sizeof(float) +
+  size_t smem = (size_t)(kGroups * 2 * npad + N + N / 8) * sizeof(float2) +
                 (size_t)p.mel_nnz * sizeof(float) + (size_t)3 * p.n_mels * sizeof(int) +
                 (size_t)p.n_mels * p.W * sizeof(float) + 16;
   if (smem > 227 * 1024) { c->set_error("ww_logmel: configuration exceeds shared memory"); return WW_ERR_INVALID; }
