@@ -193,6 +193,7 @@ def reference_arm(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_ranks):
     """BASELINE.json configs 2 (log-mel only, 16,384 clips) and 4 (1 h streaming, 10 ms hop): extra JSON lines."""
+    import torch.distributed as dist
     import wakeword_jupyterlab_b200 as ww
     from wakeword_jupyterlab_b200.sharding import window_shards
     from oracle import recipe as R
@@ -241,6 +242,14 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
             loss, _ = tr.train_step(x, y)
         e1.record(); barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        # data-parallel replicas must hold identical weights after the all-reduced steps (they start identical and see
+        # the same averaged gradient)
+        in_sync = True
+        if world > 1:
+            chk = torch.stack([p.detach().double().sum() for p in net.parameters()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            in_sync = bool(torch.equal(lo, hi))
         flop = 1.419e9 * B
         if rank == 0:
             print(json.dumps({"metric": "clips_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "clips/s",
@@ -249,7 +258,7 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
                               "data": "synthetic",
                               "config": {"workload": "config5: CNN+LSTM training step (fwd+bwd+Adam), on-GPU features",
                                          "clips_per_gpu": B, "allreduce": "nccl sum of the flat fp32 gradient buffer" if world > 1 else "none",
-                                         "loss": float(loss.item())},
+                                         "loss": float(loss.item()), "replicas_in_sync": in_sync},
                               "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
                                            "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                            "frac": flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,

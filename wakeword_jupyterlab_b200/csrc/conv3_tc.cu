@@ -22,8 +22,9 @@
 //
 // Work item = (clip, group of G <= 4 consecutive 128-pixel tiles) so that every weight stage fetched from L2
 // feeds up to 512 pixels; all 512 TMEM columns hold the group's fp32 accumulators.
-//   warp 0      loader (one thread): activation k-slice planes (2 x 1-D cp.async.bulk per 16-channel slice,
-//               ring of 4 slices = the whole K) and the weight ring (3-6 stages x 24 KB = (k-slice, 3 taps));
+//   warp 0      loader (one thread): activation planes of a 32-channel slice pair (4 fp16 + 2 e4m3 1-D cp.async.bulk;
+//               two pairs = the whole K, each refilled for the next item as soon as it is consumed) and the weight
+//               ring (3 stages x 36 KB = (slice pair, tap row): 9 MMAs per accumulator half);
 //   warp 1      MMA issuer (one thread): descriptors are 64-bit adds on precomputed bases;
 //   warps 2-9   epilogue: tcgen05.ld (lane = channel, 32 pixels per load) -> bias + ReLU + padding mask
 //               (precomputed bit masks) -> per-thread sum over pixels -> one deterministic partial per
@@ -44,7 +45,7 @@ constexpr int C3_THREADS = 320;     // warp 0 loader, warp 1 MMA, warps 2-9 epil
 struct Conv3Params {
   const __half* act2;             // [B][8 planes][npix][8 fp16]
   const uint8_t* act2_8;          // [B][4 planes][npix][16 e4m3]
-  const unsigned char* w3s;       // [j 4][tap row 3] stages of {hi fp16 [tap 3][kc 2][cout 128][8], lo e4m3 [tap 3][kc 2][cout 128][16]}
+  const unsigned char* w3s;       // [pair 2][tap row 3] stages of 36 KB (tc_common.cuh), weights scaled by 2^k
   float inv_scale;                // 2^-k
   const float* b3;                // [128]
   const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   float* b3s = reinterpret_cast<float*>(w_s + NST * C3_STAGE_BYTES);
   float* scratch = b3s + 128;                                   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 256);
-  uint64_t* a_full = bars;                 // [4]
-  uint64_t* a_empty = bars + 4;            // [4]
+  uint64_t* a_full = bars;                 // [2] per slice pair (32 input channels)
+  uint64_t* a_empty = bars + 4;            // [2]
   uint64_t* w_full = bars + 8;             // [NST_MAX]
   uint64_t* w_empty = bars + 8 + C3_NST_MAX;   // [NST_MAX]
   uint64_t* t_full = bars + 8 + 2 * C3_NST_MAX;   // [2] accumulator halves: tiles (0,1) = TMEM cols 0..255, tiles (2,3) = 256..511
@@ -101,31 +102,31 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     if (lane == 0) {
       int it = 0;
       uint32_t st = 0, wpar = 1;        // weight ring position and the parity to wait for on w_empty
+      constexpr uint32_t wbytes = NPASS == 2 ? C3_STAGE_BYTES : 2 * C3_PART_BYTES;
       for (int item = item_lo; item < item_hi; ++item, ++it) {
         const int b = item / g.n_groups, grp = item - b * g.n_groups;
         const int n_t = grp_tiles(g, grp);
         const uint32_t nload = (uint32_t)(n_t * 128 + 2 * g.P + 2) * 16u;
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) +
                                     ((size_t)b * 8 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
-        for (int j = 0; j < 4; ++j) {
-          mbar_wait(a_empty + j, (it & 1) ^ 1, 40);
-          if (j == 0) C3_TRACE(0);
-          const bool lo_pass = NPASS == 2 && (j & 1);         // the e4m3 planes of channels 32 (j >> 1) .. + 31 ride with odd j
-          mbar_arrive_expect_tx(a_full + j, (lo_pass ? 4 : 2) * nload);
+        const unsigned char* src8 = p.act2_8 + ((size_t)b * 4 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
+        for (int pr = 0; pr < 2; ++pr) {
+          // activations of the pair: 4 fp16 planes (chunks of 8 channels) + 2 e4m3 planes (chunks of 16 channels)
+          mbar_wait(a_empty + pr, (it & 1) ^ 1, 40);
+          if (pr == 0) C3_TRACE(0);
+          mbar_arrive_expect_tx(a_full + pr, (NPASS == 2 ? 6 : 4) * nload);
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl)      // planes kc = 2j, 2j+1
-            bulk_g2s(a_s + (size_t)(2 * j + pl) * plane_bytes, src0 + (size_t)(2 * j + pl) * g.npix * 16, nload, a_full + j);
-          if (lo_pass) {
-            const unsigned char* src8 = p.act2_8 + ((size_t)b * 4 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
+          for (int pl = 0; pl < 4; ++pl)
+            bulk_g2s(a_s + (size_t)(4 * pr + pl) * plane_bytes, src0 + (size_t)(4 * pr + pl) * g.npix * 16, nload, a_full + pr);
+          if (NPASS == 2) {
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl)
-              bulk_g2s(a8_s + (size_t)(j - 1 + pl) * plane_bytes, src8 + (size_t)(j - 1 + pl) * g.npix * 16, nload, a_full + j);
+              bulk_g2s(a8_s + (size_t)(2 * pr + pl) * plane_bytes, src8 + (size_t)(2 * pr + pl) * g.npix * 16, nload, a_full + pr);
           }
           for (int tt = 0; tt < 3; ++tt) {
             mbar_wait(w_empty + st, wpar, 41);
-            const uint32_t wbytes = lo_pass ? C3_STAGE_BYTES : C3_HALF_BYTES;
             mbar_arrive_expect_tx(w_full + st, wbytes);
-            bulk_g2s(w_s + st * C3_STAGE_BYTES, p.w3s + (size_t)(j * 3 + tt) * C3_STAGE_BYTES, wbytes, w_full + st);
+            bulk_g2s(w_s + st * C3_STAGE_BYTES, p.w3s + (size_t)(pr * 3 + tt) * C3_STAGE_BYTES, wbytes, w_full + st);
             if (++st == (uint32_t)NST) { st = 0; wpar ^= 1; }
           }
         }
@@ -133,26 +134,23 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer.  The whole warp runs the loop so that descriptors stay warp-uniform
-    // (uniform registers feed UTCHMMA directly); only the elected lane issues.
-    const bool leader = (lane == 0);
+    // (uniform registers feed UTCHMMA directly); only the elected lane issues, one straight-line region per stage visit.
     constexpr uint32_t idesc256 = make_idesc(128, 256), idesc128 = make_idesc(128, 128);
     const uint64_t wdesc0 = make_desc(smem_u32(w_s), 2048, 128);              // weights: kc stride 2 KB
     const uint64_t pdesc0 = make_desc(smem_u32(a_s), plane_bytes, 128);       // pixels: kc stride = 1 plane
     const uint64_t p8desc0 = make_desc(smem_u32(a8_s), plane_bytes, 128);     // e4m3 pixels: 16-channel chunk stride = 1 plane
     const uint32_t plane_u = plane_bytes >> 4;
-    // One (tap, pass) step for accumulator half `h` (0: tiles 0,1   1: tiles 2,3) of k-slice j from weight stage st.
-    // pass 0: fp16 W_hi * a over the 16 channels of slice j; pass 1 (odd j only): e4m3 W_lo * a over the 32 channels
-    // of slices j-1 and j.  The caller holds the elect.sync guard.
-    auto step = [&](uint32_t st, int j, int tt, int tl, int ps, int h, uint32_t idesc, uint32_t acc) {
-      const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1));   // tap (ky, kx) = (tt, tl)
-      if (ps == 0) {
-        const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + tl * 4096) >> 4);
-        const uint64_t pd = pdesc0 + (uint64_t)(2 * j * plane_u + row_off + h * 256);
-        umma_f16(tmem_base + h * 256, wd, pd, idesc, acc);
-      } else if (j & 1) {
-        const uint64_t wd = wdesc0 + (uint64_t)((st * C3_STAGE_BYTES + C3_HALF_BYTES + tl * 4096) >> 4);
-        const uint64_t pd = p8desc0 + (uint64_t)((j - 1) * plane_u + row_off + h * 256);
-        umma_f8(tmem_base + h * 256, wd, pd, idesc, acc);
+    // The 9 (6 in fp16 mode) MMAs one stage feeds into accumulator half `h` (0: tiles 0,1   1: tiles 2,3): per tap of the
+    // row, fp16 W_hi * a over the two 16-channel slices of pair `pr`, then e4m3 W_lo * a over its 32 channels.
+    auto stage_mmas = [&](uint32_t slot, int pr, int tt, int h, uint32_t idesc, bool first) {
+      const uint32_t d = tmem_base + h * 256;
+#pragma unroll
+      for (int tl = 0; tl < 3; ++tl) {
+        const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1)) + h * 256;   // tap (ky, kx) = (tt, tl)
+        const uint64_t wd = wdesc0 + (uint64_t)((slot * C3_STAGE_BYTES + tl * 4096) >> 4);
+        umma_f16(d, wd, pdesc0 + (uint64_t)(4 * pr * plane_u + row_off), idesc, !(first && tl == 0));
+        umma_f16(d, wd + (C3_PART_BYTES >> 4), pdesc0 + (uint64_t)((4 * pr + 2) * plane_u + row_off), idesc, 1);
+        if (NPASS == 2) umma_f8(d, wd + (2 * C3_PART_BYTES >> 4), p8desc0 + (uint64_t)(2 * pr * plane_u + row_off), idesc, 1);
       }
     };
     int it = 0, it1 = 0;      // it1 counts the groups that use accumulator half 1 (its barriers flip only then)
@@ -166,64 +164,75 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       const uint32_t id1 = n_t >= 4 ? idesc256 : idesc128;
       const bool second = n_t >= 3;
       const uint32_t par = it & 1;
-      // The first and the last k-slice run the two accumulator halves one after the other (the three weight
-      // stages of that slice stay resident for both sweeps), so that the epilogue of half 0 overlaps the last
-      // sweep of half 1, and the epilogue of half 1 overlaps the first sweep of half 0 of the NEXT group.
-      for (int j = 0; j < 4; ++j) {
-        mbar_wait(a_full + j, par, 51);
-        C3_TRACE(2 + j);
-        if (j == 0 || j == 3) {
-          if (j == 0) { mbar_wait(t_empty + 0, par ^ 1, 50); C3_TRACE(1); }
-          uint32_t s1 = st, p1 = wpar;
-          for (int tt = 0; tt < 3; ++tt) {
-            mbar_wait(w_full + s1, p1, 52);
-            tc_fence_after();
-            if (elect_one()) {          // one guarded straight-line region per weight stage: descriptors stay uniform
-#pragma unroll
-              for (int tl = 0; tl < 3; ++tl)
-#pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) step(s1, j, tt, tl, ps, 0, id0, (j | tt | tl | ps) != 0);
-            }
-            __syncwarp();
-            s1 = ring_next(s1, p1);
-          }
-          if (j == 3) { if (elect_one()) umma_commit(t_full + 0); }
-          if (j == 0 && second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
+      // Stage order of an item: S0 S1 | S2 S3 | S4 S5.  The first two and the last two stages run the accumulator halves
+      // one after the other (h0 of both stages, then h1 of both), the middle two interleave them: the epilogue of half 0
+      // then overlaps the last h1 sweep, the epilogue of half 1 overlaps the first h0 sweep of the NEXT item, and each
+      // has 2 x 1,152 tensor cycles to finish.
+      // ---- head: S0, S1 (pair 0, tap rows 0, 1)
+      mbar_wait(a_full + 0, par, 51);
+      C3_TRACE(2);
+      mbar_wait(t_empty + 0, par ^ 1, 50);
+      C3_TRACE(1);
+      {
+        uint32_t s1 = st, p1 = wpar;
+        for (int k = 0; k < 2; ++k) {
+          mbar_wait(w_full + s1, p1, 52);
           tc_fence_after();
-          for (int tt = 0; tt < 3; ++tt) {
-            if (elect_one()) {
-              if (second) {
-#pragma unroll
-                for (int tl = 0; tl < 3; ++tl)
-#pragma unroll
-                  for (int ps = 0; ps < NPASS; ++ps) step(st, j, tt, tl, ps, 1, id1, (j | tt | tl | ps) != 0);
-              }
-              umma_commit(w_empty + st);
-            }
-            __syncwarp();
-            st = ring_next(st, wpar);
-          }
-          if (j == 3 && second) { if (elect_one()) umma_commit(t_full + 1); ++it1; }
-        } else {
-          for (int tt = 0; tt < 3; ++tt) {
-            mbar_wait(w_full + st, wpar, 52);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-              for (int tl = 0; tl < 3; ++tl)
-#pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) {
-                  step(st, j, tt, tl, ps, 0, id0, 1);
-                  if (second) step(st, j, tt, tl, ps, 1, id1, 1);
-                }
-              umma_commit(w_empty + st);
-            }
-            __syncwarp();
-            st = ring_next(st, wpar);
-          }
+          if (elect_one()) stage_mmas(s1, 0, k, 0, id0, k == 0);
+          __syncwarp();
+          s1 = ring_next(s1, p1);
         }
-        if (elect_one()) umma_commit(a_empty + j);
+        if (second) mbar_wait(t_empty + 1, (it1 & 1) ^ 1, 53);
+        tc_fence_after();
+        for (int k = 0; k < 2; ++k) {
+          if (elect_one()) {
+            if (second) stage_mmas(st, 0, k, 1, id1, k == 0);
+            umma_commit(w_empty + st);
+          }
+          __syncwarp();
+          st = ring_next(st, wpar);
+        }
+      }
+      // ---- middle: S2 (pair 0, tap row 2), S3 (pair 1, tap row 0), halves interleaved
+      for (int k = 2; k < 4; ++k) {
+        if (k == 3) { mbar_wait(a_full + 1, par, 51); C3_TRACE(3); }
+        mbar_wait(w_full + st, wpar, 52);
+        tc_fence_after();
+        if (elect_one()) {
+          stage_mmas(st, k / 3, k % 3, 0, id0, false);
+          if (second) stage_mmas(st, k / 3, k % 3, 1, id1, false);
+          umma_commit(w_empty + st);
+          if (k == 2) umma_commit(a_empty + 0);
+        }
         __syncwarp();
+        st = ring_next(st, wpar);
+      }
+      // ---- tail: S4, S5 (pair 1, tap rows 1, 2)
+      {
+        uint32_t s1 = st, p1 = wpar;
+        for (int k = 1; k < 3; ++k) {
+          mbar_wait(w_full + s1, p1, 52);
+          tc_fence_after();
+          if (elect_one()) {
+            stage_mmas(s1, 1, k, 0, id0, false);
+            if (k == 2) umma_commit(t_full + 0);
+          }
+          __syncwarp();
+          s1 = ring_next(s1, p1);
+        }
+        for (int k = 1; k < 3; ++k) {
+          if (elect_one()) {
+            if (second) stage_mmas(st, 1, k, 1, id1, false);
+            umma_commit(w_empty + st);
+            if (k == 2) {
+              if (second) umma_commit(t_full + 1);
+              umma_commit(a_empty + 1);
+            }
+          }
+          __syncwarp();
+          st = ring_next(st, wpar);
+        }
+        if (second) ++it1;
       }
       C3_TRACE(6);
     }
@@ -307,26 +316,23 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
   if (rc) return rc;
   std::vector<float> w((size_t)128 * 64 * 9);       // [cout][cin][tap]
   WW_CHECK(c, cudaMemcpy(w.data(), c->w["conv3.weight"], w.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  std::vector<unsigned char> s((size_t)12 * C3_STAGE_BYTES, 0);      // 12 stages (slice j, tap row)
+  std::vector<unsigned char> s((size_t)C3_STAGES_PER_ITEM * C3_STAGE_BYTES, 0);
   const float sc = weight_scale(w);
   c->w3_inv_scale = 1.0f / sc;
-  for (int j = 0; j < 4; ++j)
-    for (int tap = 0; tap < 9; ++tap)
-      for (int kc = 0; kc < 2; ++kc)
-        for (int n = 0; n < 128; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = j * 16 + kc * 8 + e;
-            const float v = w[((size_t)n * 64 + ci) * 9 + tap] * sc;
-            const uint16_t hi = f2h(v);
-            const int tt = tap / 3, tl = tap % 3;
-            // stage (j, tt): hi half [tl][kc][cout][8 fp16]
-            unsigned char* stg = s.data() + ((size_t)j * 3 + tt) * C3_STAGE_BYTES;
-            memcpy(stg + (((size_t)tl * 2 + kc) * 128 + n) * 16 + e * 2, &hi, 2);
-            // lo half lives in the stage of the ODD slice of the pair: [tl][kc8][cout][16 e4m3], kc8 = 16-channel chunk
-            const int jo = j | 1, c32 = ci & 31;
-            unsigned char* stg_lo = s.data() + ((size_t)jo * 3 + tt) * C3_STAGE_BYTES + C3_HALF_BYTES;
-            stg_lo[(((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] = f2e4m3(v - h2f(hi));
-          }
+  for (int n = 0; n < 128; ++n)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = w[((size_t)n * 64 + ci) * 9 + tap] * sc;
+        const uint16_t hi = f2h(v);
+        const int pr = ci >> 5, c32 = ci & 31, tt = tap / 3, tl = tap % 3;
+        unsigned char* stg = s.data() + (size_t)(pr * 3 + tt) * C3_STAGE_BYTES;
+        // hi part of slice (c32 >> 4) of the pair: [tl][kc][cout][8 fp16], kc = 8-channel chunk within the slice
+        unsigned char* hp = stg + (size_t)(c32 >> 4) * C3_PART_BYTES;
+        memcpy(hp + (((size_t)tl * 2 + ((c32 >> 3) & 1)) * 128 + n) * 16 + (c32 & 7) * 2, &hi, 2);
+        // lo part of the pair: [tl][kc16][cout][16 e4m3], kc16 = 16-channel chunk
+        unsigned char* lp = stg + (size_t)2 * C3_PART_BYTES;
+        lp[(((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] = f2e4m3(v - h2f(hi));
+      }
   if (!c->d_w3_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w3_split, s.size()));
   WW_CHECK(c, cudaMemcpy(c->d_w3_split, s.data(), s.size(), cudaMemcpyHostToDevice));
 

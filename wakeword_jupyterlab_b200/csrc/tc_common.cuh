@@ -232,11 +232,15 @@ inline float weight_scale(const std::vector<float>& w) {
   return ldexpf(1.0f, k);
 }
 
-constexpr int C3_NST_MAX = 6;                            // conv3 weight ring stages (as many as shared memory allows)
+// conv3 weight stage = everything tap row tt needs from one PAIR of 16-channel slices (32 input channels):
+//   [hi fp16 of slice 2p: tap 3][kc 2][cout 128][8] 12 KB | [hi fp16 of slice 2p+1] 12 KB | [lo e4m3 of the pair:
+//   tap 3][kc16 2][cout 128][16] 12 KB   = 36 KB, the operand of 9 MMAs per accumulator half (1,152 tensor cycles).
+// 6 stages per item; global memory holds them in consumption order (pair, tap row).
+constexpr int C3_PART_BYTES = 3 * 2 * 128 * 16;          // 12 KB
+constexpr int C3_STAGE_BYTES = 3 * C3_PART_BYTES;        // 36 KB
+constexpr int C3_STAGES_PER_ITEM = 6;
+constexpr int C3_NST_MAX = 4;                            // ring slots (as many as shared memory allows)
 constexpr int C3_NST_MIN = 3;
-constexpr int C3_HALF_BYTES = 3 * 2 * 128 * 16;          // [tap 3][kc 2][cout 128][16 B] = 12 KB
-constexpr int C3_STAGE_BYTES = 2 * C3_HALF_BYTES;        // fp16 hi weights of (16-channel slice j, tap row); for odd j also
-                                                         // the e4m3 lo weights of the 32-channel slice pair (j-1, j)
 
 inline size_t conv3_smem_bytes(int nsl3, int nst) {
   return (size_t)12 * nsl3 * 16 + (size_t)nst * C3_STAGE_BYTES + 128 * 4 + 256 * 4 + 32 * 8 + 64;
