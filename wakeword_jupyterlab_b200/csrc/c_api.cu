@@ -5,6 +5,7 @@
 #include <string.h>
 #include <algorithm>
 #include <numeric>
+#include <utility>
 
 namespace {
 
@@ -632,33 +633,42 @@ static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const f
     a_dev.snr_db = (float*)(base + (size_t)7 * B); a_dev.gain = (float*)(base + (size_t)8 * B);
   }
   if ((rc = ww_prepare_weights(c, st))) return rc;
-  // Two streams: the copy engine moves chunk i+1 host->device while the SMs score chunk i.
+  // Two streams: the copy engine moves piece i+1 host->device while the SMs score piece i.  Pieces ramp up
+  // geometrically (512, 1024, ... clips, then full chunks) so that only a fraction of a millisecond of copy is exposed
+  // before the first kernel starts; copying a clip is faster than scoring it, so later copies stay ahead.
   if (!c->copy_stream) WW_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   char* d_in = (char*)c->d_host_in;
   const char* h_in = (const char*)clips_host;
-  const int n_chunks = (B + c->chunk - 1) / c->chunk;
-  while ((int)c->copy_events.size() < n_chunks) {
+  std::vector<std::pair<int, int>> pieces;          // (first clip, clips)
+  for (int b0 = 0, sz = std::min(512, c->chunk); b0 < B; ) {
+    const int nb = std::min(sz, B - b0);
+    pieces.emplace_back(b0, nb);
+    b0 += nb;
+    sz = std::min(2 * sz, c->chunk);
+  }
+  const int n_pieces = (int)pieces.size();
+  while ((int)c->copy_events.size() < n_pieces) {
     cudaEvent_t e;
     WW_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->copy_events.push_back(e);
   }
-  for (int i = 0; i < n_chunks; ++i) {
-    const int b0 = i * c->chunk, nb = std::min(c->chunk, B - b0);
+  for (int i = 0; i < n_pieces; ++i) {
+    const int b0 = pieces[i].first, nb = pieces[i].second;
     WW_CHECK(c, cudaMemcpyAsync(d_in + (size_t)b0 * N * esz, h_in + (size_t)b0 * N * esz, (size_t)nb * N * esz,
                                 cudaMemcpyHostToDevice, c->copy_stream));
     WW_CHECK(c, cudaEventRecord(c->copy_events[i], c->copy_stream));
   }
-  for (int i = 0; i < n_chunks; ++i) {
-    const int b0 = i * c->chunk, nb = std::min(c->chunk, B - b0);
+  for (int i = 0; i < n_pieces; ++i) {
+    const int b0 = pieces[i].first, nb = pieces[i].second;
     WW_CHECK(c, cudaStreamWaitEvent(st, c->copy_events[i], 0));
     ww_aug a = a_dev;
     if (aug_host) {
       a.flags += b0; a.shift += b0; a.rs_orig += b0; a.rs_new += b0; a.crop_off += b0;
       a.noise_idx += b0; a.noise_off += b0; a.snr_db += b0; a.gain += b0;
     }
-    // the head (whole batch) runs with the last chunk
+    // the head (whole batch) runs with the last piece
     rc = score_impl(c, d_in + (size_t)b0 * N * esz, pcm16, N, bank_dev, bank_rows, bank_len, aug_host ? &a : nullptr,
-                    normalize, d_logits, d_prob, d_dec, nb, st, b0, i == n_chunks - 1);
+                    normalize, d_logits, d_prob, d_dec, nb, st, b0, i == n_pieces - 1);
     if (rc) return rc;
   }
   if (logits_host) WW_CHECK(c, cudaMemcpyAsync(logits_host, d_logits, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));

@@ -48,11 +48,9 @@ struct Conv12Params {
   uint8_t* act2_8;                // [B][4 planes (chunks of 16 channels)][npix][16 e4m3]: operand of conv3's W_lo pass
   float inv_s1, inv_s2;           // 2^-k1, 2^-k2
   int B;
-  int spin;                       // WW_C12_SPIN: poll the mbarriers instead of suspending (experiment switch)
   Geom g;
 };
 
-#define C12_WAIT(bar, par, code) do { if (p.spin) mbar_wait_spin(bar, par, code); else mbar_wait(bar, par, code); } while (0)
 
 // two floats -> packed fp16x2 with ReLU folded into the conversion
 __device__ __forceinline__ uint32_t pack_f16_relu(float lo, float hi) {
@@ -129,14 +127,14 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int b = item / items_per_clip, tp = item - b * items_per_clip;
         const int st = it % P_STAGES;
-        C12_WAIT(p_empty + st, ((it / P_STAGES) & 1) ^ 1, 10);
+        mbar_wait(p_empty + st, ((it / P_STAGES) & 1) ^ 1, 10);
         mbar_arrive_expect_tx(p_full + st, patch_bytes);
         bulk_g2s(patch + (size_t)st * g.patch_f, p.in_pad + (size_t)b * g.npix_in + 256 * tp, patch_bytes, p_full + st);
       }
     }
   } else if (warp == 1) {
     // ===================== conv1 MMA issuer (whole warp runs the loop; tcgen05 instructions guarded by elect.sync)
-    C12_WAIT(w_full, 0, 20);
+    mbar_wait(w_full, 0, 20);
     constexpr uint32_t idesc64 = make_idesc(128, 64);
     const uint64_t adesc0 = make_desc(smem_u32(a1), 128 * 16, 128);      // K-chunk stride = 128 rows x 16 B
     const uint64_t bdesc0 = make_desc(smem_u32(w1s), 64 * 16, 128);      // K-chunk stride = 64 rows x 16 B
@@ -144,8 +142,8 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1), par = (g1 / A1_SLOTS) & 1;
-        C12_WAIT(a1_full + s, par, 21);
-        C12_WAIT(d1_empty + s, par ^ 1, 22);
+        mbar_wait(a1_full + s, par, 21);
+        mbar_wait(d1_empty + s, par ^ 1, 22);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = adesc0 + (uint64_t)((s * A1_SLOT_BYTES) >> 4);
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   } else if (warp == 2) {
     // ===================== conv2 MMA issuer: tile 0 then tile 1 of every item, 18 MMAs each, issued from one
     // elect.sync region of straight-line code (descriptor = loop-invariant base + precomputed offset)
-    C12_WAIT(w_full, 0, 30);
+    mbar_wait(w_full, 0, 30);
     constexpr uint32_t idesc = NPASS == 2 ? make_idesc(128, 128) : make_idesc(128, 64);
     const uint64_t bdesc0 = make_desc(smem_u32(w2s), 2048, 128);
     const uint64_t adesc0 = make_desc(smem_u32(a2), (uint32_t)g.nsl2 * 16u, 128);
@@ -171,11 +169,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
-      C12_WAIT(a2_full + buf, (it >> 1) & 1, 31);
+      mbar_wait(a2_full + buf, (it >> 1) & 1, 31);
       const uint64_t adesc = adesc0 + (uint64_t)((buf * a2_bytes) >> 4);
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
-        C12_WAIT(t_empty + t, (it & 1) ^ 1, 32);
+        mbar_wait(t_empty + t, (it & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t d = tmem_base + 256 + t * 128;
         const uint64_t ad_t = adesc + (uint64_t)(t * 128);
@@ -201,11 +199,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int st = it % P_STAGES;
-      C12_WAIT(p_full + st, (it / P_STAGES) & 1, 40);
+      mbar_wait(p_full + st, (it / P_STAGES) & 1, 40);
       const float* pt = patch + (size_t)st * g.patch_f;
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1);
-        C12_WAIT(a1_empty + s, ((g1 / A1_SLOTS) & 1) ^ 1, 41);
+        mbar_wait(a1_empty + s, ((g1 / A1_SLOTS) & 1) ^ 1, 41);
         // act1 pixel l of the item sits at padded index pbase + l; its 3x3 neighbourhood starts at patch[l]
         const float* c0 = pt + 128 * m + r;
         uint32_t hi[5], lo[5];
@@ -240,11 +238,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
       const int tp = item % items_per_clip;
       const int pbase = 256 * tp - 1 - g.P - 1;
       const int buf = it & 1;
-      C12_WAIT(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
+      mbar_wait(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
       unsigned char* ab = a2 + buf * a2_bytes;
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1);
-        C12_WAIT(d1_full + s, (g1 / A1_SLOTS) & 1, 51);
+        mbar_wait(d1_full + s, (g1 / A1_SLOTS) & 1, 51);
         tc_fence_after();
         uint32_t r0[16], r1[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64 + half * 16;
@@ -281,7 +279,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
       const int b = item / items_per_clip, tp = item - b * items_per_clip;
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
-        C12_WAIT(t_full + t, it & 1, 60);
+        mbar_wait(t_full + t, it & 1, 60);
         tc_fence_after();
         uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + t * 128 + hc * 32;
@@ -407,7 +405,6 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   p.in_pad = in_pad; p.w1s = c->d_w1_split; p.w2s = c->d_w2_split;
   memcpy(p.b1, c->h_b1.data(), sizeof(p.b1));
   memcpy(p.b2, c->h_b2.data(), sizeof(p.b2));
-  p.spin = getenv("WW_C12_SPIN") != nullptr;
   p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.inv_s1 = c->w1_inv_scale; p.inv_s2 = c->w2_inv_scale; p.B = B; p.g = g;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
   ProfScope prof(c, WW_STAGE_CONV12, st);

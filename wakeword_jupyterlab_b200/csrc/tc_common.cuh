@@ -51,19 +51,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     if (++spins > (1u << 17)) mbar_timeout(code);      // ~2.6 s of 20 us suspensions
   }
 }
-// Latency-critical waits (fine-grained producer/consumer hops): plain try_wait polling, no suspension, so the waiter
-// resumes within a few cycles of the phase flip.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, int code) {
-  uint32_t spins = 0, ok = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > (1u << 28)) mbar_timeout(code);
-  } while (!ok);
-}
 // roles off the critical path (producers / epilogue warps) use the same hardware-suspended wait
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) { mbar_wait(bar, parity, code); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
