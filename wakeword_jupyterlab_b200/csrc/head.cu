@@ -30,7 +30,7 @@ struct DenseParams {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(kThreads) gated_dense_kernel(DenseParams p) {
+__global__ void __launch_bounds__(kThreads, 3) gated_dense_kernel(DenseParams p) {
   __shared__ __align__(16) float xs[KC][TM];          // [k][clip]
   __shared__ __align__(16) float ws[KC][3][TN];       // [k][gate][unit]
   const int tid = threadIdx.x;
