@@ -358,3 +358,50 @@ def test_full_size_properties(ww):
     assert torch.equal(out.amax(dim=(1, 2, 3)), torch.zeros(16384, device="cuda"))
     scaled = eng.logmel(clips[:64] * 0.37, normalize=True)       # peak normalisation removes gain
     assert (scaled - out[:64]).abs().max() < 1e-3
+
+
+def test_full_size_score_properties(ww, golden_dir):
+    """BASELINE config-3 scale (65,536 clips, 16 chunks): size-independent properties instead of an oracle pass --
+    every copy of a clip scores bit-identically wherever it sits in the batch, and identically to a small-batch run
+    (no cross-clip leakage through the pipelined kernels, the padded workspaces or the chunking)."""
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    net = _load(ww, sd, mode="split2")
+    n_base, reps = 256, 256
+    base = R.make_clips(n_base, seed=31)
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n_base, seed=5)
+    fields = ("flags", "shift", "rs_orig", "rs_new", "crop_off", "noise_idx", "noise_off", "snr_db", "gain")
+    big = ww.AugBatch(*[np.tile(getattr(p, f), reps) for f in fields])
+    clips = torch.from_numpy(base).cuda().repeat(reps, 1)                     # 65,536 clips, 4.2 GB
+    logits, prob1, dec = ww.score_clips(clips, net, aug=big, noise_bank=bank)
+    torch.cuda.synchronize()
+    small = ww.score_clips(torch.from_numpy(base).cuda(), net, aug=_aug_to_ww(ww, p), noise_bank=bank)
+    assert logits.shape == (n_base * reps, 2)
+    assert torch.equal(logits.view(reps, n_base, 2), small[0].expand(reps, n_base, 2))
+    assert torch.equal(dec.view(reps, n_base), small[2].expand(reps, n_base))
+    assert torch.isfinite(prob1).all() and 0 < int(dec[:n_base].sum()) < n_base
+
+
+def test_streaming_frame_reuse_matches_the_direct_path(ww, golden_dir, monkeypatch):
+    """windows read their interior STFT frames from the shared cache; the result must equal the
+    path that transforms every frame of every window (fp32 and int16 PCM input)."""
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    net = _load(ww, sd)
+    audio = R.make_clips(12, seed=77).reshape(-1)                       # 12 s: 1,101 windows at the 10 ms hop
+    pcm = np.clip(np.round(audio * 32768.0), -32768, 32767).astype(np.int16)
+    for sig in (audio, pcm):
+        monkeypatch.delenv("WW_STREAM_NO_REUSE", raising=False)
+        p_reuse, d_reuse = ww.score_stream(sig, net, hop_samples=160)
+        monkeypatch.setenv("WW_STREAM_NO_REUSE", "1")
+        p_direct, d_direct = ww.score_stream(sig, net, hop_samples=160)
+        monkeypatch.delenv("WW_STREAM_NO_REUSE", raising=False)
+        assert p_reuse.shape == (1 + (len(audio) - 16000) // 160,)
+        # not bit-identical: a frame shares its complex FFT with a different partner frame in the two paths
+        assert (p_reuse - p_direct).abs().max() < 1e-5 and torch.equal(d_reuse, d_direct)
+    # a hop that shares no frame grid with the STFT hop falls back to the direct path and still works
+    p_odd, _ = ww.score_stream(audio, net, hop_samples=170)
+    wins = np.stack([audio[k * 170:k * 170 + 16000] for k in (0, 5)])
+    ref = M.forward_numpy(LM.audio_to_mel_batch(_norm(wins))[:, None], sd, np.float64)
+    assert np.abs(p_odd.cpu().numpy()[[0, 5]] - M.prob_and_decision(ref, 0.8)[0]).max() < 1e-4

@@ -2,6 +2,7 @@
 #include "ctx.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <numeric>
@@ -146,7 +147,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_h); cudaFree(c->ws_act2_8); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
-  cudaFree(c->d_scalar); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
+  cudaFree(c->d_scalar); cudaFree(c->d_stream_cache); cudaFree(c->d_stream_bmax); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -526,7 +527,8 @@ int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* strea
 // (whole batch) runs only when run_head is set, over clips [0, pool_off + B).
 static int score_impl(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, const float* bank, int bank_rows,
                       int64_t bank_len, const ww_aug* aug, int normalize, float* logits, float* prob1,
-                      uint8_t* decision, int64_t B, cudaStream_t st, int64_t pool_off = 0, bool run_head = true) {
+                      uint8_t* decision, int64_t B, cudaStream_t st, int64_t pool_off = 0, bool run_head = true,
+                      const StreamReuse* sr = nullptr) {
   int rc = ensure_workspaces(c);
   if (rc) return rc;
   if ((rc = ww_prepare_weights(c, st))) return rc;
@@ -549,7 +551,11 @@ static int score_impl(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stri
     const bool tc = c->cfg.conv_mode != WW_CONV_FP32;
     const LogmelOut lo = tc ? ww_conv_tc_logmel_out(c, c->ws_logmel_pad)
                             : LogmelOut{c->ws_logmel, c->W, 0, (int64_t)c->cfg.n_mels * c->W};
-    if ((rc = ww_launch_logmel_ex(c, src, in16, stride, lo, nb, aug ? 0 : normalize, st))) return rc;
+    if (sr) {                                         // streaming windows with cached interior frames
+      StreamReuse w = *sr;
+      w.abs_start0 = b0 * clip_stride;
+      if ((rc = ww_launch_logmel_stream(c, src, in16, stride, lo, nb, 1, &w, st))) return rc;
+    } else if ((rc = ww_launch_logmel_ex(c, src, in16, stride, lo, nb, aug ? 0 : normalize, st))) return rc;
     if ((rc = conv_chunk(c, tc ? c->ws_logmel_pad : c->ws_logmel, nb, pool_off + b0, st))) return rc;
   }
   if (!run_head) return WW_OK;
@@ -590,8 +596,41 @@ static int stream_entry(ww_ctx* c, const void* audio, int pcm16, int64_t T, int 
     return WW_ERR_INVALID;
   }
   cudaSetDevice(c->device);
-  return score_impl(c, audio, pcm16, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win,
-                    (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // Frame reuse: windows k and k' share every STFT frame that starts at the same sample and
+  // lies inside both, and peak normalisation only scales the power spectrum.  The mel energies of all frames starting
+  // at multiples of g = gcd(window hop, frame hop) are computed once; a window then transforms only the frames that
+  // touch its zero padding.  Used when it at least halves the number of transforms.
+  const int N = c->cfg.n_fft, hop = c->cfg.hop_length, ns = c->cfg.n_samples;
+  const int g = std::gcd(hop_samples, hop);
+  const int t_lo = (N / 2 + hop - 1) / hop, t_hi = (ns - N / 2) / hop;
+  const int64_t n_cache = T >= N ? (T - N) / g + 1 : 0;
+  const int64_t n_interior = (int64_t)std::max(0, t_hi - t_lo + 1) * n_win;
+  const bool reuse = getenv("WW_STREAM_NO_REUSE") == nullptr && n_win > 1 && (N / 2) % g == 0 && ns % hop_samples == 0 &&
+                     T < ((int64_t)1 << 30) * (pcm16 ? 2 : 1) && n_cache * 2 <= n_interior;
+  if (!reuse)
+    return score_impl(c, audio, pcm16, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win, st);
+  int rc;
+  const int64_t n_bm = (T + hop_samples - 1) / hop_samples;
+  if ((rc = ensure_buffer(c, (void**)&c->d_stream_cache, &c->stream_cache_bytes, (size_t)n_cache * c->cfg.n_mels * 4))) return rc;
+  if ((rc = ensure_buffer(c, (void**)&c->d_stream_bmax, &c->stream_bmax_bytes, (size_t)n_bm * 4))) return rc;
+  if ((rc = ww_launch_blockmax(c, audio, pcm16, T, hop_samples, c->d_stream_bmax, n_bm, st))) return rc;
+  StreamReuse sr;
+  sr.mode = 1; sr.cache = c->d_stream_cache; sr.n_cache = n_cache; sr.cache_g = g; sr.abs_start0 = 0;
+  sr.blockmax = c->d_stream_bmax; sr.bm_block = hop_samples; sr.n_total = T;
+  const int W = c->W;
+  const int64_t n_blocks = (n_cache + W - 1) / W;
+  for (int64_t blk0 = 0; blk0 < n_blocks; blk0 += (1 << 20)) {          // launches of at most 2^20 frame blocks
+    const int nb = (int)std::min<int64_t>(1 << 20, n_blocks - blk0);
+    StreamReuse s1 = sr;
+    s1.cache = sr.cache + (size_t)blk0 * W * c->cfg.n_mels;
+    s1.n_cache = n_cache - blk0 * W;
+    s1.n_total = T - blk0 * W * g;
+    const void* src = static_cast<const char*>(audio) + (size_t)blk0 * W * g * (pcm16 ? 2 : 4);
+    if ((rc = ww_launch_logmel_stream(c, src, pcm16, (int64_t)W * g, LogmelOut{nullptr, 0, 0, 0}, nb, 0, &s1, st))) return rc;
+  }
+  sr.mode = 2;
+  return score_impl(c, audio, pcm16, hop_samples, nullptr, 0, 0, nullptr, 1, nullptr, prob1, decision, n_win, st, 0, true, &sr);
 }
 
 int ww_score_stream(ww_ctx* c, const float* audio, int64_t T, int hop_samples, float* prob1, uint8_t* decision,

@@ -118,6 +118,8 @@ struct ww_ctx {
   int n_pool_part = 0;
   bool ws_ready = false;
   unsigned int* d_scalar = nullptr;   // scratch word for ww_normalize
+  float* d_stream_cache = nullptr; size_t stream_cache_bytes = 0;      // streaming: mel energies of the unique frames
+  float* d_stream_bmax = nullptr; size_t stream_bmax_bytes = 0;        // streaming: block maxima of |x|
   uint32_t* d_tc_mask = nullptr;      // conv3 tile validity masks [T3][4]
   std::vector<float> h_w1t, h_b1, h_b2;   // host copies of conv1 weights [9][32], conv1/conv2 bias: passed as kernel parameters
   // host staging for ww_score_host
@@ -157,6 +159,16 @@ int ww_launch_logmel(ww_ctx* c, const void* clips, int pcm16, int64_t clip_strid
                      cudaStream_t st);                        // out: plain [B][1][n_mels][W]
 int ww_launch_logmel_ex(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
                         int normalize, cudaStream_t st);
+// streaming frame reuse (logmel.cu): mode 1 = build the cache of raw mel energies of frames starting every cache_g
+// samples; mode 2 = windows whose interior frames are read from that cache
+struct StreamReuse {
+  int mode; float* cache; int64_t n_cache; int cache_g; int64_t abs_start0; const float* blockmax; int bm_block;
+  int64_t n_total;
+};
+int ww_launch_logmel_stream(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
+                            int normalize, const StreamReuse* sp, cudaStream_t st);
+int ww_launch_blockmax(ww_ctx* c, const void* x, int pcm16, int64_t n, int block, float* out, int64_t n_blocks,
+                       cudaStream_t st);
 int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st);
 int ww_launch_augment(ww_ctx* c, const void* clips, int pcm16, const float* bank, int bank_rows, int64_t bank_len,
                       const ww_aug* p, float* out, int B, cudaStream_t st);

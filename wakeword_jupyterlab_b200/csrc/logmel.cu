@@ -150,6 +150,19 @@ struct LogmelParams {
   const int* mel_len;
   const int* mel_off;
   const float* mel_w;
+  // Streaming frame reuse.  mode 0: plain.  mode 1 (cache build): "clip" b is a block of W
+  // consecutive cache frames, frame t starts at sample (b W + t) cache_g of `clips`, no centre offset; the raw mel
+  // energies go to cache[(b W + t)][n_mels].  mode 2 (window): only the frame pairs that touch the zero padding of the
+  // window are transformed; the interior frames come from the cache (energies of the raw signal, scaled by 1/peak^2
+  // like every other frame), the window peak from block maxima of |x|.
+  int mode;
+  float* cache;            // [n_cache][n_mels]
+  int64_t n_cache;         // cache frames
+  int cache_g;             // samples between consecutive cache frames
+  int64_t abs_start0;      // mode 2: absolute sample index of window 0 of this launch
+  const float* blockmax;   // mode 2: max |x| over consecutive blocks of bm_block samples
+  int bm_block;
+  int64_t n_total;         // mode 1: samples available from `clips`
 };
 
 __device__ __forceinline__ float block_max(float v, float* red, int tid) {
@@ -206,7 +219,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const TIn* __restrict__ x = static_cast<const TIn*>(p.clips) + (int64_t)b * p.clip_stride;
     float inv_peak = 1.0f;
-    if (p.normalize) {
+    if (p.mode == 2) {
+      const int64_t j0 = (p.abs_start0 + (int64_t)b * p.clip_stride) / p.bm_block;
+      float m = 0.0f;
+      for (int i = tid; i < n_samples / p.bm_block; i += kThreads) m = fmaxf(m, __ldg(p.blockmax + j0 + i));
+      const float peak = block_max(m, red, tid);
+      inv_peak = (peak > 0.0f) ? 1.0f / peak : 1.0f;
+    } else if (p.normalize) {
       float m = 0.0f;
       for (int i = tid; i < n_samples; i += kThreads) m = fmaxf(m, fabsf(ldin(x, i)));
       const float peak = block_max(m, red, tid);
@@ -216,10 +235,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     float2* za = zbuf + grp * 2 * NPAD;
     float2* zb = za + NPAD;
     const int n_pairs = (W + 1) >> 1;
-    for (int pr = grp; pr < n_pairs; pr += kGroups) {
+    // frames [t_lo, t_hi] lie fully inside the window; mode 2 transforms only the pairs [0, pe_lo) and [pe_hi, n_pairs)
+    const int t_lo = ((N >> 1) + hop - 1) / hop, t_hi = (n_samples - (N >> 1)) / hop;
+    const int pe_lo = p.mode == 2 ? min((t_lo + 1) >> 1, n_pairs) : n_pairs;
+    const int pe_hi = p.mode == 2 ? max(min((t_hi + 1) >> 1, n_pairs), pe_lo) : n_pairs;
+    const int n_do = pe_lo + (n_pairs - pe_hi);
+    const int f_hop = p.mode == 1 ? p.cache_g : hop, f_off = p.mode == 1 ? 0 : -(N >> 1);
+    // valid sample indices relative to x: [0, limit)
+    const long long left = (long long)p.n_total - (long long)b * p.clip_stride;
+    const unsigned limit = p.mode == 1 ? (unsigned)(left < (1ll << 30) ? (left > 0 ? left : 0) : (1ll << 30)) : (unsigned)n_samples;
+    for (int e = grp; e < n_do; e += kGroups) {
+      const int pr = e < pe_lo ? e : pe_hi + (e - pe_lo);
       const int t0 = 2 * pr, t1 = 2 * pr + 1;
-      const int s0 = hop * t0 - (N >> 1);
-      const int s1 = (t1 < W) ? hop * t1 - (N >> 1) : (1 << 30);
+      const int s0 = f_hop * t0 + f_off;
+      const int s1 = (t1 < W) ? f_hop * t1 + f_off : (1 << 30);
       // ---- first stage: radix 8 straight from global (framing + window), NS = 1
       {
         constexpr int NB = N >> 3;
@@ -230,8 +259,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             const int n = gt + r * NB;
             const float w = __ldg(win + n);
             const int i0 = s0 + n, i1 = s1 + n;
-            const float a = ((unsigned)i0 < (unsigned)n_samples) ? ldin(x, i0) : 0.0f;
-            const float c = ((unsigned)i1 < (unsigned)n_samples) ? ldin(x, i1) : 0.0f;
+            const float a = ((unsigned)i0 < limit) ? ldin(x, i0) : 0.0f;
+            const float c = ((unsigned)i1 < limit) ? ldin(x, i1) : 0.0f;
             v[r] = make_float2(w * a, w * c);
           }
           dft8(v);
@@ -278,7 +307,29 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       }
       if (((LOG2N - 3 + 2) / 3) < 2) group_sync(grp);      // fewer than two ping-pong stages: the next pair would overwrite z
     }
+    if (p.mode == 2) {
+      // interior frames from the cache: frame t of this window starts at absolute sample a = start + hop t - N/2
+      const int t_a = 2 * pe_lo, n_int = 2 * pe_hi - t_a;
+      const int64_t a0 = p.abs_start0 + (int64_t)b * p.clip_stride - (N >> 1);
+      for (int i = tid; i < n_int * n_mels; i += kThreads) {
+        const int tt = i / n_mels, m = i - tt * n_mels, t = t_a + tt;
+        if (t < W) {
+          const int64_t idx = (a0 + (int64_t)hop * t) / p.cache_g;
+          mel_s[m * W + t] = __ldg(p.cache + idx * n_mels + m) * scale;
+        }
+      }
+    }
     __syncthreads();
+    if (p.mode == 1) {
+      // cache build: raw mel energies, frame-major
+      for (int i = tid; i < W * n_mels; i += kThreads) {
+        const int t = i / n_mels, m = i - t * n_mels;
+        const int64_t f = (int64_t)b * W + t;
+        if (f < p.n_cache) p.cache[f * n_mels + m] = mel_s[m * W + t];
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- power_to_db(ref=max, amin, top_db)
     const int total = n_mels * W;
     float m = 0.0f;
@@ -324,8 +375,42 @@ int ww_launch_logmel(ww_ctx* c, const void* clips, int pcm16, int64_t clip_strid
 
 int ww_launch_logmel_ex(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
                         int normalize, cudaStream_t st) {
+  return ww_launch_logmel_stream(c, clips, pcm16, clip_stride, out, B, normalize, nullptr, st);
+}
+
+namespace {
+__global__ void blockmax_kernel(const void* __restrict__ x, int pcm16, int64_t n, int block, float* __restrict__ out, int64_t n_blocks) {
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n_blocks) return;
+  const int lane = threadIdx.x & 31;
+  float m = 0.0f;
+  for (int i = lane; i < block; i += 32) {
+    const int64_t k = j * block + i;
+    if (k < n) m = fmaxf(m, fabsf(pcm16 ? (float)static_cast<const int16_t*>(x)[k] * (1.0f / 32768.0f) : static_cast<const float*>(x)[k]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[j] = m;
+}
+}  // namespace
+
+int ww_launch_blockmax(ww_ctx* c, const void* x, int pcm16, int64_t n, int block, float* out, int64_t n_blocks, cudaStream_t st) {
+  if (n_blocks <= 0) return WW_OK;
+  blockmax_kernel<<<(unsigned)((n_blocks + 7) / 8), 256, 0, st>>>(x, pcm16, n, block, out, n_blocks);
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+// sp == nullptr: plain log-mel.  sp->mode 1: build the frame-energy cache (clips = the whole signal, B = blocks of W
+// cache frames).  sp->mode 2: sliding windows whose interior frames come from the cache.
+int ww_launch_logmel_stream(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
+                            int normalize, const StreamReuse* sp, cudaStream_t st) {
   if (B <= 0) return WW_OK;
   LogmelParams p;
+  p.mode = sp ? sp->mode : 0;
+  p.cache = sp ? sp->cache : nullptr; p.n_cache = sp ? sp->n_cache : 0; p.cache_g = sp ? sp->cache_g : 1;
+  p.abs_start0 = sp ? sp->abs_start0 : 0; p.blockmax = sp ? sp->blockmax : nullptr; p.bm_block = sp ? sp->bm_block : 1;
+  p.n_total = sp ? sp->n_total : 0;
   p.clips = clips; p.clip_stride = clip_stride; p.out = out; p.B = B; p.normalize = normalize;
   p.n_samples = c->cfg.n_samples; p.hop = c->cfg.hop_length; p.W = c->W;
   p.n_mels = c->cfg.n_mels; p.mel_nnz = c->mel_nnz;
