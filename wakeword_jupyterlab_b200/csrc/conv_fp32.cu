@@ -17,6 +17,18 @@ namespace {
 
 constexpr int TH = 8, TW = 32, kThreads = TH * TW;
 
+// Packed fp32x2 FMA (Blackwell): two IEEE fma.rn per instruction on a 64-bit register pair.  A 3-register FFMA issues
+// every other cycle per scheduler; FFMA2 is what reaches the fp32 peak.  Each lane is an ordinary fma.rn, so results
+// are bit-identical to the scalar form.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
 // EPI: 0 = bias + ReLU -> [B][COUT][H][W];  1 = bias + ReLU + sum over the tile -> [B][n_tiles][COUT] (POOL);
 //      2 = data gradient (training): no bias, out = aux > 0 ? acc : 0 with aux = the forward activation of the layer
 //          below (ReLU derivative), `wt` = the flipped / transposed weights.
@@ -42,9 +54,9 @@ conv3x3_relu_kernel(const float* __restrict__ in,     // [B][CIN][H][W]
   const int b = blockIdx.z;
   const float* inb = in + (size_t)b * CIN * H * W;
 
-  float acc[COUT_TILE];
+  f32x2 acc2[COUT_TILE / 2];
 #pragma unroll
-  for (int i = 0; i < COUT_TILE; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < COUT_TILE / 2; ++i) acc2[i] = 0ull;
 
   for (int c0 = 0; c0 < CIN; c0 += CC) {
     __syncthreads();
@@ -69,17 +81,19 @@ conv3x3_relu_kernel(const float* __restrict__ in,     // [B][CIN][H][W]
       for (int k = 0; k < 9; ++k) v[k] = s_in[c][ty + k / 3][tx + k % 3];
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
+        const f32x2 vv = pack2(v[k], v[k]);
 #pragma unroll
         for (int co = 0; co < COUT_TILE; co += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&s_w[c][k][co]);
-          acc[co + 0] = fmaf(v[k], w4.x, acc[co + 0]);
-          acc[co + 1] = fmaf(v[k], w4.y, acc[co + 1]);
-          acc[co + 2] = fmaf(v[k], w4.z, acc[co + 2]);
-          acc[co + 3] = fmaf(v[k], w4.w, acc[co + 3]);
+          const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(&s_w[c][k][co]);    // (w0, w1), (w2, w3)
+          ffma2(acc2[co / 2], vv, w4.x);
+          ffma2(acc2[co / 2 + 1], vv, w4.y);
         }
       }
     }
   }
+  float acc[COUT_TILE];
+#pragma unroll
+  for (int i = 0; i < COUT_TILE / 2; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
 
   const int y = y0 + ty, x = x0 + tx;
   const bool valid = (y < H) && (x < W);
@@ -138,11 +152,11 @@ conv3x3_wgrad_kernel(const float* __restrict__ x,      // [B][CIN][H][W]
   const int cg = tid & 7, ci_l = tid >> 3;                        // 4 co per thread, one ci
   const int co0 = blockIdx.x * WG_CO, ci0 = blockIdx.y * WG_CI, slice = blockIdx.z;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
-  float acc[4][9];
+  f32x2 acc2[2][9];                                                 // (co 0, co 1) and (co 2, co 3) per tap
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[a][k] = 0.0f;
+    for (int k = 0; k < 9; ++k) acc2[a][k] = 0ull;
   const int b_lo = slice * clips_per_slice, b_hi = min(B, b_lo + clips_per_slice);
   for (int b = b_lo; b < b_hi; ++b) {
     for (int tile = 0; tile < tiles_x * tiles_y; ++tile) {
@@ -165,29 +179,32 @@ conv3x3_wgrad_kernel(const float* __restrict__ x,      // [B][CIN][H][W]
       __syncthreads();
 #pragma unroll 1
       for (int ty = 0; ty < TH; ++ty) {
-        float w0[3], w1[3], w2[3];                                   // sliding 3x3 window: columns tx-1, tx, tx+1
+        f32x2 w0[3], w1[3], w2[3];                                   // sliding 3x3 window (each value twice): columns tx-1, tx, tx+1
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { w0[r] = s_x[ci_l][ty + r][0]; w1[r] = s_x[ci_l][ty + r][1]; }
+        for (int r = 0; r < 3; ++r) {
+          const float a0 = s_x[ci_l][ty + r][0], a1 = s_x[ci_l][ty + r][1];
+          w0[r] = pack2(a0, a0); w1[r] = pack2(a1, a1);
+        }
 #pragma unroll 4
         for (int tx = 0; tx < TW; ++tx) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) w2[r] = s_x[ci_l][ty + r][tx + 2];
-          const float4 d4 = *reinterpret_cast<const float4*>(&s_dy[ty * TW + tx][cg * 4]);
-          const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+          for (int r = 0; r < 3; ++r) { const float a2 = s_x[ci_l][ty + r][tx + 2]; w2[r] = pack2(a2, a2); }
+          const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(&s_dy[ty * TW + tx][cg * 4]);   // (dy0, dy1), (dy2, dy3)
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              acc[a][r * 3 + 0] = fmaf(d[a], w0[r], acc[a][r * 3 + 0]);
-              acc[a][r * 3 + 1] = fmaf(d[a], w1[r], acc[a][r * 3 + 1]);
-              acc[a][r * 3 + 2] = fmaf(d[a], w2[r], acc[a][r * 3 + 2]);
-            }
+          for (int r = 0; r < 3; ++r) {
+            ffma2(acc2[0][r * 3 + 0], d4.x, w0[r]); ffma2(acc2[1][r * 3 + 0], d4.y, w0[r]);
+            ffma2(acc2[0][r * 3 + 1], d4.x, w1[r]); ffma2(acc2[1][r * 3 + 1], d4.y, w1[r]);
+            ffma2(acc2[0][r * 3 + 2], d4.x, w2[r]); ffma2(acc2[1][r * 3 + 2], d4.y, w2[r]);
+          }
 #pragma unroll
           for (int r = 0; r < 3; ++r) { w0[r] = w1[r]; w1[r] = w2[r]; }
         }
       }
     }
   }
+  float acc[4][9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { unpack2(acc2[0][k], acc[0][k], acc[1][k]); unpack2(acc2[1][k], acc[2][k], acc[3][k]); }
   const int ci = ci0 + ci_l;
   if (ci < CIN) {
 #pragma unroll
