@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < P_STAGES; ++i) { mbar_init(p_full + i, 1); mbar_init(p_empty + i, 128); }
+    for (int i = 0; i < P_STAGES; ++i) { mbar_init(p_full + i, 1); mbar_init(p_empty + i, 4); }
     for (int i = 0; i < A1_SLOTS; ++i) {
-      mbar_init(a1_full + i, 128); mbar_init(a1_empty + i, 1);
-      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 256);
+      mbar_init(a1_full + i, 4); mbar_init(a1_empty + i, 1);
+      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 8);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a2_full + i, 256); mbar_init(a2_empty + i, 1);
-      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256);
+      mbar_init(a2_full + i, 8); mbar_init(a2_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8);
     }
     fence_barrier_init();
   }
@@ -222,9 +222,9 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         *reinterpret_cast<uint4*>(dst + 2 * 128 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         *reinterpret_cast<uint4*>(dst + 3 * 128 * 16) = make_uint4(lo[4], 0u, 0u, 0u);
         fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(a1_full + s);
+        mbar_arrive_warp(a1_full + s, lane);
       }
-      mbar_arrive(p_empty + st);
+      mbar_arrive_warp(p_empty + st, lane);
     }
   } else if (warp < 15) {
     // ===================== conv1 epilogue: D1 -> act1 (fp16) = conv2's A operand
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         tmem_ld16_nowait(taddr + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(d1_empty + s);
+        mbar_arrive_warp(d1_empty + s, lane);
         const int l = 128 * m + r;
         if (l < NL) {
           int y, x;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         }
       }
       fence_proxy_async();
-      mbar_arrive(a2_full + buf);
+      mbar_arrive_warp(a2_full + buf, lane);
     }
   } else {
     // ===================== conv2 epilogue
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         if (NPASS == 2) tmem_ld32_nowait(taddr + 64, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(t_empty + t);
+        mbar_arrive_warp(t_empty + t, lane);
         const int s = 256 * tp + t * 128 + q * 32 + lane;
         int y, x;
         const bool ok = pix_valid(s - 1, g, y, x);

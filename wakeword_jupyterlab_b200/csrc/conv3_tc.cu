@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < C3_NST_MAX; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
           }
         }
         tc_fence_before();
-        mbar_arrive(t_empty + h);
+        mbar_arrive_warp(t_empty + h, lane);
         if (warp == 2 && h == 0) C3_TRACE(8);
         if (h) ++it1;
       }
