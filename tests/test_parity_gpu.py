@@ -405,3 +405,23 @@ def test_streaming_frame_reuse_matches_the_direct_path(ww, golden_dir, monkeypat
     wins = np.stack([audio[k * 170:k * 170 + 16000] for k in (0, 5)])
     ref = M.forward_numpy(LM.audio_to_mel_batch(_norm(wins))[:, None], sd, np.float64)
     assert np.abs(p_odd.cpu().numpy()[[0, 5]] - M.prob_and_decision(ref, 0.8)[0]).max() < 1e-4
+
+
+def test_augment_normalise_is_the_ieee_quotient(ww):
+    """The augment kernel divides a clip by its peak through one correctly rounded reciprocal + an FMA correction
+    (Markstein); the result must be bit-identical to numpy's x / max|x| (normalize_audio, :73-76), including peaks whose
+    significand is all ones (where the shortcut is not valid and the kernel takes the IEEE divide) and tiny samples."""
+    rng = np.random.default_rng(123)
+    n = 600
+    clips = (rng.standard_normal((n, 16000)) * rng.uniform(1e-3, 3.0, (n, 1))).astype(np.float32)
+    clips[1, :100] = 0.0
+    clips[2] *= np.float32(1e-20)                                          # tiny samples
+    clips[3, 7] = np.float32(np.nextafter(np.float32(2.0), np.float32(0.0)))   # peak 1.9999999 = all-ones significand
+    clips[3] = np.clip(clips[3], -1.9, 1.9); clips[3, 7] = np.nextafter(np.float32(2.0), np.float32(0.0))
+    clips[4, 9] = np.float32(1e-42)                                        # a subnormal sample
+    z = np.zeros(n, np.int32)
+    for flag in (A.F_NORM_IN, A.F_NORM_OUT):
+        p = ww.AugBatch(np.full(n, flag, np.uint32), z, z + 100, z + 100, z, z, z, np.zeros(n, np.float32), np.ones(n, np.float32))
+        out = ww.get_engine().augment(clips, p).cpu().numpy()
+        ref = clips / np.abs(clips).max(axis=1, keepdims=True)
+        assert np.array_equal(out, ref)

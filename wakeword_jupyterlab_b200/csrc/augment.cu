@@ -77,6 +77,26 @@ __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, in
   b = MAX ? warp_max(rb) : warp_sum(rb);
 }
 
+// x / m for a whole clip with ONE correctly rounded reciprocal: q = x r, e = x - m q (exact, FMA), result = q + e r.
+// With r = RN(1 / m) this is the correctly rounded quotient (Markstein's theorem) unless the significand of m is all
+// ones or the quotient is subnormal; those cases take the IEEE divide.  3 FMA-pipe instructions instead of ~12.
+struct ClipDiv {
+  float m, r;
+  bool fast;
+  __device__ __forceinline__ float operator()(float x) const {
+    const float q = x * r;
+    if (!fast || (q != 0.0f && fabsf(q) < 1e-30f)) return __fdiv_rn(x, m);
+    return fmaf(fmaf(-m, q, x), r, q);
+  }
+};
+__device__ __forceinline__ ClipDiv make_clip_div(float m) {
+  ClipDiv d;
+  d.m = m;
+  d.r = __fdiv_rn(1.0f, m);                            // correctly rounded reciprocal
+  d.fast = (__float_as_uint(m) & 0x7fffffu) != 0x7fffffu && m > 1e-30f && m < 1e30f;
+  return d;
+}
+
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst)), "l"(src) : "memory");
@@ -181,8 +201,9 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
     if (flags & WW_AUG_NORM_IN) {
       block_reduce2<true>(m, dummy, red, tid);
       if (m > 0.0f) {
+        const ClipDiv dv = make_clip_div(m);
 #pragma unroll
-        for (int e = 0; e < kMaxPerThread; ++e) o[e] = __fdiv_rn(o[e], m);
+        for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
       }
     }
 
@@ -301,8 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       for (int e = 0; e < kMaxPerThread; ++e) mo = fmaxf(mo, fabsf(o[e]));
       block_reduce2<true>(mo, dummy, red, tid);
       if (mo > 0.0f) {
+        const ClipDiv dv = make_clip_div(mo);
 #pragma unroll
-        for (int e = 0; e < kMaxPerThread; ++e) o[e] = __fdiv_rn(o[e], mo);
+        for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
       }
     }
     float* __restrict__ dst = p.out + (int64_t)b * N;
