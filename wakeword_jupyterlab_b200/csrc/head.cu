@@ -30,6 +30,16 @@ struct DenseParams {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// packed fp32x2 FMA (two IEEE fma.rn per instruction; a 3-register FFMA only issues every other cycle)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
 __global__ void __launch_bounds__(kThreads, 3) gated_dense_kernel(DenseParams p) {
   __shared__ __align__(16) float xs[KC][TM];          // [k][clip]
   __shared__ __align__(16) float ws[KC][3][TN];       // [k][gate][unit]
@@ -37,13 +47,11 @@ __global__ void __launch_bounds__(kThreads, 3) gated_dense_kernel(DenseParams p)
   const int tx = tid & 15, ty = tid >> 4;             // units tx*4.., clips ty*4..
   const int b0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
 
-  float acc[3][4][4];
+  f32x2 acc2[3][4][2];                                 // [gate][clip][unit pair]
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc[g][c][u] = 0.0f;
+    for (int c = 0; c < 4; ++c) { acc2[g][c][0] = 0ull; acc2[g][c][1] = 0ull; }
 
   for (int k0 = 0; k0 < p.K; k0 += KC) {
     __syncthreads();
@@ -73,18 +81,26 @@ __global__ void __launch_bounds__(kThreads, 3) gated_dense_kernel(DenseParams p)
 #pragma unroll 8
     for (int k = 0; k < KC; ++k) {
       const float4 xv = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
-      const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+      const f32x2 xx[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
-        const float4 wv = *reinterpret_cast<const float4*>(&ws[k][g][tx * 4]);
-        const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(&ws[k][g][tx * 4]);     // (w0, w1), (w2, w3)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[g][c][u] = fmaf(x[c], w[u], acc[g][c][u]);
+        for (int c = 0; c < 4; ++c) {
+          ffma2(acc2[g][c][0], xx[c], wv.x);
+          ffma2(acc2[g][c][1], xx[c], wv.y);
+        }
       }
     }
   }
+  float acc[3][4][4];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      unpack2(acc2[g][c][0], acc[g][c][0], acc[g][c][1]);
+      unpack2(acc2[g][c][1], acc[g][c][2], acc[g][c][3]);
+    }
   // ---- gate epilogue: h = sigmoid(o) * tanh(sigmoid(i) * tanh(g))
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
