@@ -39,7 +39,7 @@ N_SAMPLES = 16000
 FLOP_PER_CLIP = {"conv3": 2 * 2560 * 128 * 576, "conv2": 2 * 2560 * 64 * 288, "conv1": 2 * 2560 * 32 * 9,
                  "total": 475.5e6}
 METRIC = "clips_per_sec_augment_logmel_cnn_lstm_score"
-DTYPE_NAMES = {"fp32": "f32", "split2": "fp16 activations x (fp16 hi + fp16 lo) weights, fp32 accumulate", "fp16": "fp16 (fp32 accumulate)"}
+DTYPE_NAMES = {"fp32": "f32", "split2": "fp16 activations x (fp16 hi + e4m3 lo) weights on tcgen05, fp32 accumulate; fp32 front-end and head", "fp16": "fp16 (fp32 accumulate)"}
 
 
 def load_peaks():

@@ -141,6 +141,19 @@ __device__ __forceinline__ void fetch_prm(const AugKParams& p, ClipPrm& q, int b
   }
 }
 
+// NZ4 groups of four taps, fully unrolled: acc0 takes the even taps, acc1 the odd ones, in tap order
+template <int NZ4>
+__device__ __forceinline__ void taps4(const float4* __restrict__ kr4, const float* __restrict__ sp, float& acc0, float& acc1) {
+#pragma unroll
+  for (int k4 = 0; k4 < NZ4; ++k4) {
+    const float4 w = kr4[k4];
+    acc0 = fmaf(w.x, sp[4 * k4], acc0);
+    acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
+    acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
+    acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -247,12 +260,19 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
                 // interior: no edge clipping, no wrap inside the (padded) tap window
                 const float4* kr4 = reinterpret_cast<const float4*>(kr);
                 const float* sp = cur + src;
-                for (int k4 = 0; k4 < nz4; ++k4) {
-                  const float4 w = kr4[k4];
-                  acc0 = fmaf(w.x, sp[4 * k4], acc0);
-                  acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
-                  acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
-                  acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
+                // the usual table widths as straight-line code (same summation order as the rolled loop)
+                switch (nz4) {
+                  case 4: taps4<4>(kr4, sp, acc0, acc1); break;
+                  case 5: taps4<5>(kr4, sp, acc0, acc1); break;
+                  case 6: taps4<6>(kr4, sp, acc0, acc1); break;
+                  default:
+                    for (int k4 = 0; k4 < nz4; ++k4) {
+                      const float4 w = kr4[k4];
+                      acc0 = fmaf(w.x, sp[4 * k4], acc0);
+                      acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
+                      acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
+                      acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
+                    }
                 }
               } else {
                 const int k0 = x0 < 0 ? -x0 : 0;

@@ -29,6 +29,8 @@
 
 using namespace tc;
 
+#define C12_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 40 && lane == 0) p.trace[it * 16 + (slot)] = clock64(); } while (0)
+
 namespace {
 
 constexpr int C12_THREADS = 23 * 32;
@@ -49,6 +51,7 @@ struct Conv12Params {
   float inv_s1, inv_s2;           // 2^-k1, 2^-k2
   int B;
   Geom g;
+  long long* trace;               // debug (WW_TC_TRACE=1): per-item role timestamps of CTA 0
 };
 
 
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         const int b = item / items_per_clip, tp = item - b * items_per_clip;
         const int st = it % P_STAGES;
         mbar_wait(p_empty + st, ((it / P_STAGES) & 1) ^ 1, 10);
+        C12_TRACE(0);
         mbar_arrive_expect_tx(p_full + st, patch_bytes);
         bulk_g2s(patch + (size_t)st * g.patch_f, p.in_pad + (size_t)b * g.npix_in + 256 * tp, patch_bytes, p_full + st);
       }
@@ -139,11 +143,13 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     const uint64_t adesc0 = make_desc(smem_u32(a1), 128 * 16, 128);      // K-chunk stride = 128 rows x 16 B
     const uint64_t bdesc0 = make_desc(smem_u32(w1s), 64 * 16, 128);      // K-chunk stride = 64 rows x 16 B
     uint32_t g1 = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1), par = (g1 / A1_SLOTS) & 1;
         mbar_wait(a1_full + s, par, 21);
         mbar_wait(d1_empty + s, par ^ 1, 22);
+        if (m == 0) C12_TRACE(2);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = adesc0 + (uint64_t)((s * A1_SLOT_BYTES) >> 4);
@@ -170,10 +176,12 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait(a2_full + buf, (it >> 1) & 1, 31);
+      C12_TRACE(5);
       const uint64_t adesc = adesc0 + (uint64_t)((buf * a2_bytes) >> 4);
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         mbar_wait(t_empty + t, (it & 1) ^ 1, 32);
+        C12_TRACE(6 + t);
         tc_fence_after();
         const uint32_t d = tmem_base + 256 + t * 128;
         const uint64_t ad_t = adesc + (uint64_t)(t * 128);
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int st = it % P_STAGES;
       mbar_wait(p_full + st, (it / P_STAGES) & 1, 40);
+      if (warp == 3) C12_TRACE(1);
       const float* pt = patch + (size_t)st * g.patch_f;
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1);
@@ -239,6 +248,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
       const int pbase = 256 * tp - 1 - g.P - 1;
       const int buf = it & 1;
       mbar_wait(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
+      if (warp == 7) C12_TRACE(3);
       unsigned char* ab = a2 + buf * a2_bytes;
       for (int m = 0; m < NM; ++m, ++g1) {
         const uint32_t s = g1 & (A1_SLOTS - 1);
@@ -267,6 +277,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
         }
       }
       fence_proxy_async();
+      if (warp == 7) C12_TRACE(4);
       mbar_arrive_warp(a2_full + buf, lane);
     }
   } else {
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         mbar_wait(t_full + t, it & 1, 60);
+        if (warp == 15) C12_TRACE(8 + 2 * t);
         tc_fence_after();
         uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + t * 128 + hc * 32;
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             dst8[(size_t)(hc * 2 + k2) * g.npix] = u8;
           }
         }
+        if (warp == 15) C12_TRACE(9 + 2 * t);
       }
     }
   }
@@ -406,10 +419,28 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   memcpy(p.b1, c->h_b1.data(), sizeof(p.b1));
   memcpy(p.b2, c->h_b2.data(), sizeof(p.b2));
   p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.inv_s1 = c->w1_inv_scale; p.inv_s2 = c->w2_inv_scale; p.B = B; p.g = g;
+  static long long* d_trace = nullptr;
+  const bool tracing = getenv("WW_TC_TRACE") != nullptr;
+  if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 40 * 16 * 8); }
+  if (tracing) cudaMemset(d_trace, 0, 40 * 16 * 8);
+  p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
-  ProfScope prof(c, WW_STAGE_CONV12, st);
-  if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
-  else conv12_kernel<2><<<grid, C12_THREADS, smem, st>>>(p);
-  WW_LAUNCH_CHECK(c);
+  {
+    ProfScope prof(c, WW_STAGE_CONV12, st);
+    if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
+    else conv12_kernel<2><<<grid, C12_THREADS, smem, st>>>(p);
+    WW_LAUNCH_CHECK(c);
+  }
+  if (tracing) {
+    long long h[40 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "conv12 trace: load | im2col p_full | mma1 first | epi1 start end | mma2: a2_full t_empty0 t_empty1 | epi2: t_full0 done0 t_full1 done1\n");
+    for (int i = 0; i < 24; ++i) {
+      fprintf(stderr, "item %2d:", i);
+      for (int k = 0; k < 12; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - h[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return WW_OK;
 }

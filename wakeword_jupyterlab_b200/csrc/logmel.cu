@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     }
   }
   __syncthreads();
+  // the eight window taps this thread applies in the first stage are the same for every frame: keep them in registers
+  float wv[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) wv[r] = ((N >> 3) >= kGT || gt < (N >> 3)) ? __ldg(win + gt + r * (N >> 3)) : 0.0f;
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const TIn* __restrict__ x = static_cast<const TIn*>(p.clips) + (int64_t)b * p.clip_stride;
@@ -273,14 +277,22 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         constexpr int NB = N >> 3;
         if (NB >= kGT || gt < NB) {
           float2 v[8];
+          if (s0 >= 0 && t1 < W && (unsigned)(s1 + N) <= limit) {
+            // both frames lie inside the clip (all but the first and last pair or two): no bounds checks
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int n = gt + r * NB;
-            const float w = __ldg(win + n);
-            const int i0 = s0 + n, i1 = s1 + n;
-            const float a = ((unsigned)i0 < limit) ? ldin(x, i0) : 0.0f;
-            const float c = ((unsigned)i1 < limit) ? ldin(x, i1) : 0.0f;
-            v[r] = make_float2(w * a, w * c);
+            for (int r = 0; r < 8; ++r) {
+              const int n = gt + r * NB;
+              v[r] = make_float2(wv[r] * ldin(x, s0 + n), wv[r] * ldin(x, s1 + n));
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int n = gt + r * NB;
+              const int i0 = s0 + n, i1 = s1 + n;
+              const float a = ((unsigned)i0 < limit) ? ldin(x, i0) : 0.0f;
+              const float c = ((unsigned)i1 < limit) ? ldin(x, i1) : 0.0f;
+              v[r] = make_float2(wv[r] * a, wv[r] * c);
+            }
           }
           dft8(v);
           const int wb = gt * 8 + (gt >> 2);
