@@ -77,6 +77,15 @@ __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, in
   b = MAX ? warp_max(rb) : warp_sum(rb);
 }
 
+// block maximum of non-negative floats (they order like their bit patterns): one redux.sync per warp, twice
+__device__ __forceinline__ float block_max_nonneg(float v, float* red, int tid) {
+  const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = __uint_as_float(w);
+  __syncthreads();
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(red[tid & 31])));   // kThreads / 32 == 32 partials
+}
+
 // x / m for a whole clip with ONE correctly rounded reciprocal: q = x r, e = x - m q (exact, FMA), result = q + e r.
 // With r = RN(1 / m) this is the correctly rounded quotient (Markstein's theorem) unless the significand of m is all
 // ones or the quotient is subnormal; those cases take the IEEE divide.  3 FMA-pipe instructions instead of ~12.
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
 
     // ---- load own samples from the stage, peak normalise
     float o[kMaxPerThread];
-    float m = 0.0f, dummy = 0.0f;
+    float m = 0.0f;
 #pragma unroll
     for (int e = 0; e < kMaxPerThread; ++e) {
       const int i = slot_index(tid, e);
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       m = fmaxf(m, fabsf(o[e]));
     }
     if (flags & WW_AUG_NORM_IN) {
-      block_reduce2<true>(m, dummy, red, tid);
+      m = block_max_nonneg(m, red, tid);
       if (m > 0.0f) {
         const ClipDiv dv = make_clip_div(m);
 #pragma unroll
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
               const float* kr = kern + ph * pitch;
               int src = x0 - s;
               if (src < 0) src += N;
-              if (x0 >= 0 && x0 + d.nz <= N && src >= 0 && src + d.nz <= N) {
+              if ((unsigned)x0 <= (unsigned)(N - d.nz) && (unsigned)src <= (unsigned)(N - d.nz)) {
                 // interior: no edge clipping, no wrap inside the (padded) tap window
                 const float4* kr4 = reinterpret_cast<const float4*>(kr);
                 const float* sp = cur + src;
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       float mo = 0.0f;
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) mo = fmaxf(mo, fabsf(o[e]));
-      block_reduce2<true>(mo, dummy, red, tid);
+      mo = block_max_nonneg(mo, red, tid);
       if (mo > 0.0f) {
         const ClipDiv dv = make_clip_div(mo);
 #pragma unroll

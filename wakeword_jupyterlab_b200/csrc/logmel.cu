@@ -27,7 +27,17 @@ constexpr int kThreads = kGroups * kGT;
 constexpr float kAmin = 1e-10f;
 constexpr float kTopDb = 80.0f;
 
-__device__ __forceinline__ int padi(int i) { return i + (i >> 5); }   // de-conflict strided Stockham stores
+// Physical slot of logical FFT element i in a buffer WRITTEN by the stage whose NS is NSW: an XOR swizzle (a bijection
+// inside every aligned run of 16 elements, so the next stage's loads of 16 consecutive butterflies stay conflict-free and
+// no padding is needed) that spreads the strided stores of the writing stage over all banks:
+//   NSW = 1 (radix-8 from global, thread t writes 8t .. 8t+7):  i ^ ((i >> 4) & 7)       -> 16 lanes hit 16 bank pairs
+//   NSW = 8 (thread (a, k) writes 64a + 8r + k):                 i ^ (((i >> 6) & 1) << 3) -> runs of a, a+1 are 16 banks apart
+//   NSW >= 32: the stores of a warp are already consecutive, no swizzle.
+template <int NSW> __device__ __forceinline__ int lay(int i) {
+  if constexpr (NSW == 1) return i ^ ((i >> 4) & 7);
+  else if constexpr (NSW == 8) return i ^ (((i >> 6) & 1) << 3);
+  else return i;
+}
 
 // complex add / sub as ONE packed fp32x2 instruction (two IEEE adds; a scalar FADD only issues every other cycle)
 __device__ __forceinline__ unsigned long long as_u64(float2 v) {
@@ -94,20 +104,24 @@ __device__ __forceinline__ void group_sync(int grp) {
 // Stockham stage (radix R, NS = product of the radices already applied) from one buffer of the group into the other
 // (ping-pong: one barrier per stage).
 // Butterfly j: v[r] = zin[j + r*N/R] * w^r,  w = exp(-2 pi i k / (NS R)), k = j % NS (compact table `ts[k]`);
-// zout[(j - k) * R + k + r * NS] = DFT_R(v)[r].
-template <int N, int R, int NS>
+// zout[(j - k) * R + k + r * NS] = DFT_R(v)[r].   zin has the layout of the previous stage (NS / its radix), zout lay<NS>.
+template <int N, int R, int NS, int NSPREV>
 __device__ __forceinline__ void stockham_stage(const float2* zin, float2* zout, const float2* __restrict__ ts, int gt, int grp) {
   constexpr int NB = N / R;                               // butterflies (multiple of 32)
   constexpr int ITERS = NB > kGT ? NB / kGT : 1;
-  constexpr int RSTEP = NB + NB / 32;                     // padded distance between the R inputs
   float2 v[ITERS][R];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int j = gt + it * kGT;
     if (NB >= kGT || j < NB) {
-      const int rb = padi(j);
+      if constexpr (NB % 128 == 0) {                      // the swizzle does not depend on r
+        const int rb = lay<NSPREV>(j);
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[it][r] = zin[rb + r * RSTEP];
+        for (int r = 0; r < R; ++r) v[it][r] = zin[rb + r * NB];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it][r] = zin[lay<NSPREV>(j + r * NB)];
+      }
       const float2 w1 = ts[j & (NS - 1)];
       float2 w = w1;
 #pragma unroll
@@ -124,13 +138,13 @@ __device__ __forceinline__ void stockham_stage(const float2* zin, float2* zout, 
     if (NB >= kGT || j < NB) {
       const int k = j & (NS - 1);
       const int base = (j - k) * R + k;
-      if (NS % 32 == 0) {
-        const int wb = padi(base);
+      if constexpr (NS == 8 && R == 8) {
+        const int sw = ((base >> 6) & 1) << 3;            // base = 64a + k: bit 3 (= r & 1) flips for odd a
 #pragma unroll
-        for (int r = 0; r < R; ++r) zout[wb + r * (NS + NS / 32)] = v[it][r];
+        for (int r = 0; r < R; ++r) zout[(base + r * NS) ^ sw] = v[it][r];
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) zout[padi(base + r * NS)] = v[it][r];
+        for (int r = 0; r < R; ++r) zout[lay<NS>(base + r * NS)] = v[it][r];
       }
     }
   }
@@ -140,15 +154,16 @@ __device__ __forceinline__ void stockham_stage(const float2* zin, float2* zout, 
 // remaining stages after the first radix-8 one: radices 8, 8, ..., then 4 or 2; compact twiddle tables
 // (stage table k -> T[k * N / (NS R)]) are packed one after the other in `twc`; the last stage (step 1) reads `tw`.
 // returns the buffer that holds the spectrum
-template <int N, int NS, int REM, int OFF>
+template <int N, int NS, int REM, int OFF, int NSPREV>
 __device__ __forceinline__ float2* run_stages(float2* zin, float2* zout, const float2* tw, const float2* twc, int gt, int grp) {
   if constexpr (REM > 0) {
     constexpr int LG = REM >= 3 ? 3 : REM;
     constexpr int R = 1 << LG;
     constexpr int TSTEP = N / (NS * R);
-    stockham_stage<N, R, NS>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
-    return run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0)>(zout, zin, tw, twc, gt, grp);
+    stockham_stage<N, R, NS, NSPREV>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+    return run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0), NS>(zout, zin, tw, twc, gt, grp);
   } else {
+    static_assert(NSPREV >= 32, "the last stage must leave the spectrum unskewed");
     return zin;
   }
 }
@@ -199,7 +214,7 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid) {
 template <int LOG2N, typename TIn>
 __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams p) {
   constexpr int N = 1 << LOG2N;
-  constexpr int NPAD = N + (N >> 5) + 8;
+  constexpr int NPAD = N + 8;
   constexpr int NBINS = N / 2 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* zbuf = reinterpret_cast<float2*>(smem_raw);          // [kGroups][2][NPAD]: ping-pong FFT buffers
@@ -208,12 +223,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
   const float* __restrict__ win = p.window;                    // [N] read once per frame pair through L1
   float* melw = reinterpret_cast<float*>(twc + N / 8);         // [mel_nnz]
   int* mst = reinterpret_cast<int*>(melw + p.mel_nnz);         // [3][n_mels] start, len, off
-  float* mel_s = reinterpret_cast<float*>(mst + 3 * p.n_mels); // [n_mels * W]
+  float* mel_s = reinterpret_cast<float*>(mst + 3 * p.n_mels); // [n_mels][MP], odd pitch MP = W | 1: the per-band stores of a warp hit different banks
   __shared__ float red[kThreads / 32];
 
   const int tid = threadIdx.x;
   const int grp = tid / kGT, gt = tid % kGT;
   const int n_samples = p.n_samples, hop = p.hop, W = p.W, n_mels = p.n_mels;
+  const int MP = W | 1;
 
   // ---- tables -> shared memory (once per CTA)
   for (int i = tid; i < N; i += kThreads) tw[i] = p.twiddle[i];
@@ -295,24 +311,24 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
             }
           }
           dft8(v);
-          const int wb = gt * 8 + (gt >> 2);
+          const int wb = gt * 8, sw = (gt >> 1) & 7;       // lay<1>(8 gt + r) = 8 gt + (r ^ ((gt >> 1) & 7))
 #pragma unroll
-          for (int r = 0; r < 8; ++r) za[wb + r] = v[r];
+          for (int r = 0; r < 8; ++r) za[wb + (r ^ sw)] = v[r];
         }
       }
       group_sync(grp);
       // Each stage reads one buffer and writes the other.  The mel projection of the previous pair read the buffer the
       // spectrum ends in; it is next written two barriers from here at the earliest, so no barrier is needed after it.
-      float2* z = run_stages<N, 8, LOG2N - 3, 0>(za, zb, tw, twc, gt, grp);
+      float2* z = run_stages<N, 8, LOG2N - 3, 0, 1>(za, zb, tw, twc, gt, grp);
       // ---- Hermitian split + power, in place: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2.
       // Bin k reads z[k] and z[N-k] and is the only reader of both, so no sync is needed before the store.
 #pragma unroll
       for (int k = gt; k < NBINS; k += kGT) {
-        const float2 zk = z[padi(k)];
-        const float2 zn = z[padi((N - k) & (N - 1))];
+        const float2 zk = z[k];
+        const float2 zn = z[(N - k) & (N - 1)];
         const float ar = zk.x + zn.x, ai = zk.y - zn.y;
         const float br = zk.y + zn.y, bi = zk.x - zn.x;
-        z[padi(k)] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+        z[k] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
       }
       group_sync(grp);
       // ---- banded mel projection: 2 lanes per band, both frames at once
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 #pragma unroll 4
           for (int i = half; i < len; i += 2) {
             const float w = melw[off + i];
-            const float2 pw = z[padi(st + i)];
+            const float2 pw = z[st + i];
             a0 = fmaf(w, pw.x, a0);
             a1 = fmaf(w, pw.y, a1);
           }
@@ -332,8 +348,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
         if (m < n_mels && half == 0) {
-          mel_s[m * W + t0] = a0 * scale;
-          if (t1 < W) mel_s[m * W + t1] = a1 * scale;
+          mel_s[m * MP + t0] = a0 * scale;
+          if (t1 < W) mel_s[m * MP + t1] = a1 * scale;
         }
       }
       if (((LOG2N - 3 + 2) / 3) < 2) group_sync(grp);      // fewer than two ping-pong stages: the next pair would overwrite z
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         const int tt = i / n_mels, m = i - tt * n_mels, t = t_a + tt;
         if (t < W) {
           const int64_t idx = (a0 + (int64_t)hop * t) / p.cache_g;
-          mel_s[m * W + t] = __ldg(p.cache + idx * n_mels + m) * scale;
+          mel_s[m * MP + t] = __ldg(p.cache + idx * n_mels + m) * scale;
         }
       }
     }
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       for (int i = tid; i < W * n_mels; i += kThreads) {
         const int t = i / n_mels, m = i - t * n_mels;
         const int64_t f = (int64_t)b * W + t;
-        if (f < p.n_cache) p.cache[f * n_mels + m] = mel_s[m * W + t];
+        if (f < p.n_cache) p.cache[f * n_mels + m] = mel_s[m * MP + t];
       }
       __syncthreads();
       continue;
@@ -364,15 +380,15 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     // ---- power_to_db(ref=max, amin, top_db)
     const int total = n_mels * W;
     float m = 0.0f;
-    for (int i = tid; i < total; i += kThreads) m = fmaxf(m, mel_s[i]);
+    const uint32_t magicW = 0xffffffffu / (uint32_t)W + 1u;             // i / W == umulhi(i, magicW) for i, W < 2^16
+    for (int i = tid; i < total; i += kThreads) m = fmaxf(m, mel_s[i + (int)__umulhi((uint32_t)i, magicW) * (MP - W)]);
     const float ref = block_max(m, red, tid);
     // explicit _rn ops: an FMA contraction here would make the per-clip maximum land at +-1 ulp instead of 0 dB
     const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(kAmin, ref)));
     float* __restrict__ o = p.out.ptr + (int64_t)b * p.out.stride + p.out.off;
-    const uint32_t magicW = 0xffffffffu / (uint32_t)W + 1u;             // i / W == umulhi(i, magicW) for i, W < 2^16
     for (int i = tid; i < total; i += kThreads) {
-      float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i]))), ref_db);
       const int m = (int)__umulhi((uint32_t)i, magicW);
+      float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i + m * (MP - W)]))), ref_db);
       o[m * p.out.pitch + (i - m * W)] = fmaxf(v, -kTopDb);
     }
     __syncthreads();
@@ -448,10 +464,10 @@ int ww_launch_logmel_stream(ww_ctx* c, const void* clips, int pcm16, int64_t cli
   p.window = c->d_window; p.twiddle = c->d_twiddle;
   p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off; p.mel_w = c->d_mel_w;
   const int N = c->cfg.n_fft;
-  const int npad = N + (N >> 5) + 8;
+  const int npad = N + 8;
   size_t smem = (size_t)(kGroups * 2 * npad + N + N / 8) * sizeof(float2) +
                 (size_t)p.mel_nnz * sizeof(float) + (size_t)3 * p.n_mels * sizeof(int) +
-                (size_t)p.n_mels * p.W * sizeof(float) + 16;
+                (size_t)p.n_mels * (p.W | 1) * sizeof(float) + 16;
   if (smem > 227 * 1024) { c->set_error("ww_logmel: configuration exceeds shared memory"); return WW_ERR_INVALID; }
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
