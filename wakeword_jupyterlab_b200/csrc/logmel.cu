@@ -151,6 +151,55 @@ __device__ __forceinline__ void stockham_stage(const float2* zin, float2* zout, 
   group_sync(grp);
 }
 
+// (|X_even[k]|^2, |X_odd[k]|^2) of the two real frames packed into one complex FFT, from Z[k] and Z[N-k]
+__device__ __forceinline__ float2 pair_power(float2 zk, float2 zn) {
+  const float ar = zk.x + zn.x, ai = zk.y - zn.y;
+  const float br = zk.y + zn.y, bi = zk.x - zn.x;
+  return make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+}
+
+// LAST Stockham stage fused with the Hermitian split, for N / R == 2 kGT (two butterflies per thread, NS == N / R):
+// thread t takes the butterflies j and NS - j (t = 0: the two self-paired ones, 0 and NS / 2), so the outputs
+// X[j + r NS] and their mirror bins X[N - (j + r NS)] = X[(NS - j) + (R-1-r) NS] are in the SAME thread: the spectrum is
+// never stored, only the powers zout[k] = (|X_even[k]|^2, |X_odd[k]|^2), k <= N/2.
+template <int N, int R, int NS, int NSPREV>
+__device__ __forceinline__ void last_stage_power(const float2* zin, float2* zout, const float2* __restrict__ ts, int gt, int grp) {
+  static_assert(N / R == 2 * kGT && NS == N / R && NSPREV >= 32, "fused last stage: two butterflies per thread");
+  const bool t0 = gt == 0;
+  const int j0 = gt, j1 = t0 ? NS / 2 : NS - gt;
+  float2 a[R], b[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { a[r] = zin[j0 + r * NS]; b[r] = zin[j1 + r * NS]; }
+  {
+    const float2 wa1 = ts[j0], wb1 = ts[j1];
+    float2 wa = wa1, wb = wb1;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+      a[r] = cmul(a[r], wa);
+      b[r] = cmul(b[r], wb);
+      if (r + 1 < R) { wa = cmul(wa, wa1); wb = cmul(wb, wb1); }
+    }
+  }
+  dftR<R>(a);
+  dftR<R>(b);
+  // a[r] = X[j0 + r NS], b[r] = X[j1 + r NS]
+#pragma unroll
+  for (int r = 0; r < R / 2; ++r) {
+    // t > 0: mirror of j0 + r NS is j1 + (R-1-r) NS and vice versa;  t = 0: 0 + r NS <-> 0 + ((R-r) % R) NS, NS/2 + r NS <-> NS/2 + (R-1-r) NS
+    const float2 ma = t0 ? a[(R - r) % R] : b[R - 1 - r];
+    const float2 mb = t0 ? b[R - 1 - r] : a[R - 1 - r];
+    zout[j0 + r * NS] = pair_power(a[r], ma);
+    zout[j1 + r * NS] = pair_power(b[r], mb);
+  }
+  if (t0) zout[N / 2] = pair_power(a[R / 2], a[R / 2]);      // Nyquist bin (its own mirror)
+  group_sync(grp);
+}
+
+template <int LOG2N> __host__ __device__ constexpr bool fused_last_stage() {
+  constexpr int rem = LOG2N - 3, lg = rem % 3 == 0 ? 3 : rem % 3;
+  return rem > 0 && ((1 << LOG2N) >> lg) == 2 * kGT;
+}
+
 // remaining stages after the first radix-8 one: radices 8, 8, ..., then 4 or 2; compact twiddle tables
 // (stage table k -> T[k * N / (NS R)]) are packed one after the other in `twc`; the last stage (step 1) reads `tw`.
 // returns the buffer that holds the spectrum
@@ -160,7 +209,12 @@ __device__ __forceinline__ float2* run_stages(float2* zin, float2* zout, const f
     constexpr int LG = REM >= 3 ? 3 : REM;
     constexpr int R = 1 << LG;
     constexpr int TSTEP = N / (NS * R);
-    stockham_stage<N, R, NS, NSPREV>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+    if constexpr (REM == LG && N / R == 2 * kGT) {
+      last_stage_power<N, R, NS, NSPREV>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+      return zout;                                          // holds the POWERS of bins 0 .. N/2
+    } else {
+      stockham_stage<N, R, NS, NSPREV>(zin, zout, TSTEP > 1 ? twc + OFF : tw, gt, grp);
+    }
     return run_stages<N, NS * R, REM - LG, OFF + (TSTEP > 1 ? NS : 0), NS>(zout, zin, tw, twc, gt, grp);
   } else {
     static_assert(NSPREV >= 32, "the last stage must leave the spectrum unskewed");
@@ -320,17 +374,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
       // Each stage reads one buffer and writes the other.  The mel projection of the previous pair read the buffer the
       // spectrum ends in; it is next written two barriers from here at the earliest, so no barrier is needed after it.
       float2* z = run_stages<N, 8, LOG2N - 3, 0, 1>(za, zb, tw, twc, gt, grp);
-      // ---- Hermitian split + power, in place: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2.
-      // Bin k reads z[k] and z[N-k] and is the only reader of both, so no sync is needed before the store.
+      // ---- Hermitian split + power: z[k] <- (|X_even[k]|^2, |X_odd[k]|^2) for k <= N/2: done inside the last stage
+      // when that stage has two butterflies per thread (n_fft 2048 and 1024), else in place here (bin k reads z[k] and
+      // z[N-k] and is the only reader of both, so no sync is needed before the store).
+      if constexpr (!fused_last_stage<LOG2N>()) {
 #pragma unroll
-      for (int k = gt; k < NBINS; k += kGT) {
-        const float2 zk = z[k];
-        const float2 zn = z[(N - k) & (N - 1)];
-        const float ar = zk.x + zn.x, ai = zk.y - zn.y;
-        const float br = zk.y + zn.y, bi = zk.x - zn.x;
-        z[k] = make_float2(0.25f * (ar * ar + ai * ai), 0.25f * (br * br + bi * bi));
+        for (int k = gt; k < NBINS; k += kGT) z[k] = pair_power(z[k], z[(N - k) & (N - 1)]);
+        group_sync(grp);
       }
-      group_sync(grp);
       // ---- banded mel projection: 2 lanes per band, both frames at once
       for (int mb = 0; mb < n_mels; mb += kGT / 2) {
         const int m = mb + (gt >> 1), half = gt & 1;
