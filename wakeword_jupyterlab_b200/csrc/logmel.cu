@@ -382,14 +382,15 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         for (int k = gt; k < NBINS; k += kGT) z[k] = pair_power(z[k], z[(N - k) & (N - 1)]);
         group_sync(grp);
       }
-      // ---- banded mel projection: 2 lanes per band, both frames at once
-      for (int mb = 0; mb < n_mels; mb += kGT / 2) {
-        const int m = mb + (gt >> 1), half = gt & 1;
+      // ---- banded mel projection: 4 lanes per band (4 consecutive bins = one 32-byte run per band and load: fewer
+      // bank conflicts than 2 x 16 bands per warp), both frames at once
+      for (int mb = 0; mb < n_mels; mb += kGT / 4) {
+        const int m = mb + (gt >> 2), q = gt & 3;
         float a0 = 0.0f, a1 = 0.0f;
         if (m < n_mels) {
           const int st = mst[m], len = mst[n_mels + m], off = mst[2 * n_mels + m];
 #pragma unroll 4
-          for (int i = half; i < len; i += 2) {
+          for (int i = q; i < len; i += 4) {
             const float w = melw[off + i];
             const float2 pw = z[st + i];
             a0 = fmaf(w, pw.x, a0);
@@ -398,7 +399,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         }
         a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-        if (m < n_mels && half == 0) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        if (m < n_mels && q == 0) {
           mel_s[m * MP + t0] = a0 * scale;
           if (t1 < W) mel_s[m * MP + t1] = a1 * scale;
         }
