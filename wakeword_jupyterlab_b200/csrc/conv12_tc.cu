@@ -10,7 +10,7 @@
 // pixels (3x3 halo), i.e. NM = ceil(NL / 128) conv1 M-tiles.  Warp roles (23 warps):
 //   warp 0      loader: conv1/conv2 weights once (resident, 76 KB), then one 1-D bulk copy per item (3-stage ring);
 //   warp 1      conv1 MMA issuer: per M-tile two K = 16 steps,  D1[128 px, 64] = A1[128 px, 32] x [W1_hi ; W1_lo]^T
-//               with A1 row = (9 taps as fp16 hi | 9 taps as fp16 lo)  -- K = 9 padded to 16, twice;
+//               with A1 row = (taps 0-7 hi | tap 8 hi, tap 8 lo, 0.. | taps 0-7 lo | 0..)  -- K = 32;
 //   warp 2      conv2 MMA issuer (tile 0, then tile 1: the epilogue of one tile overlaps the MMAs of the other; the 18
 //               MMAs of a tile are straight-line code inside one elect.sync region): per 3x3 tap and 16-channel k-slice
 //                 D2[:, 0:128] += A2 x [W2_hi ; W2_lo]^T   (N = 128; WW_CONV_FP16: N = 64, W2_hi only)
@@ -35,7 +35,7 @@ namespace {
 
 constexpr int C12_THREADS = 23 * 32;
 constexpr int W2_BYTES = 9 * 4 * 128 * 16;   // [tap][kc 4][n' 128 = 64 hi + 64 lo][8 fp16]
-constexpr int W1_BYTES = 4 * 64 * 16;        // [kc 4][n' 64 = 32 hi + 32 lo][8 fp16]; kc 2,3 repeat kc 0,1 (for the lo taps)
+constexpr int W1_BYTES = 4 * 64 * 16;        // [kc 4][n' 64 = 32 hi + 32 lo][8 fp16]; K layout: see the im2col warps
 constexpr int A1_SLOT_BYTES = 4 * 128 * 16;  // one conv1 M-tile: [kc 4][row 128][8 fp16]
 constexpr int A1_SLOTS = 4;
 constexpr int P_STAGES = 3;
@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     }
     fence_barrier_init();
   }
+  for (int i = tid * 16; i < A1_SLOTS * A1_SLOT_BYTES; i += C12_THREADS * 16)   // zero K padding of the conv1 A ring
+    *reinterpret_cast<uint4*>(a1 + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
   if (warp == 1) tmem_alloc(tmem_slot, 512);      // D1 ring: columns 64 s (s < 4); D2 tiles: columns 256 + 128 t
   tc_fence_before();
   __syncthreads();
@@ -225,11 +228,12 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
           hi[k] = pack_f16(v[2 * k], v[2 * k + 1]);
           lo[k] = pack_f16(v[2 * k] - h_lo(hi[k]), v[2 * k + 1] - h_hi(hi[k]));
         }
+        // K chunks of a row: [hi taps 0-7 | hi tap 8, lo tap 8, 0 x6 | lo taps 0-7 | 0 x8]; the zeros were written once
+        // at kernel start, so a row costs 16 + 4 + 16 bytes of shared-memory stores (the kernel is shared-memory bound)
         unsigned char* dst = a1 + s * A1_SLOT_BYTES + r * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(dst + 128 * 16) = make_uint4(hi[4], 0u, 0u, 0u);
+        *reinterpret_cast<uint32_t*>(dst + 128 * 16) = (hi[4] & 0xffffu) | (lo[4] << 16);
         *reinterpret_cast<uint4*>(dst + 2 * 128 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(dst + 3 * 128 * 16) = make_uint4(lo[4], 0u, 0u, 0u);
         fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive_warp(a1_full + s, lane);
       }
@@ -373,11 +377,11 @@ int ww_conv12_tc_prepare(ww_ctx* c) {
     std::vector<uint16_t> s((size_t)W1_BYTES / 2, 0);
     const float sc = weight_scale(w);
     c->w1_inv_scale = 1.0f / sc;
-    for (int kc = 0; kc < 4; ++kc)                   // K = [taps 0..7 | tap 8, 0 x7] for the hi taps, again for the lo taps
+    for (int kc = 0; kc < 3; ++kc)                   // K = [taps 0..7 (x hi taps) | tap 8, tap 8, 0 x6 (x hi8, lo8) | taps 0..7 (x lo taps) | 0 x8]
       for (int n = 0; n < 32; ++n)
         for (int e = 0; e < 8; ++e) {
-          const int tap = (kc & 1) * 8 + e;
-          if (tap >= 9) continue;
+          if (kc == 1 && e >= 2) continue;
+          const int tap = kc == 1 ? 8 : e;
           const float v = w[(size_t)n * 9 + tap] * sc;
           const uint16_t hi = f2h(v), lo = f2h(v - h2f(hi));
           s[((size_t)kc * 64 + n) * 8 + e] = hi;
