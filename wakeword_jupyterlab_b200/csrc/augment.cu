@@ -64,12 +64,12 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// two independent block reductions at once (sum or max); ends with every thread holding both results
+// two independent block reductions at once (sum or max); ends with every thread holding both results.
+// Every call site has its OWN 64-float scratch row, rewritten one clip (several barriers) later, so one barrier suffices.
 template <bool MAX>
 __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, int tid) {
   a = MAX ? warp_max(a) : warp_sum(a);
   b = MAX ? warp_max(b) : warp_sum(b);
-  __syncthreads();
   if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = b; }
   __syncthreads();
   const float ra = red[tid & 31], rb = red[32 + (tid & 31)];       // kThreads / 32 == 32 partials each
@@ -80,7 +80,6 @@ __device__ __forceinline__ void block_reduce2(float& a, float& b, float* red, in
 // block maximum of non-negative floats (they order like their bit patterns): one redux.sync per warp, twice
 __device__ __forceinline__ float block_max_nonneg(float v, float* red, int tid) {
   const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
-  __syncthreads();
   if ((tid & 31) == 0) red[tid >> 5] = __uint_as_float(w);
   __syncthreads();
   return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(red[tid & 31])));   // kThreads / 32 == 32 partials
@@ -166,7 +165,7 @@ __device__ __forceinline__ void taps4(const float4* __restrict__ kr4, const floa
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[64];
+  __shared__ float red4[4][64];                      // one scratch row per reduction site
   __shared__ ClipPrm prm[2];
   const int tid = threadIdx.x;
   const int N = p.N;
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       m = fmaxf(m, fabsf(o[e]));
     }
     if (flags & WW_AUG_NORM_IN) {
-      m = block_max_nonneg(m, red, tid);
+      m = block_max_nonneg(m, red4[0], tid);
       if (m > 0.0f) {
         const ClipDiv dv = make_clip_div(m);
 #pragma unroll
@@ -323,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
         sc = fmaf(o[e], o[e], sc);
         sn = fmaf(n[e], n[e], sn);
       }
-      block_reduce2<false>(sc, sn, red, tid);
+      block_reduce2<false>(sc, sn, red4[1], tid);
       const float scalarclean = target / sqrtf(sc / (float)N), scalarnoise = target / sqrtf(sn / (float)N);
       // the reference re-measures both RMS values after scaling (audiolib.py:60,65)
       float sc2 = 0.0f, sn2 = 0.0f;
@@ -334,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
         sc2 = fmaf(o[e], o[e], sc2);
         sn2 = fmaf(n[e], n[e], sn2);
       }
-      block_reduce2<false>(sc2, sn2, red, tid);
+      block_reduce2<false>(sc2, sn2, red4[2], tid);
       const float rc2 = sqrtf(sc2 / (float)N), rn2 = sqrtf(sn2 / (float)N);
       const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);          // audiolib.py:68 (sqrt quirk kept)
 #pragma unroll
@@ -349,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       float mo = 0.0f;
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) mo = fmaxf(mo, fabsf(o[e]));
-      mo = block_max_nonneg(mo, red, tid);
+      mo = block_max_nonneg(mo, red4[3], tid);
       if (mo > 0.0f) {
         const ClipDiv dv = make_clip_div(mo);
 #pragma unroll
