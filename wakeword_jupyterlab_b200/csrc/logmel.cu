@@ -337,33 +337,46 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
     // valid sample indices relative to x: [0, limit)
     const long long left = (long long)p.n_total - (long long)b * p.clip_stride;
     const unsigned limit = p.mode == 1 ? (unsigned)(left < (1ll << 30) ? (left > 0 ? left : 0) : (1ll << 30)) : (unsigned)n_samples;
+    // raw samples of this thread's first-stage inputs (8 per frame); fetched one pair AHEAD, before the mel projection of
+    // the current pair, so the global-load latency hides behind it
+    float ra[8], rc[8];
+    auto fetch = [&](int e) {
+      constexpr int NB = N >> 3;
+      const int pr = e < pe_lo ? e : pe_hi + (e - pe_lo);
+      const int t1 = 2 * pr + 1;
+      const int s0 = f_hop * (2 * pr) + f_off;
+      const int s1 = (t1 < W) ? f_hop * t1 + f_off : (1 << 30);
+      if (NB >= kGT || gt < NB) {
+        if (s0 >= 0 && t1 < W && (unsigned)(s1 + N) <= limit) {
+          // both frames lie inside the clip (all but the first and last pair or two): no bounds checks
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int n = gt + r * NB;
+            ra[r] = ldin(x, s0 + n);
+            rc[r] = ldin(x, s1 + n);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int n = gt + r * NB;
+            const int i0 = s0 + n, i1 = s1 + n;
+            ra[r] = ((unsigned)i0 < limit) ? ldin(x, i0) : 0.0f;
+            rc[r] = ((unsigned)i1 < limit) ? ldin(x, i1) : 0.0f;
+          }
+        }
+      }
+    };
+    if (grp < n_do) fetch(grp);
     for (int e = grp; e < n_do; e += kGroups) {
       const int pr = e < pe_lo ? e : pe_hi + (e - pe_lo);
       const int t0 = 2 * pr, t1 = 2 * pr + 1;
-      const int s0 = f_hop * t0 + f_off;
-      const int s1 = (t1 < W) ? f_hop * t1 + f_off : (1 << 30);
-      // ---- first stage: radix 8 straight from global (framing + window), NS = 1
+      // ---- first stage: radix 8 on the prefetched samples (framing + window), NS = 1
       {
         constexpr int NB = N >> 3;
         if (NB >= kGT || gt < NB) {
           float2 v[8];
-          if (s0 >= 0 && t1 < W && (unsigned)(s1 + N) <= limit) {
-            // both frames lie inside the clip (all but the first and last pair or two): no bounds checks
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int n = gt + r * NB;
-              v[r] = make_float2(wv[r] * ldin(x, s0 + n), wv[r] * ldin(x, s1 + n));
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int n = gt + r * NB;
-              const int i0 = s0 + n, i1 = s1 + n;
-              const float a = ((unsigned)i0 < limit) ? ldin(x, i0) : 0.0f;
-              const float c = ((unsigned)i1 < limit) ? ldin(x, i1) : 0.0f;
-              v[r] = make_float2(wv[r] * a, wv[r] * c);
-            }
-          }
+          for (int r = 0; r < 8; ++r) v[r] = make_float2(wv[r] * ra[r], wv[r] * rc[r]);
           dft8(v);
           const int wb = gt * 8, sw = (gt >> 1) & 7;       // lay<1>(8 gt + r) = 8 gt + (r ^ ((gt >> 1) & 7))
 #pragma unroll
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
         for (int k = gt; k < NBINS; k += kGT) z[k] = pair_power(z[k], z[(N - k) & (N - 1)]);
         group_sync(grp);
       }
+      if (e + kGroups < n_do) fetch(e + kGroups);
       // ---- banded mel projection: 4 lanes per band (4 consecutive bins = one 32-byte run per band and load: fewer
       // bank conflicts than 2 x 16 bands per warp), both frames at once
       for (int mb = 0; mb < n_mels; mb += kGT / 4) {
