@@ -192,7 +192,7 @@ int ensure_pool(ww_ctx* c, int64_t B) {
   if ((rc = ensure_buffer(c, (void**)&c->ws_pool_part, &dummy, (size_t)cap * part_cap * 128 * 4))) return rc;
   for (int i = 0; i < 2; ++i) {
     dummy = 0;
-    if ((rc = ensure_buffer(c, (void**)&c->ws_h[i], &dummy, (size_t)cap * c->cfg.hidden_size * 4))) return rc;
+    if ((rc = ensure_buffer(c, (void**)&c->ws_h[i], &dummy, (size_t)cap * std::max(c->cfg.hidden_size, 128) * 4))) return rc;
   }
   c->pool_cap_clips = cap;
   c->pool_part_cap = (int)part_cap;

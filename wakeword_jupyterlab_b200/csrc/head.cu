@@ -14,6 +14,8 @@
 // partial sums (fixed order) / (H*W).  A last small kernel does Linear + softmax + threshold (one warp per clip).
 #include "ctx.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int TM = 64, TN = 64, KC = 32, kThreads = 256;
@@ -127,6 +129,112 @@ __global__ void __launch_bounds__(kThreads, 3) gated_dense_kernel(DenseParams p)
   }
 }
 
+// ---- pipelined variant (K % 32 == 0, H % 64 == 0, plain [B][K] input): the same tile shape and the same per-thread
+// accumulation order (bit-identical results), but both tiles arrive by cp.async into a two-deep ring, so the L2 latency of
+// chunk i+1 hides behind the FMAs of chunk i (one barrier per chunk).  x tile kept [clip][k] (pitch 36 floats: the two
+// clip groups of a warp read banks 16 apart), read as one 128-bit load per clip and four k.
+constexpr int XP = KC + 4;
+constexpr size_t kPipeSmem = 2 * ((size_t)TM * XP + (size_t)KC * 3 * TN) * sizeof(float);
+
+__device__ __forceinline__ void cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 3) gated_dense_pipe_kernel(DenseParams p) {
+  extern __shared__ __align__(16) float hs[];
+  float* xs = hs;                                       // [2][TM][XP]
+  float* ws = hs + 2 * TM * XP;                         // [2][KC][3][TN]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int b0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+
+  auto load_chunk = [&](int k0, int buf) {
+    float* xb = xs + buf * TM * XP;
+    float* wb = ws + buf * KC * 3 * TN;
+    for (int i = tid; i < TM * (KC / 4); i += kThreads) {            // 64 clips x 8 pieces of 16 bytes
+      const int clip = i >> 3, q = i & 7;
+      const int b = min(b0 + clip, p.B - 1);                           // rows past the batch repeat the last clip (never stored)
+      cp16(xb + clip * XP + q * 4, p.x + (size_t)b * p.K + k0 + q * 4);
+    }
+    for (int i = tid; i < KC * 3 * (TN / 4); i += kThreads) {          // 96 rows x 16 pieces
+      const int row = i >> 4, q = i & 15;                              // row = k * 3 + g
+      cp16(wb + row * TN + q * 4, p.wt + ((size_t)k0 * 3 + row) * p.H + j0 + q * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  f32x2 acc2[3][4][2];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc2[g][c][0] = 0ull; acc2[g][c][1] = 0ull; }
+
+  const int n_chunks = p.K / KC;
+  load_chunk(0, 0);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                     // chunk ch landed for everyone; everyone finished chunk ch-1
+    if (ch + 1 < n_chunks) load_chunk((ch + 1) * KC, (ch + 1) & 1);
+    const float* xb = xs + (ch & 1) * TM * XP + ty * 4 * XP;
+    const float* wb = ws + (ch & 1) * KC * 3 * TN + tx * 4;
+#pragma unroll 2
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      float4 xv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xv[c] = *reinterpret_cast<const float4*>(xb + c * XP + k4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        f32x2 xx[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float v = kk == 0 ? xv[c].x : kk == 1 ? xv[c].y : kk == 2 ? xv[c].z : xv[c].w;
+          xx[c] = pack2(v, v);
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wb + ((k4 + kk) * 3 + g) * TN);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            ffma2(acc2[g][c][0], xx[c], wv.x);
+            ffma2(acc2[g][c][1], xx[c], wv.y);
+          }
+        }
+      }
+    }
+  }
+  // ---- gate epilogue: h = sigmoid(o) * tanh(sigmoid(i) * tanh(g))
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int b = b0 + ty * 4 + c;
+    if (b >= p.B) continue;
+    float a[3][4];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) { unpack2(acc2[g][c][0], a[g][0], a[g][1]); unpack2(acc2[g][c][1], a[g][2], a[g][3]); }
+    float h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + tx * 4 + u;
+      const float gi = a[0][u] + __ldg(p.bias + j);
+      const float gg = a[1][u] + __ldg(p.bias + p.H + j);
+      const float go = a[2][u] + __ldg(p.bias + 2 * p.H + j);
+      h[u] = sigmoidf_acc(go) * tanhf(sigmoidf_acc(gi) * tanhf(gg));
+    }
+    *reinterpret_cast<float4*>(p.out + (size_t)b * p.H + j0 + tx * 4) = make_float4(h[0], h[1], h[2], h[3]);
+  }
+}
+
+// finishes the global mean: x0[b][k] = (sum of the conv kernel's per-group partials, fixed order) * scale
+__global__ void pool_finish_kernel(const float* __restrict__ part, int n_part, float scale, float* __restrict__ x0, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i >> 7;
+    const int k = (int)(i & 127);
+    const float* pp = part + (b * n_part) * 128 + k;
+    float v = 0.0f;
+    for (int t = 0; t < n_part; ++t) v += __ldg(pp + (size_t)t * 128);
+    x0[i] = v * scale;
+  }
+}
+
 struct FcParams {
   const float* h;          // [B][H]
   const float* fc_w;       // [n_classes][H]
@@ -171,14 +279,29 @@ int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decis
   const int H = c->cfg.hidden_size;
   ProfScope prof(c, WW_STAGE_HEAD, st);
   const float* x = c->ws_pool_part;
+  const bool pipe = (H % TN) == 0;                      // K is 128 or H: multiples of KC whenever H % 64 == 0
+  if (pipe) {
+    static bool configured = false;
+    if (!configured) {
+      WW_CHECK(c, cudaFuncSetAttribute(gated_dense_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
+      configured = true;
+    }
+    // ws_h[1] (>= 128 floats per clip) holds the finished mean until layer 1 overwrites it with its own output
+    const int64_t n = (int64_t)B * 128;
+    pool_finish_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, st>>>(
+        c->ws_pool_part, c->n_pool_part, 1.0f / (float)(c->cfg.n_mels * c->W), c->ws_h[1], n);
+    WW_LAUNCH_CHECK(c);
+    x = c->ws_h[1];
+  }
   for (int l = 0; l < c->cfg.num_layers; ++l) {
     DenseParams p;
-    p.x = x; p.n_part = (l == 0) ? c->n_pool_part : 0;
+    p.x = x; p.n_part = (l == 0 && !pipe) ? c->n_pool_part : 0;
     p.x_scale = 1.0f / (float)(c->cfg.n_mels * c->W);
     p.wt = c->d_head_wt[l]; p.bias = c->d_head_b[l];
     p.out = c->ws_h[l & 1]; p.B = B; p.K = (l == 0) ? 128 : H; p.H = H;
     dim3 grid((B + TM - 1) / TM, (H + TN - 1) / TN);
-    gated_dense_kernel<<<grid, kThreads, 0, st>>>(p);
+    if (pipe) gated_dense_pipe_kernel<<<grid, kThreads, kPipeSmem, st>>>(p);
+    else gated_dense_kernel<<<grid, kThreads, 0, st>>>(p);
     WW_LAUNCH_CHECK(c);
     x = p.out;
   }
