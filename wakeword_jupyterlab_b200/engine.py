@@ -38,9 +38,27 @@ class AugBatch:
         return [np.ascontiguousarray(getattr(self, n), dtype=dt) for n, dt in self._FIELDS]
 
     def ratios(self):
+        """Distinct (orig, new) resample ratios of the clips that have the speed stage (what ww_prepare_resample needs).
+        Linear-time for the usual case of small non-negative integers (a bincount per field, no Python loop over the
+        clips), and remembered per batch object: the arrays are host-drawn once."""
+        cached = getattr(self, "_ratios", None)
+        if cached is not None and cached[0] == (id(self.flags), id(self.rs_orig), id(self.rs_new)):
+            return cached[1]
         f = np.asarray(self.flags)
         sel = (f & _lib.AUG_SPEED) != 0
-        return sorted(set(zip(np.asarray(self.rs_orig)[sel].tolist(), np.asarray(self.rs_new)[sel].tolist())))
+        o, n = np.asarray(self.rs_orig)[sel], np.asarray(self.rs_new)[sel]
+        if o.size == 0:
+            out = []
+        elif o.min() >= 0 and n.min() >= 0 and o.max() < 4096 and n.max() < 4096:
+            out = []
+            for nv in np.flatnonzero(np.bincount(n)):            # usually a single value (new = 100)
+                for ov in np.flatnonzero(np.bincount(o[n == nv])):
+                    out.append((int(ov), int(nv)))
+            out.sort()
+        else:
+            out = sorted(set(zip(o.tolist(), n.tolist())))
+        object.__setattr__(self, "_ratios", ((id(self.flags), id(self.rs_orig), id(self.rs_new)), out))
+        return out
 
 
 def _cfg_key(ac, mc, threshold, conv_mode, n_samples, chunk):
