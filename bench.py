@@ -291,6 +291,34 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
                                      "seconds_per_hour_of_audio": ms * 1e-3, "x_realtime": 3600.0 / (ms * 1e-3)}}))
 
 
+class numa_local:
+    """Context manager: run the body on the CPUs NVML names as local to `dev` (so host buffers allocated and first
+    touched inside land on that NUMA node), then restore the affinity.  Best effort: silently a no-op without NVML."""
+
+    def __init__(self, dev):
+        self.dev, self.old = dev, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            self.old = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+        except Exception as e:      # noqa: BLE001
+            sys.stderr.write(f"[bench] NUMA binding skipped: {e}\n")
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except OSError:
+                pass
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -399,11 +427,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         # host buffers hold the clips as they are on disk: int16 PCM (ww_score_host_pcm16; --e2e-fp32 for fp32 buffers)
-        h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32 if args.e2e_fp32 else torch.int16, pin_memory=True)
-        h_clips.copy_(clips if args.e2e_fp32 else clips_pcm)
-        h_out = (torch.empty((B, 2), dtype=torch.float32, pin_memory=True),
-                 torch.empty((B,), dtype=torch.float32, pin_memory=True),
-                 torch.empty((B,), dtype=torch.uint8, pin_memory=True))
+        with numa_local(dev):     # pinned pages are first-touched on the NUMA node next to this rank's GPU
+            h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32 if args.e2e_fp32 else torch.int16, pin_memory=True)
+            h_clips.copy_(clips if args.e2e_fp32 else clips_pcm)
+            h_out = (torch.empty((B, 2), dtype=torch.float32, pin_memory=True),
+                     torch.empty((B,), dtype=torch.float32, pin_memory=True),
+                     torch.empty((B,), dtype=torch.uint8, pin_memory=True))
         for _ in range(2):
             eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
         barrier()
