@@ -462,7 +462,10 @@ def main():
     tp = os.path.join(ROOT, "profiles", "conv3_traffic_bytes_per_launch.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(conv_mode)
+            tj = json.load(open(tp))
+            traffic = tj.get(conv_mode)
+            if traffic is not None:     # measured on a launch of `clips_per_profiled_launch` clips; DRAM traffic is per clip
+                traffic = traffic / tj.get("clips_per_profiled_launch", 4096) * clips_per_launch
         except Exception:
             traffic = None
     roof = {"bound": "tensor", "kernel": "conv3+relu+mean (" + conv_mode + ")", "achieved": achieved, "peak": peak,
