@@ -643,6 +643,10 @@ int ww_score_stream_pcm16(ww_ctx* c, const int16_t* audio, int64_t T, int hop_sa
   return stream_entry(c, audio, 1, T, hop_samples, prob1, decision, n_win, stream);
 }
 
+constexpr double kH2DRamp = 1.3;     // growth of the host->device pieces (WW_H2D_RAMP overrides, for tuning)
+constexpr int kH2DCap = 8192;        // largest piece on the host path (<= the work chunk)
+constexpr int kH2DFirst = 384;       // clips in the first piece (its copy is exposed)
+
 static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const float* bank_dev, int bank_rows,
                            int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                            float* prob1_host, uint8_t* decision_host, int B) {
@@ -673,18 +677,23 @@ static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const f
   }
   if ((rc = ww_prepare_weights(c, st))) return rc;
   // Two streams: the copy engine moves piece i+1 host->device while the SMs score piece i.  Pieces ramp up
-  // geometrically (512, 1024, ... clips, then full chunks) so that only a fraction of a millisecond of copy is exposed
+  // geometrically (384, 512, 768, 1024, ... clips up to the work chunk) so that only a fraction of a millisecond of copy is exposed
   // before the first kernel starts; copying a clip is faster than scoring it, so later copies stay ahead.
   if (!c->copy_stream) WW_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   char* d_in = (char*)c->d_host_in;
   const char* h_in = (const char*)clips_host;
   std::vector<std::pair<int, int>> pieces;          // (first clip, clips)
-  const int piece_cap = std::min(c->chunk, 4096);    // host path: finer pieces keep the copy / compute overlap tight (measured)
-  for (int b0 = 0, sz = std::min(512, piece_cap); b0 < B; ) {
+  // Piece k+1 is copied while piece k is scored, so it may only be as much larger as copying a clip is faster than scoring
+  // it (~1.3x with int16 PCM over PCIe 5); a doubling ramp stalls the SMs at every step of the ramp (measured: 2 ms).
+  static const int cap_env = getenv("WW_H2D_CAP") ? std::max(64, atoi(getenv("WW_H2D_CAP"))) : kH2DCap;
+  const int piece_cap = std::min(c->chunk, cap_env);
+  static const double ramp = getenv("WW_H2D_RAMP") ? std::max(1.05, atof(getenv("WW_H2D_RAMP"))) : (double)kH2DRamp;
+  static const int first = getenv("WW_H2D_FIRST") ? std::max(64, atoi(getenv("WW_H2D_FIRST"))) : kH2DFirst;
+  for (int b0 = 0, sz = std::min(first, piece_cap); b0 < B; ) {
     const int nb = std::min(sz, B - b0);
     pieces.emplace_back(b0, nb);
     b0 += nb;
-    sz = std::min(2 * sz, piece_cap);
+    sz = std::min((((int)(sz * ramp) + 127) / 128) * 128, piece_cap);
   }
   const int n_pieces = (int)pieces.size();
   while ((int)c->copy_events.size() < n_pieces) {
