@@ -10,14 +10,14 @@ rectangular-window spectrum (which lets all frames of a clip be overlapping VIEW
 or has to be multiplied in before the split.
 
 This is test tooling: it imports the CPU oracle and never runs in the product path.
-    python tools/gemm_fft_probe.py
+    python tests/probes/gemm_fft_probe.py
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 from oracle import logmel as LM  # noqa: E402
 from oracle import recipe as R  # noqa: E402
 

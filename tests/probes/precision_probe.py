@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """CPU probe: which operand of conv2 / conv3 needs how many bits to stay inside the 1e-4 logit gate?
 
-    python tools/precision_probe.py
+    python tests/probes/precision_probe.py
 
 Emulates the tensor-core operand roundings in torch (fp64 accumulate) on the committed golden weights and the recipe
 clips, and prints the logit error (max |d| / max |ref|) of every scheme in DESIGN.md section 4.  Result: activation
@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 from oracle import augment as A, logmel as LM, model as M, recipe as R   # noqa: E402
 
 f16 = lambda x: x.to(torch.float16).to(torch.float32)                    # noqa: E731
@@ -61,7 +61,7 @@ def pooled(x, sd, scheme):
 
 def main():
     torch.set_num_threads(8)
-    golden = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+    golden = os.path.join(os.path.dirname(__file__), "..", "golden")
     clips = R.make_clips(32, seed=1234)
     norm = np.stack([A.normalize_audio(c) for c in clips]).astype(np.float32)
     feats = torch.from_numpy(LM.audio_to_mel_batch(norm)[:, None])

@@ -2,7 +2,7 @@
 """CPU probe for the round-2 tensor-core TRAINING step: which operand of the conv backward GEMMs
 needs how many fp16 terms to keep the gradients inside the 1e-4 gate of tests/test_train_gpu.py?
 
-    python tools/train_precision_probe.py
+    python tests/probes/train_precision_probe.py
 
 The conv stack's backward is six GEMMs: dgrad3 / dgrad2 (dY x W, per pixel: rounding errors of dY are independent from
 pixel to pixel, those of W are the same everywhere) and wgrad3 / wgrad2 / wgrad1 (dY x A summed over ALL pixels and clips:
@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn.grad import conv2d_input, conv2d_weight
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 from oracle import augment as A, logmel as LM, recipe as R   # noqa: E402
 
 
