@@ -111,6 +111,36 @@ def synth_clips_device(n, device, seed):
     return pcm.to(torch.float32) / 32768.0, pcm
 
 
+def seeded_state_dict(hidden=256, layers=2, n_classes=2, seed=0):
+    """Random-init weights of the reference architecture, default-init shaped (U(-1/sqrt(fan_in), 1/sqrt(fan_in)), SURVEY.md
+    appendix C) from a numpy PCG64 stream.  Same draws as the oracle's recipe, restated here so that the measured arm
+    imports nothing from oracle/."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def u(shape, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    for name, cout, cin in (("conv1", 32, 1), ("conv2", 64, 32), ("conv3", 128, 64)):
+        sd[f"{name}.weight"] = u((cout, cin, 3, 3), cin * 9)
+        sd[f"{name}.bias"] = u((cout,), cin * 9)
+    for layer in range(layers):
+        in_sz = 128 if layer == 0 else hidden
+        sd[f"lstm.weight_ih_l{layer}"] = u((4 * hidden, in_sz), hidden)
+        sd[f"lstm.weight_hh_l{layer}"] = u((4 * hidden, hidden), hidden)
+        sd[f"lstm.bias_ih_l{layer}"] = u((4 * hidden,), hidden)
+        sd[f"lstm.bias_hh_l{layer}"] = u((4 * hidden,), hidden)
+    sd["fc.weight"] = u((n_classes, hidden), hidden)
+    sd["fc.bias"] = u((n_classes,), hidden)
+    return sd
+
+
+def make_noise_bank(m=20, length=5 * 16000, seed=4321):
+    """20 x 80,000 samples of 0.1 N(0,1) (the reference's background recipe, wakeword_training_script.py:382-388)."""
+    return (0.1 * np.random.default_rng(seed).standard_normal((m, length))).astype(np.float32)
+
+
 def draw_aug(n, seed):
     """Host draws, reference stage order (oracle.recipe.draw_aug_params restated with numpy for speed)."""
     from wakeword_jupyterlab_b200 import AugBatch, _lib
@@ -139,7 +169,7 @@ def cpu_reference_pass(n_clips, threads, seed=1234):
     clips = R.make_clips(n_clips, seed=seed)
     bank = R.make_noise_bank()
     p = R.draw_aug_params(n_clips)
-    sd = {k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()}
+    sd = {k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()}
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
     aug = A.augment_batch(clips, bank, p)                               # per clip, like augment_audio
@@ -196,7 +226,6 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
     import torch.distributed as dist
     import wakeword_jupyterlab_b200 as ww
     from wakeword_jupyterlab_b200.sharding import window_shards
-    from oracle import recipe as R
     peaks = load_peaks()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.workload == "logmel":
@@ -230,7 +259,7 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
         class MC(ww.ModelConfig):
             DROPOUT = 0.0
         net = ww.WakewordModel(MC).to(dev).train()
-        net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
         tr = ww.WakewordTrainer(net, dev)
         g = torch.Generator(device=dev).manual_seed(7 + rank)
         x = torch.randn((B, 1, 80, 32), device=dev, generator=g) * 15.0 - 40.0
@@ -268,7 +297,7 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
     T, N, hop = 57_600_000, N_SAMPLES, 160
     w0, n_win, s0, n_audio = window_shards(T, N, hop, world)[rank]
     net = ww.WakewordModel().to(dev).eval()
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
     net.conv_mode = conv_mode
     base = synth_clips_device(64, dev, seed=1234)[0].reshape(-1)                  # recipe audio, tiled over the hour
     audio = base.repeat((n_audio + base.numel() - 1) // base.numel())[:n_audio].contiguous()
@@ -346,7 +375,6 @@ def main():
     import torch.distributed as dist
     import wakeword_jupyterlab_b200 as ww
     from wakeword_jupyterlab_b200 import _lib, processor
-    from oracle import recipe as R
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -386,11 +414,11 @@ def main():
         return
     B = args.clips
     net = ww.WakewordModel().to(dev).eval()
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in R.seeded_state_dict(256, seed=0).items()})
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
     net.conv_mode = conv_mode
     eng = net.engine()
     clips, clips_pcm = synth_clips_device(B, dev, seed=1234 + rank)
-    bank = torch.from_numpy(R.make_noise_bank()).to(dev)
+    bank = torch.from_numpy(make_noise_bank()).to(dev)
     aug = draw_aug(B, seed=2024 + rank)
     aug_struct, keep = eng._aug_struct(aug, B)
     logits = torch.empty((B, 2), device=dev); prob1 = torch.empty((B,), device=dev)
