@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WW_ABI_VERSION 2
+#define WW_ABI_VERSION 3
 
 /* error codes */
 #define WW_OK 0
@@ -186,6 +186,13 @@ int64_t ww_train_n_params(ww_ctx* ctx);                /* floats in the flat gra
 float* ww_train_grad_buffer(ww_ctx* ctx);              /* device pointer of the flat gradient buffer */
 int ww_train_param_range(ww_ctx* ctx, const char* name, int64_t* offset, int64_t* count);
 int ww_get_weights(ww_ctx* ctx, const char* name, float* dst); /* dst: device or host pointer */
+/* Adam state, for optimizer.state_dict() of best_wakeword_model.pth (wakeword_training_script.py:326-334) and for giving
+ * every WakewordTrainer its own optimiser on a shared context: exp_avg / exp_avg_sq of one parameter (device or host
+ * pointers, NULL = skip) and the step counter. */
+int ww_train_get_moments(ww_ctx* ctx, const char* name, float* exp_avg, float* exp_avg_sq);
+int ww_train_set_moments(ww_ctx* ctx, const char* name, const float* exp_avg, const float* exp_avg_sq);
+int64_t ww_train_get_step(ww_ctx* ctx);
+int ww_train_set_step(ww_ctx* ctx, int64_t step);
 
 /* ---- per-stage device timing for benchmarks: CUDA events recorded on the launching stream around
  *      each stage's kernels while enabled.  ww_profile_read synchronises, returns the summed

@@ -92,3 +92,33 @@ def load_reference():
                 sys.modules[k] = v
     _ref_module = mod
     return mod
+
+
+_audiolib_module = None
+
+
+def load_audiolib():
+    """The UNMODIFIED vendored MS-SNSD ``audiolib.py`` (stock/ms_snsd/MS-SNSD/audiolib.py), imported with ``soundfile``
+    stubbed (audiolib.py:7 imports it at module level; ``snr_mixer`` :55-71 itself is plain numpy)."""
+    global _audiolib_module
+    if _audiolib_module is not None:
+        return _audiolib_module
+    path = os.path.join(REFERENCE_DIR, "stock", "ms_snsd", "MS-SNSD", "audiolib.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
+    stub_needed = importlib.util.find_spec("soundfile") is None
+    saved = sys.modules.get("soundfile")
+    if stub_needed:
+        sys.modules["soundfile"] = types.ModuleType("soundfile")
+    try:
+        spec = importlib.util.spec_from_file_location("_ww_reference_audiolib", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if stub_needed:
+            if saved is None:
+                sys.modules.pop("soundfile", None)
+            else:
+                sys.modules["soundfile"] = saved
+    _audiolib_module = mod
+    return mod

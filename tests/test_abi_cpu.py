@@ -28,7 +28,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.ww_abi_version() == 2
+    assert lib.ww_abi_version() == 3
 
 
 def test_config_struct_layout_matches_header():

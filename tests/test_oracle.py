@@ -132,3 +132,26 @@ def test_aug_param_draws_are_deterministic_and_bounded():
     for b in np.nonzero(sp)[0]:
         out_len = A.resample_plan(p.rs_orig[b], 100, 16000)[4]
         assert 0 <= p.crop_off[b] <= max(0, out_len - 16000)
+
+
+# ------------------------------------------------------------------ snr_mixer pinned to the reference run
+def test_snr_mixer_restatement_matches_the_unmodified_reference(golden_dir):
+    """tests/golden/snr_mixer.npz holds outputs of the UNMODIFIED stock/ms_snsd/MS-SNSD/audiolib.py:55-71 (generated by
+    tests/golden/make_golden_snr.py); the restatement must reproduce them bit for bit on the same float32 inputs."""
+    g = np.load(os.path.join(golden_dir, "snr_mixer.npz"))
+    n = int(g["n"])
+    clips = R.make_clips(n, seed=int(g["clip_seed"]))
+    bank = R.make_noise_bank(seed=int(g["bank_seed"]))
+    for b in range(n):
+        seg = bank[g["noise_idx"][b], g["noise_off"][b]:g["noise_off"][b] + clips.shape[1]]
+        clean, noise, noisy = A.snr_mixer(clips[b].astype(np.float32), seg.astype(np.float32), np.float32(g["snr"][b]))
+        assert np.array_equal(np.asarray(noisy, np.float32), g["noisy_f32"][b])
+        assert np.abs(np.asarray(noisy, np.float64) - g["noisy_f64"][b]).max() < 1e-6
+        if b == 0:
+            assert np.array_equal(np.asarray(clean, np.float32), g["clean_f32"][0])
+            assert np.array_equal(np.asarray(noise, np.float32), g["noise_f32"][0])
+    # the stage of the batched oracle (what the CUDA kernel is compared with) is the same function
+    p = A.AugParams(np.full(n, A.F_NOISE, np.uint32), *[np.zeros(n, np.int32)] * 4, g["noise_idx"], g["noise_off"],
+                    g["snr"], np.ones(n, np.float32))
+    p.rs_orig = p.rs_new = np.full(n, 100, np.int32)
+    assert np.array_equal(A.augment_batch(clips, bank, p), g["noisy_f32"])

@@ -33,6 +33,7 @@ EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_f
            "ww_score_host", "ww_kernel_launches", "ww_conv_mode", "ww_normalize", "ww_profile", "ww_profile_read",
            "ww_train_backward", "ww_train_apply", "ww_train_step", "ww_train_reset", "ww_train_n_params",
            "ww_train_grad_buffer", "ww_train_param_range", "ww_get_weights",
+           "ww_train_get_moments", "ww_train_set_moments", "ww_train_get_step", "ww_train_set_step",
            "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
@@ -83,6 +84,11 @@ def load():
         lib.ww_train_grad_buffer.restype = vp
         lib.ww_train_param_range.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
         lib.ww_get_weights.argtypes = [vp, C.c_char_p, vp]
+        lib.ww_train_get_moments.argtypes = [vp, C.c_char_p, vp, vp]
+        lib.ww_train_set_moments.argtypes = [vp, C.c_char_p, vp, vp]
+        lib.ww_train_get_step.argtypes = [vp]
+        lib.ww_train_get_step.restype = i64
+        lib.ww_train_set_step.argtypes = [vp, i64]
         lib.ww_kernel_launches.argtypes = [vp]
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]

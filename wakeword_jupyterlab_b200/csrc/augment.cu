@@ -31,6 +31,7 @@ namespace {
 constexpr int kThreads = 1024;
 constexpr int kMaxPerThread = 16;     // n_samples <= kThreads * kMaxPerThread
 constexpr int kTblWords = 2560;       // shared-memory room for one ratio's compact polyphase table
+constexpr int kPad = 32;              // zero floats in front of and behind every float sample buffer (fixed-phase gather)
 
 struct AugKParams {
   const void* clips;                  // fp32 or int16
@@ -162,6 +163,45 @@ __device__ __forceinline__ void taps4(const float4* __restrict__ kr4, const floa
   }
 }
 
+// Fixed-phase gather.  Thread t < S (S = n * floor(kThreads / n)) owns the outputs i = t + m S: their phase
+// ph = (t + crop) mod n is the same for every m, so the thread reads its tap row ONCE into registers and every output costs
+// NZ4 * 4 sample loads and FMAs, nothing else (the consecutive outputs of a warp read consecutive-ish samples: one or two
+// wavefronts per load).  `xr` is the ROLLED clip with kPad zeros on either side, so the edges of the clip and the wrap point
+// of the roll need no special case; summation order = taps4 (even taps -> acc0, odd taps -> acc1).
+template <int NZ4>
+__device__ __forceinline__ void gather_fixed_phase(const float* __restrict__ xr, const float* __restrict__ tbl, int pitch,
+                                                   const RsDesc& d, int crop, int out_len, int N, int S, int tid,
+                                                   float (&o)[kMaxPerThread]) {
+  const int* lo_t = reinterpret_cast<const int*>(tbl + d.n * pitch);
+  const int j0 = tid + crop;
+  const int qq0 = j0 / d.n, ph = j0 - qq0 * d.n;
+  float w[4 * NZ4];
+  const float4* kr4 = reinterpret_cast<const float4*>(tbl + ph * pitch);
+#pragma unroll
+  for (int k4 = 0; k4 < NZ4; ++k4) {
+    const float4 v = kr4[k4];
+    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+  }
+  const float* sp = xr + (qq0 * d.o - d.width + lo_t[ph]);      // >= xr - width: inside the leading pad
+  const int xstep = (S / d.n) * d.o;
+#pragma unroll
+  for (int e = 0; e < kMaxPerThread; ++e) {
+    const int i = tid + e * S;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (i < N && i + crop < out_len) {
+#pragma unroll
+      for (int k4 = 0; k4 < NZ4; ++k4) {
+        acc0 = fmaf(w[4 * k4], sp[4 * k4], acc0);
+        acc1 = fmaf(w[4 * k4 + 1], sp[4 * k4 + 1], acc1);
+        acc0 = fmaf(w[4 * k4 + 2], sp[4 * k4 + 2], acc0);
+        acc1 = fmaf(w[4 * k4 + 3], sp[4 * k4 + 3], acc1);
+      }
+    }
+    o[e] = acc0 + acc1;
+    sp += xstep;
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -169,13 +209,26 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
   __shared__ ClipPrm prm[2];
   const int tid = threadIdx.x;
   const int N = p.N;
-  const int NP = (N + 3) & ~3;                      // every buffer is padded to whole float4 / short4 groups
+  const int NP = (N + 7) & ~7;                      // every buffer is padded to whole 16-byte groups
   constexpr bool kInPlace = sizeof(TIn) == 4;        // fp32 input: the stage buffer doubles as the gather source
-  TIn* stage0 = reinterpret_cast<TIn*>(smem_raw);
-  TIn* stage1 = stage0 + NP;
-  float* curf = kInPlace ? nullptr : reinterpret_cast<float*>(stage1 + NP);
-  float* noise_s = kInPlace ? reinterpret_cast<float*>(stage1 + NP) : curf + NP;
+  // float sample buffers carry kPad zero floats on either side (written once, below): the fixed-phase gather reads past
+  // the ends of the clip instead of clipping its tap window
+  constexpr int kPadIn = kInPlace ? kPad : 0;        // pad of a stage buffer in elements of TIn
+  const int SP = NP + 2 * kPadIn;
+  TIn* stage0 = reinterpret_cast<TIn*>(smem_raw) + kPadIn;
+  TIn* stage1 = stage0 + SP;
+  float* curf = kInPlace ? nullptr : reinterpret_cast<float*>(stage1 + SP) + kPad;
+  float* noise_s = kInPlace ? reinterpret_cast<float*>(stage1 + SP - kPadIn) : curf + NP + kPad;
   float* tbl = noise_s + NP;
+  if (kInPlace) {
+    for (int k = tid; k < 2 * (2 * kPad + NP - N); k += kThreads) {
+      float* base = reinterpret_cast<float*>((k & 1) ? stage1 : stage0);
+      const int r = k >> 1;
+      base[r < kPad ? r - kPad : N + (r - kPad)] = 0.0f;
+    }
+  } else {
+    for (int r = tid; r < 2 * kPad + NP - N; r += kThreads) curf[r < kPad ? r - kPad : N + (r - kPad)] = 0.0f;
+  }
 
   int it = 0;
   // prologue: parameters and raw samples of the first clip
@@ -228,23 +281,50 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       }
     }
 
+    // fixed-phase gather (see gather_fixed_phase): thread t < S owns outputs t + m S from here on
+    const int S = rs_ok ? d.n * (kThreads / max(d.n, 1)) : kThreads;
+    const bool fixed = rs_ok && in_smem && d.n <= kThreads && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8 &&
+                       (N + S - 1) / S <= kMaxPerThread;
+    const int ss = fixed ? S : kThreads;               // owner stride of the register tile after the gather
     if (flags & (WW_AUG_SHIFT | WW_AUG_SPEED)) {
       // ---- one gather through shared memory: out[i] = sum_k kern[ph][k] * rolled[x0 + k],  rolled[t] = in[(t - shift) mod N]
-      if (!kInPlace || (flags & WW_AUG_NORM_IN)) {
+      int s = (flags & WW_AUG_SHIFT) ? q.shift % N : 0;
+      if (s < 0) s += N;
+      if (fixed) {
+        if (kInPlace && !(flags & WW_AUG_NORM_IN)) __syncthreads();      // every thread has read its samples: roll in place
+#pragma unroll
+        for (int e = 0; e < kMaxPerThread; ++e) {
+          const int i = slot_index(tid, e);
+          int dpos = i + s;
+          if (dpos >= N) dpos -= N;
+          if (i < N) cur[dpos] = o[e];
+        }
+      } else if (!kInPlace || (flags & WW_AUG_NORM_IN)) {
 #pragma unroll
         for (int e = 0; e < kMaxPerThread; ++e) {
           const int i = slot_index(tid, e);
           if (i < N) cur[i] = o[e];
         }
       }
-      int s = (flags & WW_AUG_SHIFT) ? q.shift % N : 0;
-      if (s < 0) s += N;
       cp_wait<2>();                                    // G1 (table) landed; G2 / G3 may still be in flight
       __syncthreads();
       if (do_speed) {
         if (!rs_ok) {
 #pragma unroll
           for (int e = 0; e < kMaxPerThread; ++e) o[e] = __int_as_float(0x7fc00000);   // loud: NaN clip
+        } else if (fixed) {
+          const int out_len = (d.n * N + d.o - 1) / d.o;                             // ceil(n*N/o), < 2^31
+          const int crop = (out_len > N) ? q.crop : 0;
+          if (tid < S) {
+            switch (d.nz >> 2) {
+              case 4: gather_fixed_phase<4>(cur, tbl, pitch, d, crop, out_len, N, S, tid, o); break;
+              case 5: gather_fixed_phase<5>(cur, tbl, pitch, d, crop, out_len, N, S, tid, o); break;
+              default: gather_fixed_phase<6>(cur, tbl, pitch, d, crop, out_len, N, S, tid, o); break;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < kMaxPerThread; ++e) o[e] = 0.0f;
+          }
         } else {
           const float* kern = in_smem ? tbl : p.rs_kern + d.offset;
           const int* lo_t = reinterpret_cast<const int*>(kern + d.n * pitch);
@@ -253,8 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
           const int crop = (out_len > N) ? q.crop : 0;
           const uint32_t magic = 0xffffffffu / (uint32_t)d.n + 1u;                   // j / n == umulhi(j, magic) for j, n < 2^16
           const int nz4 = d.nz >> 2;                                                 // table rows are zero-padded to x4 taps
-#pragma unroll
-          for (int e = 0; e < kMaxPerThread; ++e) {
+#pragma unroll 1
+          for (int e = 0; e < kMaxPerThread; ++e) {                                   // rare fallback: kept small
             const int i = slot_index(tid, e);
             float acc0 = 0.0f, acc1 = 0.0f;
             const int j = i + crop;                                                  // resampled-domain index
@@ -268,19 +348,12 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
                 // interior: no edge clipping, no wrap inside the (padded) tap window
                 const float4* kr4 = reinterpret_cast<const float4*>(kr);
                 const float* sp = cur + src;
-                // the usual table widths as straight-line code (same summation order as the rolled loop)
-                switch (nz4) {
-                  case 4: taps4<4>(kr4, sp, acc0, acc1); break;
-                  case 5: taps4<5>(kr4, sp, acc0, acc1); break;
-                  case 6: taps4<6>(kr4, sp, acc0, acc1); break;
-                  default:
-                    for (int k4 = 0; k4 < nz4; ++k4) {
-                      const float4 w = kr4[k4];
-                      acc0 = fmaf(w.x, sp[4 * k4], acc0);
-                      acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
-                      acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
-                      acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
-                    }
+                for (int k4 = 0; k4 < nz4; ++k4) {
+                  const float4 w = kr4[k4];
+                  acc0 = fmaf(w.x, sp[4 * k4], acc0);
+                  acc1 = fmaf(w.y, sp[4 * k4 + 1], acc1);
+                  acc0 = fmaf(w.z, sp[4 * k4 + 2], acc0);
+                  acc1 = fmaf(w.w, sp[4 * k4 + 3], acc1);
                 }
               } else {
                 const int k0 = x0 < 0 ? -x0 : 0;
@@ -294,7 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
                 }
               }
             }
-            o[e] = acc0 + acc1;
+            const float v = acc0 + acc1;
+#pragma unroll
+            for (int k = 0; k < kMaxPerThread; ++k)                                  // static indices keep o[] in registers
+              if (k == e) o[k] = v;
           }
         }
       } else {
@@ -317,8 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       float sc = 0.0f, sn = 0.0f;
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) {
-        const int i = slot_index(tid, e);
-        n[e] = (i < N) ? noise_s[i] : 0.0f;
+        const int i = tid + e * ss;
+        n[e] = (tid < ss && i < N) ? noise_s[i] : 0.0f;
         sc = fmaf(o[e], o[e], sc);
         sn = fmaf(n[e], n[e], sn);
       }
@@ -358,8 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
     float* __restrict__ dst = p.out + (int64_t)b * N;
 #pragma unroll
     for (int e = 0; e < kMaxPerThread; ++e) {
-      const int i = slot_index(tid, e);
-      if (i < N) dst[i] = o[e];
+      const int i = tid + e * ss;
+      if (tid < ss && i < N) dst[i] = o[e];
     }
     // the __syncthreads at the top of the next iteration orders this clip's shared-memory reads (cur, tbl, noise)
     // before the next clip's cp.async writes and in-place normalise
@@ -396,14 +472,12 @@ int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaS
 
 template <typename TIn>
 static int launch_augment_t(ww_ctx* c, const AugKParams& p, cudaStream_t st) {
-  const int NP = (p.N + 3) & ~3;
-  const size_t smem = (size_t)2 * NP * sizeof(TIn) + (sizeof(TIn) == 4 ? 0 : (size_t)NP * 4) + (size_t)NP * 4 +
-                      (size_t)kTblWords * 4;
-  static size_t configured = 0;
-  if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(augment_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  const int NP = (p.N + 7) & ~7;
+  // stage x2 (+ pads when the fp32 stage doubles as the gather source) | float copy + pads (int16 input) | noise | table
+  const size_t smem = (sizeof(TIn) == 4 ? (size_t)2 * (NP + 2 * kPad) * 4 : (size_t)2 * NP * 2 + (size_t)(NP + 2 * kPad) * 4) +
+                      (size_t)NP * 4 + (size_t)kTblWords * 4;
+  // opt in on every launch: the attribute is per device, a process may drive several
+  WW_CHECK(c, cudaFuncSetAttribute(augment_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(c->sm_count, p.B);
   ProfScope prof(c, WW_STAGE_AUGMENT, st);
   augment_kernel<TIn><<<grid, kThreads, smem, st>>>(p);

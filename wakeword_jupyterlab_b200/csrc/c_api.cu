@@ -150,6 +150,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_scalar); cudaFree(c->d_stream_cache); cudaFree(c->d_stream_bmax); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+  if (c->apply_event) cudaEventDestroy(c->apply_event);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   return 0;
@@ -532,6 +533,12 @@ static int score_impl(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stri
   int rc = ensure_workspaces(c);
   if (rc) return rc;
   if ((rc = ww_prepare_weights(c, st))) return rc;
+  // ensure_pool re-allocates without keeping contents: a caller that scores a batch in pieces (pool_off > 0) must
+  // have sized the pool for the whole batch before its first piece
+  if (pool_off > 0 && pool_off + B > c->pool_cap_clips) {
+    c->set_error("score: pool partials not sized for the whole batch before a piece-wise call");
+    return WW_ERR_INVALID;
+  }
   if ((rc = ensure_pool(c, pool_off + B))) return rc;
   const int N = c->cfg.n_samples;
   for (int64_t b0 = 0; b0 < B; b0 += c->chunk) {
@@ -676,6 +683,9 @@ static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const f
     a_dev.snr_db = (float*)(base + (size_t)7 * B); a_dev.gain = (float*)(base + (size_t)8 * B);
   }
   if ((rc = ww_prepare_weights(c, st))) return rc;
+  // the conv partials of every piece stay live until the head runs with the last one: size the pool for the whole
+  // batch now (growing it between pieces would drop the earlier pieces' partials)
+  if ((rc = ensure_pool(c, B))) return rc;
   // Two streams: the copy engine moves piece i+1 host->device while the SMs score piece i.  Pieces ramp up
   // geometrically (384, 512, 768, 1024, ... clips up to the work chunk) so that only a fraction of a millisecond of copy is exposed
   // before the first kernel starts; copying a clip is faster than scoring it, so later copies stay ahead.

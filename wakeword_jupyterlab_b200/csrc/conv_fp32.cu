@@ -305,11 +305,8 @@ int ww_train_conv_backward(ww_ctx* c, const float* x, int B, const float* act1, 
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH, n_tiles = tiles_x * tiles_y;
   const int cps = (B + slices - 1) / slices;
   dim3 block(kThreads);
-  static bool configured = false;
-  if (!configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-    configured = true;
-  }
+  // per device, not per process: set on every call (cheap)
+  WW_CHECK(c, cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
   auto wgrad = [&](const float* xin, const float* dy, int CIN, int COUT, float* gw, float* gb) -> int {
     conv3x3_wgrad_kernel<<<dim3((COUT + WG_CO - 1) / WG_CO, (CIN + WG_CI - 1) / WG_CI, slices), block, WG_SMEM, st>>>(
         xin, dy, part, B, CIN, COUT, H, W, cps);

@@ -96,6 +96,7 @@ struct ww_ctx {
   float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
   float* d_bias_sum[8] = {};                           // per layer: [4H] b_ih + b_hh in reference row order (training)
   TrainState train;
+  cudaEvent_t apply_event = nullptr;                    // recorded after the Adam kernels of ww_train_apply
   __half* d_w2_split = nullptr;                        // conv2 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w3_split = nullptr;                        // conv3 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w1_split = nullptr;                        // conv1 weights * 2^k, fp16 hi/lo, K = 9 padded to 16, twice

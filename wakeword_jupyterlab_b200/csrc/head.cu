@@ -281,11 +281,8 @@ int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decis
   const float* x = c->ws_pool_part;
   const bool pipe = (H % TN) == 0;                      // K is 128 or H: multiples of KC whenever H % 64 == 0
   if (pipe) {
-    static bool configured = false;
-    if (!configured) {
-      WW_CHECK(c, cudaFuncSetAttribute(gated_dense_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
-      configured = true;
-    }
+    // per device, not per process: set on every call (cheap)
+    WW_CHECK(c, cudaFuncSetAttribute(gated_dense_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem));
     // ws_h[1] (>= 128 floats per clip) holds the finished mean until layer 1 overwrites it with its own output
     const int64_t n = (int64_t)B * 128;
     pool_finish_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, st>>>(

@@ -465,11 +465,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_kernel(const LogmelParams 
 
 template <int LOG2N, typename TIn>
 int launch_tt(ww_ctx* c, const LogmelParams& p, size_t smem, int grid, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel<LOG2N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // per device, not per process: set on every call (cheap)
+  WW_CHECK(c, cudaFuncSetAttribute(logmel_kernel<LOG2N, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(c, WW_STAGE_LOGMEL, st);
   logmel_kernel<LOG2N, TIn><<<grid, kThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);

@@ -268,7 +268,49 @@ int ww_get_weights(ww_ctx* c, const char* name, float* dst) {
   size_t n = 1;
   for (int64_t d : c->w_shape[name]) n *= (size_t)d;
   cudaSetDevice(c->device);
+  // the Adam kernels of the last ww_train_apply ran on the caller's stream, which a blocking copy on the legacy stream does
+  // not wait for when that stream is non-blocking: order the copy behind them explicitly
+  if (c->apply_event) WW_CHECK(c, cudaEventSynchronize(c->apply_event));
   WW_CHECK(c, cudaMemcpy(dst, it->second, n * 4, cudaMemcpyDefault));
+  return WW_OK;
+}
+
+// Adam state of one parameter (torch.optim.Adam's exp_avg / exp_avg_sq) and the shared step counter: what
+// optimizer.state_dict() holds in the reference's best_wakeword_model.pth (wakeword_training_script.py:326-334).
+// Pointers may be device or host memory; NULL skips that moment.
+int ww_train_get_moments(ww_ctx* c, const char* name, float* exp_avg, float* exp_avg_sq) {
+  if (!c || !name) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  int rc = ensure_train(c, 0);
+  if (rc) return rc;
+  auto it = c->train.offset.find(name);
+  if (it == c->train.offset.end()) { c->set_error(std::string("train: unknown parameter ") + name); return WW_ERR_INVALID; }
+  const size_t bytes = (size_t)c->train.count[name] * 4;
+  if (c->apply_event) WW_CHECK(c, cudaEventSynchronize(c->apply_event));
+  if (exp_avg) WW_CHECK(c, cudaMemcpy(exp_avg, c->train.m + it->second, bytes, cudaMemcpyDefault));
+  if (exp_avg_sq) WW_CHECK(c, cudaMemcpy(exp_avg_sq, c->train.v + it->second, bytes, cudaMemcpyDefault));
+  return WW_OK;
+}
+
+int ww_train_set_moments(ww_ctx* c, const char* name, const float* exp_avg, const float* exp_avg_sq) {
+  if (!c || !name) return WW_ERR_INVALID;
+  cudaSetDevice(c->device);
+  int rc = ensure_train(c, 0);
+  if (rc) return rc;
+  auto it = c->train.offset.find(name);
+  if (it == c->train.offset.end()) { c->set_error(std::string("train: unknown parameter ") + name); return WW_ERR_INVALID; }
+  const size_t bytes = (size_t)c->train.count[name] * 4;
+  WW_CHECK(c, cudaDeviceSynchronize());
+  if (exp_avg) WW_CHECK(c, cudaMemcpy(c->train.m + it->second, exp_avg, bytes, cudaMemcpyDefault));
+  if (exp_avg_sq) WW_CHECK(c, cudaMemcpy(c->train.v + it->second, exp_avg_sq, bytes, cudaMemcpyDefault));
+  return WW_OK;
+}
+
+int64_t ww_train_get_step(ww_ctx* c) { return c ? c->train.step : -1; }
+
+int ww_train_set_step(ww_ctx* c, int64_t step) {
+  if (!c || step < 0) return WW_ERR_INVALID;
+  c->train.step = step;
   return WW_OK;
 }
 
@@ -349,6 +391,7 @@ int ww_train_reset(ww_ctx* c) {
   int rc = ensure_train(c, 0);
   if (rc) return rc;
   c->train.step = 0;
+  WW_CHECK(c, cudaDeviceSynchronize());
   WW_CHECK(c, cudaMemset(c->train.m, 0, c->train.n_flat * 4));
   WW_CHECK(c, cudaMemset(c->train.v, 0, c->train.n_flat * 4));
   return WW_OK;
@@ -373,6 +416,8 @@ int ww_train_apply(ww_ctx* c, float lr, float beta1, float beta2, float eps, flo
     WW_LAUNCH_CHECK(c);
   }
   c->weights_dirty = true;      // prepared (transposed / split) forms are rebuilt at the next forward
+  if (!c->apply_event) WW_CHECK(c, cudaEventCreateWithFlags(&c->apply_event, cudaEventDisableTiming));
+  WW_CHECK(c, cudaEventRecord(c->apply_event, st));     // ww_get_weights / ww_train_get_moments wait for it
   return WW_OK;
 }
 
