@@ -97,6 +97,9 @@ struct ClipDiv {
     if (!fast || (q != 0.0f && fabsf(q) < 1e-30f)) return __fdiv_rn(x, m);
     return fmaf(fmaf(-m, q, x), r, q);
   }
+  // x * RN(1 / m): within 1 ulp of the quotient.  Used where the samples pass through an inexact stage (resampling, noise
+  // mix) before or after the division anyway, so that nothing downstream is bit-comparable with numpy in the first place.
+  __device__ __forceinline__ float approx(float x) const { return x * r; }
 };
 __device__ __forceinline__ ClipDiv make_clip_div(float m) {
   ClipDiv d;
@@ -188,14 +191,14 @@ __device__ __forceinline__ void gather_fixed_phase(const float* __restrict__ xr,
   for (int e = 0; e < kMaxPerThread; ++e) {
     const int i = tid + e * S;
     float acc0 = 0.0f, acc1 = 0.0f;
-    if (i < N && i + crop < out_len) {
+    // outputs past the clip or past the resampled length read the leading zero pad instead (4 NZ4 <= 24 < kPad): no branch
+    const float* sq = (i < N && i + crop < out_len) ? sp : xr - kPad;
 #pragma unroll
-      for (int k4 = 0; k4 < NZ4; ++k4) {
-        acc0 = fmaf(w[4 * k4], sp[4 * k4], acc0);
-        acc1 = fmaf(w[4 * k4 + 1], sp[4 * k4 + 1], acc1);
-        acc0 = fmaf(w[4 * k4 + 2], sp[4 * k4 + 2], acc0);
-        acc1 = fmaf(w[4 * k4 + 3], sp[4 * k4 + 3], acc1);
-      }
+    for (int k4 = 0; k4 < NZ4; ++k4) {
+      acc0 = fmaf(w[4 * k4], sq[4 * k4], acc0);
+      acc1 = fmaf(w[4 * k4 + 1], sq[4 * k4 + 1], acc1);
+      acc0 = fmaf(w[4 * k4 + 2], sq[4 * k4 + 2], acc0);
+      acc1 = fmaf(w[4 * k4 + 3], sq[4 * k4 + 3], acc1);
     }
     o[e] = acc0 + acc1;
     sp += xstep;
@@ -272,12 +275,20 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       o[e] = (i < N) ? cvt_in(st[i]) : 0.0f;
       m = fmaxf(m, fabsf(o[e]));
     }
+    // normalize_audio is the IEEE quotient wherever its result is bit-comparable with numpy (no resampling / noise mix on
+    // the clip); clips that go through those stages take one multiply per sample instead (1 ulp)
+    const bool inexact = (flags & (WW_AUG_SPEED | WW_AUG_NOISE)) != 0;
     if (flags & WW_AUG_NORM_IN) {
       m = block_max_nonneg(m, red4[0], tid);
       if (m > 0.0f) {
         const ClipDiv dv = make_clip_div(m);
+        if (inexact && dv.fast) {
 #pragma unroll
-        for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
+          for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv.approx(o[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
+        }
       }
     }
 
@@ -399,7 +410,10 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
         sn = fmaf(n[e], n[e], sn);
       }
       block_reduce2<false>(sc, sn, red4[1], tid);
-      const float scalarclean = target / sqrtf(sc / (float)N), scalarnoise = target / sqrtf(sn / (float)N);
+      // every warp runs these scalar chains in lockstep with nothing to overlap them: MUFU approximations (2 ulp, against
+      // the stage's 5e-5 tolerance) keep them a handful of instructions long
+      const float inv_n = 1.0f / (float)N;
+      const float scalarclean = target * rsqrtf(sc * inv_n), scalarnoise = target * rsqrtf(sn * inv_n);
       // the reference re-measures both RMS values after scaling (audiolib.py:60,65)
       float sc2 = 0.0f, sn2 = 0.0f;
 #pragma unroll
@@ -410,8 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
         sn2 = fmaf(n[e], n[e], sn2);
       }
       block_reduce2<false>(sc2, sn2, red4[2], tid);
-      const float rc2 = sqrtf(sc2 / (float)N), rn2 = sqrtf(sn2 / (float)N);
-      const float noisescalar = sqrtf(rc2 / exp10f(snr / 20.0f) / rn2);          // audiolib.py:68 (sqrt quirk kept)
+      // noisescalar = sqrt(rmsclean / 10^(snr/20) / rmsnoise), audiolib.py:68 (sqrt quirk kept)
+      //             = (sc2 / sn2)^(1/4) * 2^(-snr log2(10) / 40)
+      const float noisescalar = rsqrtf(rsqrtf(__fdividef(sc2, sn2))) * exp2f(snr * -0.0830482023721841f);
 #pragma unroll
       for (int e = 0; e < kMaxPerThread; ++e) o[e] = o[e] + n[e] * noisescalar;
     }
@@ -427,8 +442,13 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
       mo = block_max_nonneg(mo, red4[3], tid);
       if (mo > 0.0f) {
         const ClipDiv dv = make_clip_div(mo);
+        if (inexact && dv.fast) {
 #pragma unroll
-        for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
+          for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv.approx(o[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kMaxPerThread; ++e) o[e] = dv(o[e]);
+        }
       }
     }
     float* __restrict__ dst = p.out + (int64_t)b * N;

@@ -331,7 +331,7 @@ int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t) {
         memcpy(hp + (((size_t)tl * 2 + ((c32 >> 3) & 1)) * 128 + n) * 16 + (c32 & 7) * 2, &hi, 2);
         // lo part of the pair: [tl][kc16][cout][16 e4m3], kc16 = 16-channel chunk
         unsigned char* lp = stg + (size_t)2 * C3_PART_BYTES;
-        lp[(((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] = f2e4m3(v - h2f(hi));
+        lp[(((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] = f2e4m3(ldexpf(v - h2f(hi), c->act2_lo_shift));   // its operand is act2 x 2^-shift
       }
   if (!c->d_w3_split) WW_CHECK(c, cudaMalloc((void**)&c->d_w3_split, s.size()));
   WW_CHECK(c, cudaMemcpy(c->d_w3_split, s.data(), s.size(), cudaMemcpyHostToDevice));
@@ -363,7 +363,7 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
     conf = smem;
   }
   Conv3Params p;
-  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.w3s = reinterpret_cast<const unsigned char*>(c->d_w3_split); p.inv_scale = c->w3_inv_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
+  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.w3s = reinterpret_cast<const unsigned char*>(c->d_w3_split); p.inv_scale = c->w3_inv_scale / c->act2_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
   p.pool_part = c->pool_cur; p.B = B; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;

@@ -101,6 +101,8 @@ struct ww_ctx {
   __half* d_w3_split = nullptr;                        // conv3 weights * 2^k, fp16 hi/lo, UMMA canonical layout
   __half* d_w1_split = nullptr;                        // conv1 weights * 2^k, fp16 hi/lo, K = 9 padded to 16, twice
   float w1_inv_scale = 1.0f, w2_inv_scale = 1.0f, w3_inv_scale = 1.0f;      // 2^-k per layer
+  float act1_scale = 1.0f, act2_scale = 1.0f;                               // power-of-two scales of the stored fp16 activations
+  int act2_lo_shift = 0;                                                    // e4m3 copy of act2 = fp16 copy x 2^-shift (conv12_tc.cu)
 
   // ---- workspaces (chunk clips)
   float* ws_clips = nullptr;     // [chunk][n_samples] augmented clips
