@@ -241,79 +241,81 @@ def reference_arm(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------
-def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_ranks):
-    """BASELINE.json configs 2 (log-mel only, 16,384 clips) and 4 (1 h streaming, 10 ms hop): extra JSON lines."""
+# BASELINE.json configs 2, 4 and 5.  Each returns a dict on every rank (rank 0 prints / embeds it); `--workload X` prints
+# it as its own JSON line, the default run embeds short versions under "secondary" of the ONE contract line.
+def measure_logmel(ww, dev, rank, world, steps, warmup, barrier, max_over_ranks, B=16384):
+    """config 2: log-mel only, 16,384 clips per GPU (HBM roofline: 74,240 algorithmic bytes per clip)."""
+    peaks = load_peaks()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng = ww.get_engine(device=dev.index)
+    clips, _ = synth_clips_device(B, dev, seed=1234 + rank)
+    out = torch.empty((B, 1, 80, eng.W), device=dev)
+    for _ in range(warmup):
+        eng.logmel(clips, normalize=False, out=out)
+    barrier(); e0.record()
+    for _ in range(steps):
+        eng.logmel(clips, normalize=False, out=out)
+    e1.record(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    gbs = 74240.0 * B / (ms * 1e-3) / 1e9
+    return {"metric": "clips_per_sec_logmel_only", "value": B * world / (ms * 1e-3), "unit": "clips/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "config2: log-mel only (80 mels, 80x32)",
+                                            "clips_per_gpu": B, "l2": "input 1.05 GB > L2"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_clip": 74240}}
+
+
+def measure_train(ww, dev, rank, world, steps, warmup, barrier, max_over_ranks, B=4096):
+    """config 5: CNN+LSTM training step (fwd + bwd + Adam) on on-GPU features, batch 4096 per GPU, gradient all-reduce
+    over NCCL when world > 1 (dropout off: its masks are inputs of the kernels, not work)."""
     import torch.distributed as dist
-    import wakeword_jupyterlab_b200 as ww
+    peaks = load_peaks()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    class MC(ww.ModelConfig):
+        DROPOUT = 0.0
+    net = ww.WakewordModel(MC).to(dev).train()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
+    tr = ww.WakewordTrainer(net, dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    x = torch.randn((B, 1, 80, 32), device=dev, generator=g) * 15.0 - 40.0
+    y = torch.randint(0, 2, (B,), device=dev, generator=g)
+    for _ in range(warmup):
+        tr.train_step(x, y)
+    barrier(); e0.record()
+    for _ in range(steps):
+        loss, _ = tr.train_step(x, y)
+    e1.record(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    # data-parallel replicas must hold identical weights after the all-reduced steps (they start identical and see
+    # the same averaged gradient)
+    in_sync = True
+    if world > 1:
+        chk = torch.stack([p.detach().double().sum() for p in net.parameters()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
+    flop = 1.419e9 * B
+    return {"metric": "clips_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "clips/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config5: CNN+LSTM training step (fwd+bwd+Adam), on-GPU features",
+                       "clips_per_gpu": B, "allreduce": "nccl sum of the flat fp32 gradient buffer" if world > 1 else "none",
+                       "loss": float(loss.item()), "replicas_in_sync": in_sync},
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "note": "fp32 on CUDA cores (exact); tcgen05 dgrad/wgrad is not built yet"}}
+
+
+def measure_stream(ww, dev, rank, world, steps, warmup, barrier, max_over_ranks, conv_mode):
+    """config 4: 1 h of 16 kHz audio, 1 s windows every 10 ms, each scored like predict_wakeword; the windows are split
+    into `world` contiguous time ranges (strong scaling)."""
     from wakeword_jupyterlab_b200.sharding import window_shards
     peaks = load_peaks()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if args.workload == "logmel":
-        B = 16384 if args.clips == CLIPS_PER_GPU else args.clips
-        eng = ww.get_engine(device=dev.index)
-        clips, _ = synth_clips_device(B, dev, seed=1234 + rank)
-        out = torch.empty((B, 1, 80, eng.W), device=dev)
-        for _ in range(args.warmup):
-            eng.logmel(clips, normalize=False, out=out)
-        barrier(); e0.record()
-        for _ in range(args.steps):
-            eng.logmel(clips, normalize=False, out=out)
-        e1.record(); barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        gbs = 74240.0 * B / (ms * 1e-3) / 1e9
-        if rank == 0:
-            print(json.dumps({"metric": "clips_per_sec_logmel_only", "value": B * world / (ms * 1e-3), "unit": "clips/s",
-                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic", "config": {"workload": "config2: log-mel only (80 mels, 80x32)",
-                                                              "clips_per_gpu": B, "l2": "input 1.05 GB > L2"},
-                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                           "frac": gbs / peaks["hbm_gbs"], "traffic": None,
-                                           "algorithmic_bytes_per_clip": 74240}}))
-        return
-    if args.workload == "train":
-        # ---- config 5: CNN+LSTM training step (fwd + bwd + Adam) on on-GPU features, batch 4096 per GPU, gradient
-        # all-reduce over NCCL when world > 1 (dropout off: its masks are inputs of the kernels, not work)
-        B = 4096 if args.clips == CLIPS_PER_GPU else args.clips
-
-        class MC(ww.ModelConfig):
-            DROPOUT = 0.0
-        net = ww.WakewordModel(MC).to(dev).train()
-        net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
-        tr = ww.WakewordTrainer(net, dev)
-        g = torch.Generator(device=dev).manual_seed(7 + rank)
-        x = torch.randn((B, 1, 80, 32), device=dev, generator=g) * 15.0 - 40.0
-        y = torch.randint(0, 2, (B,), device=dev, generator=g)
-        for _ in range(args.warmup):
-            tr.train_step(x, y)
-        barrier(); e0.record()
-        for _ in range(args.steps):
-            loss, _ = tr.train_step(x, y)
-        e1.record(); barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        # data-parallel replicas must hold identical weights after the all-reduced steps (they start identical and see
-        # the same averaged gradient)
-        in_sync = True
-        if world > 1:
-            chk = torch.stack([p.detach().double().sum() for p in net.parameters()])
-            lo, hi = chk.clone(), chk.clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            in_sync = bool(torch.equal(lo, hi))
-        flop = 1.419e9 * B
-        if rank == 0:
-            print(json.dumps({"metric": "clips_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "clips/s",
-                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic",
-                              "config": {"workload": "config5: CNN+LSTM training step (fwd+bwd+Adam), on-GPU features",
-                                         "clips_per_gpu": B, "allreduce": "nccl sum of the flat fp32 gradient buffer" if world > 1 else "none",
-                                         "loss": float(loss.item()), "replicas_in_sync": in_sync},
-                              "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
-                                           "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                           "frac": flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
-                                           "note": "round-1 arithmetic is fp32 on CUDA cores (exact); tcgen05 dgrad/wgrad is next"}}))
-        return
-    # ---- streaming: 1 h of 16 kHz audio, 1 s windows every 10 ms, each scored like predict_wakeword
     T, N, hop = 57_600_000, N_SAMPLES, 160
     w0, n_win, s0, n_audio = window_shards(T, N, hop, world)[rank]
     net = ww.WakewordModel().to(dev).eval()
@@ -322,50 +324,40 @@ def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_rank
     base = synth_clips_device(64, dev, seed=1234)[0].reshape(-1)                  # recipe audio, tiled over the hour
     audio = base.repeat((n_audio + base.numel() - 1) // base.numel())[:n_audio].contiguous()
     eng = net.engine()
-    for _ in range(max(1, args.warmup - 2)):
+    for _ in range(warmup):
         eng.score_stream(audio, hop)
     barrier(); e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         prob1, dec = eng.score_stream(audio, hop)
     e1.record(); barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    total_win = 1 + (T - N) // hop
+    tfs = total_win * FLOP_PER_CLIP["total"] / (ms * 1e-3) / 1e12 / world
+    return {"metric": "windows_per_sec_streaming_1h_10ms_hop", "value": total_win / (ms * 1e-3),
+            "unit": "windows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPE_NAMES[conv_mode], "data": "synthetic",
+            "config": {"workload": "config4: sliding-window detection over 1 h of 16 kHz audio",
+                       "windows": total_win, "hop_samples": hop, "conv_mode": conv_mode,
+                       "seconds_per_hour_of_audio": ms * 1e-3, "x_realtime": 3600.0 / (ms * 1e-3)},
+            "roofline": {"bound": "tensor", "achieved": tfs, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": tfs / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "note": "475.5 MFLOP per window (SURVEY 8d) per GPU"}}
+
+
+def secondary_workload(args, rank, world, dev, conv_mode, barrier, max_over_ranks):
+    """`--workload logmel|stream|train`: one JSON line for that configuration."""
+    import wakeword_jupyterlab_b200 as ww
+    if args.workload == "logmel":
+        r = measure_logmel(ww, dev, rank, world, args.steps, args.warmup, barrier, max_over_ranks,
+                           16384 if args.clips == CLIPS_PER_GPU else args.clips)
+    elif args.workload == "train":
+        r = measure_train(ww, dev, rank, world, args.steps, args.warmup, barrier, max_over_ranks,
+                          4096 if args.clips == CLIPS_PER_GPU else args.clips)
+    else:
+        r = measure_stream(ww, dev, rank, world, args.steps, max(1, args.warmup - 2), barrier, max_over_ranks, conv_mode)
     if rank == 0:
-        total_win = 1 + (T - N) // hop
-        print(json.dumps({"metric": "windows_per_sec_streaming_1h_10ms_hop", "value": total_win / (ms * 1e-3),
-                          "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": DTYPE_NAMES[conv_mode], "data": "synthetic",
-                          "config": {"workload": "config4: sliding-window detection over 1 h of 16 kHz audio",
-                                     "windows": total_win, "hop_samples": hop, "conv_mode": conv_mode,
-                                     "seconds_per_hour_of_audio": ms * 1e-3, "x_realtime": 3600.0 / (ms * 1e-3)}}))
-
-
-class numa_local:
-    """Context manager: run the body on the CPUs NVML names as local to `dev` (so host buffers allocated and first
-    touched inside land on that NUMA node), then restore the affinity.  Best effort: silently a no-op without NVML."""
-
-    def __init__(self, dev):
-        self.dev, self.old = dev, None
-
-    def __enter__(self):
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
-            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
-            self.old = os.sched_getaffinity(0)
-            pynvml.nvmlDeviceSetCpuAffinity(h)
-        except Exception as e:      # noqa: BLE001
-            sys.stderr.write(f"[bench] NUMA binding skipped: {e}\n")
-        return self
-
-    def __exit__(self, *exc):
-        if self.old is not None:
-            try:
-                os.sched_setaffinity(0, self.old)
-            except OSError:
-                pass
-        return False
+        print(json.dumps(r))
 
 
 def main():
@@ -381,6 +373,7 @@ def main():
                          "train = config 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short config 2 / 4 / 5 and strong-scaling legs")
     ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg with fp32 host buffers instead of int16 PCM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -437,63 +430,104 @@ def main():
     net.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(256, seed=0).items()})
     net.conv_mode = conv_mode
     eng = net.engine()
-    clips, clips_pcm = synth_clips_device(B, dev, seed=1234 + rank)
     bank = torch.from_numpy(make_noise_bank()).to(dev)
-    aug = draw_aug(B, seed=2024 + rank)
-    aug_struct, keep = eng._aug_struct(aug, B)
-    logits = torch.empty((B, 2), device=dev); prob1 = torch.empty((B,), device=dev)
-    dec = torch.empty((B,), device=dev, dtype=torch.uint8)
 
-    def step():
-        eng.score_prepared(clips, aug_struct, bank, True, logits, prob1, dec)
+    def run_score(Bn, steps, warmup, want_e2e, sample_clocks):
+        """One measurement of the scoring path on Bn clips per GPU: device-resident (CUDA events, max over ranks) and,
+        optionally, end to end through ww_score_host_pcm16 from pinned host buffers."""
+        clips, clips_pcm = synth_clips_device(Bn, dev, seed=1234 + rank)
+        aug = draw_aug(Bn, seed=2024 + rank)
+        aug_struct, keep = eng._aug_struct(aug, Bn)
+        logits = torch.empty((Bn, 2), device=dev); prob1 = torch.empty((Bn,), device=dev)
+        dec = torch.empty((Bn,), device=dev, dtype=torch.uint8)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    eng.profile(True)
-    eng.profile_read(reset=True)
-    l0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launches - l0
-    stages = eng.profile_read(reset=True)
-    eng.profile(False)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
+        def step():
+            eng.score_prepared(clips, aug_struct, bank, True, logits, prob1, dec)
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        eng.profile(True)
+        eng.profile_read(reset=True)
+        l0 = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        r = {"B": Bn, "launches": eng.launches - l0, "stages": eng.profile_read(reset=True), "ms_step": ms_total / steps,
+             "clocks": sampler.stop() if (rank == 0 and sample_clocks) else None, "e2e": None}
+        eng.profile(False)
+        if want_e2e:
+            # host buffers hold the clips as they are on disk: int16 PCM (ww_score_host_pcm16; --e2e-fp32 for fp32 buffers),
+            # in pinned memory placed on this GPU's NUMA node by the library (ww_host_alloc)
+            h_clips = eng.host_buffer((Bn, N_SAMPLES), torch.float32 if args.e2e_fp32 else torch.int16)
+            h_clips.copy_(clips if args.e2e_fp32 else clips_pcm)
+            h_out = (eng.host_buffer((Bn, 2), torch.float32), eng.host_buffer((Bn,), torch.float32),
+                     eng.host_buffer((Bn,), torch.uint8))
+            for _ in range(2):
+                eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
+            barrier()
+            e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+            assert torch.equal(h_out[2].to(dev), dec), "e2e decisions differ from the device-resident run"
+            # what the box can deliver: every rank copies the same pinned buffer H2D at the same time, nothing else running
+            d_tmp = torch.empty_like(h_clips, device=dev)
+            d_tmp.copy_(h_clips, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                d_tmp.copy_(h_clips, non_blocking=True)
+            barrier()
+            copy_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+            nbytes = Bn * N_SAMPLES * h_clips.element_size()
+            r["e2e"] = {"value": Bn * world / (e2e_ms / 1e3), "unit": "clips/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(nbytes + Bn * 9 * 4), "d2h_bytes_per_step": int(Bn * (2 * 4 + 4 + 1)),
+                        "host_input": "fp32 clips" if args.e2e_fp32 else "int16 PCM clips (as stored in the reference's WAV files)",
+                        "h2d_ceiling_gbs": nbytes * world / (copy_ms * 1e-3) / 1e9,
+                        "h2d_ceiling_ms_per_step": copy_ms,
+                        "pinned": {"numa_node_of_gpu": getattr(h_clips, "ww_node", -1),
+                                   "placement": {0: "plain pinned", 1: "mbind", 2: "first touch on a local CPU"}[getattr(h_clips, "ww_numa", 0)]}}
+            del h_clips, h_out, d_tmp
+        return r
+
+    main_r = run_score(B, args.steps, args.warmup, not args.no_e2e, True)
+    ms_step, launches, stages, clocks, e2e = main_r["ms_step"], main_r["launches"], main_r["stages"], main_r["clocks"], main_r["e2e"]
     value = B * world / (ms_step / 1e3)
 
-    # ---- e2e through the host-buffer C-ABI entry (pinned host memory in, host memory out)
-    e2e = None
-    if not args.no_e2e:
-        # host buffers hold the clips as they are on disk: int16 PCM (ww_score_host_pcm16; --e2e-fp32 for fp32 buffers)
-        with numa_local(dev):     # pinned pages are first-touched on the NUMA node next to this rank's GPU
-            h_clips = torch.empty((B, N_SAMPLES), dtype=torch.float32 if args.e2e_fp32 else torch.int16, pin_memory=True)
-            h_clips.copy_(clips if args.e2e_fp32 else clips_pcm)
-            h_out = (torch.empty((B, 2), dtype=torch.float32, pin_memory=True),
-                     torch.empty((B,), dtype=torch.float32, pin_memory=True),
-                     torch.empty((B,), dtype=torch.uint8, pin_memory=True))
-        for _ in range(2):
-            eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.score_host(h_clips, aug=aug, noise_bank=bank, normalize=True, out=h_out)
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-        assert torch.equal(h_out[2].to(dev), dec), "e2e decisions differ from the device-resident run"
-        e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "clips/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(B * N_SAMPLES * h_clips.element_size() + B * 9 * 4),
-               "d2h_bytes_per_step": int(B * (2 * 4 + 4 + 1)),
-               "host_input": "fp32 clips" if args.e2e_fp32 else "int16 PCM clips (as stored in the reference's WAV files)"}
+    # ---- SURVEY 8e strong scaling: the SAME 65,536 clips split 65,536 / N per GPU (at N = 1 it is the line above)
+    strong = None
+    if not args.no_secondary:
+        if world == 1:
+            strong = {"global_clips": B, "clips_per_gpu": B, "value": value, "ms_per_step": ms_step,
+                      "e2e_value": e2e["value"] if e2e else None, "note": "N = 1: identical to the weak-scaling line"}
+        else:
+            Bs = max(1, B // world)
+            sr = run_score(Bs, args.steps, args.warmup, not args.no_e2e, False)
+            strong = {"global_clips": Bs * world, "clips_per_gpu": Bs, "value": Bs * world / (sr["ms_step"] / 1e3),
+                      "ms_per_step": sr["ms_step"], "e2e_value": sr["e2e"]["value"] if sr["e2e"] else None,
+                      "e2e_ms_per_step": sr["e2e"]["ms_per_step"] if sr["e2e"] else None,
+                      "h2d_ceiling_gbs": sr["e2e"]["h2d_ceiling_gbs"] if sr["e2e"] else None}
+
+    # ---- BASELINE configs 2, 4, 5 in short form (every rank takes part; rank 0 embeds them)
+    secondary = None
+    if not args.no_secondary:
+        secondary = {}
+        for name, fn in (("logmel", lambda: measure_logmel(ww, dev, rank, world, 10, 3, barrier, max_over_ranks)),
+                         ("stream", lambda: measure_stream(ww, dev, rank, world, 2, 1, barrier, max_over_ranks, conv_mode)),
+                         ("train", lambda: measure_train(ww, dev, rank, world, 3, 1, barrier, max_over_ranks))):
+            r = fn()
+            secondary[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "roofline") if k in r}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -538,7 +572,7 @@ def main():
                       "conv_mode": conv_mode, "sharding": f"batch-sharded x{world}, no collective",
                       "l2": "inputs (4.2 GB/GPU) larger than L2; no explicit flush"},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-           "stage_ms_per_step": stage_ms, "cpu_baseline": cpu}
+           "stage_ms_per_step": stage_ms, "cpu_baseline": cpu, "strong": strong, "secondary": secondary}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

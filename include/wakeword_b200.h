@@ -143,6 +143,14 @@ int ww_score_host(ww_ctx* ctx, const float* clips_host, const float* noise_bank_
                   int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                   float* prob1_host, uint8_t* decision_host, int B);
 
+/* ---- pinned host buffers for the *_host entries, placed on the NUMA node of the context's GPU (sysfs numa_node of its
+ *      PCI function) so that eight ranks on a two-socket box do not all copy out of one socket's memory.
+ *      *how: 0 = plain pinned memory, 1 = mbind(MPOL_BIND), 2 = first touch from a CPU of that node.
+ *      The reference's counterpart is the DataLoader's pin_memory=True (wakeword_training_script.py:461-463). */
+void* ww_host_alloc(ww_ctx* ctx, size_t bytes, int* how);
+void ww_host_free(ww_ctx* ctx, void* ptr);
+int ww_host_numa_node(ww_ctx* ctx); /* -1 = unknown */
+
 /* ---- int16 PCM inputs.  The reference's clips are 16-bit WAV files that
  *      librosa.load turns into float32 as s / 32768 (AudioProcessor.load_audio, wakeword_training_script.py:65-71;
  *      the synthetic recipe writes them with sf.write, :359-388).  These entries take the int16 samples as they are

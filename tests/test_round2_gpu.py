@@ -291,3 +291,93 @@ def test_predict_wakeword_on_a_real_wav(ww, golden_dir, tmp_path):
         seen.add(is_ww)
     assert seen == {True, False}
     assert ww.predict_wakeword(str(tmp_path / "nope.wav"), net, proc, torch.device("cuda")) == (False, 0.0)
+
+
+# ------------------------------------------------------------------ dataset / device-fed loader
+def _make_wavs(tmp_path, n, lengths=None, seed=0):
+    clips = R.make_clips(n, seed=seed)
+    files = []
+    for i in range(n):
+        L = 16000 if lengths is None else lengths[i % len(lengths)]
+        x = np.tile(clips[i], 2)[:L]
+        _write_wav(tmp_path / f"f{seed}_{i}.wav", 0.8 * x / np.abs(x).max())
+        files.append(str(tmp_path / f"f{seed}_{i}.wav"))
+    return files
+
+
+def test_dataset_items_and_device_loader_agree_with_the_per_file_path(ww, tmp_path):
+    import random
+    proc = ww.AudioProcessor()
+    for lengths in (None, (16000, 9000, 12345), (16000, 20000, 30000)):     # exact / short (pad) / long (random crop)
+        pos = _make_wavs(tmp_path, 5, lengths, seed=1)
+        neg = _make_wavs(tmp_path, 6, lengths, seed=2) + [str(tmp_path / "missing.wav")]
+        ds = ww.WakewordDataset(pos, neg, proc)
+        random.seed(11)
+        items = [ds[i] for i in range(len(ds))]
+        x0, y0 = items[0]
+        assert tuple(x0.shape) == (1, 80, 32) and x0.dtype == torch.float32 and int(y0) == 1 and int(items[-1][1]) == 0
+        assert tuple(items[-1][0].shape) == (1, 80, 31) and not items[-1][0].any()          # failed file: zeros(80, 31)
+        loader = ww.DeviceFeatureLoader(pos, neg, proc, batch_size=4)
+        random.seed(11)                                                     # same crop draws, same order (no shuffle)
+        feats, labels = zip(*list(loader))
+        assert len(loader) == 3 and [f.shape[0] for f in feats] == [4, 4, 4]
+        feats, labels = torch.cat(feats), torch.cat(labels)
+        assert feats.is_cuda and tuple(feats.shape) == (12, 1, 80, 32) and tuple(labels.shape) == (12, 1)
+        assert labels.flatten().tolist() == [1] * 5 + [0] * 7
+        for i in range(11):
+            assert (feats[i, 0].cpu() - items[i][0][0]).abs().max() < 1e-3, (lengths, i)
+        assert not feats[11].any()
+
+
+def test_training_epoch_from_the_device_loader_matches_feature_fed_steps(ww, tmp_path):
+    """One epoch of WakewordTrainer.train_epoch over the device-fed loader (int16 PCM -> ww_augment_pcm16 -> ww_logmel ->
+    ww_train_backward, nothing leaves the device) reproduces the losses of stepping on the same features handed in from
+    outside; then an augmented epoch runs and the reference's epoch driver (train) saves a loadable best checkpoint."""
+    class MC(ww.ModelConfig):
+        DROPOUT = 0.0
+    proc = ww.AudioProcessor(noise_bank=R.make_noise_bank())
+    pos, neg = _make_wavs(tmp_path, 6, seed=3), _make_wavs(tmp_path, 10, seed=4)
+    loader = ww.DeviceFeatureLoader(pos, neg, proc, batch_size=8)
+
+    def fresh():
+        torch.manual_seed(9)
+        m = ww.WakewordModel(MC).cuda()
+        return m, ww.WakewordTrainer(m, "cuda")
+
+    m1, t1 = fresh()
+    m1.train()
+    losses_loader = [float(t1.train_step(x, y.squeeze())[0]) for x, y in loader]
+    feats = [(proc.audio_to_mel_batch(np.stack([proc.normalize_audio(proc.load_audio(f)) for f in fs])), lab)
+             for fs, lab in (((pos + neg)[:8], [1] * 6 + [0] * 2), ((pos + neg)[8:], [0] * 8))]
+    m2, t2 = fresh()
+    m2.train()
+    losses_feat = [float(t2.train_step(x, torch.tensor(lab).cuda())[0]) for x, lab in feats]
+    assert np.allclose(losses_loader, losses_feat, rtol=1e-5, atol=1e-6), (losses_loader, losses_feat)
+    # the reference's epoch driver on device-fed loaders (augmented training set, plain validation set)
+    m3, t3 = fresh()
+    t3.best_checkpoint_path = str(tmp_path / "best_wakeword_model.pth")
+    train_loader = ww.DeviceFeatureLoader(pos, neg, proc, batch_size=8, shuffle=True, augment=True)
+    t3.train(train_loader, loader, epochs=2)
+    assert len(t3.train_losses) == 2 and all(np.isfinite(t3.train_losses)) and len(t3.val_accuracies) == 2
+    ck = torch.load(t3.best_checkpoint_path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "val_acc", "train_acc", "train_loss", "val_loss"}
+    assert set(ck["optimizer_state_dict"]) == {"state", "param_groups"} and len(ck["optimizer_state_dict"]["state"]) == len(ck["model_state_dict"])
+    m4 = ww.WakewordModel(MC).cuda()
+    ww.load_checkpoint(t3.best_checkpoint_path, m4)
+
+
+def test_pinned_host_buffers_from_the_library(ww):
+    """ww_host_alloc: pinned (cudaHostRegister) host memory placed next to the GPU; usable by the host entry."""
+    eng = ww.get_engine()
+    h = eng.host_buffer((64, 16000), torch.int16)
+    assert h.shape == (64, 16000) and h.dtype == torch.int16 and not h.any() and h.ww_numa in (0, 1, 2)
+    pcm = np.clip(np.round(R.make_clips(64, seed=4) * 32768.0), -32768, 32767).astype(np.int16)
+    h.copy_(torch.from_numpy(pcm))
+    sd = R.seeded_state_dict(256, seed=0)
+    net = _load(ww, sd)
+    a = net.engine().score_host(h, normalize=True)
+    b = net.engine().score(torch.from_numpy(pcm).cuda(), normalize=True)
+    assert np.array_equal(a[0], b[0].cpu().numpy())
+    v = h[:3]
+    del h
+    assert v.shape == (3, 16000) and np.array_equal(v.numpy(), pcm[:3])       # views keep the mapping alive

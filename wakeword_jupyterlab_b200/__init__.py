@@ -7,9 +7,12 @@ from .model import WakewordModel
 from .predict import predict_wakeword, score_clips, score_stream
 from .processor import AudioProcessor
 from .trainer import WakewordTrainer
-from .checkpoint import load_checkpoint, save_best_checkpoint, save_final_checkpoint
+from .checkpoint import (load_checkpoint, load_deployment_package, save_best_checkpoint, save_deployment_package,
+                         save_final_checkpoint)
+from .dataset import DeviceFeatureLoader, WakewordDataset
 
 __all__ = ["AudioConfig", "ModelConfig", "TrainingConfig", "AugmentationConfig", "ReadmeAudioConfig",
            "ReadmeModelConfig", "AudioProcessor", "WakewordModel", "predict_wakeword", "score_clips",
            "score_stream", "AugBatch", "Engine", "get_engine", "WakewordTrainer", "load_checkpoint", "save_best_checkpoint",
-           "save_final_checkpoint"]
+           "save_final_checkpoint", "save_deployment_package", "load_deployment_package", "WakewordDataset",
+           "DeviceFeatureLoader"]

@@ -34,6 +34,7 @@ EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_f
            "ww_train_backward", "ww_train_apply", "ww_train_step", "ww_train_reset", "ww_train_n_params",
            "ww_train_grad_buffer", "ww_train_param_range", "ww_get_weights",
            "ww_train_get_moments", "ww_train_set_moments", "ww_train_get_step", "ww_train_set_step",
+           "ww_host_alloc", "ww_host_free", "ww_host_numa_node",
            "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
@@ -89,6 +90,11 @@ def load():
         lib.ww_train_get_step.argtypes = [vp]
         lib.ww_train_get_step.restype = i64
         lib.ww_train_set_step.argtypes = [vp, i64]
+        lib.ww_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int)]
+        lib.ww_host_alloc.restype = vp
+        lib.ww_host_free.argtypes = [vp, vp]
+        lib.ww_host_free.restype = None
+        lib.ww_host_numa_node.argtypes = [vp]
         lib.ww_kernel_launches.argtypes = [vp]
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]

@@ -47,3 +47,47 @@ def save_final_checkpoint(path, model, best_val_acc, device, training_config=Non
                 "config": {"model": _cfg_dict(model.config), "audio": _cfg_dict(model.audio_config),
                            "training": _cfg_dict(training_config or TrainingConfig)},
                 "best_val_acc": best_val_acc, "device": str(device)}, path)
+
+
+def save_deployment_package(path, model, checkpoint=None, device="cuda", architecture_path=None):
+    """The notebook's deployment package (wakeword_training.ipynb:951-977): state dict + the model / audio configuration
+    values + training info + class names, same keys and nesting.  ``checkpoint`` is the dictionary of
+    ``best_wakeword_model.pth`` (``val_acc`` / ``epoch`` are read with the notebook's defaults).  When
+    ``architecture_path`` is given, the plain-text summary of :980-991 (``model_architecture.txt``) is written too."""
+    mc, ac = model.config, model.audio_config
+    checkpoint = checkpoint or {}
+    pkg = {
+        "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+        "model_config": {k: getattr(mc, k) for k in ("HIDDEN_SIZE", "NUM_LAYERS", "DROPOUT", "NUM_CLASSES")},
+        "audio_config": {k: getattr(ac, k) for k in ("SAMPLE_RATE", "DURATION", "N_MELS", "N_FFT", "HOP_LENGTH", "FMIN", "FMAX")},
+        "training_info": {"best_val_accuracy": checkpoint.get("val_acc", 0), "epoch": checkpoint.get("epoch", 0) + 1,
+                          "device": str(device)},
+        "classes": list(CLASS_NAMES),
+    }
+    torch.save(pkg, path)
+    if architecture_path:
+        with open(architecture_path, "w") as f:
+            f.write("Wakeword Detection Model Architecture\n")
+            f.write("================================\n\n")
+            f.write("Model Type: CNN + LSTM\n")
+            f.write(f"Input Shape: (1, {ac.N_MELS}, 31)\n")
+            f.write(f"Hidden Size: {mc.HIDDEN_SIZE}\n")
+            f.write(f"Number of Layers: {mc.NUM_LAYERS}\n")
+            f.write(f"Dropout: {mc.DROPOUT}\n")
+            f.write(f"Number of Classes: {mc.NUM_CLASSES}\n")
+            f.write(f"Parameters: {sum(p.numel() for p in model.parameters()):,}\n")
+            f.write(f"Device: {device}\n")
+    return pkg
+
+
+def load_deployment_package(path, device="cuda"):
+    """Rebuild a ``WakewordModel`` from a deployment package: configuration classes are reconstructed from the stored
+    values (the notebook's consumer does the same by hand) and the weights loaded."""
+    from .config import AudioConfig, ModelConfig
+    from .model import WakewordModel
+    pkg = torch.load(path, map_location="cpu", weights_only=False)
+    MC = type("ModelConfig", (ModelConfig,), dict(pkg.get("model_config", {})))
+    AC = type("AudioConfig", (AudioConfig,), dict(pkg.get("audio_config", {})))
+    model = WakewordModel(MC, AC)
+    model.load_state_dict(pkg["model_state_dict"])
+    return model.to(device).eval(), pkg

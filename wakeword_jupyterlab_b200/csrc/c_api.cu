@@ -1,9 +1,14 @@
 // C ABI of libwakeword_b200.so: context, tables, weights, stage orchestration.  See include/wakeword_b200.h.
 #include "ctx.cuh"
 
+#include <errno.h>
 #include <math.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <algorithm>
 #include <numeric>
 #include <utility>
@@ -749,6 +754,109 @@ int ww_score_host_pcm16(ww_ctx* c, const int16_t* clips_host, const float* bank_
                         uint8_t* decision_host, int B) {
   return score_host_impl(c, clips_host, 1, bank_dev, bank_rows, bank_len, aug_host, normalize, logits_host, prob1_host,
                          decision_host, B);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pinned host buffers next to the GPU.  On a two-socket box the pages of a plain cudaHostAlloc land on the NUMA node of the
+// allocating thread; with eight ranks feeding eight GPUs from one node the host->device copies of ww_score_host share one
+// socket's memory controllers and the inter-socket link (round 1: 185 GB/s aggregate, 0.62 scaling efficiency end to end).
+// ww_host_alloc places the pages on the GPU's own node (sysfs numa_node of its PCI function): mbind(MPOL_BIND) on an
+// anonymous mapping, or, where the container's seccomp profile refuses mbind, first touch from a thread moved onto a CPU
+// of that node; then cudaHostRegister.  `how` reports what happened: 0 = plain pinned memory (node unknown / nothing
+// worked), 1 = mbind, 2 = first touch on a local CPU.
+namespace {
+
+int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// CPUs of a NUMA node, from sysfs cpulist ("0-31,64-95")
+std::vector<int> node_cpus(int node) {
+  std::vector<int> out;
+  const std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return out;
+  int a, b;
+  char sep;
+  while (fscanf(f, "%d", &a) == 1) {
+    b = a;
+    if (fscanf(f, "%c", &sep) == 1 && sep == '-') {
+      if (fscanf(f, "%d", &b) != 1) b = a;
+      if (fscanf(f, "%c", &sep) != 1) sep = 0;
+    }
+    for (int c = a; c <= b; ++c) out.push_back(c);
+    if (sep != ',') break;
+  }
+  fclose(f);
+  return out;
+}
+
+struct HostBuf { void* p; size_t bytes; int device; };
+std::vector<HostBuf> g_host_bufs;
+
+}  // namespace
+
+int ww_host_numa_node(ww_ctx* c) { return c ? gpu_numa_node(c->device) : -1; }
+
+void* ww_host_alloc(ww_ctx* c, size_t bytes, int* how) {
+  if (how) *how = 0;
+  if (!c || bytes == 0) return nullptr;
+  cudaSetDevice(c->device);
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  const size_t len = (bytes + page - 1) / page * page;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) { c->set_error("ww_host_alloc: mmap failed"); return nullptr; }
+  int method = 0;
+  const int node = gpu_numa_node(c->device);
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+#ifdef SYS_mbind
+    if (syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, (unsigned long)(8 * sizeof(mask)), 0u) == 0) method = 1;
+#endif
+    if (method == 0) {
+      const std::vector<int> cpus = node_cpus(node);
+      cpu_set_t old, want;
+      CPU_ZERO(&want);
+      for (int cpu : cpus) if (cpu < CPU_SETSIZE) CPU_SET(cpu, &want);
+      if (!cpus.empty() && sched_getaffinity(0, sizeof(old), &old) == 0 && sched_setaffinity(0, sizeof(want), &want) == 0) {
+        memset(p, 0, len);                         // first touch on a CPU of the GPU's node
+        sched_setaffinity(0, sizeof(old), &old);
+        method = 2;
+      }
+    }
+  }
+  if (method != 2) memset(p, 0, len);              // fault the pages in (under the mbind policy when it was accepted)
+  if (cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    munmap(p, len);
+    c->set_error("ww_host_alloc: cudaHostRegister failed");
+    return nullptr;
+  }
+  g_host_bufs.push_back(HostBuf{p, len, c->device});
+  if (how) *how = method;
+  return p;
+}
+
+void ww_host_free(ww_ctx*, void* p) {          // the context may already be gone (finalizers at interpreter exit): not touched
+  if (!p) return;
+  for (size_t i = 0; i < g_host_bufs.size(); ++i)
+    if (g_host_bufs[i].p == p) {
+      cudaSetDevice(g_host_bufs[i].device);
+      cudaHostUnregister(p);
+      munmap(p, g_host_bufs[i].bytes);
+      g_host_bufs.erase(g_host_bufs.begin() + i);
+      return;
+    }
 }
 
 }  // extern "C"

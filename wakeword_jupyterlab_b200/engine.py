@@ -143,6 +143,26 @@ class Engine:
             self._chk(self.lib.ww_profile_read(self._ctx, -1, None, None), "ww_profile_read")
         return out
 
+    # ------------------------------------------------------------------ pinned host buffers next to the GPU
+    def host_buffer(self, shape, dtype):
+        """Pinned host tensor whose pages sit on the NUMA node of this engine's GPU (``ww_host_alloc``); falls back to plain
+        pinned memory where the kernel allows neither mbind nor a local first touch.  ``tensor.ww_numa`` says which
+        (0 plain, 1 mbind, 2 first touch) and ``tensor.ww_node`` the node.  Freed with the tensor."""
+        dtype = torch.empty((), dtype=dtype).dtype
+        n = int(np.prod(shape)) if len(shape) else 1
+        nbytes = max(1, n * torch.empty((), dtype=dtype).element_size())
+        how = C.c_int(0)
+        ptr = self.lib.ww_host_alloc(self._ctx, nbytes, C.byref(how))
+        if not ptr:
+            self._chk(-2, "ww_host_alloc")
+        import weakref
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(buf, self.lib.ww_host_free, self._ctx, ptr)     # numpy / torch views keep `buf` alive
+        np_dt = {torch.int16: np.int16, torch.float32: np.float32, torch.uint8: np.uint8, torch.int32: np.int32}[dtype]
+        t = torch.from_numpy(np.ctypeslib.as_array(buf).view(np_dt)[:n].reshape(shape))
+        t.ww_numa, t.ww_node = how.value, int(self.lib.ww_host_numa_node(self._ctx))
+        return t
+
     # ------------------------------------------------------------------ weights
     def set_weights(self, state_dict):
         """state_dict: name -> torch tensor / ndarray (reference state_dict keys)."""
