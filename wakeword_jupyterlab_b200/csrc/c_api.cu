@@ -88,6 +88,7 @@ int build_tables(ww_ctx* c) {
     for (int k = lo; k <= hi; ++k) packed.push_back(fb[(size_t)m * n_bins + k]);
   }
   c->mel_nnz = (int)packed.size();
+  c->h_mel_start = start; c->h_mel_len = len;
   if ((rc = upload(c, &c->d_mel_start, start))) return rc;
   if ((rc = upload(c, &c->d_mel_len, len))) return rc;
   if ((rc = upload(c, &c->d_mel_off, off))) return rc;
@@ -140,6 +141,7 @@ std::vector<float> fetch(ww_ctx* c, const std::string& name) {
 int free_all(ww_ctx* c) {
   cudaFree(c->d_window); cudaFree(c->d_twiddle); cudaFree(c->d_mel_start); cudaFree(c->d_mel_len);
   cudaFree(c->d_mel_off); cudaFree(c->d_mel_w); cudaFree(c->d_rs_kern); cudaFree(c->d_rs_desc);
+  cudaFree(c->d_tc_f32); cudaFree(c->d_tc_f64hi); cudaFree(c->d_tc_f64lo); cudaFree(c->d_tc_tw); cudaFree(c->d_tc_rot); cudaFree(c->d_tc_tasks);
   for (auto& kv : c->w) cudaFree(kv.second);
   for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
   for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); cudaFree(c->d_bias_sum[i]); }

@@ -79,6 +79,13 @@ struct ww_ctx {
   int* d_mel_off = nullptr;      // [n_mels] offset into d_mel_w
   float* d_mel_w = nullptr;      // packed non-zero weights
   int mel_nnz = 0;
+  std::vector<int> h_mel_start, h_mel_len;      // host copies (task table of the tensor-core log-mel kernel)
+  // ---- tensor-core log-mel (logmel_tc.cu): DFT matrices as fp16 hi / lo in UMMA layouts, twiddles, mel task table
+  int tc_lm_ready = 0;                          // 0 = not tried, 1 = ready, -1 = configuration outside the kernel's domain
+  int tc_lm_tasks = 0;
+  __half *d_tc_f32 = nullptr, *d_tc_f64hi = nullptr, *d_tc_f64lo = nullptr;
+  float2 *d_tc_tw = nullptr, *d_tc_rot = nullptr;
+  uint32_t* d_tc_tasks = nullptr;
 
   // ---- resample tables
   std::vector<ResampleTable> rs_tables;
@@ -170,6 +177,8 @@ struct StreamReuse {
 };
 int ww_launch_logmel_stream(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
                             int normalize, const StreamReuse* sp, cudaStream_t st);
+int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B, int normalize,
+                        cudaStream_t st);    // WW_OK = launched, 1 = outside its domain (use the FFT kernel), < 0 = error
 int ww_launch_blockmax(ww_ctx* c, const void* x, int pcm16, int64_t n, int block, float* out, int64_t n_blocks,
                        cudaStream_t st);
 int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st);

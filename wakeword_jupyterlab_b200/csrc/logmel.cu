@@ -518,6 +518,10 @@ int ww_launch_blockmax(ww_ctx* c, const void* x, int pcm16, int64_t n, int block
 int ww_launch_logmel_stream(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B,
                             int normalize, const StreamReuse* sp, cudaStream_t st) {
   if (B <= 0) return WW_OK;
+  if (!sp) {             // plain log-mel: the tensor-core kernel where it applies (the reference's own preset)
+    const int rc = ww_launch_logmel_tc(c, clips, pcm16, clip_stride, out, B, normalize, st);
+    if (rc <= 0) return rc;
+  }
   LogmelParams p;
   p.mode = sp ? sp->mode : 0;
   p.cache = sp ? sp->cache : nullptr; p.n_cache = sp ? sp->n_cache : 0; p.cache_g = sp ? sp->cache_g : 1;

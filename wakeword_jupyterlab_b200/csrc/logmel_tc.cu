@@ -1,0 +1,549 @@
+// K2 on the tensor core: framing + Hann + STFT power + mel + dB for the reference's own preset (n_fft = win = 2048, hop 512,
+// 16,000 samples -> 80 x 32), the DFT as two tcgen05 GEMM stages (sm_100a).
+//
+// Replaces AudioProcessor.audio_to_mel (/root/reference/wakeword_training_script.py:85-101: librosa melspectrogram +
+// power_to_db(ref=max)) like logmel.cu does; logmel.cu (shared-memory FFT) stays the kernel of every other configuration
+// and of the streaming modes.
+//
+// Factorisation 2048 = 64 x 32, n = n1 + 64 n2, k = 32 k1 + k2 (n1, k1 < 64; n2, k2 < 32):
+//     X[32 k1 + k2] = sum_n1 W64^(n1 k1) [ W2048^(n1 k2) sum_n2 x[n1 + 64 n2] W32^(n2 k2) ]
+//   * the zero-padded clip (18,432 samples = 288 rows of 64) lives in shared memory ONCE as fp16 hi and lo copies of
+//     x * 2^k / peak-normalised scale; frame t starts at row 8 t, so the A operand of a frame pair is an MN-major
+//     SWIZZLE_NONE *view* of those bytes (start t * 1 KB, M-core stride 128 B, K-core stride 1 KB): nothing is framed or
+//     windowed on CUDA cores (validated by tools/mn_major_view_check.cu and tools/gemm_fft_proto.cu on a B200);
+//   * stage 1 (K = 32):  D1[(t, n1), (re | im of k2) x (hi | lo of F32)] = x_hi [F_hi | F_lo] + x_lo F_hi   (3 products);
+//   * epilogue 1 (thread = (t, n1)): twiddle W2048^(n1 k2), the Hann window as the 3-tap filter
+//     0.5 Y[k2] - 0.25 (Y[k2-1] + Y[k2+1]) over k2 (with the k1 carry W64^(+-n1) at the ends), fp16 hi/lo split ->
+//     Y' = stage-3 A operand (MN-major, M = (frame, k2), K = n1 re | n1 im);
+//   * stage 3 (K = 128, N = 64 = re | im of k1 < 32):  D3 = Y'_hi F64_hi + Y'_lo F64_hi + Y'_hi F64_lo;
+//     bin 1024 (k1 = 32) is not computed: the launcher takes this kernel only when no mel filter touches it (true for the
+//     reference's fmax = 8000 = Nyquist, where librosa's last filter ends at bin 1023);
+//   * epilogue 3 (thread = (frame, k2)): power of bins 32 k1 + k2 -> shared-memory tile P4[bin] = (4 frames);
+//   * mel warps: banded projection (2-16 lanes per band, one 128-bit load serves 4 frames), then per clip max -> dB -> store.
+// One persistent CTA per SM, 21 warps: 0 MMA issuer | 1-8 epilogue 1 (two frame pairs in flight) | 9-12 epilogue 3 |
+// 13-16 mel + dB | 17-20 converter (peak of the NEXT clip, then fp32 / int16 -> fp16 hi / lo in chunks of 2,048 padded
+// samples that are released group by group, so conversion overlaps the GEMMs of the previous clip).
+// Peak normalisation is a scale of the power spectrum: the clip is always transformed at unit peak (any input magnitude
+// fits fp16 hi/lo), and `normalize = 0` multiplies the mel energies by peak^2 again.
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+#include <vector>
+
+using namespace tc;
+
+namespace {
+
+constexpr int kNfft = 2048, kN1 = 64, kN2 = 32, kW = 32, kSamples = 16000, kHop = 512, kBins = kNfft / 2 + 1;
+constexpr int kRows = 288;                           // padded clip rows of 64 samples
+constexpr int kChunks = 9;                           // converter chunks of 32 rows (2,048 padded samples)
+constexpr int kClipBytes = kRows * 64 * 2;           // one fp16 copy of the padded clip: [row block][col chunk 8][row % 8][8]
+constexpr int kF32Bytes = 4 * 128 * 16;              // stage-1 B: [kc 4][n 128 = re hi | im hi | re lo | im lo][8]
+constexpr int kN3 = 64;                              // stage-3 N: re of k1 0..31 | im of k1 0..31
+constexpr int kF64Bytes = 16 * kN3 * 16;             // stage-3 B (hi or lo): [kc 16][n 64][8]
+constexpr int kYBytes = 16 * 2048;                   // stage-3 A (hi or lo), MN-major: [m chunk 16][k row 128][8]
+constexpr int kP4Bytes = 1024 * 16;                  // power tile: [bin 1024] x (4 frames) fp32
+constexpr int kMelPitch = kW + 1;
+constexpr int kMaxMels = 80, kMaxNnz = 2304, kMaxTasks = 1024;
+constexpr float kFScale = 1024.0f, kYScale = 4096.0f;
+constexpr int kWarps = 21, kThreads = kWarps * 32;
+constexpr float kAmin = 1e-10f, kTopDb = 80.0f;
+
+constexpr size_t kSmem = 2 * (size_t)kClipBytes + kF32Bytes + 2 * (size_t)kF64Bytes + 2 * (size_t)kYBytes + kP4Bytes +
+                         (size_t)kMaxMels * kMelPitch * 4 + (size_t)kMaxNnz * 4 + (size_t)kMaxTasks * 4 +
+                         (size_t)3 * kMaxMels * 4 + 64 * 8 + 128;
+
+__host__ __device__ constexpr uint32_t idesc_a_mn(int M, int N) { return make_idesc(M, N) | (1u << 15); }
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld1_nowait(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+// v -> fp16 hi + fp16 lo (v = hi + lo to ~22 bits), two values at a time
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(a, b);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(a - h.x, b - h.y);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// 8 consecutive samples starting at a multiple of 8 (16-byte aligned rows: checked by the launcher)
+__device__ __forceinline__ void ld8(const float* x, int i, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x + i)), b = __ldg(reinterpret_cast<const float4*>(x + i + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const int16_t* x, int i, float* v) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + i));
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = (float)(int16_t)(w[k] & 0xffffu) * (1.0f / 32768.0f);
+    v[2 * k + 1] = (float)(int16_t)(w[k] >> 16) * (1.0f / 32768.0f);
+  }
+}
+
+struct TcLogmelParams {
+  const void* clips;
+  int64_t clip_stride;           // samples
+  LogmelOut out;
+  int B, normalize, n_mels, mel_nnz, n_tasks;
+  const __half* f32;             // pre-tiled stage-1 B
+  const __half* f64hi;           // pre-tiled stage-3 B
+  const __half* f64lo;
+  const float2* tw;              // [64][32] exp(-2 pi i n1 k2 / 2048)
+  const float2* rot;             // [64]     exp(-2 pi i n1 / 64)
+  const float* mel_w;            // packed non-zero filterbank weights
+  const int* mel_start;          // [n_mels] first bin / bins / offset into mel_w
+  const int* mel_len;
+  const int* mel_off;
+  const uint32_t* tasks;         // mel | lane j << 8 | lanes << 16, groups of `lanes` consecutive entries, lanes descending
+};
+
+template <typename TIn>
+__global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_constant__ TcLogmelParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* xhi = smem;
+  unsigned char* xlo = xhi + kClipBytes;
+  unsigned char* f32 = xlo + kClipBytes;
+  unsigned char* f64hi = f32 + kF32Bytes;
+  unsigned char* f64lo = f64hi + kF64Bytes;
+  unsigned char* yhi = f64lo + kF64Bytes;
+  unsigned char* ylo = yhi + kYBytes;
+  float4* p4 = reinterpret_cast<float4*>(ylo + kYBytes);
+  float* mel_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(p4) + kP4Bytes);   // [n_mels][33]
+  float* melw = mel_s + kMaxMels * kMelPitch;
+  uint32_t* tasks = reinterpret_cast<uint32_t*>(melw + kMaxNnz);
+  int* mst = reinterpret_cast<int*>(tasks + kMaxTasks);                                      // [3][kMaxMels]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mst + 3 * kMaxMels);
+  uint64_t* x_full = bars;            // [9]  converter warps -> issuer (chunk of 32 rows converted)
+  uint64_t* x_empty = bars + 9;       // [9]  stage-1 MMAs that read the chunk are done -> converter
+  uint64_t* d1_full = bars + 18;      // [2]  pair h
+  uint64_t* d1_empty = bars + 20;     // [2]
+  uint64_t* y_full = bars + 22;       // [1]  8 epilogue-1 warps
+  uint64_t* y_empty = bars + 23;      // [1]  stage-3 MMAs done
+  uint64_t* d3_full = bars + 24;      // [2]
+  uint64_t* d3_empty = bars + 26;     // [2]
+  uint64_t* p_full = bars + 28;       // [1]  4 epilogue-3 warps
+  uint64_t* p_empty = bars + 29;      // [1]  4 mel warps
+  float2* scale_ring = reinterpret_cast<float2*>(bars + 32);   // [4] per clip: (1 / (2^k peak F), mel energy factor)
+  float* red = reinterpret_cast<float*>(scale_ring + 4);       // [8] reduction scratch: [0,4) converter, [4,8) mel warps
+  uint32_t* slot = reinterpret_cast<uint32_t*>(red + 8);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int n_mels = p.n_mels;
+
+  // ---- one-time setup: tables, zero padding of the clip copies, barriers, TMEM
+  for (int i = tid * 16; i < kF32Bytes; i += kThreads * 16)
+    *reinterpret_cast<uint4*>(f32 + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.f32) + i);
+  for (int i = tid * 16; i < kF64Bytes; i += kThreads * 16) {
+    *reinterpret_cast<uint4*>(f64hi + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.f64hi) + i);
+    *reinterpret_cast<uint4*>(f64lo + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.f64lo) + i);
+  }
+  for (int i = tid * 16; i < kClipBytes; i += kThreads * 16) {     // centre padding (rows 0-15, 266-287) stays zero
+    *reinterpret_cast<uint4*>(xhi + i) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(xlo + i) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < p.mel_nnz; i += kThreads) melw[i] = p.mel_w[i];
+  for (int i = tid; i < p.n_tasks; i += kThreads) tasks[i] = p.tasks[i];
+  for (int i = tid; i < n_mels; i += kThreads) {
+    mst[i] = p.mel_start[i]; mst[kMaxMels + i] = p.mel_len[i]; mst[2 * kMaxMels + i] = p.mel_off[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kChunks; ++i) { mbar_init(x_full + i, 4); mbar_init(x_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 4);
+      mbar_init(d3_full + i, 1); mbar_init(d3_empty + i, 4);
+    }
+    mbar_init(y_full, 8); mbar_init(y_empty, 1);
+    mbar_init(p_full, 4); mbar_init(p_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);          // D1: columns 128 h (h < 2); D3: columns 256 + 64 b (b < 2)
+  fence_proxy_async();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = *slot;
+  const int n_my = ((int)blockIdx.x < p.B) ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // clips of this CTA
+  const uint32_t n_groups = (uint32_t)n_my * 8u;
+
+  if (warp == 0) {
+    // ===================== MMA issuer: S1(G + 1) is issued before S3(G), across clip boundaries too
+    const uint64_t b1 = make_desc(smem_u32(f32), 128 * 16, 128);
+    const uint64_t b3h = make_desc(smem_u32(f64hi), kN3 * 16, 128), b3l = make_desc(smem_u32(f64lo), kN3 * 16, 128);
+    const uint64_t a3h = make_desc(smem_u32(yhi), 128, 2048), a3l = make_desc(smem_u32(ylo), 128, 2048);
+    auto stage1 = [&](uint32_t G) {
+      const uint32_t ci = G >> 3, g = G & 7;
+      if (g == 0) mbar_wait(x_full + 0, ci & 1, 10);
+      mbar_wait(x_full + g + 1, ci & 1, 11);                       // frames 4g .. 4g+3 read rows 32 g .. 32 g + 55
+#pragma unroll 1
+      for (uint32_t h = 0; h < 2; ++h) {
+        mbar_wait(d1_empty + h, (G & 1) ^ 1, 12);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t t0 = 4 * g + 2 * h, d = tm + h * 128;
+          const uint64_t ah = make_desc(smem_u32(xhi) + t0 * 1024u, 1024, 128), al = make_desc(smem_u32(xlo) + t0 * 1024u, 1024, 128);
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            umma_f16(d, ah + (uint64_t)((s * 2 * 1024) >> 4), b1 + (uint64_t)((s * 2 * 128 * 16) >> 4), idesc_a_mn(128, 128), s);
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            umma_f16(d, al + (uint64_t)((s * 2 * 1024) >> 4), b1 + (uint64_t)((s * 2 * 128 * 16) >> 4), idesc_a_mn(128, 64), 1);
+          umma_commit(d1_full + h);
+          if (h == 1) {
+            umma_commit(x_empty + g);                              // chunk g is not read by any later group of this clip
+            if (g == 7) umma_commit(x_empty + 8);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    auto stage3 = [&](uint32_t G) {
+      const uint32_t buf = G & 1;
+      mbar_wait(y_full, G & 1, 13);
+      mbar_wait(d3_empty + buf, ((G >> 1) & 1) ^ 1, 14);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tm + 256 + buf * kN3;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint64_t a = prod == 1 ? a3l : a3h, b = prod == 2 ? b3l : b3h;
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            umma_f16(d, a + (uint64_t)((s * 2 * 128) >> 4), b + (uint64_t)((s * 2 * kN3 * 16) >> 4), idesc_a_mn(128, kN3), (prod | s) != 0);
+        }
+        umma_commit(d3_full + buf);
+        umma_commit(y_empty);
+      }
+      __syncwarp();
+    };
+    if (n_groups) stage1(0);
+    for (uint32_t G = 0; G < n_groups; ++G) {
+      if (G + 1 < n_groups) stage1(G + 1);
+      stage3(G);
+    }
+  } else if (warp <= 8) {
+    // ===================== epilogue 1: thread = (frame 2h + f of the group, n1); TMEM lane quadrant = warp & 3
+    const int q = warp & 3, h = (warp - 1) >> 2, m = q * 32 + lane, f = m >> 6, n1 = m & 63;
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+    const float2 rp = __ldg(p.rot + n1);                           // W64^(n1)
+    const float4* twp = reinterpret_cast<const float4*>(p.tw + n1 * kN2);
+    const uint32_t dbase = tm + h * 128 + lane_addr;
+    const int fslot = 2 * h + f;
+    for (uint32_t G = 0; G < n_groups; ++G) {
+      mbar_wait(d1_full + h, G & 1, 20);
+      tc_fence_after();
+      const float inv = scale_ring[(G >> 3) & 3].x;                // written by the converter before the clip's first chunk
+      // column c of D1: re hi c, im hi 32 + c, re lo 64 + c, im lo 96 + c
+      auto load_chunk = [&](int c, float2* y) {
+        uint32_t r0[8], r1[8], r2[8], r3[8];
+        tmem_ld8_nowait(dbase + 8 * c, r0);
+        tmem_ld8_nowait(dbase + 32 + 8 * c, r1);
+        tmem_ld8_nowait(dbase + 64 + 8 * c, r2);
+        tmem_ld8_nowait(dbase + 96 + 8 * c, r3);
+        float4 w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w4[e] = __ldg(twp + 4 * c + e);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float re = (__uint_as_float(r0[e]) + __uint_as_float(r2[e])) * inv;
+          const float im = (__uint_as_float(r1[e]) + __uint_as_float(r3[e])) * inv;
+          const float2 w = (e & 1) ? make_float2(w4[e >> 1].z, w4[e >> 1].w) : make_float2(w4[e >> 1].x, w4[e >> 1].y);
+          y[e] = cmul(make_float2(re, im), w);
+        }
+      };
+      float2 cur[8], nxt[8], prev, y32;
+      {
+        uint32_t a0, a1, a2, a3;                                    // Y[31] for the left end: Y[-1] = W64^(-n1) Y[31]
+        tmem_ld1_nowait(dbase + 31, a0);
+        tmem_ld1_nowait(dbase + 63, a1);
+        tmem_ld1_nowait(dbase + 95, a2);
+        tmem_ld1_nowait(dbase + 127, a3);
+        const float2 w31 = __ldg(p.tw + n1 * kN2 + 31);
+        tmem_ld_wait();
+        const float2 y31 = cmul(make_float2((__uint_as_float(a0) + __uint_as_float(a2)) * inv,
+                                            (__uint_as_float(a1) + __uint_as_float(a3)) * inv), w31);
+        prev = make_float2(y31.x * rp.x + y31.y * rp.y, y31.y * rp.x - y31.x * rp.y);       // conj(rp) * y31
+      }
+      load_chunk(0, cur);
+      y32 = cmul(cur[0], rp);                                        // Y[32] = W64^(n1) Y[0]
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < 3) load_chunk(c + 1, nxt);
+        if (c == 2) {                                                // every TMEM read of this pair is done
+          tc_fence_before();
+          mbar_arrive_warp(d1_empty + h, lane);
+        }
+        if (c == 0) mbar_wait(y_empty, (G & 1) ^ 1, 21);             // stage 3 of the previous group has read Y'
+        uint32_t zr_h[4], zr_l[4], zi_h[4], zi_l[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          float zr[2], zi[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int e = 2 * e2 + u;
+            const float2 l = e == 0 ? prev : cur[e - 1];
+            const float2 r = e == 7 ? (c < 3 ? nxt[0] : y32) : cur[e + 1];
+            zr[u] = (0.5f * cur[e].x - 0.25f * (l.x + r.x)) * (kYScale / 32.0f);
+            zi[u] = (0.5f * cur[e].y - 0.25f * (l.y + r.y)) * (kYScale / 32.0f);
+          }
+          split2(zr[0], zr[1], zr_h[e2], zr_l[e2]);
+          split2(zi[0], zi[1], zi_h[e2], zi_l[e2]);
+        }
+        const int mc = fslot * 4 + c;
+        const uint32_t off_r = mc * 2048 + (n1 >> 3) * 128 + (n1 & 7) * 16, off_i = off_r + 8 * 128;   // K rows n1 and 64 + n1
+        *reinterpret_cast<uint4*>(yhi + off_r) = make_uint4(zr_h[0], zr_h[1], zr_h[2], zr_h[3]);
+        *reinterpret_cast<uint4*>(ylo + off_r) = make_uint4(zr_l[0], zr_l[1], zr_l[2], zr_l[3]);
+        *reinterpret_cast<uint4*>(yhi + off_i) = make_uint4(zi_h[0], zi_h[1], zi_h[2], zi_h[3]);
+        *reinterpret_cast<uint4*>(ylo + off_i) = make_uint4(zi_l[0], zi_l[1], zi_l[2], zi_l[3]);
+        prev = cur[7];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(y_full, lane);
+    }
+  } else if (warp <= 12) {
+    // ===================== epilogue 3: thread = (frame slot q of the group, k2 = lane); columns k1 (re) and 32 + k1 (im)
+    const int q = warp & 3;
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+    const float inv = 32.0f / (kYScale * kFScale);
+    float* pf = reinterpret_cast<float*>(p4) + q;                  // P4[bin].f[q]
+    for (uint32_t G = 0; G < n_groups; ++G) {
+      const uint32_t buf = G & 1;
+      mbar_wait(d3_full + buf, (G >> 1) & 1, 30);
+      tc_fence_after();
+      const uint32_t d = tm + 256 + buf * kN3 + lane_addr;
+      uint32_t cr[16], ci[16];
+      tmem_ld16_nowait(d, cr);
+      tmem_ld16_nowait(d + 32, ci);
+      tmem_ld_wait();
+      mbar_wait(p_empty, (G & 1) ^ 1, 31);                         // the mel warps are done with the previous tile
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float re = __uint_as_float(cr[k1]) * inv, im = __uint_as_float(ci[k1]) * inv;
+        pf[(32 * k1 + lane) * 4] = re * re + im * im;
+      }
+      tmem_ld16_nowait(d + 16, cr);
+      tmem_ld16_nowait(d + 48, ci);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(d3_empty + buf, lane);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const float re = __uint_as_float(cr[k1]) * inv, im = __uint_as_float(ci[k1]) * inv;
+        pf[(32 * (k1 + 16) + lane) * 4] = re * re + im * im;
+      }
+      mbar_arrive_warp(p_full, lane);
+    }
+  } else if (warp <= 16) {
+    // ===================== mel projection of every group, then per clip: max -> dB -> store
+    const int mt = tid - 13 * 32;                                  // 0 .. 127
+    for (uint32_t G = 0; G < n_groups; ++G) {
+      const uint32_t ci = G >> 3, g = G & 7;
+      mbar_wait(p_full, G & 1, 40);
+      const float pscale = scale_ring[ci & 3].y;
+      for (int t0 = 0; t0 < p.n_tasks; t0 += 128) {
+        const int t = t0 + mt;
+        const uint32_t e = t < p.n_tasks ? tasks[t] : (1u << 16);
+        const int mel = e & 255, j = (e >> 8) & 255, lanes = (int)(e >> 16);
+        const int st = mst[mel], len = t < p.n_tasks ? mst[kMaxMels + mel] : 0, off = mst[2 * kMaxMels + mel];
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int i = j; i < len; i += lanes) {
+          const float w = melw[off + i];
+          const float4 v = p4[st + i];
+          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {                            // lane groups are aligned to their size
+          const float sx = __shfl_xor_sync(0xffffffffu, acc.x, o), sy = __shfl_xor_sync(0xffffffffu, acc.y, o);
+          const float sz = __shfl_xor_sync(0xffffffffu, acc.z, o), sw = __shfl_xor_sync(0xffffffffu, acc.w, o);
+          if (o < lanes) { acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sw; }
+        }
+        if (j == 0 && t < p.n_tasks) {
+          float* ms = mel_s + mel * kMelPitch + 4 * g;
+          ms[0] = acc.x * pscale; ms[1] = acc.y * pscale; ms[2] = acc.z * pscale; ms[3] = acc.w * pscale;
+        }
+      }
+      mbar_arrive_warp(p_empty, lane);                             // P4 may be overwritten
+      if (g == 7) {
+        // ---- power_to_db(ref = max, amin, top_db) over the clip's [n_mels][32] tile (same operations as logmel.cu)
+        const int clip = (int)blockIdx.x + (int)ci * (int)gridDim.x;
+        named_sync(2, 128);
+        const int total = n_mels * kW;
+        float mx = 0.0f;
+        for (int i = mt; i < total; i += 128) mx = fmaxf(mx, mel_s[i + (i >> 5)]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[4 + (mt >> 5)] = mx;
+        named_sync(2, 128);
+        const float ref = fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]));
+        const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(kAmin, ref)));
+        float* __restrict__ o = p.out.ptr + (int64_t)clip * p.out.stride + p.out.off;
+        for (int i = mt; i < total; i += 128) {
+          const int mm = i >> 5;
+          const float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i + mm]))), ref_db);
+          o[mm * p.out.pitch + (i & 31)] = fmaxf(v, -kTopDb);
+        }
+        named_sync(2, 128);                                          // mel_s / red are rewritten by the next clip
+      }
+    }
+  } else {
+    // ===================== converter: peak of the clip, then 8 samples -> one 16-byte store into each fp16 copy
+    const int ct = tid - 17 * 32;                                  // 0 .. 127
+    for (int ci = 0; ci < n_my; ++ci) {
+      const int clip = (int)blockIdx.x + ci * (int)gridDim.x;
+      const TIn* x = static_cast<const TIn*>(p.clips) + (int64_t)clip * p.clip_stride;
+      float mx = 0.0f;
+      for (int u = ct; u < kSamples / 8; u += 128) {
+        float v[8];
+        ld8(x, 8 * u, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, fabsf(v[e]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      named_sync(1, 128);                                          // red[0..3] of the previous clip has been read
+      if (lane == 0) red[ct >> 5] = mx;
+      named_sync(1, 128);
+      const float peak = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      // x * xs has its peak in [2048, 4096): hi is an 11-bit fp16, lo the next 11 bits.  A silent clip transforms to zeros.
+      float xs = 0.0f, inv1 = 0.0f;
+      if (peak > 0.0f && peak < 3.0e38f) {
+        int ex;
+        frexpf(peak, &ex);                                         // peak = fr 2^ex, fr in [0.5, 1)
+        xs = ldexpf(1.0f, min(12 - ex, 100));
+        inv1 = 1.0f / (xs * peak * kFScale);                       // spectrum of the clip at unit peak
+      }
+      if (ct == 0) scale_ring[ci & 3] = make_float2(inv1, p.normalize ? 1.0f : peak * peak);
+      for (int c = 0; c < kChunks; ++c) {
+        mbar_wait(x_empty + c, (ci & 1) ^ 1, 50);
+        // chunk c = padded samples [2048 c, 2048 c + 2048) = clip samples [2048 c - 1024, 2048 c + 1024)
+        const int s_lo = max(0, 2048 * c - 1024), s_hi = min(kSamples, 2048 * c + 1024);
+        for (int u = s_lo / 8 + ct; u < s_hi / 8; u += 128) {
+          float v[8];
+          ld8(x, 8 * u, v);
+          const int i = kNfft / 2 + 8 * u, r = i >> 6, c8 = (i & 63) >> 3;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split2(v[2 * e] * xs, v[2 * e + 1] * xs, hi[e], lo[e]);
+          const uint32_t off = ((((r >> 3) * 8 + c8) * 8 + (r & 7)) * 8) * 2;
+          *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive_warp(x_full + c, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+void split_host(double v, uint16_t& hi, uint16_t& lo) {
+  hi = f2h((float)v);
+  lo = f2h((float)(v - (double)h2f(hi)));
+}
+
+}  // namespace
+
+// DFT matrices (fp16 hi / lo, UMMA canonical layouts), twiddles and the mel task table: built once per context
+static int logmel_tc_prepare(ww_ctx* c) {
+  if (c->tc_lm_ready) return c->tc_lm_ready > 0 ? WW_OK : 1;
+  c->tc_lm_ready = -1;
+  const ww_config& g = c->cfg;
+  if (g.n_fft != kNfft || g.win_length != kNfft || g.hop_length != kHop || g.n_samples != kSamples ||
+      g.n_mels > kMaxMels || c->mel_nnz > kMaxNnz || c->W != kW)
+    return 1;
+  // no filter may touch bin 1024 (not computed); lanes per band by length
+  std::vector<uint32_t> tasks;
+  const int lane_opts[4] = {16, 8, 4, 2};
+  for (int lo : lane_opts)
+    for (int m = 0; m < g.n_mels; ++m) {
+      const int len = c->h_mel_len[m];
+      if (len > 0 && c->h_mel_start[m] + len > kBins - 1) return 1;
+      const int want = len > 53 ? 16 : len > 26 ? 8 : len > 13 ? 4 : 2;
+      if (want != lo) continue;
+      for (int j = 0; j < lo; ++j) tasks.push_back((uint32_t)m | ((uint32_t)j << 8) | ((uint32_t)lo << 16));
+    }
+  if ((int)tasks.size() > kMaxTasks) return 1;
+  const double PI = 3.14159265358979323846;
+  std::vector<uint16_t> f32(kF32Bytes / 2, 0), f64h(kF64Bytes / 2, 0), f64l(kF64Bytes / 2, 0);
+  for (int k2 = 0; k2 < kN2; ++k2)
+    for (int n2 = 0; n2 < kN2; ++n2) {
+      const double a = -2 * PI * ((k2 * n2) % kN2) / kN2;
+      uint16_t rh, rl, ih, il;
+      split_host(cos(a) * kFScale, rh, rl);
+      split_host(sin(a) * kFScale, ih, il);
+      auto at = [&](int n) -> uint16_t& { return f32[((size_t)(n2 / 8) * 128 + n) * 8 + n2 % 8]; };
+      at(k2) = rh; at(32 + k2) = ih; at(64 + k2) = rl; at(96 + k2) = il;
+    }
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int n1 = 0; n1 < kN1; ++n1) {
+      const double a = -2 * PI * ((k1 * n1) % kN1) / kN1, fr = cos(a) * kFScale, fi = sin(a) * kFScale;
+      auto put = [&](int n, int k, double v) {
+        uint16_t h, l;
+        split_host(v, h, l);
+        const size_t e = ((size_t)(k / 8) * kN3 + n) * 8 + k % 8;
+        f64h[e] = h; f64l[e] = l;
+      };
+      put(k1, n1, fr); put(k1, 64 + n1, -fi);           // re: Yr cos - Yi sin
+      put(32 + k1, n1, fi); put(32 + k1, 64 + n1, fr);  // im: Yr sin + Yi cos
+    }
+  std::vector<float2> tw((size_t)kN1 * kN2), rot(kN1);
+  for (int n1 = 0; n1 < kN1; ++n1) {
+    for (int k2 = 0; k2 < kN2; ++k2)
+      tw[(size_t)n1 * kN2 + k2] = make_float2((float)cos(-2 * PI * n1 * k2 / kNfft), (float)sin(-2 * PI * n1 * k2 / kNfft));
+    rot[n1] = make_float2((float)cos(-2 * PI * n1 / kN1), (float)sin(-2 * PI * n1 / kN1));
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+    WW_CHECK(c, cudaMalloc(dst, bytes));
+    WW_CHECK(c, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return WW_OK;
+  };
+  int rc;
+  if ((rc = up((void**)&c->d_tc_f32, f32.data(), kF32Bytes))) return rc;
+  if ((rc = up((void**)&c->d_tc_f64hi, f64h.data(), kF64Bytes))) return rc;
+  if ((rc = up((void**)&c->d_tc_f64lo, f64l.data(), kF64Bytes))) return rc;
+  if ((rc = up((void**)&c->d_tc_tw, tw.data(), tw.size() * sizeof(float2)))) return rc;
+  if ((rc = up((void**)&c->d_tc_rot, rot.data(), rot.size() * sizeof(float2)))) return rc;
+  if ((rc = up((void**)&c->d_tc_tasks, tasks.data(), tasks.size() * 4))) return rc;
+  c->tc_lm_tasks = (int)tasks.size();
+  c->tc_lm_ready = 1;
+  return WW_OK;
+}
+
+// Returns WW_OK when the tensor-core kernel was launched, 1 when this call is outside its domain (the caller then uses
+// the shared-memory FFT kernel of logmel.cu), a negative error code otherwise.
+int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B, int normalize,
+                        cudaStream_t st) {
+  static const char* force = getenv("WW_LOGMEL_KERNEL");            // "fft" / "tc" for A/B runs; default: tc where it applies
+  if (force && force[0] == 'f') return 1;
+  const int align = pcm16 ? 8 : 4;                                  // 16-byte rows
+  if ((clip_stride % align) != 0 || (reinterpret_cast<uintptr_t>(clips) & 15) != 0) return 1;
+  int rc = logmel_tc_prepare(c);
+  if (rc) return rc;
+  TcLogmelParams p;
+  p.clips = clips; p.clip_stride = clip_stride; p.out = out; p.B = B; p.normalize = normalize;
+  p.n_mels = c->cfg.n_mels; p.mel_nnz = c->mel_nnz; p.n_tasks = c->tc_lm_tasks;
+  p.f32 = c->d_tc_f32; p.f64hi = c->d_tc_f64hi; p.f64lo = c->d_tc_f64lo; p.tw = c->d_tc_tw; p.rot = c->d_tc_rot;
+  p.mel_w = c->d_mel_w; p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off;
+  p.tasks = c->d_tc_tasks;
+  const int grid = std::min(c->sm_count, B);
+  ProfScope prof(c, WW_STAGE_LOGMEL, st);
+  if (pcm16) {
+    WW_CHECK(c, cudaFuncSetAttribute(logmel_tc_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    logmel_tc_kernel<int16_t><<<grid, kThreads, kSmem, st>>>(p);
+  } else {
+    WW_CHECK(c, cudaFuncSetAttribute(logmel_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    logmel_tc_kernel<float><<<grid, kThreads, kSmem, st>>>(p);
+  }
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
