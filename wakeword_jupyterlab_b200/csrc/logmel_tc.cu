@@ -20,9 +20,10 @@
 //     reference's fmax = 8000 = Nyquist, where librosa's last filter ends at bin 1023);
 //   * epilogue 3 (thread = (frame, k2)): power of bins 32 k1 + k2 -> shared-memory tile P4[bin] = (4 frames);
 //   * mel warps: banded projection (2-16 lanes per band, one 128-bit load serves 4 frames), then per clip max -> dB -> store.
-// One persistent CTA per SM, 21 warps: 0 MMA issuer | 1-8 epilogue 1 (two frame pairs in flight) | 9-12 epilogue 3 |
-// 13-16 mel + dB | 17-20 converter (peak of the NEXT clip, then fp32 / int16 -> fp16 hi / lo in chunks of 2,048 padded
-// samples that are released group by group, so conversion overlaps the GEMMs of the previous clip).
+// One persistent CTA per SM, 16 warps (128 registers each: the epilogue-1 warps keep a whole Y' row in registers so that
+// only their 16 stores sit between two stage-3 GEMMs): warp 0 MMA issuer | 1-3 converter (peak of the NEXT clip, then
+// fp32 / int16 -> fp16 hi / lo in chunks of 2,048 padded samples that are released group by group, so conversion overlaps
+// the GEMMs of the previous clip) | 4-11 epilogue 1 (two frame pairs in flight) | 12-15 epilogue 3 + mel + dB.
 // Peak normalisation is a scale of the power spectrum: the clip is always transformed at unit peak (any input magnitude
 // fits fp16 hi/lo), and `normalize = 0` multiplies the mel energies by peak^2 again.
 #include "tc_common.cuh"
@@ -47,7 +48,10 @@ constexpr int kP4Bytes = 1024 * 16;                  // power tile: [bin 1024] x
 constexpr int kMelPitch = kW + 1;
 constexpr int kMaxMels = 80, kMaxNnz = 2304, kMaxTasks = 1024;
 constexpr float kFScale = 1024.0f, kYScale = 4096.0f;
-constexpr int kWarps = 21, kThreads = kWarps * 32;
+constexpr int kWarps = 16, kThreads = kWarps * 32;      // 512 threads: 128 registers each (ptxas budgets the whole kernel by
+                                                       // the smallest setmaxnreg value, so the roles share one budget instead)
+constexpr int kConvWarps = 3;
+constexpr int kMelRounds = 4, kMelTaps = 8;            // lane-tasks per epilogue-3 thread; taps per lane-task (registers)
 constexpr float kAmin = 1e-10f, kTopDb = 80.0f;
 
 constexpr size_t kSmem = 2 * (size_t)kClipBytes + kF32Bytes + 2 * (size_t)kF64Bytes + 2 * (size_t)kYBytes + kP4Bytes +
@@ -104,7 +108,50 @@ struct TcLogmelParams {
   const int* mel_len;
   const int* mel_off;
   const uint32_t* tasks;         // mel | lane j << 8 | lanes << 16, groups of `lanes` consecutive entries, lanes descending
+  long long* trace;              // debug (WW_TC_TRACE=1): per-group role timestamps of CTA 0
 };
+
+#define LM_TRACE(G, slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && (G) < 40) p.trace[(G) * 16 + (slot)] = clock64(); } while (0)
+
+// Banded mel projection of one power tile (4 frames) by the four epilogue-3 warps.  Every band has 2-16 lanes (entries of
+// `tasks`, aligned groups); a thread owns the same kMelRounds lane-tasks for the whole kernel, so their bin offsets and
+// weights (at most kMelTaps per lane) live in registers: per group a task is kMelTaps 128-bit loads (one serves the four
+// frames), the FMAs, a shuffle reduction over the band's lanes and one store by lane 0: mel_s[mel][4 g + f].
+struct MelTask {
+  float w[kMelTaps];
+  int base, step, cnt, lanes, dst;     // first bin, bin stride (= lanes), valid taps, lanes of the band, mel * kMelPitch or -1
+};
+__device__ __forceinline__ void mel_task_init(MelTask& k, const float* melw, const int* mst, const uint32_t* tasks, int n_tasks, int t) {
+  const uint32_t e = t < n_tasks ? tasks[t] : (1u << 16);
+  const int mel = e & 255, j = (e >> 8) & 255, lanes = (int)(e >> 16);
+  const int st = mst[mel], len = t < n_tasks ? mst[kMaxMels + mel] : 0, off = mst[2 * kMaxMels + mel];
+  k.base = st + j; k.step = lanes; k.lanes = lanes;
+  k.cnt = len > j ? (len - j + lanes - 1) / lanes : 0;
+  k.dst = (j == 0 && t < n_tasks) ? mel * kMelPitch : -1;
+#pragma unroll
+  for (int u = 0; u < kMelTaps; ++u) k.w[u] = u < k.cnt ? melw[off + j + u * lanes] : 0.0f;
+}
+__device__ __forceinline__ void mel_task_run(const MelTask& k, const float4* __restrict__ p4, float* __restrict__ mel_s, int g, float pscale) {
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+  for (int u = 0; u < kMelTaps; ++u) {
+    if (u < k.cnt) {
+      const float4 v = p4[k.base + u * k.step];
+      acc.x = fmaf(k.w[u], v.x, acc.x); acc.y = fmaf(k.w[u], v.y, acc.y);
+      acc.z = fmaf(k.w[u], v.z, acc.z); acc.w = fmaf(k.w[u], v.w, acc.w);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {                              // lane groups are aligned to their size
+    const float sx = __shfl_xor_sync(0xffffffffu, acc.x, o), sy = __shfl_xor_sync(0xffffffffu, acc.y, o);
+    const float sz = __shfl_xor_sync(0xffffffffu, acc.z, o), sw = __shfl_xor_sync(0xffffffffu, acc.w, o);
+    if (o < k.lanes) { acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sw; }
+  }
+  if (k.dst >= 0) {
+    float* ms = mel_s + k.dst + 4 * g;
+    ms[0] = acc.x * pscale; ms[1] = acc.y * pscale; ms[2] = acc.z * pscale; ms[3] = acc.w * pscale;
+  }
+}
 
 template <typename TIn>
 __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_constant__ TcLogmelParams p) {
@@ -130,8 +177,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
   uint64_t* y_empty = bars + 23;      // [1]  stage-3 MMAs done
   uint64_t* d3_full = bars + 24;      // [2]
   uint64_t* d3_empty = bars + 26;     // [2]
-  uint64_t* p_full = bars + 28;       // [1]  4 epilogue-3 warps
-  uint64_t* p_empty = bars + 29;      // [1]  4 mel warps
   float2* scale_ring = reinterpret_cast<float2*>(bars + 32);   // [4] per clip: (1 / (2^k peak F), mel energy factor)
   float* red = reinterpret_cast<float*>(scale_ring + 4);       // [8] reduction scratch: [0,4) converter, [4,8) mel warps
   uint32_t* slot = reinterpret_cast<uint32_t*>(red + 8);
@@ -155,13 +200,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     mst[i] = p.mel_start[i]; mst[kMaxMels + i] = p.mel_len[i]; mst[2 * kMaxMels + i] = p.mel_off[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < kChunks; ++i) { mbar_init(x_full + i, 4); mbar_init(x_empty + i, 1); }
+    for (int i = 0; i < kChunks; ++i) { mbar_init(x_full + i, kConvWarps); mbar_init(x_empty + i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 4);
       mbar_init(d3_full + i, 1); mbar_init(d3_empty + i, 4);
     }
     mbar_init(y_full, 8); mbar_init(y_empty, 1);
-    mbar_init(p_full, 4); mbar_init(p_empty, 4);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(slot, 512);          // D1: columns 128 h (h < 2); D3: columns 256 + 64 b (b < 2)
@@ -180,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
       const uint32_t ci = G >> 3, g = G & 7;
       if (g == 0) mbar_wait(x_full + 0, ci & 1, 10);
       mbar_wait(x_full + g + 1, ci & 1, 11);                       // frames 4g .. 4g+3 read rows 32 g .. 32 g + 55
+      LM_TRACE(G, 0);
 #pragma unroll 1
       for (uint32_t h = 0; h < 2; ++h) {
         mbar_wait(d1_empty + h, (G & 1) ^ 1, 12);
@@ -205,7 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     auto stage3 = [&](uint32_t G) {
       const uint32_t buf = G & 1;
       mbar_wait(y_full, G & 1, 13);
+      LM_TRACE(G, 1);
       mbar_wait(d3_empty + buf, ((G >> 1) & 1) ^ 1, 14);
+      LM_TRACE(G, 2);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tm + 256 + buf * kN3;
@@ -226,155 +273,201 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
       if (G + 1 < n_groups) stage1(G + 1);
       stage3(G);
     }
-  } else if (warp <= 8) {
+  } else if (warp < 4) {
+    // ===================== converter (runs ahead of the GEMMs by up to a clip): peak of the clip, then per chunk 8 samples ->
+    // one 16-byte store into each fp16 copy.  Global loads are issued in batches so that a chunk costs one round trip.
+    constexpr int CT = kConvWarps * 32;
+    const int ct = tid - 32;                                       // 0 .. 95
+    for (int ci = 0; ci < n_my; ++ci) {
+      const int clip = (int)blockIdx.x + ci * (int)gridDim.x;
+      const TIn* x = static_cast<const TIn*>(p.clips) + (int64_t)clip * p.clip_stride;
+      float mx = 0.0f;
+      for (int u0 = ct; u0 < kSamples / 8; u0 += 4 * CT) {
+        float v[4][8];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int u = u0 + b * CT;
+          if (u < kSamples / 8) ld8(x, 8 * u, v[b]);
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[b][e] = 0.0f;
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mx = fmaxf(mx, fabsf(v[b][e]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      named_sync(1, CT);                                           // red[0..2] of the previous clip has been read
+      if (lane == 0) red[ct >> 5] = mx;
+      named_sync(1, CT);
+      const float peak = fmaxf(fmaxf(red[0], red[1]), red[2]);
+      // x * xs has its peak in [2048, 4096): hi is an 11-bit fp16, lo the next 11 bits.  A silent clip transforms to zeros.
+      float xs = 0.0f, inv1 = 0.0f;
+      if (peak > 0.0f && peak < 3.0e38f) {
+        int ex;
+        frexpf(peak, &ex);                                         // peak = fr 2^ex, fr in [0.5, 1)
+        xs = ldexpf(1.0f, min(12 - ex, 100));
+        inv1 = 1.0f / (xs * peak * kFScale);                       // spectrum of the clip at unit peak
+      }
+      if (ct == 0) scale_ring[ci & 3] = make_float2(inv1, p.normalize ? 1.0f : peak * peak);
+      for (int c = 0; c < kChunks; ++c) {
+        // chunk c = padded samples [2048 c, 2048 c + 2048) = clip samples [2048 c - 1024, 2048 c + 1024): <= 256 units of 8
+        const int s_lo = max(0, 2048 * c - 1024), s_hi = min(kSamples, 2048 * c + 1024);
+        float v[3][8];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const int u = s_lo / 8 + ct + b * CT;
+          if (u < s_hi / 8) ld8(x, 8 * u, v[b]);
+        }
+        mbar_wait(x_empty + c, (ci & 1) ^ 1, 50);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const int u = s_lo / 8 + ct + b * CT;
+          if (u < s_hi / 8) {
+            const int i = kNfft / 2 + 8 * u, r = i >> 6, c8 = (i & 63) >> 3;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2(v[b][2 * e] * xs, v[b][2 * e + 1] * xs, hi[e], lo[e]);
+            const uint32_t off = ((((r >> 3) * 8 + c8) * 8 + (r & 7)) * 8) * 2;
+            *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive_warp(x_full + c, lane);
+      }
+    }
+  } else if (warp < 12) {
     // ===================== epilogue 1: thread = (frame 2h + f of the group, n1); TMEM lane quadrant = warp & 3
-    const int q = warp & 3, h = (warp - 1) >> 2, m = q * 32 + lane, f = m >> 6, n1 = m & 63;
+    const int q = warp & 3, h = (warp - 4) >> 2, m = q * 32 + lane, f = m >> 6, n1 = m & 63;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     const float2 rp = __ldg(p.rot + n1);                           // W64^(n1)
-    const float4* twp = reinterpret_cast<const float4*>(p.tw + n1 * kN2);
+    // twiddles W2048^(n1 k2) by recurrence (step w1, chunk anchors by w8: at most 10 products deep): no table in the loop
+    const float2 w1 = __ldg(p.tw + n1 * kN2 + 1), w8 = __ldg(p.tw + n1 * kN2 + 8);
     const uint32_t dbase = tm + h * 128 + lane_addr;
-    const int fslot = 2 * h + f;
+    const uint32_t off0 = (uint32_t)(2 * h + f) * 4u * 2048u + (uint32_t)(n1 >> 3) * 128u + (uint32_t)(n1 & 7) * 16u;
     for (uint32_t G = 0; G < n_groups; ++G) {
       mbar_wait(d1_full + h, G & 1, 20);
+      if (warp == 4) LM_TRACE(G, 3);
       tc_fence_after();
       const float inv = scale_ring[(G >> 3) & 3].x;                // written by the converter before the clip's first chunk
+      const float c1 = 0.5f * (kYScale / 32.0f) * inv, c2 = 0.25f * (kYScale / 32.0f) * inv;
       // column c of D1: re hi c, im hi 32 + c, re lo 64 + c, im lo 96 + c
-      auto load_chunk = [&](int c, float2* y) {
-        uint32_t r0[8], r1[8], r2[8], r3[8];
-        tmem_ld8_nowait(dbase + 8 * c, r0);
-        tmem_ld8_nowait(dbase + 32 + 8 * c, r1);
-        tmem_ld8_nowait(dbase + 64 + 8 * c, r2);
-        tmem_ld8_nowait(dbase + 96 + 8 * c, r3);
-        float4 w4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) w4[e] = __ldg(twp + 4 * c + e);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float re = (__uint_as_float(r0[e]) + __uint_as_float(r2[e])) * inv;
-          const float im = (__uint_as_float(r1[e]) + __uint_as_float(r3[e])) * inv;
-          const float2 w = (e & 1) ? make_float2(w4[e >> 1].z, w4[e >> 1].w) : make_float2(w4[e >> 1].x, w4[e >> 1].y);
-          y[e] = cmul(make_float2(re, im), w);
-        }
-      };
-      float2 cur[8], nxt[8], prev, y32;
+      float2 p2, p1, y0;                                             // Y[k-2], Y[k-1] of the running 3-tap, Y[0]
       {
-        uint32_t a0, a1, a2, a3;                                    // Y[31] for the left end: Y[-1] = W64^(-n1) Y[31]
+        // left end: Y[-1] = W64^(-n1) Y[31] = W64^(-n1) W2048^(31 n1) D[31] = conj(w1) D[31]
+        uint32_t a0, a1, a2, a3;
         tmem_ld1_nowait(dbase + 31, a0);
         tmem_ld1_nowait(dbase + 63, a1);
         tmem_ld1_nowait(dbase + 95, a2);
         tmem_ld1_nowait(dbase + 127, a3);
-        const float2 w31 = __ldg(p.tw + n1 * kN2 + 31);
         tmem_ld_wait();
-        const float2 y31 = cmul(make_float2((__uint_as_float(a0) + __uint_as_float(a2)) * inv,
-                                            (__uint_as_float(a1) + __uint_as_float(a3)) * inv), w31);
-        prev = make_float2(y31.x * rp.x + y31.y * rp.y, y31.y * rp.x - y31.x * rp.y);       // conj(rp) * y31
+        const float dr = __uint_as_float(a0) + __uint_as_float(a2), di = __uint_as_float(a1) + __uint_as_float(a3);
+        p2 = make_float2(dr * w1.x + di * w1.y, di * w1.x - dr * w1.y);
       }
-      load_chunk(0, cur);
-      y32 = cmul(cur[0], rp);                                        // Y[32] = W64^(n1) Y[0]
+      uint32_t zrh[16], zrl[16], zih[16], zil[16];                  // the whole Y' row of this thread, packed fp16 pairs
+      float zr_e = 0.0f, zi_e = 0.0f;
+      // Hann 3-tap with one element of lag: z[k-1] = c1 Y[k-1] - c2 (Y[k-2] + Y[k])
+      auto emit = [&](int k, float2 l, float2 m_, float2 r) {
+        const float zr = c1 * m_.x - c2 * (l.x + r.x), zi = c1 * m_.y - c2 * (l.y + r.y);
+        if (k & 1) {
+          split2(zr_e, zr, zrh[k >> 1], zrl[k >> 1]);
+          split2(zi_e, zi, zih[k >> 1], zil[k >> 1]);
+        } else {
+          zr_e = zr; zi_e = zi;
+        }
+      };
+      float2 wa = make_float2(1.0f, 0.0f);                           // anchor W2048^(8 c n1)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (c < 3) load_chunk(c + 1, nxt);
-        if (c == 2) {                                                // every TMEM read of this pair is done
+        uint32_t r0[8], r2[8];
+        float re[8], im[8];
+        tmem_ld8_nowait(dbase + 8 * c, r0);
+        tmem_ld8_nowait(dbase + 64 + 8 * c, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) re[e] = __uint_as_float(r0[e]) + __uint_as_float(r2[e]);
+        tmem_ld8_nowait(dbase + 32 + 8 * c, r0);
+        tmem_ld8_nowait(dbase + 96 + 8 * c, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) im[e] = __uint_as_float(r0[e]) + __uint_as_float(r2[e]);
+        if (c == 3) {                                                // every TMEM read of this pair is done
           tc_fence_before();
           mbar_arrive_warp(d1_empty + h, lane);
         }
-        if (c == 0) mbar_wait(y_empty, (G & 1) ^ 1, 21);             // stage 3 of the previous group has read Y'
-        uint32_t zr_h[4], zr_l[4], zi_h[4], zi_l[4];
+        float2 w = wa;
+        if (c < 3) wa = cmul(wa, w8);
 #pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          float zr[2], zi[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int e = 2 * e2 + u;
-            const float2 l = e == 0 ? prev : cur[e - 1];
-            const float2 r = e == 7 ? (c < 3 ? nxt[0] : y32) : cur[e + 1];
-            zr[u] = (0.5f * cur[e].x - 0.25f * (l.x + r.x)) * (kYScale / 32.0f);
-            zi[u] = (0.5f * cur[e].y - 0.25f * (l.y + r.y)) * (kYScale / 32.0f);
-          }
-          split2(zr[0], zr[1], zr_h[e2], zr_l[e2]);
-          split2(zi[0], zi[1], zi_h[e2], zi_l[e2]);
+        for (int e = 0; e < 8; ++e) {
+          const int k = 8 * c + e;
+          const float2 y = (k == 0) ? make_float2(re[0], im[0]) : cmul(make_float2(re[e], im[e]), w);
+          if (e < 7) w = cmul(w, w1);
+          if (k == 0) { y0 = y; p1 = y; }
+          else { emit(k - 1, p2, p1, y); p2 = p1; p1 = y; }
         }
-        const int mc = fslot * 4 + c;
-        const uint32_t off_r = mc * 2048 + (n1 >> 3) * 128 + (n1 & 7) * 16, off_i = off_r + 8 * 128;   // K rows n1 and 64 + n1
-        *reinterpret_cast<uint4*>(yhi + off_r) = make_uint4(zr_h[0], zr_h[1], zr_h[2], zr_h[3]);
-        *reinterpret_cast<uint4*>(ylo + off_r) = make_uint4(zr_l[0], zr_l[1], zr_l[2], zr_l[3]);
-        *reinterpret_cast<uint4*>(yhi + off_i) = make_uint4(zi_h[0], zi_h[1], zi_h[2], zi_h[3]);
-        *reinterpret_cast<uint4*>(ylo + off_i) = make_uint4(zi_l[0], zi_l[1], zi_l[2], zi_l[3]);
-        prev = cur[7];
+      }
+      emit(31, p2, p1, cmul(y0, rp));                                // Y[32] = W64^(n1) Y[0]
+      if (warp == 4) LM_TRACE(G, 4);
+      mbar_wait(y_empty, (G & 1) ^ 1, 21);
+      if (warp == 4) LM_TRACE(G, 5);                           // stage 3 of the previous group has read Y'
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off_r = off0 + c * 2048u, off_i = off_r + 8 * 128;      // K rows n1 and 64 + n1
+        *reinterpret_cast<uint4*>(yhi + off_r) = make_uint4(zrh[4 * c], zrh[4 * c + 1], zrh[4 * c + 2], zrh[4 * c + 3]);
+        *reinterpret_cast<uint4*>(ylo + off_r) = make_uint4(zrl[4 * c], zrl[4 * c + 1], zrl[4 * c + 2], zrl[4 * c + 3]);
+        *reinterpret_cast<uint4*>(yhi + off_i) = make_uint4(zih[4 * c], zih[4 * c + 1], zih[4 * c + 2], zih[4 * c + 3]);
+        *reinterpret_cast<uint4*>(ylo + off_i) = make_uint4(zil[4 * c], zil[4 * c + 1], zil[4 * c + 2], zil[4 * c + 3]);
       }
       fence_proxy_async();
       mbar_arrive_warp(y_full, lane);
+      if (warp == 4) LM_TRACE(G, 6);
     }
-  } else if (warp <= 12) {
-    // ===================== epilogue 3: thread = (frame slot q of the group, k2 = lane); columns k1 (re) and 32 + k1 (im)
-    const int q = warp & 3;
+  } else {
+    // ===================== epilogue 3 + mel: thread = (frame slot q of the group, k2 = lane) for the power tile; then the
+    // same four warps project the tile onto the mel bands; per clip: max -> dB -> store
+    const int q = warp & 3, mt = tid - 12 * 32;                    // mt 0 .. 127
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     const float inv = 32.0f / (kYScale * kFScale);
     float* pf = reinterpret_cast<float*>(p4) + q;                  // P4[bin].f[q]
+    MelTask mk[kMelRounds];
+#pragma unroll
+    for (int r = 0; r < kMelRounds; ++r) mel_task_init(mk[r], melw, mst, tasks, p.n_tasks, r * 128 + mt);
     for (uint32_t G = 0; G < n_groups; ++G) {
-      const uint32_t buf = G & 1;
+      const uint32_t buf = G & 1, ci = G >> 3, g = G & 7;
       mbar_wait(d3_full + buf, (G >> 1) & 1, 30);
+      if (warp == 12) LM_TRACE(G, 7);
       tc_fence_after();
       const uint32_t d = tm + 256 + buf * kN3 + lane_addr;
-      uint32_t cr[16], ci[16];
-      tmem_ld16_nowait(d, cr);
-      tmem_ld16_nowait(d + 32, ci);
-      tmem_ld_wait();
-      mbar_wait(p_empty, (G & 1) ^ 1, 31);                         // the mel warps are done with the previous tile
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) {
-        const float re = __uint_as_float(cr[k1]) * inv, im = __uint_as_float(ci[k1]) * inv;
-        pf[(32 * k1 + lane) * 4] = re * re + im * im;
-      }
-      tmem_ld16_nowait(d + 16, cr);
-      tmem_ld16_nowait(d + 48, ci);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_warp(d3_empty + buf, lane);
+      for (int half = 0; half < 2; ++half) {
+        uint32_t cr[16], cim[16];
+        tmem_ld16_nowait(d + 16 * half, cr);
+        tmem_ld16_nowait(d + 32 + 16 * half, cim);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive_warp(d3_empty + buf, lane);
+        }
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) {
-        const float re = __uint_as_float(cr[k1]) * inv, im = __uint_as_float(ci[k1]) * inv;
-        pf[(32 * (k1 + 16) + lane) * 4] = re * re + im * im;
+        for (int k1 = 0; k1 < 16; ++k1) {
+          const float re = __uint_as_float(cr[k1]) * inv, im = __uint_as_float(cim[k1]) * inv;
+          pf[(32 * (k1 + 16 * half) + lane) * 4] = re * re + im * im;
+        }
       }
-      mbar_arrive_warp(p_full, lane);
-    }
-  } else if (warp <= 16) {
-    // ===================== mel projection of every group, then per clip: max -> dB -> store
-    const int mt = tid - 13 * 32;                                  // 0 .. 127
-    for (uint32_t G = 0; G < n_groups; ++G) {
-      const uint32_t ci = G >> 3, g = G & 7;
-      mbar_wait(p_full, G & 1, 40);
+      if (warp == 12) LM_TRACE(G, 8);
+      named_sync(2, 128);                                          // the power tile of the group is complete
       const float pscale = scale_ring[ci & 3].y;
-      for (int t0 = 0; t0 < p.n_tasks; t0 += 128) {
-        const int t = t0 + mt;
-        const uint32_t e = t < p.n_tasks ? tasks[t] : (1u << 16);
-        const int mel = e & 255, j = (e >> 8) & 255, lanes = (int)(e >> 16);
-        const int st = mst[mel], len = t < p.n_tasks ? mst[kMaxMels + mel] : 0, off = mst[2 * kMaxMels + mel];
-        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (int i = j; i < len; i += lanes) {
-          const float w = melw[off + i];
-          const float4 v = p4[st + i];
-          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-        }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {                            // lane groups are aligned to their size
-          const float sx = __shfl_xor_sync(0xffffffffu, acc.x, o), sy = __shfl_xor_sync(0xffffffffu, acc.y, o);
-          const float sz = __shfl_xor_sync(0xffffffffu, acc.z, o), sw = __shfl_xor_sync(0xffffffffu, acc.w, o);
-          if (o < lanes) { acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sw; }
-        }
-        if (j == 0 && t < p.n_tasks) {
-          float* ms = mel_s + mel * kMelPitch + 4 * g;
-          ms[0] = acc.x * pscale; ms[1] = acc.y * pscale; ms[2] = acc.z * pscale; ms[3] = acc.w * pscale;
-        }
-      }
-      mbar_arrive_warp(p_empty, lane);                             // P4 may be overwritten
+      for (int r = 0; r < kMelRounds; ++r) mel_task_run(mk[r], p4, mel_s, (int)g, pscale);
+      if (warp == 12) LM_TRACE(G, 10);
+      named_sync(2, 128);                                          // every band of the group is in mel_s; the tile is free
       if (g == 7) {
         // ---- power_to_db(ref = max, amin, top_db) over the clip's [n_mels][32] tile (same operations as logmel.cu)
         const int clip = (int)blockIdx.x + (int)ci * (int)gridDim.x;
-        named_sync(2, 128);
         const int total = n_mels * kW;
         float mx = 0.0f;
         for (int i = mt; i < total; i += 128) mx = fmaxf(mx, mel_s[i + (i >> 5)]);
@@ -390,54 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
           const float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(kAmin, mel_s[i + mm]))), ref_db);
           o[mm * p.out.pitch + (i & 31)] = fmaxf(v, -kTopDb);
         }
-        named_sync(2, 128);                                          // mel_s / red are rewritten by the next clip
-      }
-    }
-  } else {
-    // ===================== converter: peak of the clip, then 8 samples -> one 16-byte store into each fp16 copy
-    const int ct = tid - 17 * 32;                                  // 0 .. 127
-    for (int ci = 0; ci < n_my; ++ci) {
-      const int clip = (int)blockIdx.x + ci * (int)gridDim.x;
-      const TIn* x = static_cast<const TIn*>(p.clips) + (int64_t)clip * p.clip_stride;
-      float mx = 0.0f;
-      for (int u = ct; u < kSamples / 8; u += 128) {
-        float v[8];
-        ld8(x, 8 * u, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, fabsf(v[e]));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      named_sync(1, 128);                                          // red[0..3] of the previous clip has been read
-      if (lane == 0) red[ct >> 5] = mx;
-      named_sync(1, 128);
-      const float peak = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-      // x * xs has its peak in [2048, 4096): hi is an 11-bit fp16, lo the next 11 bits.  A silent clip transforms to zeros.
-      float xs = 0.0f, inv1 = 0.0f;
-      if (peak > 0.0f && peak < 3.0e38f) {
-        int ex;
-        frexpf(peak, &ex);                                         // peak = fr 2^ex, fr in [0.5, 1)
-        xs = ldexpf(1.0f, min(12 - ex, 100));
-        inv1 = 1.0f / (xs * peak * kFScale);                       // spectrum of the clip at unit peak
-      }
-      if (ct == 0) scale_ring[ci & 3] = make_float2(inv1, p.normalize ? 1.0f : peak * peak);
-      for (int c = 0; c < kChunks; ++c) {
-        mbar_wait(x_empty + c, (ci & 1) ^ 1, 50);
-        // chunk c = padded samples [2048 c, 2048 c + 2048) = clip samples [2048 c - 1024, 2048 c + 1024)
-        const int s_lo = max(0, 2048 * c - 1024), s_hi = min(kSamples, 2048 * c + 1024);
-        for (int u = s_lo / 8 + ct; u < s_hi / 8; u += 128) {
-          float v[8];
-          ld8(x, 8 * u, v);
-          const int i = kNfft / 2 + 8 * u, r = i >> 6, c8 = (i & 63) >> 3;
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split2(v[2 * e] * xs, v[2 * e + 1] * xs, hi[e], lo[e]);
-          const uint32_t off = ((((r >> 3) * 8 + c8) * 8 + (r & 7)) * 8) * 2;
-          *reinterpret_cast<uint4*>(xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(xlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async();
-        mbar_arrive_warp(x_full + c, lane);
+        named_sync(2, 128);                                          // red / mel_s are rewritten by the next clip
+        if (warp == 12) LM_TRACE(G, 11);
       }
     }
   }
@@ -469,10 +516,11 @@ static int logmel_tc_prepare(ww_ctx* c) {
       const int len = c->h_mel_len[m];
       if (len > 0 && c->h_mel_start[m] + len > kBins - 1) return 1;
       const int want = len > 53 ? 16 : len > 26 ? 8 : len > 13 ? 4 : 2;
+      if (len > kMelTaps * want) return 1;
       if (want != lo) continue;
       for (int j = 0; j < lo; ++j) tasks.push_back((uint32_t)m | ((uint32_t)j << 8) | ((uint32_t)lo << 16));
     }
-  if ((int)tasks.size() > kMaxTasks) return 1;
+  if ((int)tasks.size() > kMelRounds * 128) return 1;
   const double PI = 3.14159265358979323846;
   std::vector<uint16_t> f32(kF32Bytes / 2, 0), f64h(kF64Bytes / 2, 0), f64l(kF64Bytes / 2, 0);
   for (int k2 = 0; k2 < kN2; ++k2)
@@ -535,6 +583,11 @@ int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_st
   p.f32 = c->d_tc_f32; p.f64hi = c->d_tc_f64hi; p.f64lo = c->d_tc_f64lo; p.tw = c->d_tc_tw; p.rot = c->d_tc_rot;
   p.mel_w = c->d_mel_w; p.mel_start = c->d_mel_start; p.mel_len = c->d_mel_len; p.mel_off = c->d_mel_off;
   p.tasks = c->d_tc_tasks;
+  static long long* d_trace = nullptr;
+  const bool tracing = getenv("WW_TC_TRACE") != nullptr;
+  if (tracing && !d_trace) cudaMalloc((void**)&d_trace, 40 * 16 * 8);
+  if (tracing) cudaMemset(d_trace, 0, 40 * 16 * 8);
+  p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B);
   ProfScope prof(c, WW_STAGE_LOGMEL, st);
   if (pcm16) {
@@ -545,5 +598,17 @@ int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_st
     logmel_tc_kernel<float><<<grid, kThreads, kSmem, st>>>(p);
   }
   WW_LAUNCH_CHECK(c);
+  if (tracing) {
+    long long h[40 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "logmel_tc trace (cycles): S1 ready | S3: y_full, d3_empty | ep1: d1_full, computed, y_empty, stored | ep3: d3_full, tile written, B, mel done, A | conv at B\n");
+    const long long t0 = h[0];
+    for (int i = 0; i < 40; ++i) {
+      fprintf(stderr, "grp %2d:", i);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return WW_OK;
 }
