@@ -40,7 +40,7 @@ constexpr int kNfft = 2048, kN1 = 64, kN2 = 32, kW = 32, kSamples = 16000, kHop 
 constexpr int kRows = 288;                           // padded clip rows of 64 samples
 constexpr int kChunks = 9;                           // converter chunks of 32 rows (2,048 padded samples)
 constexpr int kClipBytes = kRows * 64 * 2;           // one fp16 copy of the padded clip: [row block][col chunk 8][row % 8][8]
-constexpr int kF32Bytes = 4 * 128 * 16;              // stage-1 B: [kc 4][n 128 = re hi | im hi | re lo | im lo][8]
+constexpr int kF32Bytes = 4 * 128 * 16;              // stage-1 B: [kc 4][n 128 = (re, im) x 32 of F_hi | the same of F_lo][8]
 constexpr int kN3 = 64;                              // stage-3 N: re of k1 0..31 | im of k1 0..31
 constexpr int kF64Bytes = 16 * kN3 * 16;             // stage-3 B (hi or lo): [kc 16][n 64][8]
 constexpr int kYBytes = 16 * 2048;                   // stage-3 A (hi or lo), MN-major: [m chunk 16][k row 128][8]
@@ -51,6 +51,8 @@ constexpr float kFScale = 1024.0f, kYScale = 4096.0f;
 constexpr int kWarps = 16, kThreads = kWarps * 32;      // 512 threads: 128 registers each (ptxas budgets the whole kernel by
                                                        // the smallest setmaxnreg value, so the roles share one budget instead)
 constexpr int kConvWarps = 3;
+constexpr bool kTcDefault = true;                      // which kernel ww_logmel takes where both apply (see profiles/: A/B)
+constexpr unsigned kPollNs = 32;                       // sleep between mbarrier polls (see mbar_wait_sleep)
 constexpr int kMelRounds = 4, kMelTaps = 8;            // lane-tasks per epilogue-3 thread; taps per lane-task (registers)
 constexpr float kAmin = 1e-10f, kTopDb = 80.0f;
 
@@ -74,6 +76,35 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = pack_f16(a, b);
   const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = pack_f16(a - h.x, b - h.y);
+}
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): one instruction for both components of a complex value
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 un2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld2_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -127,29 +158,54 @@ __device__ __forceinline__ void mel_task_init(MelTask& k, const float* melw, con
   const int st = mst[mel], len = t < n_tasks ? mst[kMaxMels + mel] : 0, off = mst[2 * kMaxMels + mel];
   k.base = st + j; k.step = lanes; k.lanes = lanes;
   k.cnt = len > j ? (len - j + lanes - 1) / lanes : 0;
-  k.dst = (j == 0 && t < n_tasks) ? mel * kMelPitch : -1;
+  k.dst = t < n_tasks ? mel * kMelPitch : -1;          // every lane of the band: lanes j < 4 store one frame each
 #pragma unroll
   for (int u = 0; u < kMelTaps; ++u) k.w[u] = u < k.cnt ? melw[off + j + u * lanes] : 0.0f;
 }
-__device__ __forceinline__ void mel_task_run(const MelTask& k, const float4* __restrict__ p4, float* __restrict__ mel_s, int g, float pscale) {
-  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+// Two lane-tasks at once (their loads, FMAs and reductions interleave: the four warps that run this are latency bound).
+// Reduction over the L lanes of a band by exchanging halves: after the xor-1 step a lane keeps two of the four frames, after
+// the xor-2 step one (frame 2 (j & 1) + ((j >> 1) & 1)); xor 4 / 8 then sum whole values: 5 shuffles instead of 16.
+__device__ __forceinline__ void mel_task_run2(const MelTask& ka, const MelTask& kb, const float4* __restrict__ p4,
+                                              float* __restrict__ mel_s, int g, float pscale, int lane) {
+  // unconditional loads (taps past the band have weight 0 and read a clamped, valid bin): all are in flight at once
+  float4 va[kMelTaps], vb[kMelTaps];
+#pragma unroll
+  for (int u = 0; u < kMelTaps; ++u) va[u] = p4[min(ka.base + u * ka.step, 1023)];
+#pragma unroll
+  for (int u = 0; u < kMelTaps; ++u) vb[u] = p4[min(kb.base + u * kb.step, 1023)];
+  float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a;
 #pragma unroll
   for (int u = 0; u < kMelTaps; ++u) {
-    if (u < k.cnt) {
-      const float4 v = p4[k.base + u * k.step];
-      acc.x = fmaf(k.w[u], v.x, acc.x); acc.y = fmaf(k.w[u], v.y, acc.y);
-      acc.z = fmaf(k.w[u], v.z, acc.z); acc.w = fmaf(k.w[u], v.w, acc.w);
-    }
+    a.x = fmaf(ka.w[u], va[u].x, a.x); a.y = fmaf(ka.w[u], va[u].y, a.y);
+    a.z = fmaf(ka.w[u], va[u].z, a.z); a.w = fmaf(ka.w[u], va[u].w, a.w);
+    b.x = fmaf(kb.w[u], vb[u].x, b.x); b.y = fmaf(kb.w[u], vb[u].y, b.y);
+    b.z = fmaf(kb.w[u], vb[u].z, b.z); b.w = fmaf(kb.w[u], vb[u].w, b.w);
   }
+  const bool odd = lane & 1, hi2 = lane & 2;          // lane groups are aligned to their size: lane bits = bits of j
+  // xor 1: even lanes keep frames 0, 1, odd lanes frames 2, 3
+  float a0 = odd ? a.z : a.x, a1 = odd ? a.w : a.y, b0 = odd ? b.z : b.x, b1 = odd ? b.w : b.y;
+  a0 += __shfl_xor_sync(0xffffffffu, odd ? a.x : a.z, 1); a1 += __shfl_xor_sync(0xffffffffu, odd ? a.y : a.w, 1);
+  b0 += __shfl_xor_sync(0xffffffffu, odd ? b.x : b.z, 1); b1 += __shfl_xor_sync(0xffffffffu, odd ? b.y : b.w, 1);
+  // xor 2 (bands of 4+ lanes): lanes with bit 1 clear keep the first of their two frames, the others the second
+  const float sa = __shfl_xor_sync(0xffffffffu, hi2 ? a0 : a1, 2), sb = __shfl_xor_sync(0xffffffffu, hi2 ? b0 : b1, 2);
+  float ra = (hi2 ? a1 : a0) + sa, rb = (hi2 ? b1 : b0) + sb;
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {                              // lane groups are aligned to their size
-    const float sx = __shfl_xor_sync(0xffffffffu, acc.x, o), sy = __shfl_xor_sync(0xffffffffu, acc.y, o);
-    const float sz = __shfl_xor_sync(0xffffffffu, acc.z, o), sw = __shfl_xor_sync(0xffffffffu, acc.w, o);
-    if (o < k.lanes) { acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sw; }
+  for (int o = 4; o <= 8; o <<= 1) {
+    const float ta = __shfl_xor_sync(0xffffffffu, ra, o), tb = __shfl_xor_sync(0xffffffffu, rb, o);
+    if (o < ka.lanes) ra += ta;
+    if (o < kb.lanes) rb += tb;
   }
-  if (k.dst >= 0) {
-    float* ms = mel_s + k.dst + 4 * g;
-    ms[0] = acc.x * pscale; ms[1] = acc.y * pscale; ms[2] = acc.z * pscale; ms[3] = acc.w * pscale;
+  // stores: bands of 2 lanes hold two frames per lane (2 (j & 1), + 1), wider bands one frame in their lanes j < 4
+  const int j = lane & 15;
+  if (ka.dst >= 0) {
+    float* ms = mel_s + ka.dst + 4 * g;
+    if (ka.lanes == 2) { ms[2 * (j & 1)] = a0 * pscale; ms[2 * (j & 1) + 1] = a1 * pscale; }
+    else if ((j & (ka.lanes - 1)) < 4) ms[2 * (j & 1) + ((j >> 1) & 1)] = ra * pscale;
+  }
+  if (kb.dst >= 0) {
+    float* ms = mel_s + kb.dst + 4 * g;
+    if (kb.lanes == 2) { ms[2 * (j & 1)] = b0 * pscale; ms[2 * (j & 1) + 1] = b1 * pscale; }
+    else if ((j & (kb.lanes - 1)) < 4) ms[2 * (j & 1) + ((j >> 1) & 1)] = rb * pscale;
   }
 }
 
@@ -222,12 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     const uint64_t a3h = make_desc(smem_u32(yhi), 128, 2048), a3l = make_desc(smem_u32(ylo), 128, 2048);
     auto stage1 = [&](uint32_t G) {
       const uint32_t ci = G >> 3, g = G & 7;
-      if (g == 0) mbar_wait(x_full + 0, ci & 1, 10);
-      mbar_wait(x_full + g + 1, ci & 1, 11);                       // frames 4g .. 4g+3 read rows 32 g .. 32 g + 55
+      if (g == 0) mbar_wait_sleep(x_full + 0, ci & 1, 10, kPollNs);
+      mbar_wait_sleep(x_full + g + 1, ci & 1, 11, kPollNs);                       // frames 4g .. 4g+3 read rows 32 g .. 32 g + 55
       LM_TRACE(G, 0);
 #pragma unroll 1
       for (uint32_t h = 0; h < 2; ++h) {
-        mbar_wait(d1_empty + h, (G & 1) ^ 1, 12);
+        mbar_wait_sleep(d1_empty + h, (G & 1) ^ 1, 12, kPollNs);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t t0 = 4 * g + 2 * h, d = tm + h * 128;
@@ -249,9 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     };
     auto stage3 = [&](uint32_t G) {
       const uint32_t buf = G & 1;
-      mbar_wait(y_full, G & 1, 13);
+      mbar_wait_sleep(y_full, G & 1, 13, kPollNs);
       LM_TRACE(G, 1);
-      mbar_wait(d3_empty + buf, ((G >> 1) & 1) ^ 1, 14);
+      mbar_wait_sleep(d3_empty + buf, ((G >> 1) & 1) ^ 1, 14, kPollNs);
       LM_TRACE(G, 2);
       tc_fence_after();
       if (elect_one()) {
@@ -322,7 +378,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
           const int u = s_lo / 8 + ct + b * CT;
           if (u < s_hi / 8) ld8(x, 8 * u, v[b]);
         }
-        mbar_wait(x_empty + c, (ci & 1) ^ 1, 50);
+        {                                                          // the converter runs far ahead: sleep between polls
+          uint32_t spins = 0;
+          while (!mbar_try_wait(x_empty + c, (ci & 1) ^ 1)) {
+            __nanosleep(500);
+            if (++spins > (1u << 22)) mbar_timeout(50);
+          }
+        }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
           const int u = s_lo / 8 + ct + b * CT;
@@ -345,86 +407,102 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     const int q = warp & 3, h = (warp - 4) >> 2, m = q * 32 + lane, f = m >> 6, n1 = m & 63;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     const float2 rp = __ldg(p.rot + n1);                           // W64^(n1)
-    // twiddles W2048^(n1 k2) by recurrence (step w1, chunk anchors by w8: at most 10 products deep): no table in the loop
+    // twiddles w_k = W2048^(n1 k) inside a chunk of 8 by the three-term recurrence w_{k+1} = 2 cos(t) w_k - w_{k-1} (two FMAs
+    // per step, at most 7 steps from an exact-to-1-ulp restart), chunk anchors W2048^(8 c n1) by products of w8
     const float2 w1 = __ldg(p.tw + n1 * kN2 + 1), w8 = __ldg(p.tw + n1 * kN2 + 8);
+    const float tc2 = 2.0f * w1.x;
     const uint32_t dbase = tm + h * 128 + lane_addr;
     const uint32_t off0 = (uint32_t)(2 * h + f) * 4u * 2048u + (uint32_t)(n1 >> 3) * 128u + (uint32_t)(n1 & 7) * 16u;
     for (uint32_t G = 0; G < n_groups; ++G) {
-      mbar_wait(d1_full + h, G & 1, 20);
+      mbar_wait_sleep(d1_full + h, G & 1, 20, kPollNs);
       if (warp == 4) LM_TRACE(G, 3);
       tc_fence_after();
       const float inv = scale_ring[(G >> 3) & 3].x;                // written by the converter before the clip's first chunk
       const float c1 = 0.5f * (kYScale / 32.0f) * inv, c2 = 0.25f * (kYScale / 32.0f) * inv;
-      // column c of D1: re hi c, im hi 32 + c, re lo 64 + c, im lo 96 + c
-      float2 p2, p1, y0;                                             // Y[k-2], Y[k-1] of the running 3-tap, Y[0]
+      const unsigned long long pc1 = pk2(c1, c1), nc2 = pk2(-c2, -c2);
+      // D1 columns: (re, im) of k2 at 2 k2, 2 k2 + 1 from the F_hi half, the same again at 64 + ... from the F_lo half
+      unsigned long long p2, p1, y0;                                 // Y[k-2], Y[k-1] of the running 3-tap, Y[0] (packed re, im)
       {
         // left end: Y[-1] = W64^(-n1) Y[31] = W64^(-n1) W2048^(31 n1) D[31] = conj(w1) D[31]
-        uint32_t a0, a1, a2, a3;
-        tmem_ld1_nowait(dbase + 31, a0);
-        tmem_ld1_nowait(dbase + 63, a1);
-        tmem_ld1_nowait(dbase + 95, a2);
-        tmem_ld1_nowait(dbase + 127, a3);
+        uint32_t a[2], b[2];
+        tmem_ld2_nowait(dbase + 62, a);
+        tmem_ld2_nowait(dbase + 126, b);
         tmem_ld_wait();
-        const float dr = __uint_as_float(a0) + __uint_as_float(a2), di = __uint_as_float(a1) + __uint_as_float(a3);
-        p2 = make_float2(dr * w1.x + di * w1.y, di * w1.x - dr * w1.y);
+        const float dr = __uint_as_float(a[0]) + __uint_as_float(b[0]), di = __uint_as_float(a[1]) + __uint_as_float(b[1]);
+        p2 = pk2(dr * w1.x + di * w1.y, di * w1.x - dr * w1.y);
       }
       uint32_t zrh[16], zrl[16], zih[16], zil[16];                  // the whole Y' row of this thread, packed fp16 pairs
       float zr_e = 0.0f, zi_e = 0.0f;
-      // Hann 3-tap with one element of lag: z[k-1] = c1 Y[k-1] - c2 (Y[k-2] + Y[k])
-      auto emit = [&](int k, float2 l, float2 m_, float2 r) {
-        const float zr = c1 * m_.x - c2 * (l.x + r.x), zi = c1 * m_.y - c2 * (l.y + r.y);
+      // Hann 3-tap with one element of lag: z[k-1] = c1 Y[k-1] - c2 (Y[k-2] + Y[k]), both components per instruction
+      auto emit = [&](int k, unsigned long long l, unsigned long long m_, unsigned long long r) {
+        const float2 z = un2(fma2(add2(l, r), nc2, mul2(m_, pc1)));
         if (k & 1) {
-          split2(zr_e, zr, zrh[k >> 1], zrl[k >> 1]);
-          split2(zi_e, zi, zih[k >> 1], zil[k >> 1]);
+          split2(zr_e, z.x, zrh[k >> 1], zrl[k >> 1]);
+          split2(zi_e, z.y, zih[k >> 1], zil[k >> 1]);
         } else {
-          zr_e = zr; zi_e = zi;
+          zr_e = z.x; zi_e = z.y;
         }
       };
-      float2 wa = make_float2(1.0f, 0.0f);                           // anchor W2048^(8 c n1)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r0[8], r2[8];
-        float re[8], im[8];
-        tmem_ld8_nowait(dbase + 8 * c, r0);
-        tmem_ld8_nowait(dbase + 64 + 8 * c, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) re[e] = __uint_as_float(r0[e]) + __uint_as_float(r2[e]);
-        tmem_ld8_nowait(dbase + 32 + 8 * c, r0);
-        tmem_ld8_nowait(dbase + 96 + 8 * c, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) im[e] = __uint_as_float(r0[e]) + __uint_as_float(r2[e]);
-        if (c == 3) {                                                // every TMEM read of this pair is done
-          tc_fence_before();
-          mbar_arrive_warp(d1_empty + h, lane);
-        }
-        float2 w = wa;
-        if (c < 3) wa = cmul(wa, w8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = 8 * c + e;
-          const float2 y = (k == 0) ? make_float2(re[0], im[0]) : cmul(make_float2(re[e], im[e]), w);
-          if (e < 7) w = cmul(w, w1);
-          if (k == 0) { y0 = y; p1 = y; }
-          else { emit(k - 1, p2, p1, y); p2 = p1; p1 = y; }
-        }
-      }
-      emit(31, p2, p1, cmul(y0, rp));                                // Y[32] = W64^(n1) Y[0]
-      if (warp == 4) LM_TRACE(G, 4);
-      mbar_wait(y_empty, (G & 1) ^ 1, 21);
-      if (warp == 4) LM_TRACE(G, 5);                           // stage 3 of the previous group has read Y'
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off_r = off0 + c * 2048u, off_i = off_r + 8 * 128;      // K rows n1 and 64 + n1
+      // chunk c of the row (k2 = 8 c .. 8 c + 7) -> Y' (K rows n1 and 64 + n1 of m chunk 4 fslot + c)
+      auto store_chunk = [&](int c) {
+        const uint32_t off_r = off0 + c * 2048u, off_i = off_r + 8 * 128;
         *reinterpret_cast<uint4*>(yhi + off_r) = make_uint4(zrh[4 * c], zrh[4 * c + 1], zrh[4 * c + 2], zrh[4 * c + 3]);
         *reinterpret_cast<uint4*>(ylo + off_r) = make_uint4(zrl[4 * c], zrl[4 * c + 1], zrl[4 * c + 2], zrl[4 * c + 3]);
         *reinterpret_cast<uint4*>(yhi + off_i) = make_uint4(zih[4 * c], zih[4 * c + 1], zih[4 * c + 2], zih[4 * c + 3]);
         *reinterpret_cast<uint4*>(ylo + off_i) = make_uint4(zil[4 * c], zil[4 * c + 1], zil[4 * c + 2], zil[4 * c + 3]);
+      };
+      float2 wa = make_float2(1.0f, 0.0f);                           // anchor W2048^(8 c n1)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rh[8], rl[8];
+        float2 wc = wa, wm = make_float2(wa.x * w1.x + wa.y * w1.y, wa.y * w1.x - wa.x * w1.y);   // w_0, w_{-1} = w_0 conj(w1)
+        if (c < 3) wa = cmul(wa, w8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = 8 * c + e;
+          if ((e & 3) == 0) {                                        // four k2 at a time (registers)
+            tmem_ld8_nowait(dbase + 16 * c + 2 * e, rh);
+            tmem_ld8_nowait(dbase + 64 + 16 * c + 2 * e, rl);
+            tmem_ld_wait();
+            if (k == 28) {                                           // every TMEM read of this pair is done
+              tc_fence_before();
+              mbar_arrive_warp(d1_empty + h, lane);
+            }
+          }
+          const int e4 = e & 3;
+          const float2 d = un2(add2(pk2(__uint_as_float(rh[2 * e4]), __uint_as_float(rh[2 * e4 + 1])),
+                                    pk2(__uint_as_float(rl[2 * e4]), __uint_as_float(rl[2 * e4 + 1]))));
+          const float2 yv = cmul(d, wc);
+          const unsigned long long y = pk2(yv.x, yv.y);
+          if (e < 7) {
+            const float2 wn = make_float2(fmaf(tc2, wc.x, -wm.x), fmaf(tc2, wc.y, -wm.y));
+            wm = wc; wc = wn;
+          }
+          if (k == 0) { y0 = y; p1 = y; }
+          else { emit(k - 1, p2, p1, y); p2 = p1; p1 = y; }
+          if (k == 16) {
+            // chunks 0-2 are complete and wait in registers (the whole row would not fit): by now the stage-3 GEMM of the
+            // previous group (1,450 cycles) has normally released Y'; only the last quarter of the row is computed after it
+            if (warp == 4) LM_TRACE(G, 4);
+            mbar_wait_sleep(y_empty, (G & 1) ^ 1, 21, kPollNs);
+            if (warp == 4) LM_TRACE(G, 5);
+            store_chunk(0); store_chunk(1);
+          }
+          if (k == 24) {
+            store_chunk(2);
+          }
+        }
       }
+      {
+        const float2 y0v = un2(y0);
+        const float2 y32 = cmul(y0v, rp);                            // Y[32] = W64^(n1) Y[0]
+        emit(31, p2, p1, pk2(y32.x, y32.y));
+      }
+      store_chunk(3);
       fence_proxy_async();
       mbar_arrive_warp(y_full, lane);
       if (warp == 4) LM_TRACE(G, 6);
+      if (warp == 11) LM_TRACE(G, 15);
     }
   } else {
     // ===================== epilogue 3 + mel: thread = (frame slot q of the group, k2 = lane) for the power tile; then the
@@ -438,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
     for (int r = 0; r < kMelRounds; ++r) mel_task_init(mk[r], melw, mst, tasks, p.n_tasks, r * 128 + mt);
     for (uint32_t G = 0; G < n_groups; ++G) {
       const uint32_t buf = G & 1, ci = G >> 3, g = G & 7;
-      mbar_wait(d3_full + buf, (G >> 1) & 1, 30);
+      mbar_wait_sleep(d3_full + buf, (G >> 1) & 1, 30, kPollNs);
       if (warp == 12) LM_TRACE(G, 7);
       tc_fence_after();
       const uint32_t d = tm + 256 + buf * kN3 + lane_addr;
@@ -458,13 +536,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
           pf[(32 * (k1 + 16 * half) + lane) * 4] = re * re + im * im;
         }
       }
-      if (warp == 12) LM_TRACE(G, 8);
+      LM_TRACE(G, 8 + (warp - 12));
       named_sync(2, 128);                                          // the power tile of the group is complete
+      if (warp == 12) LM_TRACE(G, 12);
       const float pscale = scale_ring[ci & 3].y;
 #pragma unroll
-      for (int r = 0; r < kMelRounds; ++r) mel_task_run(mk[r], p4, mel_s, (int)g, pscale);
-      if (warp == 12) LM_TRACE(G, 10);
+      for (int r = 0; r < kMelRounds; r += 2) mel_task_run2(mk[r], mk[r + 1], p4, mel_s, (int)g, pscale, lane);
+      if (warp == 12) LM_TRACE(G, 13);
       named_sync(2, 128);                                          // every band of the group is in mel_s; the tile is free
+      if (warp == 12) LM_TRACE(G, 14);
       if (g == 7) {
         // ---- power_to_db(ref = max, amin, top_db) over the clip's [n_mels][32] tile (same operations as logmel.cu)
         const int clip = (int)blockIdx.x + (int)ci * (int)gridDim.x;
@@ -484,7 +564,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_tc_kernel(const __grid_con
           o[mm * p.out.pitch + (i & 31)] = fmaxf(v, -kTopDb);
         }
         named_sync(2, 128);                                          // red / mel_s are rewritten by the next clip
-        if (warp == 12) LM_TRACE(G, 11);
       }
     }
   }
@@ -530,7 +609,7 @@ static int logmel_tc_prepare(ww_ctx* c) {
       split_host(cos(a) * kFScale, rh, rl);
       split_host(sin(a) * kFScale, ih, il);
       auto at = [&](int n) -> uint16_t& { return f32[((size_t)(n2 / 8) * 128 + n) * 8 + n2 % 8]; };
-      at(k2) = rh; at(32 + k2) = ih; at(64 + k2) = rl; at(96 + k2) = il;
+      at(2 * k2) = rh; at(2 * k2 + 1) = ih; at(64 + 2 * k2) = rl; at(65 + 2 * k2) = il;   // (re, im) adjacent: packed fp32 adds
     }
   for (int k1 = 0; k1 < 32; ++k1)
     for (int n1 = 0; n1 < kN1; ++n1) {
@@ -571,8 +650,8 @@ static int logmel_tc_prepare(ww_ctx* c) {
 // the shared-memory FFT kernel of logmel.cu), a negative error code otherwise.
 int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B, int normalize,
                         cudaStream_t st) {
-  static const char* force = getenv("WW_LOGMEL_KERNEL");            // "fft" / "tc" for A/B runs; default: tc where it applies
-  if (force && force[0] == 'f') return 1;
+  static const char* force = getenv("WW_LOGMEL_KERNEL");            // "fft" / "tc" for A/B runs
+  if (force ? force[0] == 'f' : !kTcDefault) return 1;
   const int align = pcm16 ? 8 : 4;                                  // 16-byte rows
   if ((clip_stride % align) != 0 || (reinterpret_cast<uintptr_t>(clips) & 15) != 0) return 1;
   int rc = logmel_tc_prepare(c);
@@ -602,11 +681,11 @@ int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_st
     long long h[40 * 16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "logmel_tc trace (cycles): S1 ready | S3: y_full, d3_empty | ep1: d1_full, computed, y_empty, stored | ep3: d3_full, tile written, B, mel done, A | conv at B\n");
+    fprintf(stderr, "logmel_tc trace (cycles): S1 ready | S3: y_full, d3_empty | ep1 w4: d1_full, at wait, y_empty, stored | ep3: d3_full, tile written w12..15, after barrier, mel done, after barrier | ep1 w11 stored\n");
     const long long t0 = h[0];
     for (int i = 0; i < 40; ++i) {
       fprintf(stderr, "grp %2d:", i);
-      for (int k = 0; k < 13; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1);
+      for (int k = 0; k < 16; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }

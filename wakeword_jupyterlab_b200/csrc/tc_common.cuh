@@ -57,6 +57,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     if (++spins > (1u << 17)) mbar_timeout(code);      // ~2.6 s of 20 us suspensions
   }
 }
+// Polite wait: a failed try_wait comes back within a few cycles on this part (the suspend hint is only a hint), so a
+// spinning warp issues ~1 shared-memory-pipe operation per loop trip and, with a dozen waiting warps per CTA, saturates
+// the pipe the working warps need for LDS / STS / SHFL.  Sleeping `ns` between polls costs at most that much wake-up
+// latency and frees the pipe.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int code, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) mbar_timeout(code);
+  }
+}
 // roles off the critical path (producers / epilogue warps) use the same hardware-suspended wait
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) { mbar_wait(bar, parity, code); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
