@@ -381,3 +381,46 @@ def test_pinned_host_buffers_from_the_library(ww):
     v = h[:3]
     del h
     assert v.shape == (3, 16000) and np.array_equal(v.numpy(), pcm[:3])       # views keep the mapping alive
+
+
+# ------------------------------------------------------------------ tensor-core log-mel (logmel_tc.cu), selected per call
+def test_tensor_core_logmel_kernel_parity(ww, golden_dir, monkeypatch):
+    """WW_LOGMEL_KERNEL=tc routes ww_logmel through the two-stage tcgen05 GEMM-DFT kernel (reference preset only); it must
+    meet the same 1e-3 dB gate against the golden fixtures of the unmodified reference / torchaudio and the oracle as the
+    default shared-memory FFT kernel, for fp32 and int16 PCM input, with and without the fused peak normalisation."""
+    monkeypatch.setenv("WW_LOGMEL_KERNEL", "tc")
+    g = np.load(os.path.join(golden_dir, "logmel_code.npz"))
+    clips = np.stack([A.normalize_audio(c) for c in R.make_clips(int(g["n"]), seed=int(g["seed"]))]).astype(np.float32)
+    eng = ww.get_engine()
+    l0 = eng.launches
+    out = eng.logmel(torch.from_numpy(clips).cuda())[:, 0].cpu().numpy()
+    assert eng.launches == l0 + 1
+    assert np.abs(out - g["logmel_reference"]).max() < 1e-3 and np.abs(out - g["logmel_torchaudio"]).max() < 1e-3
+    assert np.all(out.max(axis=(1, 2)) == 0.0) and out.min() >= -80.0
+    # more clips than SMs (several clips per CTA, the converter running a clip ahead), un-normalised inputs of very
+    # different magnitude with and without the fused normalisation
+    raw = R.make_clips(400, seed=77) * np.logspace(-4, 3, 400, dtype=np.float32)[:, None]
+    ref_n = LM.audio_to_mel_batch(np.stack([A.normalize_audio(c) for c in raw[::9]]).astype(np.float32))
+    got_n = eng.logmel(torch.from_numpy(raw).cuda(), normalize=True)[::9, 0].cpu().numpy()
+    assert np.abs(got_n - ref_n).max() < 1e-3
+    got_u = eng.logmel(torch.from_numpy(raw).cuda(), normalize=False)[::9, 0].cpu().numpy()
+    assert np.abs(got_u - LM.audio_to_mel_batch(raw[::9])).max() < 1e-3          # dB relative to the clip maximum: scale-free
+    # int16 PCM in = fp32 of the same samples, bit for bit
+    pcm = np.clip(np.round(R.make_clips(200, seed=5) * 32768.0), -32768, 32767).astype(np.int16)
+    assert torch.equal(eng.logmel(pcm, normalize=True), eng.logmel(pcm.astype(np.float32) / 32768.0, normalize=True))
+    # edge cases: silent clip -> 0 dB everywhere; an impulse (flat spectrum at the -80 dB floor region) to 5e-3 dB
+    z = np.zeros((3, 16000), np.float32); z[1, 5000] = 1.0; z[2] = clips[0]
+    e = eng.logmel(torch.from_numpy(z).cuda())[:, 0].cpu().numpy()
+    assert not e[0].any() and np.abs(e[1] - LM.audio_to_mel(z[1])).max() < 5e-3 and np.abs(e[2] - out[0]).max() == 0.0
+    # against the default kernel on the same inputs
+    monkeypatch.setenv("WW_LOGMEL_KERNEL", "fft")
+    fft = eng.logmel(torch.from_numpy(raw).cuda(), normalize=True)[::9, 0].cpu().numpy()
+    assert np.abs(fft - got_n).max() < 1e-3
+    # the fused scoring path with the tensor-core front end
+    monkeypatch.setenv("WW_LOGMEL_KERNEL", "tc")
+    sd = R.seeded_state_dict(256, seed=0)
+    net = _load(ww, sd)
+    c8 = R.make_clips(8, seed=1234)
+    logits, _, _ = ww.score_clips(torch.from_numpy(c8).cuda(), net, normalize=True)
+    ref = M.forward_numpy(LM.audio_to_mel_batch(np.stack([A.normalize_audio(c) for c in c8]).astype(np.float32))[:, None], sd, np.float64)
+    assert np.abs(logits.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4

@@ -51,7 +51,7 @@ constexpr float kFScale = 1024.0f, kYScale = 4096.0f;
 constexpr int kWarps = 16, kThreads = kWarps * 32;      // 512 threads: 128 registers each (ptxas budgets the whole kernel by
                                                        // the smallest setmaxnreg value, so the roles share one budget instead)
 constexpr int kConvWarps = 3;
-constexpr bool kTcDefault = true;                      // which kernel ww_logmel takes where both apply (see profiles/: A/B)
+constexpr bool kTcDefault = false;                     // which kernel ww_logmel takes where both apply (see profiles/: A/B)
 constexpr unsigned kPollNs = 32;                       // sleep between mbarrier polls (see mbar_wait_sleep)
 constexpr int kMelRounds = 4, kMelTaps = 8;            // lane-tasks per epilogue-3 thread; taps per lane-task (registers)
 constexpr float kAmin = 1e-10f, kTopDb = 80.0f;
@@ -650,7 +650,7 @@ static int logmel_tc_prepare(ww_ctx* c) {
 // the shared-memory FFT kernel of logmel.cu), a negative error code otherwise.
 int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_stride, LogmelOut out, int B, int normalize,
                         cudaStream_t st) {
-  static const char* force = getenv("WW_LOGMEL_KERNEL");            // "fft" / "tc" for A/B runs
+  const char* force = getenv("WW_LOGMEL_KERNEL");                   // "fft" / "tc": read per call (tests and A/B runs switch it)
   if (force ? force[0] == 'f' : !kTcDefault) return 1;
   const int align = pcm16 ? 8 : 4;                                  // 16-byte rows
   if ((clip_stride % align) != 0 || (reinterpret_cast<uintptr_t>(clips) & 15) != 0) return 1;
