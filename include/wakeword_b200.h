@@ -143,6 +143,24 @@ int ww_score_host(ww_ctx* ctx, const float* clips_host, const float* noise_bank_
                   int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                   float* prob1_host, uint8_t* decision_host, int B);
 
+/* ---- the reference's own augmentation stages: phase-vocoder time stretch / pitch shift and
+ *      Gaussian noise.  Replace librosa.effects.time_stretch + pad_or_truncate (wakeword_training_script.py:114-117),
+ *      librosa.effects.pitch_shift (:110-112) and `audio + np.random.normal(0, NOISE_FACTOR)` (:119-121), with librosa's
+ *      defaults at those call sites (n_fft 2048, hop 512: the context must have n_fft = win_length = 2048).
+ *      Per clip, host-drawn, DEVICE arrays: rate (float64: the time-step grid is computed in double like numpy's);
+ *      rs_orig / rs_new = 0 or equal: time stretch, result cropped at crop_off / zero-padded to n_samples;
+ *      otherwise pitch shift: the stretched signal is resampled rs_orig -> rs_new (ww_prepare_resample first; the rational
+ *      stand-in of sr / rate -> sr, rate = 2^(-n_steps / 12)) and fitted to n_samples.  clips[B][n_samples] -> out[B][n_samples]. */
+typedef struct ww_pvoc {
+  const double* rate;
+  const int32_t* rs_orig;
+  const int32_t* rs_new;
+  const int32_t* crop_off;
+} ww_pvoc;
+int ww_time_stretch(ww_ctx* ctx, const float* clips, const ww_pvoc* p, float* out, int B, void* stream);
+/* x[i] += sigma * N(0, 1), i < n; counter-based Philox4x32-10 stream keyed by `seed` (reproducible, order independent) */
+int ww_add_gaussian_noise(ww_ctx* ctx, float* x, int64_t n, float sigma, uint64_t seed, void* stream);
+
 /* ---- pinned host buffers for the *_host entries, placed on the NUMA node of the context's GPU (sysfs numa_node of its
  *      PCI function) so that eight ranks on a two-socket box do not all copy out of one socket's memory.
  *      *how: 0 = plain pinned memory, 1 = mbind(MPOL_BIND), 2 = first touch from a CPU of that node.

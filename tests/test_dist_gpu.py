@@ -1,0 +1,122 @@
+"""Two-GPU tests (skipped on a one-GPU box): the data-parallel training step through the C ABI's own NCCL hook
+(`ww_train_step(nccl_comm)`, csrc/train.cu) and through torch.distributed on the exposed gradient buffer."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, uid_path, out_path):
+    import torch.distributed as dist
+    import wakeword_jupyterlab_b200 as ww
+    from oracle import recipe as R
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    # ---- a raw ncclComm_t for the C ABI: ncclGetUniqueId on rank 0, shared through the store, ncclCommInitRank
+    nccl = C.CDLL("libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+    class UID(C.Structure):
+        _fields_ = [("b", C.c_char * 128)]
+    uid = UID()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+        t = torch.frombuffer(bytearray(bytes(uid.b) if False else C.string_at(C.byref(uid), 128)), dtype=torch.uint8).to(dev)
+    else:
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UID, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+
+    class MC(ww.ModelConfig):
+        DROPOUT = 0.0
+        HIDDEN_SIZE = 64
+    sd = R.seeded_state_dict(64, seed=3)
+    rng = np.random.default_rng(11)
+    X = (rng.standard_normal((2 * 6, 1, 80, 32)) * 10 - 30).astype(np.float32)
+    Y = rng.integers(0, 2, 2 * 6)
+
+    def model():
+        m = ww.WakewordModel(MC).to(dev).train()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        return m
+    # (a) C-level hook: ww_train_step with the raw communicator on this rank's half of the batch
+    m1 = model()
+    eng = m1.engine(dev)
+    eng.lib.ww_train_reset(eng._ctx)
+    x = torch.from_numpy(X[rank * 6:(rank + 1) * 6]).to(dev)
+    y = torch.from_numpy(Y[rank * 6:(rank + 1) * 6]).to(dev)
+    loss = torch.empty((), device=dev)
+    for _ in range(2):
+        rc = eng.lib.ww_train_step(eng._ctx, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), 6, C.c_void_p(loss.data_ptr()),
+                                   C.c_float(1e-3), comm, world, eng._stream())
+        assert rc == 0, eng.lib.ww_last_error(eng._ctx)
+    torch.cuda.synchronize()
+    w_c = {}
+    for name, p in m1.state_dict().items():
+        buf = torch.empty_like(p)
+        assert eng.lib.ww_get_weights(eng._ctx, name.encode(), C.c_void_p(buf.data_ptr())) == 0
+        w_c[name] = buf.cpu()
+    # (b) the Python trainer: torch.distributed all-reduce of the flat gradient buffer
+    m2 = model()
+    tr = ww.WakewordTrainer(m2, dev)
+    tr.lr = 1e-3
+    for _ in range(2):
+        tr.train_step(x, y)
+    # (c) single process on the whole batch (mean over 12 = mean of the two half-batch means)
+    ref = None
+    if rank == 0:
+        dist.barrier()
+    else:
+        dist.barrier()
+    m3 = model()
+    eng3 = m3.engine(dev)
+    tr3 = ww.WakewordTrainer(m3, dev)
+    tr3.lr = 1e-3
+    saved = (dist.get_world_size,)
+    full_x, full_y = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
+    import wakeword_jupyterlab_b200.trainer as T
+    real = T.allreduce_mean_
+    T.allreduce_mean_ = lambda flat: 1.0               # whole batch on one rank: no collective
+    try:
+        for _ in range(2):
+            tr3.train_step(full_x, full_y)
+    finally:
+        T.allreduce_mean_ = real
+    res = {"max_c_vs_py": max(float((w_c[k] - v.cpu()).abs().max()) for k, v in m2.state_dict().items()),
+           "max_dp_vs_full": max(float((m2.state_dict()[k] - v).abs().max()) for k, v in m3.state_dict().items()),
+           "checksum": float(sum(v.double().sum() for v in m2.state_dict().values()))}
+    sums = [None] * world
+    dist.all_gather_object(sums, res["checksum"])
+    res["replicas_equal"] = bool(sums[0] == sums[1])
+    if rank == 0:
+        np.save(out_path, np.array([res["max_c_vs_py"], res["max_dp_vs_full"], float(res["replicas_equal"])]))
+    nccl.ncclCommDestroy(comm)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_training_step_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path / "uid"), out), nprocs=2, join=True)
+    c_vs_py, dp_vs_full, equal = np.load(out)
+    assert equal == 1.0                      # both replicas hold the same weights after the all-reduced steps
+    assert c_vs_py < 1e-7                    # ww_train_step(nccl_comm) == backward + torch all-reduce + apply
+    assert dp_vs_full < 2e-6                 # two half batches averaged == one full batch (fp32 summation order only)

@@ -155,3 +155,40 @@ def test_snr_mixer_restatement_matches_the_unmodified_reference(golden_dir):
                     g["snr"], np.ones(n, np.float32))
     p.rs_orig = p.rs_new = np.full(n, 100, np.int32)
     assert np.array_equal(A.augment_batch(clips, bank, p), g["noisy_f32"])
+
+
+# ------------------------------------------------------------------ phase vocoder restatement (section 8 f4)
+def test_phase_vocoder_restatement_against_torch_and_torchaudio():
+    """oracle/pvoc.py restates librosa's stft / phase_vocoder / istft; librosa is not installed, so the restatement is
+    cross-checked against the independent implementations that are: torch.stft / torch.istft (same framing, window and
+    sum-of-squares normalisation) and torchaudio.functional.phase_vocoder (a port of the same librosa routine)."""
+    import torch
+    import torchaudio
+    from oracle import pvoc as P
+    y = R.make_clips(3, seed=3)[0]
+    w = torch.hann_window(2048, periodic=True)
+    D = P.stft(y)
+    Dt = torch.stft(torch.from_numpy(y), 2048, 512, 2048, w, center=True, pad_mode="constant", return_complex=True).numpy()
+    assert D.shape == (1025, 32) and np.abs(D - Dt).max() < 1e-4 * np.abs(Dt).max()
+    phi = torch.linspace(0, np.pi * 512, 1025)[..., None]
+    for rate in (0.7, 0.93, 1.0, 1.19, 1.3):
+        pv = P.phase_vocoder(D, rate)
+        pt = torchaudio.functional.phase_vocoder(torch.from_numpy(D), rate, phi).numpy()
+        assert pv.shape == pt.shape == (1025, int(np.ceil(32 / rate)))
+        assert np.abs(pv - pt).max() < 1e-3 * np.abs(pt).max()           # torchaudio accumulates the phase in float32
+        L = P.stretch_len(len(y), rate)
+        ys = P.istft(pv, L)
+        yt = torch.istft(torch.from_numpy(pv), 2048, 512, 2048, w, center=True, length=L).numpy()
+        assert len(ys) == L and np.abs(ys - yt).max() < 1e-5
+    # rate 1 is the identity up to the overlap-add round trip; the stretched length follows librosa's round()
+    assert np.abs(P.time_stretch(y, 1.0) - y).max() < 1e-5
+    assert P.stretch_len(16000, 0.7) == 22857 and P.stretch_len(16000, 1.3) == 12308
+    ps = P.pitch_shift(y, 2.0)
+    assert ps.shape == y.shape and np.isfinite(ps).all()
+    # a pure tone moves by the requested interval (spectral peak of the shifted signal)
+    t = np.arange(16000) / 16000.0
+    tone = (0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    f = np.fft.rfftfreq(16000, 1 / 16000.0)
+    for n_steps in (-3.0, 2.0):
+        peak = f[np.argmax(np.abs(np.fft.rfft(P.pitch_shift(tone, n_steps) * np.hanning(16000))))]
+        assert abs(peak / (440.0 * 2 ** (n_steps / 12.0)) - 1.0) < 5e-3

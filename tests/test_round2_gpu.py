@@ -424,3 +424,101 @@ def test_tensor_core_logmel_kernel_parity(ww, golden_dir, monkeypatch):
     logits, _, _ = ww.score_clips(torch.from_numpy(c8).cuda(), net, normalize=True)
     ref = M.forward_numpy(LM.audio_to_mel_batch(np.stack([A.normalize_audio(c) for c in c8]).astype(np.float32))[:, None], sd, np.float64)
     assert np.abs(logits.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4
+
+
+# ------------------------------------------------------------------ the reference's own augmentations
+def test_phase_vocoder_time_stretch_and_pitch_shift(ww):
+    """ww_time_stretch against oracle/pvoc.py (librosa's algorithm, cross-checked against torch / torchaudio on the CPU):
+    time stretch over the reference's rate range with pad_or_truncate and its crop offset, pitch shift over +-3
+    semitones; exact structure (zero tail where the stretched clip is shorter)."""
+    from oracle import pvoc as P
+    eng = ww.get_engine()
+    clips = R.make_clips(10, seed=12)
+    rates = np.array([0.7, 0.85, 0.93, 1.0, 1.07, 1.19, 1.3, 0.7, 1.3, 1.0])
+    crops = np.zeros(10, np.int32)
+    for b, r in enumerate(rates):
+        L = P.stretch_len(16000, r)
+        if L > 16000:
+            crops[b] = (0, L - 16000, (L - 16000) // 3)[b % 3]
+    out = eng.time_stretch(clips, rates, crops).cpu().numpy()
+    for b, r in enumerate(rates):
+        ref = P.stretch_and_fit(clips[b], float(r), int(crops[b]))
+        err = np.abs(out[b] - ref).max()
+        assert err < 2e-3, (float(r), err)                 # float32 phase accumulation over <= 46 frames vs float64
+        assert np.sqrt(np.mean((out[b] - ref) ** 2)) < 2e-4
+        L = P.stretch_len(16000, r)
+        if L < 16000:
+            assert not out[b, L:].any()
+    steps = np.array([-3.0, -1.5, -0.25, 0.0, 0.4, 2.0, 3.0])
+    ps = eng.pitch_shift(clips[:7], steps).cpu().numpy()
+    for b, n in enumerate(steps):
+        ref = P.pitch_shift(clips[b], float(n))
+        assert np.abs(ps[b] - ref).max() < 2e-3, (float(n), np.abs(ps[b] - ref).max())
+    # a pure tone moves by the requested interval
+    t = np.arange(16000) / 16000.0
+    tone = np.tile((0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32), (2, 1))
+    sh = eng.pitch_shift(tone, [-3.0, 2.0]).cpu().numpy()
+    f = np.fft.rfftfreq(16000, 1 / 16000.0)
+    for b, n in enumerate((-3.0, 2.0)):
+        peak = f[np.argmax(np.abs(np.fft.rfft(sh[b] * np.hanning(16000))))]
+        assert abs(peak / (440.0 * 2 ** (n / 12.0)) - 1.0) < 5e-3
+
+
+def test_gaussian_noise_stage_distribution(ww):
+    """`audio + np.random.normal(0, NOISE_FACTOR)` (:119-121) with a device Philox stream: distribution parity (bit parity
+    with numpy's Mersenne stream is impossible): moments, tails, independence across samples, reproducibility by seed."""
+    eng = ww.get_engine()
+    n = 1 << 22
+    x = torch.zeros(n, device="cuda")
+    eng.add_gaussian_noise(x, 0.15, seed=1234)
+    v = x.double().cpu().numpy()
+    assert abs(v.mean()) < 4 * 0.15 / np.sqrt(n) and abs(v.std() / 0.15 - 1.0) < 2e-3
+    z = v / 0.15
+    assert abs((z ** 3).mean()) < 0.01 and abs((z ** 4).mean() - 3.0) < 0.02            # skewness 0, kurtosis 3
+    for q, p in ((1.0, 0.8413447), (2.0, 0.9772499), (3.0, 0.9986501)):
+        assert abs((z < q).mean() - p) < 1e-3 and abs((z > -q).mean() - p) < 1e-3
+    assert abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 2e-3 and abs(np.corrcoef(z[:-4], z[4:])[0, 1]) < 2e-3
+    y = torch.zeros(n, device="cuda")
+    eng.add_gaussian_noise(y, 0.15, seed=1234)
+    assert torch.equal(x, y)                                                            # same seed, same stream
+    eng.add_gaussian_noise(y.zero_(), 0.15, seed=1235)
+    assert not torch.equal(x, y) and abs(np.corrcoef(v, y.double().cpu().numpy())[0, 1]) < 2e-3
+    base = torch.ones(1001, device="cuda")
+    assert abs(float(eng.add_gaussian_noise(base, 0.0, seed=5).mean()) - 1.0) == 0.0     # sigma 0: untouched; odd length
+
+
+def test_reference_stage_set_through_augment_audio(ww):
+    """AudioProcessor(stage_set="reference").augment_audio: the reference's four stages in its draw order (:103-123);
+    with a seeded `random` the deterministic stages reproduce the oracle chain, the noise stage adds N(0, 0.15^2)."""
+    import random
+    from oracle import pvoc as P
+
+    class NoNoise(ww.AugmentationConfig):
+        NOISE_FACTOR = 0.0
+    proc = ww.AudioProcessor(stage_set="reference")
+    x = A.normalize_audio(R.make_clips(1, seed=8)[0]).astype(np.float32)
+    seen = set()
+    for seed in range(8):
+        random.seed(seed); np.random.seed(seed)
+        got = proc.augment_audio(x, NoNoise)
+        random.seed(seed)
+        ref = x.copy()
+        if random.random() < 0.8:
+            ref = np.roll(ref, int(random.uniform(-0.3, 0.3) * 16000)); seen.add("shift")
+        if random.random() < 0.8:
+            ref = P.pitch_shift(ref, random.uniform(-3, 3)); seen.add("pitch")
+        if random.random() < 0.8:
+            rate = random.uniform(0.7, 1.3)
+            L = P.stretch_len(16000, rate)
+            ref = P.stretch_and_fit(ref, rate, random.randint(0, L - 16000) if L > 16000 else 0); seen.add("stretch")
+        random.random()
+        assert got.shape == x.shape and np.abs(got - ref).max() < 5e-3, (seed, np.abs(got - ref).max())
+    assert seen == {"shift", "pitch", "stretch"}
+    random.seed(3); np.random.seed(3)
+    a = proc.augment_audio(x)
+    random.seed(3); np.random.seed(3)
+    b = proc.augment_audio(x)
+    assert np.array_equal(a, b) and np.isfinite(a).all()
+    # process_audio_file(augment=True) runs the reference chain end to end
+    mel = ww.AudioProcessor(stage_set="reference").audio_to_mel(a)
+    assert mel.shape == (80, 32) and mel.max() == 0.0

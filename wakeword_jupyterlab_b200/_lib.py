@@ -23,6 +23,10 @@ class WWConfig(C.Structure):
                 ("conv_mode", C.c_int32), ("chunk_clips", C.c_int32)]
 
 
+class WWPvoc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rate", "rs_orig", "rs_new", "crop_off")]
+
+
 class WWAug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("flags", "shift", "rs_orig", "rs_new", "crop_off",
                                           "noise_idx", "noise_off", "snr_db", "gain")]
@@ -34,7 +38,7 @@ EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_f
            "ww_train_backward", "ww_train_apply", "ww_train_step", "ww_train_reset", "ww_train_n_params",
            "ww_train_grad_buffer", "ww_train_param_range", "ww_get_weights",
            "ww_train_get_moments", "ww_train_set_moments", "ww_train_get_step", "ww_train_set_step",
-           "ww_host_alloc", "ww_host_free", "ww_host_numa_node",
+           "ww_host_alloc", "ww_host_free", "ww_host_numa_node", "ww_time_stretch", "ww_add_gaussian_noise",
            "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
@@ -90,6 +94,8 @@ def load():
         lib.ww_train_get_step.argtypes = [vp]
         lib.ww_train_get_step.restype = i64
         lib.ww_train_set_step.argtypes = [vp, i64]
+        lib.ww_time_stretch.argtypes = [vp, vp, C.POINTER(WWPvoc), vp, i32, vp]
+        lib.ww_add_gaussian_noise.argtypes = [vp, vp, i64, C.c_float, C.c_uint64, vp]
         lib.ww_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int)]
         lib.ww_host_alloc.restype = vp
         lib.ww_host_free.argtypes = [vp, vp]

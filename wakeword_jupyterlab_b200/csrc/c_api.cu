@@ -154,7 +154,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
   cudaFree(c->ws_act2_h); cudaFree(c->ws_act2_8); cudaFree(c->ws_pool_part); cudaFree(c->ws_logits); cudaFree(c->ws_h[0]); cudaFree(c->ws_h[1]);
-  cudaFree(c->d_scalar); cudaFree(c->d_stream_cache); cudaFree(c->d_stream_bmax); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
+  cudaFree(c->d_pv_spec); cudaFree(c->d_scalar); cudaFree(c->d_stream_cache); cudaFree(c->d_stream_bmax); cudaFree(c->d_tc_mask); cudaFree(c->d_host_in); cudaFree(c->d_host_out); cudaFree(c->d_host_aug);
   for (ProfSlot& p : c->prof_slots) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
   if (c->apply_event) cudaEventDestroy(c->apply_event);

@@ -128,6 +128,7 @@ struct ww_ctx {
   int n_pool_part = 0;
   bool ws_ready = false;
   unsigned int* d_scalar = nullptr;   // scratch word for ww_normalize
+  float2* d_pv_spec = nullptr; size_t pv_spec_bytes = 0;              // phase vocoder: STFT scratch [clips][frames][1025]
   float* d_stream_cache = nullptr; size_t stream_cache_bytes = 0;      // streaming: mel energies of the unique frames
   float* d_stream_bmax = nullptr; size_t stream_bmax_bytes = 0;        // streaming: block maxima of |x|
   uint32_t* d_tc_mask = nullptr;      // conv3 tile validity masks [T3][4]

@@ -227,6 +227,46 @@ class Engine:
                                       C.byref(st), C.c_void_p(out.data_ptr()), B, self._stream()), "ww_augment")
         return out
 
+    # ------------------------------------------------------------------ the reference's own augmentations (section 8 f4)
+    def time_stretch(self, clips, rate, crop_off=None, rs_orig=None, rs_new=None):
+        """Phase-vocoder time stretch of every clip by its own ``rate`` (librosa.effects.time_stretch), fitted back to
+        n_samples like the reference's pad_or_truncate (crop_off = host-drawn start offset where the result is longer).
+        With rs_orig / rs_new the stretched signal is resampled rs_orig -> rs_new first (pitch shift)."""
+        x = self._dev(clips)
+        assert x.dim() == 2 and x.shape[1] == self.n_samples
+        B = x.shape[0]
+        rate = torch.as_tensor(np.asarray(rate, dtype=np.float64).reshape(-1)).to(self.device)
+        z = np.zeros(B, np.int32)
+        crop = torch.from_numpy(np.ascontiguousarray(z if crop_off is None else crop_off, dtype=np.int32)).to(self.device)
+        ro = torch.from_numpy(np.ascontiguousarray(z if rs_orig is None else rs_orig, dtype=np.int32)).to(self.device)
+        rn = torch.from_numpy(np.ascontiguousarray(z if rs_new is None else rs_new, dtype=np.int32)).to(self.device)
+        assert rate.numel() == B and crop.numel() == B
+        if rs_orig is not None:
+            for o, n in sorted(set(zip(np.asarray(rs_orig).tolist(), np.asarray(rs_new).tolist()))):
+                if o > 0 and o != n and (o, n) not in self._prepared:
+                    self._chk(self.lib.ww_prepare_resample(self._ctx, int(o), int(n)), "ww_prepare_resample")
+                    self._prepared.add((o, n))
+        out = torch.empty_like(x)
+        pv = _lib.WWPvoc(C.c_void_p(rate.data_ptr()), C.c_void_p(ro.data_ptr()), C.c_void_p(rn.data_ptr()),
+                         C.c_void_p(crop.data_ptr()))
+        self._chk(self.lib.ww_time_stretch(self._ctx, C.c_void_p(x.data_ptr()), C.byref(pv), C.c_void_p(out.data_ptr()), B,
+                                           self._stream()), "ww_time_stretch")
+        return out
+
+    def pitch_shift(self, clips, n_steps):
+        """librosa.effects.pitch_shift: stretch by 2^(-n/12), resample back (rate rounded to 1/1000), fit to n_samples."""
+        n_steps = np.asarray(n_steps, dtype=np.float64).reshape(-1)
+        rate = 2.0 ** (-n_steps / 12.0)
+        ro = np.rint(1000.0 / rate).astype(np.int32)
+        return self.time_stretch(clips, rate, None, ro, np.full(len(rate), 1000, np.int32))
+
+    def add_gaussian_noise(self, x, sigma, seed):
+        """In place: x += sigma * N(0, 1) from a Philox stream keyed by ``seed`` (``np.random.normal(0, sigma)``, :120)."""
+        assert isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        self._chk(self.lib.ww_add_gaussian_noise(self._ctx, C.c_void_p(x.data_ptr()), x.numel(), float(sigma),
+                                                 int(seed) & (2 ** 64 - 1), self._stream()), "ww_add_gaussian_noise")
+        return x
+
     def logmel(self, clips, normalize=False, out=None):
         """clips [B, n_samples] (device or host) -> device tensor [B, 1, n_mels, W] fp32 dB."""
         clips, pcm16 = self._dev_audio(clips)

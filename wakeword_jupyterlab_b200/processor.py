@@ -23,10 +23,14 @@ def _resample_plan_out_len(orig, new, n):
 
 
 class AudioProcessor:
-    def __init__(self, config=AudioConfig, device=0, noise_bank=None):
+    def __init__(self, config=AudioConfig, device=0, noise_bank=None, stage_set="north_star"):
         self.config = config
         self.device = device
         self.noise_bank = noise_bank          # optional [M, L] float32 array/tensor for the SNR-mix stage
+        # "north_star": {shift, polyphase speed, SNR noise mix} (BASELINE.json); "reference": the reference's own four
+        # stages {shift, phase-vocoder pitch shift, phase-vocoder time stretch, Gaussian noise} (:103-123)
+        assert stage_set in ("north_star", "reference")
+        self.stage_set = stage_set
         self.target_length = int(config.SAMPLE_RATE * config.DURATION)
 
     # -- engines are created lazily so that constructing the processor never touches the GPU
@@ -105,7 +109,33 @@ class AudioProcessor:
                 snr[b] = random.choice(getattr(config, "SNR_GRID_DB", (0.0, 10.0, 20.0, 30.0, 40.0)))
         return AugBatch(f, shift, ro, rn, crop, ni, no, snr, np.ones(n, np.float32))
 
+    def augment_audio_reference(self, audio, config=AugmentationConfig):
+        """The reference's stage set and draw order (:103-123): Bernoulli(p) np.roll; Bernoulli(p) pitch shift by
+        U(-PITCH_SHIFT_MAX, +) semitones; Bernoulli(p) time stretch by U(SPEED_CHANGE_MIN, MAX) + pad_or_truncate (its crop
+        offset drawn with random.randint like the reference); Bernoulli(p) Gaussian noise of std NOISE_FACTOR (values from a
+        device Philox stream seeded from np.random, the stream the reference draws its noise from)."""
+        a = np.asarray(audio, dtype=np.float32)
+        n = len(a)
+        eng = self._engine(n_samples=n)
+        x = torch.from_numpy(np.ascontiguousarray(a)).to(eng.device)[None, :]
+        if random.random() < config.AUGMENTATION_PROB:
+            shift = int(random.uniform(-config.TIME_SHIFT_MAX, config.TIME_SHIFT_MAX) * self.config.SAMPLE_RATE)
+            x = torch.roll(x, shift, dims=1)
+        if random.random() < config.AUGMENTATION_PROB:
+            n_steps = random.uniform(-config.PITCH_SHIFT_MAX, config.PITCH_SHIFT_MAX)
+            x = eng.pitch_shift(x.contiguous(), [n_steps])
+        if random.random() < config.AUGMENTATION_PROB:
+            rate = random.uniform(config.SPEED_CHANGE_MIN, config.SPEED_CHANGE_MAX)
+            L = int(round(n / rate))
+            crop = random.randint(0, L - n) if L > n else 0
+            x = eng.time_stretch(x.contiguous(), [rate], [crop])
+        if random.random() < config.AUGMENTATION_PROB:
+            x = eng.add_gaussian_noise(x.contiguous().clone(), config.NOISE_FACTOR, int(np.random.randint(0, 2 ** 31 - 1)))
+        return x[0].cpu().numpy()
+
     def augment_audio(self, audio, config=AugmentationConfig):
+        if self.stage_set == "reference":
+            return self.augment_audio_reference(audio, config)
         a = np.asarray(audio, dtype=np.float32)[None, :]
         params = self.draw_augmentation(1, config, n_samples=a.shape[1])
         eng = self._engine(n_samples=a.shape[1])
