@@ -522,3 +522,24 @@ def test_reference_stage_set_through_augment_audio(ww):
     # process_audio_file(augment=True) runs the reference chain end to end
     mel = ww.AudioProcessor(stage_set="reference").audio_to_mel(a)
     assert mel.shape == (80, 32) and mel.max() == 0.0
+
+
+def test_conv12_cta_pair_kernel_parity(ww, golden_dir, monkeypatch):
+    """WW_CONV12_PAIR=1 runs conv1 + conv2 as CTA pairs (tcgen05 cta_group::2, the weight operand split across the pair).
+    It is parity-identical to the default kernel (same operands, same accumulation order per pixel) but measured slower
+    (DESIGN.md section 8), so it is opt-in; this keeps it exercised: even and odd item counts (the dummy item of CTA 1)."""
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    net = _load(ww, sd)
+    rng = np.random.default_rng(2)
+    for B in (1, 2, 7, 300):
+        x = torch.from_numpy((rng.standard_normal((B, 1, 80, 32)) * 20 - 40).astype(np.float32)).cuda()
+        monkeypatch.setenv("WW_CONV12_PAIR", "0")
+        with torch.no_grad():
+            a = net(x)
+        monkeypatch.setenv("WW_CONV12_PAIR", "1")
+        with torch.no_grad():
+            b = net(x)
+        assert torch.equal(a, b), B
+    ref = M.forward_numpy(x[:16].cpu().numpy(), sd, np.float64)
+    assert np.abs(b[:16].cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4

@@ -337,6 +337,345 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 helpers (mechanics pinned by tools/umma_cta2_check.cu on a B200)
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all earlier MMAs of the pair -> one arrival on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// One arrival per warp on the LEADER CTA's copy of `bar` (the MMA issuers of the pair live in CTA 0): a local arrive in
+// CTA 0, a cluster-scope remote arrive from CTA 1.
+__device__ __forceinline__ void mbar_arrive_leader_warp(uint64_t* bar, int lane, uint32_t rank) {
+  __syncwarp();
+  if (lane == 0) {
+    if (rank == 0) {
+      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cluster.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+      uint32_t ra;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(0u));
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    }
+  }
+}
+// wait with cluster-scope acquire (the arrivals come from both CTAs)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int code) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 17)) mbar_timeout(code);
+  }
+}
+
+constexpr int W2H_BYTES = 9 * 4 * 64 * 16;    // this CTA's half of the stacked conv2 weights: [tap][kc 4][n' 64][8 fp16]
+constexpr int W1H_BYTES = 4 * 32 * 16;        // this CTA's half of the stacked conv1 weights: [kc 4][n' 32][8 fp16]
+
+// conv1 + conv2 as a CTA PAIR (cta_group::2): every MMA covers M = 256 = this CTA's 128 pixels + the peer's, and the stacked
+// weight operand [W_hi ; W_lo] is SPLIT between the two CTAs (CTA 0 holds W_hi, CTA 1 W_lo), so an N = 128 instruction reads
+// 4 + 2 KB of operands per CTA per 64 cycles (96 B/clk) instead of 8 KB (the whole 128 B/clk port): the LSU traffic of the
+// im2col / epilogue warps fits beside it.  Each CTA runs all roles of conv12_kernel<2> on its OWN item (256 pixels); only the
+// two MMA issuers of CTA 0 work, for both CTAs: the barriers they wait on (A1 / A2 tiles written, TMEM drained) collect the
+// arrivals of both CTAs, the barriers they signal (tcgen05.commit) are multicast to both.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C12_THREADS, 1) conv12_pair_kernel(const __grid_constant__ Conv12Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geom g = p.g;
+  const uint32_t a2_bytes = 4u * g.nsl2 * 16u;                  // one conv2 A buffer: 4 planes (chunks of 8 channels)
+  const uint32_t patch_bytes = (uint32_t)g.patch_f * 4u;
+  unsigned char* w2s = smem;
+  unsigned char* w1s = w2s + W2H_BYTES;
+  unsigned char* a1 = w1s + W1H_BYTES;                          // [A1_SLOTS][A1_SLOT_BYTES]
+  unsigned char* a2 = a1 + A1_SLOTS * A1_SLOT_BYTES;            // [2][a2_bytes]
+  float* patch = reinterpret_cast<float*>(a2 + 2 * a2_bytes);   // [P_STAGES][patch_f]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + P_STAGES * patch_bytes);
+  uint64_t* w_full = bars;                       // [1]
+  uint64_t* p_full = bars + 1;                   // [3]
+  uint64_t* p_empty = bars + 4;                  // [3]
+  uint64_t* a1_full = bars + 7;                  // [4]  (leader copy: both CTAs' im2col warps)
+  uint64_t* a1_empty = bars + 11;                // [4]
+  uint64_t* d1_full = bars + 15;                 // [4]
+  uint64_t* d1_empty = bars + 19;                // [4]  (leader copy: both CTAs' conv1 epilogue warps)
+  uint64_t* a2_full = bars + 23;                 // [2]  (leader copy)
+  uint64_t* a2_empty = bars + 25;                // [2]
+  uint64_t* t_full = bars + 27;                  // [2]
+  uint64_t* t_empty = bars + 29;                 // [2]  (leader copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < P_STAGES; ++i) { mbar_init(p_full + i, 1); mbar_init(p_empty + i, 4); }
+    for (int i = 0; i < A1_SLOTS; ++i) {
+      mbar_init(a1_full + i, 8); mbar_init(a1_empty + i, 1);
+      mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 16);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a2_full + i, 16); mbar_init(a2_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 16);
+    }
+    fence_barrier_init();
+    // this CTA's halves of the weights: rows 64 r .. (conv2) / 32 r .. (conv1) of every [n'] block
+    mbar_arrive_expect_tx(w_full, W2H_BYTES + W1H_BYTES);
+    for (int blk = 0; blk < 36; ++blk)
+      bulk_g2s(w2s + blk * 1024, reinterpret_cast<const unsigned char*>(p.w2s) + blk * 2048 + rank * 1024, 1024, w_full);
+    for (int kc = 0; kc < 4; ++kc)
+      bulk_g2s(w1s + kc * 512, reinterpret_cast<const unsigned char*>(p.w1s) + kc * 1024 + rank * 512, 512, w_full);
+  }
+  for (int i = tid * 16; i < A1_SLOTS * A1_SLOT_BYTES; i += C12_THREADS * 16)   // zero K padding of the conv1 A ring
+    *reinterpret_cast<uint4*>(a1 + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  __syncthreads();
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);     // D1 ring: columns 64 s (s < 4); D2 tiles: columns 256 + 128 t
+  mbar_wait(w_full, 0, 20);                       // this CTA's weights have landed
+  tc_fence_before();
+  cluster_sync_all();                             // both CTAs: barriers initialised, weights in place, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int items_per_clip = g.T2 >> 1;
+  const int n_items = p.B * items_per_clip;
+  const int NM = g.NM, NL = g.NL;
+  const int npairs = (int)(gridDim.x >> 1), pr = (int)(blockIdx.x >> 1);
+  // iteration `it` of this pair works on items 2 (pr + it npairs) + {0, 1}; an odd total leaves CTA 1 a dummy in the last
+  // iteration (it recomputes the last item and stores nothing)
+#define C12P_ITEM(it_) (2 * (pr + (it_) * npairs))
+
+  if (warp == 0) {
+    // ===================== loader (one thread): one 1-D bulk copy of this CTA's patch per item, 3-stage ring
+    if (lane == 0) {
+      for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+        const int item = min(C12P_ITEM(it) + (int)rank, n_items - 1);
+        const int b = item / items_per_clip, tp = item - b * items_per_clip;
+        const int st = it % P_STAGES;
+        mbar_wait(p_empty + st, ((it / P_STAGES) & 1) ^ 1, 10);
+        C12_TRACE(0);
+        mbar_arrive_expect_tx(p_full + st, patch_bytes);
+        bulk_g2s(patch + (size_t)st * g.patch_f, p.in_pad + (size_t)b * g.npix_in + 256 * tp, patch_bytes, p_full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== conv1 MMA issuer (CTA 0 only): M = 256 over the pair, N = 64 = [W1_hi (CTA 0) ; W1_lo (CTA 1)]
+    if (rank == 0) {
+      constexpr uint32_t idesc64 = make_idesc(256, 64);
+      const uint64_t adesc0 = make_desc(smem_u32(a1), 128 * 16, 128);      // K-chunk stride = 128 rows x 16 B
+      const uint64_t bdesc0 = make_desc(smem_u32(w1s), 32 * 16, 128);      // K-chunk stride = 32 rows x 16 B (this CTA's half)
+      uint32_t g1 = 0;
+      for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+        for (int m = 0; m < NM; ++m, ++g1) {
+          const uint32_t s = g1 & (A1_SLOTS - 1), par = (g1 / A1_SLOTS) & 1;
+          mbar_wait_cluster(a1_full + s, par, 21);
+          if (m == 0) C12_TRACE(12);
+          mbar_wait_cluster(d1_empty + s, par ^ 1, 22);
+          if (m == 0) C12_TRACE(2);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)((s * A1_SLOT_BYTES) >> 4);
+            umma2_f16(tmem_base + s * 64, ad, bdesc0, idesc64, 0);                                // taps as fp16 hi
+            umma2_f16(tmem_base + s * 64, ad + (2 * 128 * 16 >> 4), bdesc0 + (2 * 32 * 16 >> 4), idesc64, 1);   // taps as fp16 lo
+            umma2_commit_both(a1_empty + s);
+            umma2_commit_both(d1_full + s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== conv2 MMA issuer (CTA 0 only): tile 0 then tile 1 of both CTAs' items, 18 MMAs each
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, 128);
+      const uint64_t bdesc0 = make_desc(smem_u32(w2s), 1024, 128);           // this CTA's 64 rows per K chunk
+      const uint64_t adesc0 = make_desc(smem_u32(a2), (uint32_t)g.nsl2 * 16u, 128);
+      const uint32_t nsl = (uint32_t)g.nsl2;
+      uint32_t aoff[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) aoff[tap] = (uint32_t)((g.P + 1) + (tap / 3 - 1) * g.P + (tap % 3 - 1));
+      for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+        const int buf = it & 1;
+        mbar_wait_cluster(a2_full + buf, (it >> 1) & 1, 31);
+        C12_TRACE(5);
+        const uint64_t adesc = adesc0 + (uint64_t)((buf * a2_bytes) >> 4);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait_cluster(t_empty + t, (it & 1) ^ 1, 32);
+          C12_TRACE(6 + t);
+          tc_fence_after();
+          const uint32_t d = tmem_base + 256 + t * 128;
+          const uint64_t ad_t = adesc + (uint64_t)(t * 128);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                umma2_f16(d, ad_t + (uint64_t)(2 * j * nsl + aoff[tap]), bdesc0 + (uint64_t)(((tap * 4 + 2 * j) * 1024) >> 4),
+                          idesc, (tap | j) != 0);
+            umma2_commit_both(t_full + t);
+            if (t == 1) umma2_commit_both(a2_empty + buf);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 7) {
+    // ===================== im2col producers: thread = one row (pixel) of the current conv1 M-tile
+    const int r = (warp - 3) * 32 + lane;
+    uint32_t g1 = 0;
+    for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+      const int st = it % P_STAGES;
+      mbar_wait(p_full + st, (it / P_STAGES) & 1, 40);
+      if (warp == 3) C12_TRACE(1);
+      const float* pt = patch + (size_t)st * g.patch_f;
+      for (int m = 0; m < NM; ++m, ++g1) {
+        const uint32_t s = g1 & (A1_SLOTS - 1);
+        mbar_wait(a1_empty + s, ((g1 / A1_SLOTS) & 1) ^ 1, 41);
+        const float* c0 = pt + 128 * m + r;
+        uint32_t hi[5], lo[5];
+        float v[10];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = c0[(k / 3) * g.P + (k % 3)];
+        v[9] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          hi[k] = pack_f16(v[2 * k], v[2 * k + 1]);
+          lo[k] = pack_f16(v[2 * k] - h_lo(hi[k]), v[2 * k + 1] - h_hi(hi[k]));
+        }
+        unsigned char* dst = a1 + s * A1_SLOT_BYTES + r * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint32_t*>(dst + 128 * 16) = (hi[4] & 0xffffu) | (lo[4] << 16);
+        *reinterpret_cast<uint4*>(dst + 2 * 128 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive_leader_warp(a1_full + s, lane, rank);
+      }
+      mbar_arrive_warp(p_empty + st, lane);
+    }
+  } else if (warp < 15) {
+    // ===================== conv1 epilogue: D1 -> act1 (fp16) = conv2's A operand
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 7) >> 2;     // which 16 of the 32 conv1 channels
+    const int r = q * 32 + lane;
+    const float inv_s = p.inv_s1;
+    uint32_t g1 = 0;
+    for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+      const int item = min(C12P_ITEM(it) + (int)rank, n_items - 1);
+      const int tp = item % items_per_clip;
+      const int pbase = 256 * tp - 1 - g.P - 1;
+      const int buf = it & 1;
+      mbar_wait(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
+      if (warp == 7) C12_TRACE(3);
+      unsigned char* ab = a2 + buf * a2_bytes;
+      for (int m = 0; m < NM; ++m, ++g1) {
+        const uint32_t s = g1 & (A1_SLOTS - 1);
+        mbar_wait(d1_full + s, (g1 / A1_SLOTS) & 1, 51);
+        tc_fence_after();
+        uint32_t r0[16], r1[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * 64 + half * 16;
+        tmem_ld16_nowait(taddr, r0);
+        tmem_ld16_nowait(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_leader_warp(d1_empty + s, lane, rank);
+        const int l = 128 * m + r;
+        if (l < NL) {
+          int y, x;
+          const bool ok = pix_valid(pbase + l, g, y, x);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = fmaf(__uint_as_float(r0[k2 * 8 + e]) + __uint_as_float(r1[k2 * 8 + e]), inv_s,
+                          half ? p.b1[16 + k2 * 8 + e] : p.b1[k2 * 8 + e]);
+            *reinterpret_cast<uint4*>(ab + ((size_t)(half * 2 + k2) * g.nsl2 + l) * 16) = cvt8_relu(o, ok);
+          }
+        }
+      }
+      fence_proxy_async();
+      if (warp == 7) C12_TRACE(4);
+      mbar_arrive_leader_warp(a2_full + buf, lane, rank);
+    }
+  } else {
+    // ===================== conv2 epilogue
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int hc = (warp - 15) >> 2;      // which 32 of the 64 output channels
+    const float inv_s = p.inv_s2;
+    for (int it = 0; C12P_ITEM(it) < n_items; ++it) {
+      const int item_raw = C12P_ITEM(it) + (int)rank;
+      const bool live = item_raw < n_items;
+      const int item = live ? item_raw : n_items - 1;
+      const int b = item / items_per_clip, tp = item - b * items_per_clip;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(t_full + t, it & 1, 60);
+        if (warp == 15) C12_TRACE(8 + 2 * t);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + t * 128 + hc * 32;
+        tmem_ld32_nowait(taddr, r0);
+        tmem_ld32_nowait(taddr + 64, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_leader_warp(t_empty + t, lane, rank);
+        if (!live) continue;
+        const int s = 256 * tp + t * 128 + q * 32 + lane;
+        int y, x;
+        const bool ok = pix_valid(s - 1, g, y, x);
+        uint4* dst = reinterpret_cast<uint4*>(p.act2) + (size_t)b * 8 * g.npix + s;
+        uint4* dst8 = reinterpret_cast<uint4*>(p.act2_8) + (size_t)b * 4 * g.npix + s;
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          float o[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float acc = __uint_as_float(r0[k2 * 16 + e]) + __uint_as_float(r1[k2 * 16 + e]);
+            o[e] = fmaf(acc, inv_s, hc ? p.b2[32 + k2 * 16 + e] : p.b2[k2 * 16 + e]);
+          }
+          dst[(size_t)(hc * 4 + 2 * k2) * g.npix] = cvt8_relu(o, ok);
+          dst[(size_t)(hc * 4 + 2 * k2 + 1) * g.npix] = cvt8_relu(o + 8, ok);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] *= p.r8;
+          uint4 u8 = cvt16_e4m3<true>(o);
+          if (!ok) u8 = make_uint4(0u, 0u, 0u, 0u);
+          dst8[(size_t)(hc * 2 + k2) * g.npix] = u8;
+        }
+        if (warp == 15) C12_TRACE(9 + 2 * t);
+      }
+    }
+  }
+#undef C12P_ITEM
+  tc_fence_before();
+  cluster_sync_all();                             // both CTAs are done with the pair's TMEM and with each other's barriers
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
+size_t conv12_pair_smem(const Geom& g) {
+  return (size_t)W2H_BYTES + W1H_BYTES + A1_SLOTS * A1_SLOT_BYTES + (size_t)2 * 4 * g.nsl2 * 16 +
+         (size_t)P_STAGES * g.patch_f * 4 + 32 * 8 + 64;
+}
+
 size_t conv12_smem(const Geom& g) {
   return (size_t)W2_BYTES + W1_BYTES + A1_SLOTS * A1_SLOT_BYTES + (size_t)2 * 4 * g.nsl2 * 16 +
          (size_t)P_STAGES * g.patch_f * 4 + 32 * 8 + 64;
@@ -481,9 +820,21 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   if (tracing) cudaMemset(d_trace, 0, 40 * 16 * 8);
   p.trace = tracing ? d_trace : nullptr;
   const int grid = std::min(c->sm_count, B * (g.T2 / 2));
+  const char* pair_env = getenv("WW_CONV12_PAIR");
+  // opt-in (WW_CONV12_PAIR=1): measured SLOWER than the single-CTA kernel (20.8 vs 12.1 ms per 65,536 clips): with real,
+  // changing operands an M = 256, N = 128 pair instruction takes ~160 cycles (the same-address burst of
+  // tools/umma_cta2_check.cu ran at 64): the peer's half of B arrives over the SM-to-SM path in 128-byte SWIZZLE_NONE granules
+  const bool pair = c->cfg.conv_mode != WW_CONV_FP16 && pair_env && pair_env[0] == '1' && c->sm_count >= 2;
   {
     ProfScope prof(c, WW_STAGE_CONV12, st);
-    if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
+    if (pair) {
+      // CTA pairs (cta_group::2): an even grid, every pair walks consecutive item pairs
+      const size_t psmem = conv12_pair_smem(g);
+      WW_CHECK(c, cudaFuncSetAttribute(conv12_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      const int n_items = B * (g.T2 / 2);
+      const int pgrid = std::max(2, std::min(c->sm_count & ~1, ((n_items + 1) / 2) * 2));
+      conv12_pair_kernel<<<pgrid, C12_THREADS, psmem, st>>>(p);
+    } else if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
     else conv12_kernel<2><<<grid, C12_THREADS, smem, st>>>(p);
     WW_LAUNCH_CHECK(c);
   }
@@ -494,7 +845,7 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
     fprintf(stderr, "conv12 trace: load | im2col p_full | mma1 first | epi1 start end | mma2: a2_full t_empty0 t_empty1 | epi2: t_full0 done0 t_full1 done1\n");
     for (int i = 0; i < 24; ++i) {
       fprintf(stderr, "item %2d:", i);
-      for (int k = 0; k < 12; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - h[0] : -1);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %7lld", h[i * 16 + k] ? h[i * 16 + k] - h[0] : -1);
       fprintf(stderr, "\n");
     }
   }
