@@ -20,8 +20,12 @@
 //   (K = 32 per instruction at the cost of a K = 16 fp16 one): 1.5 passes instead of 2 (WW_CONV_SPLIT2: logits
 //   1e-6 .. 8e-6 relative on the golden weights, same as an fp16 lo).  WW_CONV_FP16 issues W_hi*a only (5e-5).
 //
-// Work item = (clip, group of G <= 4 consecutive 128-pixel tiles) so that every weight stage fetched from L2
-// feeds up to 512 pixels; all 512 TMEM columns hold the group's fp32 accumulators.
+// Work item = group of G <= 4 consecutive 128-pixel tiles of the TAPE formed by the clips of the launch (clip b + 1's
+// padded image follows clip b's at a period of 128 * T3 slots: the zero rows under one image and above the next coincide),
+// so that every weight stage fetched from L2 feeds 512 pixels and all 512 TMEM columns hold fp32 accumulators: every group
+// is full (round 1 split the 21 tiles of a clip 4,4,4,3,3,3 and the 3-tile groups ran their odd tile as N = 128 MMAs at
+// 84 % of the ideal rate against 92 %).  A group that straddles two clips loads its planes in two segments and its tiles
+// report to their own clips: the pooling partials are per TILE, so a clip's result does not depend on where it sits.
 //   warp 0      loader (one thread): activation planes of a 32-channel slice pair (4 fp16 + 2 e4m3 1-D cp.async.bulk;
 //               two pairs = the whole K, each refilled for the next item as soon as it is consumed) and the weight
 //               ring (3 stages x 36 KB = (slice pair, tap row): 9 MMAs per accumulator half);
@@ -49,7 +53,7 @@ struct Conv3Params {
   float inv_scale;                // 2^-k
   const float* b3;                // [128]
   const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
-  float* pool_part;               // [B][n_groups][128]
+  float* pool_part;               // [B][T3][128]: one partial sum per tile
   int B;
   Geom g;
   long long* trace;               // debug (WW_TC_TRACE=1): per-group role timestamps of CTA 0
@@ -91,11 +95,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  // Every CTA takes a CONTIGUOUS range of (clip, group) items, i.e. whole clips: all CTAs see the same mix of
-  // 4-tile and 3-tile groups (a strided assignment gave even CTAs only the big groups: 25 % imbalance).
-  const int n_items = p.B * g.n_groups;
+  // Every CTA takes a CONTIGUOUS range of tape groups.
+  const int n_tiles = p.B * g.T3;                       // < 2^31: a launch is one chunk of clips
+  const int n_items = (n_tiles + g.G - 1) / g.G;
   const int item_lo = (int)((long long)n_items * blockIdx.x / gridDim.x);
   const int item_hi = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+  auto item_tiles = [&](int item) { return min(g.G, n_tiles - item * g.G); };
 
   if (warp == 0) {
     // ===================== loader (one thread)
@@ -104,24 +109,34 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
       uint32_t st = 0, wpar = 1;        // weight ring position and the parity to wait for on w_empty
       constexpr uint32_t wbytes = NPASS == 2 ? C3_STAGE_BYTES : 2 * C3_PART_BYTES;
       for (int item = item_lo; item < item_hi; ++item, ++it) {
-        const int b = item / g.n_groups, grp = item - b * g.n_groups;
-        const int n_t = grp_tiles(g, grp);
-        const uint32_t nload = (uint32_t)(n_t * 128 + 2 * g.P + 2) * 16u;
-        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) +
-                                    ((size_t)b * 8 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
-        const unsigned char* src8 = p.act2_8 + ((size_t)b * 4 * g.npix + (size_t)grp_first(g, grp) * 128) * 16;
+        const int tau0 = item * g.G;                                // first tape tile of the group
+        const int b = tau0 / g.T3, t0 = tau0 - b * g.T3, n_t = item_tiles(item);
+        // window = slots [128 t0, 128 t0 + nslots) of clip b; past slot 128 T3 the tape continues with clip b + 1's slot 0
+        const uint32_t nslots = (uint32_t)(n_t * 128 + 2 * g.P + 2);
+        uint32_t n1 = nslots, n2 = 0;
+        if (128u * t0 + nslots > 128u * g.T3 && b + 1 < p.B) { n1 = 128u * (g.T3 - t0); n2 = nslots - n1; }
+        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.act2) + ((size_t)b * 8 * g.npix + (size_t)t0 * 128) * 16;
+        const unsigned char* src8 = p.act2_8 + ((size_t)b * 4 * g.npix + (size_t)t0 * 128) * 16;
+        const unsigned char* nxt0 = reinterpret_cast<const unsigned char*>(p.act2) + (size_t)(b + 1) * 8 * g.npix * 16;
+        const unsigned char* nxt8 = p.act2_8 + (size_t)(b + 1) * 4 * g.npix * 16;
         for (int pr = 0; pr < 2; ++pr) {
           // activations of the pair: 4 fp16 planes (chunks of 8 channels) + 2 e4m3 planes (chunks of 16 channels)
           mbar_wait(a_empty + pr, (it & 1) ^ 1, 40);
           if (pr == 0) C3_TRACE(0);
-          mbar_arrive_expect_tx(a_full + pr, (NPASS == 2 ? 6 : 4) * nload);
+          mbar_arrive_expect_tx(a_full + pr, (NPASS == 2 ? 6 : 4) * nslots * 16u);
 #pragma unroll
-          for (int pl = 0; pl < 4; ++pl)
-            bulk_g2s(a_s + (size_t)(4 * pr + pl) * plane_bytes, src0 + (size_t)(4 * pr + pl) * g.npix * 16, nload, a_full + pr);
+          for (int pl = 0; pl < 4; ++pl) {
+            unsigned char* dst = a_s + (size_t)(4 * pr + pl) * plane_bytes;
+            bulk_g2s(dst, src0 + (size_t)(4 * pr + pl) * g.npix * 16, n1 * 16u, a_full + pr);
+            if (n2) bulk_g2s(dst + n1 * 16u, nxt0 + (size_t)(4 * pr + pl) * g.npix * 16, n2 * 16u, a_full + pr);
+          }
           if (NPASS == 2) {
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl)
-              bulk_g2s(a8_s + (size_t)(2 * pr + pl) * plane_bytes, src8 + (size_t)(2 * pr + pl) * g.npix * 16, nload, a_full + pr);
+            for (int pl = 0; pl < 2; ++pl) {
+              unsigned char* dst = a8_s + (size_t)(2 * pr + pl) * plane_bytes;
+              bulk_g2s(dst, src8 + (size_t)(2 * pr + pl) * g.npix * 16, n1 * 16u, a_full + pr);
+              if (n2) bulk_g2s(dst + n1 * 16u, nxt8 + (size_t)(2 * pr + pl) * g.npix * 16, n2 * 16u, a_full + pr);
+            }
           }
           for (int tt = 0; tt < 3; ++tt) {
             mbar_wait(w_empty + st, wpar, 41);
@@ -157,8 +172,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     uint32_t st = 0, wpar = 0;        // weight ring position and the parity to wait for on w_full
     auto ring_next = [&](uint32_t s_, uint32_t& par_) { if (++s_ == (uint32_t)NST) { s_ = 0; par_ ^= 1; } return s_; };
     for (int item = item_lo; item < item_hi; ++item, ++it) {
-      const int grp = item % g.n_groups;
-      const int n_t = grp_tiles(g, grp);
+      const int n_t = item_tiles(item);
       // MMA shapes for this group: tiles (0,1) -> N = 256 or 128; tiles (2,3) -> N = 256, 128 or none
       const uint32_t id0 = n_t >= 2 ? idesc256 : idesc128;
       const uint32_t id1 = n_t >= 4 ? idesc256 : idesc128;
@@ -245,9 +259,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
     const float bias = b3s[ch], inv_s = p.inv_scale;
     int it = 0, it1 = 0;
     for (int item = item_lo; item < item_hi; ++item, ++it) {
-      const int b = item / g.n_groups, grp = item - b * g.n_groups;
-      const int n_t = grp_tiles(g, grp);
-      float sum = 0.0f;
+      const int tau0 = item * g.G;
+      const int n_t = item_tiles(item);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h * 2 >= n_t) break;            // half h is unused by this group (no MMAs, no barrier flips)
@@ -256,9 +269,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
         tc_fence_after();
         const int i = h * 2 + sub;
         if (i < n_t) {
-          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + (grp_first(g, grp) + i));
+          const int tau = tau0 + i;                         // tape tile -> (clip, tile of the clip)
+          const int b = tau / g.T3, t = tau - b * g.T3;
+          const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask) + t);
           const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + i * 128;
+          float sum = 0.0f;
 #pragma unroll
           for (int cp = 0; cp < 2; ++cp) {
             uint32_t r0[32], r1[32];
@@ -275,16 +291,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
             }
             sum += s0 + s1;
           }
+          // one partial per (clip, tile, channel): a clip's mean does not depend on how its tiles fell into groups
+          p.pool_part[((size_t)b * g.T3 + t) * 128 + ch] = sum;
         }
         tc_fence_before();
         mbar_arrive_warp(t_empty + h, lane);
         if (warp == 2 && h == 0) C3_TRACE(8);
         if (h) ++it1;
       }
-      scratch[sub * 128 + ch] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (sub == 0) p.pool_part[((size_t)b * g.n_groups + grp) * 128 + ch] = scratch[ch] + scratch[128 + ch];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
   tc_fence_before();
@@ -299,7 +313,7 @@ size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c) {      // fp16 planes; th
   return (size_t)8 * g.npix * 16;
 }
 
-int ww_conv_tc_groups(const ww_ctx* c) { return make_geom(c).n_groups; }
+int ww_conv_tc_groups(const ww_ctx* c) { return make_geom(c).n_groups; }      // pool partials per clip (one per tile)
 
 // where the log-mel kernel writes pixel (mel m, frame t) of clip b for the tensor-core path:
 // ptr[b * stride + off + m * pitch + t]
@@ -370,7 +384,8 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 16 * 8); }
   if (tracing) cudaMemset(d_trace, 0, 48 * 16 * 8);
   p.trace = tracing ? d_trace : nullptr;
-  const int grid = std::min(c->sm_count, B * g.n_groups);
+  const int n_items = (int)(((long long)B * g.T3 + g.G - 1) / g.G);
+  const int grid = std::min(c->sm_count, n_items);
   ProfScope prof(c, WW_STAGE_CONV3, st);
   if (c->cfg.conv_mode == WW_CONV_FP16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
   else conv3_kernel<2><<<grid, C3_THREADS, smem, st>>>(p);

@@ -184,9 +184,8 @@ __device__ __forceinline__ uint4 cvt8(const float* v) {
 struct Geom {
   int H, W, P;        // image rows (mels), cols (frames), pitch
   int npix;           // plane slots per clip (multiple of 128)
-  int T2, T3;         // conv2 tiles (npix / 128, even), conv3 tiles (ceil(H*P / 128))
-  int G, n_groups;    // conv3: max tiles per group (<= 4), groups per clip
-  int gbase, grem;    // balanced split of T3 tiles: the first `grem` groups have gbase + 1 tiles, the rest gbase
+  int T2, T3;         // conv2 tiles (npix / 128, even), conv3 tiles per clip (ceil((H+1)*P / 128)): the tape period
+  int G, n_groups;    // conv3: tiles per group (<= 4); pool partials per clip (= T3: one per tile)
   int nsl2;           // conv12 A-buffer slots = round8(256 + 2P + 2) (two tiles + halo)
   int NL, NM;         // conv1 pixels per item (256 + 2P + 2) and conv1 M-tiles per item (ceil(NL / 128))
   int lead;           // zero floats in front of padded index 0 of the padded log-mel image (2P + 3)
@@ -197,8 +196,6 @@ struct Geom {
   uint32_t magicP;    // ceil(2^32 / P): p / P == umulhi(p, magicP) for 0 <= p < 65536
 };
 
-__host__ __device__ __forceinline__ int grp_tiles(const Geom& g, int grp) { return g.gbase + (grp < g.grem ? 1 : 0); }
-__host__ __device__ __forceinline__ int grp_first(const Geom& g, int grp) { return grp * g.gbase + (grp < g.grem ? grp : g.grem); }
 
 __device__ __forceinline__ bool pix_valid(int p, const Geom& g, int& y, int& x) {
   if (p < 0) return false;
@@ -255,7 +252,10 @@ inline Geom make_geom(const ww_ctx* c) {
   g.H = c->cfg.n_mels;
   g.W = c->W;
   g.P = g.W + 1;
-  g.T3 = (g.H * g.P + 127) / 128;
+  // conv3 walks the clips of a launch as ONE pixel-linear tape with period 128 * T3 slots per clip: clip b + 1's slot 0
+  // follows clip b's slot 128 * T3 - 1, so a group of G tiles may straddle two clips and EVERY group is full.  (H+1)*P <=
+  // 128 * T3 makes the seam safe: the valid outputs of a clip then read nothing past the next clip's P + 2 leading zero slots.
+  g.T3 = ((g.H + 1) * g.P + 127) / 128;
   const int need = 2 * g.P + 128 * g.T3 + 2;
   g.T2 = (need + 127) / 128;
   g.T2 += g.T2 & 1;                   // conv12 works on tile pairs
@@ -265,9 +265,7 @@ inline Geom make_geom(const ww_ctx* c) {
     const int nsl3 = (G * 128 + 2 * g.P + 2 + 7) & ~7;
     if (conv3_smem_bytes(nsl3, C3_NST_MIN) <= 227 * 1024) { g.G = G; break; }
   }
-  g.n_groups = (g.T3 + g.G - 1) / g.G;
-  g.gbase = g.T3 / g.n_groups;
-  g.grem = g.T3 % g.n_groups;
+  g.n_groups = g.T3;
   g.nsl2 = (256 + 2 * g.P + 2 + 7) & ~7;
   g.NL = 256 + 2 * g.P + 2;
   g.NM = (g.NL + 127) / 128;
