@@ -234,6 +234,8 @@ int ww_profile_read(ww_ctx* ctx, int stage, double* total_ms, int64_t* n_launche
 /* ---- introspection for benchmarks / tests */
 int64_t ww_kernel_launches(const ww_ctx* ctx); /* kernels launched by this context so far */
 int ww_conv_mode(const ww_ctx* ctx);
+/* decision threshold of the following ww_score* calls (predict_wakeword's `threshold` argument, ipynb:871) */
+int ww_set_threshold(ww_ctx* ctx, float threshold);
 
 #ifdef __cplusplus
 }

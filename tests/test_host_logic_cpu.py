@@ -42,3 +42,29 @@ def test_ratios_follows_replaced_arrays():
     assert a.ratios() == [(80, 100), (90, 100)]
     a.rs_orig = np.asarray([120, 120, 120], np.int32)    # a new array object invalidates the memo
     assert a.ratios() == [(120, 100)]
+
+
+def test_engine_cache_is_bounded_and_threshold_is_not_part_of_the_key(monkeypatch):
+    """get_engine must not grow without bound over clip lengths / thresholds.  Engine construction is
+    stubbed (no GPU here): only the cache policy is exercised."""
+    from wakeword_jupyterlab_b200 import engine as E
+
+    made = []
+
+    class Fake:
+        def __init__(self, ac, mc, idx, threshold, cm, ns, chunk):
+            self.threshold, self.ns = threshold, ns
+            made.append(self)
+
+        def set_threshold(self, t):
+            self.threshold = float(t)
+
+    monkeypatch.setattr(E, "Engine", Fake)
+    monkeypatch.setattr(E, "_engines", {})
+    a = E.get_engine(threshold=0.8)
+    b = E.get_engine(threshold=0.5)
+    assert a is b and b.threshold == 0.5 and len(made) == 1          # a threshold sweep reuses one context
+    for n in range(1000, 1000 + 3 * E.MAX_ENGINES):
+        E.get_engine(n_samples=n)
+    assert len(E._engines) <= E.MAX_ENGINES
+    assert E.get_engine(n_samples=1000 + 3 * E.MAX_ENGINES - 1) is made[-1]       # most recent ones stay cached

@@ -38,7 +38,7 @@ EXPORTS = ["ww_abi_version", "ww_create", "ww_destroy", "ww_last_error", "ww_n_f
            "ww_train_backward", "ww_train_apply", "ww_train_step", "ww_train_reset", "ww_train_n_params",
            "ww_train_grad_buffer", "ww_train_param_range", "ww_get_weights",
            "ww_train_get_moments", "ww_train_set_moments", "ww_train_get_step", "ww_train_set_step",
-           "ww_host_alloc", "ww_host_free", "ww_host_numa_node", "ww_time_stretch", "ww_add_gaussian_noise",
+           "ww_host_alloc", "ww_host_free", "ww_host_numa_node", "ww_time_stretch", "ww_add_gaussian_noise", "ww_set_threshold",
            "ww_augment_pcm16", "ww_logmel_pcm16", "ww_score_pcm16", "ww_score_stream_pcm16", "ww_score_host_pcm16"]
 
 _lib = None
@@ -104,6 +104,7 @@ def load():
         lib.ww_kernel_launches.argtypes = [vp]
         lib.ww_kernel_launches.restype = i64
         lib.ww_conv_mode.argtypes = [vp]
+        lib.ww_set_threshold.argtypes = [vp, C.c_float]
         lib.ww_normalize.argtypes = [vp, vp, vp, i64, vp]
         lib.ww_profile.argtypes = [vp, i32]
         lib.ww_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]

@@ -229,6 +229,12 @@ int ww_n_frames(const ww_ctx* ctx) { return ctx ? ctx->W : 0; }
 int64_t ww_kernel_launches(const ww_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int ww_conv_mode(const ww_ctx* ctx) { return ctx ? ctx->cfg.conv_mode : -1; }
 
+int ww_set_threshold(ww_ctx* c, float threshold) {
+  if (!c || !(threshold >= 0.0f && threshold <= 1.0f)) return WW_ERR_INVALID;
+  c->cfg.threshold = threshold;          // read by the head kernel's parameters at the next launch
+  return WW_OK;
+}
+
 int ww_profile(ww_ctx* c, int enable) {
   if (!c) return WW_ERR_INVALID;
   c->prof_on = enable != 0;
@@ -237,7 +243,7 @@ int ww_profile(ww_ctx* c, int enable) {
 
 int ww_profile_read(ww_ctx* c, int stage, double* total_ms, int64_t* n) {
   if (!c) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   WW_CHECK(c, cudaDeviceSynchronize());
   if (stage < 0) { c->prof_used = 0; return WW_OK; }
   double tot = 0.0; int64_t cnt = 0;
@@ -278,7 +284,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
     g_create_error = "ww_create: unsupported configuration";
     return WW_ERR_INVALID;
   }
-  cudaSetDevice(device);
+  DeviceGuard dev_guard(device);
   ww_ctx* c = new ww_ctx();
   c->cfg = g;
   c->device = device;
@@ -308,7 +314,7 @@ int ww_create(ww_ctx** out, int device, const ww_config* cfg) {
 
 void ww_destroy(ww_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaDeviceSynchronize();
   free_all(c);
   delete c;
@@ -322,7 +328,7 @@ int ww_set_weights(ww_ctx* c, const char* name, const float* src, const int64_t*
   if (got != want) { c->set_error(std::string("ww_set_weights: shape mismatch for ") + name); return WW_ERR_INVALID; }
   size_t n = 1;
   for (int64_t d : want) n *= (size_t)d;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   float*& dst = c->w[name];
   if (!dst) WW_CHECK(c, cudaMalloc((void**)&dst, n * sizeof(float)));
   WW_CHECK(c, cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
@@ -335,7 +341,7 @@ int ww_prepare_resample(ww_ctx* c, int orig, int neu) {
   if (!c || orig <= 0 || neu <= 0) return WW_ERR_INVALID;
   for (const ResampleTable& t : c->rs_tables)
     if (t.orig == orig && t.neu == neu) return WW_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   const int g = std::gcd(orig, neu);
   ResampleTable t;
   t.orig = orig; t.neu = neu; t.o = orig / g; t.n = neu / g;
@@ -481,38 +487,38 @@ extern "C" {
 int ww_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, int64_t bank_len,
                const ww_aug* p, float* out, int B, void* stream) {
   if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return ww_launch_augment(c, clips, 0, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
 }
 
 int ww_augment_pcm16(ww_ctx* c, const int16_t* clips, const float* bank, int bank_rows, int64_t bank_len,
                      const ww_aug* p, float* out, int B, void* stream) {
   if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return ww_launch_augment(c, clips, 1, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
 }
 
 int ww_normalize(ww_ctx* c, const float* in, float* out, int64_t n, void* stream) {
   if (!c || !in || !out || n < 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return ww_launch_normalize(c, in, out, n, (cudaStream_t)stream);
 }
 
 int ww_logmel(ww_ctx* c, const float* clips, int64_t clip_stride, float* out, int B, int normalize, void* stream) {
   if (!c || !clips || !out || B < 0 || clip_stride <= 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return ww_launch_logmel(c, clips, 0, clip_stride, out, B, normalize, (cudaStream_t)stream);
 }
 
 int ww_logmel_pcm16(ww_ctx* c, const int16_t* clips, int64_t clip_stride, float* out, int B, int normalize, void* stream) {
   if (!c || !clips || !out || B < 0 || clip_stride <= 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return ww_launch_logmel(c, clips, 1, clip_stride, out, B, normalize, (cudaStream_t)stream);
 }
 
 int ww_forward(ww_ctx* c, const float* logmel, float* logits, int B, void* stream) {
   if (!c || !logmel || !logits || B < 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_workspaces(c);
   if (rc) return rc;
@@ -586,7 +592,7 @@ static int score_entry(ww_ctx* c, const void* clips, int pcm16, const float* ban
     c->set_error("ww_score: ww_aug has null arrays");
     return WW_ERR_INVALID;
   }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   return score_impl(c, clips, pcm16, c->cfg.n_samples, bank, bank_rows, bank_len, aug, normalize, logits, prob1,
                     decision, B, (cudaStream_t)stream);
 }
@@ -609,7 +615,7 @@ static int stream_entry(ww_ctx* c, const void* audio, int pcm16, int64_t T, int 
     c->set_error("ww_score_stream: windows exceed the audio length");
     return WW_ERR_INVALID;
   }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   // Frame reuse: windows k and k' share every STFT frame that starts at the same sample and
   // lies inside both, and peak normalisation only scales the power spectrum.  The mel energies of all frames starting
@@ -665,7 +671,7 @@ static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const f
                            int64_t bank_len, const ww_aug* aug_host, int normalize, float* logits_host,
                            float* prob1_host, uint8_t* decision_host, int B) {
   if (!c || !clips_host || B < 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = c->own_stream;
   const int N = c->cfg.n_samples, C = c->cfg.num_classes;
   const size_t esz = pcm16 ? 2 : 4;
@@ -812,7 +818,7 @@ int ww_host_numa_node(ww_ctx* c) { return c ? gpu_numa_node(c->device) : -1; }
 void* ww_host_alloc(ww_ctx* c, size_t bytes, int* how) {
   if (how) *how = 0;
   if (!c || bytes == 0) return nullptr;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   const size_t page = (size_t)sysconf(_SC_PAGESIZE);
   const size_t len = (bytes + page - 1) / page * page;
   void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
@@ -853,7 +859,7 @@ void ww_host_free(ww_ctx*, void* p) {          // the context may already be gon
   if (!p) return;
   for (size_t i = 0; i < g_host_bufs.size(); ++i)
     if (g_host_bufs[i].p == p) {
-      cudaSetDevice(g_host_bufs[i].device);
+      DeviceGuard dev_guard(g_host_bufs[i].device);
       cudaHostUnregister(p);
       munmap(p, g_host_bufs[i].bytes);
       g_host_bufs.erase(g_host_bufs.begin() + i);

@@ -29,6 +29,19 @@
     (ctx)->launches++;                                                                   \
   } while (0)
 
+// Every C entry runs on its context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct ResampleTable {
   int orig, neu;      // as passed by the caller
   int o, n;           // reduced by gcd

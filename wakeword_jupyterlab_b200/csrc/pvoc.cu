@@ -227,7 +227,7 @@ extern "C" {
 int ww_time_stretch(ww_ctx* c, const float* clips, const ww_pvoc* pv, float* out, int B, void* stream) {
   if (!c || !clips || !pv || !pv->rate || !pv->crop_off || !out || B < 0) return WW_ERR_INVALID;
   if (B == 0) return WW_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = c->cfg.n_samples, T = 1 + N / PV_HOP;
   if (c->cfg.n_fft != PV_NFFT) {            // the window / twiddle tables of the context are those of n_fft
@@ -262,7 +262,7 @@ int ww_time_stretch(ww_ctx* c, const float* clips, const ww_pvoc* pv, float* out
 int ww_add_gaussian_noise(ww_ctx* c, float* x, int64_t n, float sigma, uint64_t seed, void* stream) {
   if (!c || !x || n < 0) return WW_ERR_INVALID;
   if (n == 0) return WW_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   const int64_t quads = (n + 3) / 4;
   const int grid = (int)std::min<int64_t>((quads + 255) / 256, (int64_t)c->sm_count * 16);
   gaussian_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, sigma, (unsigned long long)seed);

@@ -237,14 +237,14 @@ extern "C" {
 
 int64_t ww_train_n_params(ww_ctx* c) {
   if (!c) return -1;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   if (ensure_train(c, 0)) return -1;
   return c->train.n_flat;
 }
 
 int ww_train_param_range(ww_ctx* c, const char* name, int64_t* offset, int64_t* count) {
   if (!c || !name) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   int rc = ensure_train(c, 0);
   if (rc) return rc;
   auto it = c->train.offset.find(name);
@@ -256,7 +256,7 @@ int ww_train_param_range(ww_ctx* c, const char* name, int64_t* offset, int64_t* 
 
 float* ww_train_grad_buffer(ww_ctx* c) {
   if (!c) return nullptr;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   if (ensure_train(c, 0)) return nullptr;
   return c->train.grad;
 }
@@ -267,7 +267,7 @@ int ww_get_weights(ww_ctx* c, const char* name, float* dst) {
   if (it == c->w.end()) { c->set_error(std::string("ww_get_weights: unknown parameter ") + name); return WW_ERR_INVALID; }
   size_t n = 1;
   for (int64_t d : c->w_shape[name]) n *= (size_t)d;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   // the Adam kernels of the last ww_train_apply ran on the caller's stream, which a blocking copy on the legacy stream does
   // not wait for when that stream is non-blocking: order the copy behind them explicitly
   if (c->apply_event) WW_CHECK(c, cudaEventSynchronize(c->apply_event));
@@ -280,7 +280,7 @@ int ww_get_weights(ww_ctx* c, const char* name, float* dst) {
 // Pointers may be device or host memory; NULL skips that moment.
 int ww_train_get_moments(ww_ctx* c, const char* name, float* exp_avg, float* exp_avg_sq) {
   if (!c || !name) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   int rc = ensure_train(c, 0);
   if (rc) return rc;
   auto it = c->train.offset.find(name);
@@ -294,7 +294,7 @@ int ww_train_get_moments(ww_ctx* c, const char* name, float* exp_avg, float* exp
 
 int ww_train_set_moments(ww_ctx* c, const char* name, const float* exp_avg, const float* exp_avg_sq) {
   if (!c || !name) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   int rc = ensure_train(c, 0);
   if (rc) return rc;
   auto it = c->train.offset.find(name);
@@ -317,7 +317,7 @@ int ww_train_set_step(ww_ctx* c, int64_t step) {
 int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, const float* drop_lstm,
                       const float* drop_out, float* loss, float* logits_out, void* stream) {
   if (!c || !x || !labels || B <= 0) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ww_prepare_weights(c, st);
   if (rc) return rc;
@@ -387,7 +387,7 @@ int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, c
 
 int ww_train_reset(ww_ctx* c) {
   if (!c) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   int rc = ensure_train(c, 0);
   if (rc) return rc;
   c->train.step = 0;
@@ -400,7 +400,7 @@ int ww_train_reset(ww_ctx* c) {
 int ww_train_apply(ww_ctx* c, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    void* stream) {
   if (!c) return WW_ERR_INVALID;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ensure_train(c, 0);
   if (rc) return rc;

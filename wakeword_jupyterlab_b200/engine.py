@@ -61,9 +61,9 @@ class AugBatch:
         return out
 
 
-def _cfg_key(ac, mc, threshold, conv_mode, n_samples, chunk):
+def _cfg_key(ac, mc, conv_mode, n_samples, chunk):
     return (ac.SAMPLE_RATE, n_samples, ac.N_FFT, ac.WIN_LENGTH, ac.HOP_LENGTH, ac.N_MELS, float(ac.FMIN),
-            float(ac.FMAX), mc.HIDDEN_SIZE, mc.NUM_LAYERS, mc.NUM_CLASSES, float(threshold), conv_mode, chunk)
+            float(ac.FMAX), mc.HIDDEN_SIZE, mc.NUM_LAYERS, mc.NUM_CLASSES, conv_mode, chunk)
 
 
 class Engine:
@@ -89,6 +89,7 @@ class Engine:
             msg = self.lib.ww_last_error(None)
             raise _lib.WakewordB200Error(f"ww_create failed (code {rc}): {msg.decode() if msg else ''}")
         self.W = self.lib.ww_n_frames(self._ctx)
+        self.threshold = float(threshold)
         self._prepared = set()
         self._weight_versions = {}
 
@@ -122,6 +123,12 @@ class Engine:
 
     def _fn(self, name, pcm16):
         return getattr(self.lib, name + "_pcm16" if pcm16 else name)
+
+    def set_threshold(self, threshold):
+        """Decision threshold of the following score calls (a per-call argument of predict_wakeword, ipynb:871)."""
+        if float(threshold) != self.threshold:
+            self._chk(self.lib.ww_set_threshold(self._ctx, float(threshold)), "ww_set_threshold")
+            self.threshold = float(threshold)
 
     @property
     def launches(self):
@@ -362,18 +369,26 @@ class Engine:
         return prob1, dec
 
 
-_engines = {}
+_engines = {}           # insertion-ordered: least recently used first
+MAX_ENGINES = 8         # every context owns device tables (and, once it scored, a multi-GB chunk workspace)
 
 
 def get_engine(audio_config=AudioConfig, model_config=ModelConfig, device=0, threshold=0.8, conv_mode="split2",
                n_samples=None, chunk_clips=0) -> Engine:
-    """Per-process cache: one Engine per (device, configuration)."""
+    """Per-process cache: one Engine per (device, configuration), least recently used ones released beyond MAX_ENGINES
+    (variable-length ``audio_to_mel`` calls create one context per clip length).  The decision threshold is a per-call
+    property of the engine (``ww_set_threshold``), not part of the key."""
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)
     ns = int(audio_config.SAMPLE_RATE * audio_config.DURATION) if n_samples is None else int(n_samples)
     cm = _lib.CONV_MODES[conv_mode] if isinstance(conv_mode, str) else conv_mode
-    key = (idx,) + _cfg_key(audio_config, model_config, threshold, cm, ns, chunk_clips)
-    eng = _engines.get(key)
+    key = (idx,) + _cfg_key(audio_config, model_config, cm, ns, chunk_clips)
+    eng = _engines.pop(key, None)
     if eng is None:
         eng = Engine(audio_config, model_config, idx, threshold, cm, ns, chunk_clips)
-        _engines[key] = eng
+        while len(_engines) >= MAX_ENGINES:
+            # dropped from the cache only: whoever still holds the engine (a trainer, a loader, a test) keeps it alive, and
+            # Engine.__del__ releases the context with the last reference
+            _engines.pop(next(iter(_engines)))
+    _engines[key] = eng                                                # most recently used last
+    eng.set_threshold(threshold)
     return eng
