@@ -16,6 +16,13 @@ from oracle import recipe as R
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _exact_backward_kernels(monkeypatch):
+    """These 1e-4 parity tests pin the EXACT fp32 backward kernels (conv_fp32.cu); the tensor-core backward pass (the
+    default, train_tc.cu) has its own tests and tolerances in tests/test_train_tc_gpu.py."""
+    monkeypatch.setenv("WW_TRAIN_KERNEL", "fp32")
+
+
 @pytest.fixture(scope="module")
 def ww():
     import wakeword_jupyterlab_b200 as w

@@ -1,0 +1,142 @@
+"""GPU tests of the tensor-core training step (train_tc.cu: the default when the context computes on the tensor cores).
+
+Its arithmetic is fp16 hi/lo-split products with fp32 accumulation, so per-pixel activations carry ~1e-4 relative error and
+a few ReLU outputs that are within that distance of zero take the other branch than in exact arithmetic: the weight
+gradients differ from float64 autograd by up to ~1.6e-3 of the tensor's largest element (the averaged quantities - loss,
+head gradients - stay at 1e-5).  That is the accuracy class of the reference's own GPU training: its script leaves
+torch.backends.cudnn.allow_tf32 at the default True, and tests/probes/tf32_grad_probe.py measures 0.5e-3 .. 1.8e-3 for
+torch's TF32 convolutions on these very inputs (profiles/r2_train_precision.txt).  The exact fp32 CUDA-core path
+(WW_TRAIN_KERNEL=fp32 / conv_mode fp32) keeps the 1e-4 parity tests of tests/test_train_gpu.py.
+
+Tolerances here: loss 1e-5 relative; conv gradients 2.5e-3, head gradients 1e-4 (max |d| / max |ref| per tensor)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import recipe as R
+from test_train_gpu import _autograd_reference
+
+pytestmark = pytest.mark.gpu
+
+CONV_TOL, HEAD_TOL = 2.5e-3, 1e-4
+
+
+@pytest.fixture(scope="module")
+def ww():
+    import wakeword_jupyterlab_b200 as w
+    from wakeword_jupyterlab_b200 import _lib
+    _lib.load()
+    return w
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+class _env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.prev = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.prev.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _trainer(ww, sd, hidden=256):
+    class MC(ww.ModelConfig):
+        HIDDEN_SIZE = hidden
+        DROPOUT = 0.0
+    net = ww.WakewordModel(MC, ww.AudioConfig).cuda().train()
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return net, ww.WakewordTrainer(net, "cuda")
+
+
+def _batch(B, seed):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy((rng.standard_normal((B, 1, 80, 32)) * 15 - 40).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.integers(0, 2, B).astype(np.int64)).cuda()
+    return x, y
+
+
+@pytest.mark.parametrize("B", [1, 5, 70, 300])
+def test_tensor_core_gradients_vs_float64_autograd(ww, B):
+    sd = R.seeded_state_dict(256, seed=2)
+    x, y = _batch(B, 100 + B)
+    with _env(WW_TRAIN_KERNEL="tc"):
+        net, tr = _trainer(ww, sd)
+        loss, logits = tr.train_step(x, y)
+        grads = {k: v.cpu().numpy().copy() for k, v in tr.gradients(net.engine()).items()}
+    ref_loss, ref = _autograd_reference(sd, x, y)
+    assert abs(loss.item() - ref_loss) < 1e-5 * abs(ref_loss)
+    report = {}
+    for name, r in ref.items():
+        if np.abs(r).max() == 0.0:
+            assert not grads[name].any(), name
+        else:
+            report[name] = _rel(grads[name], r)
+    print("B", B, {k: f"{v:.1e}" for k, v in report.items()})
+    for name, v in report.items():
+        assert v < (CONV_TOL if name.startswith("conv") else HEAD_TOL), (name, v)
+
+
+def test_tensor_core_and_fp32_kernels_agree(ww):
+    """Same inputs through both backward kernels of the library: the tensor-core result sits inside the same band."""
+    sd = R.seeded_state_dict(256, seed=5)
+    x, y = _batch(33, 7)
+    out = {}
+    for kern in ("fp32", "tc"):
+        with _env(WW_TRAIN_KERNEL=kern):
+            net, tr = _trainer(ww, sd)
+            loss, _ = tr.train_step(x, y)
+            out[kern] = (loss.item(), {k: v.cpu().numpy().copy() for k, v in tr.gradients(net.engine()).items()})
+    assert abs(out["tc"][0] - out["fp32"][0]) < 1e-5 * abs(out["fp32"][0])
+    for name, r in out["fp32"][1].items():
+        if np.abs(r).max() > 0.0:
+            assert _rel(out["tc"][1][name], r) < (CONV_TOL if name.startswith("conv") else HEAD_TOL), name
+
+
+def test_device_side_repack_equals_host_side_preparation(ww):
+    """After an optimiser step the operand forms are rebuilt by kernels (ww_train_tc_repack); the same steps with the
+    host-side preparation (WW_TRAIN_FAST=0) must give the same weights bit for bit."""
+    sd = R.seeded_state_dict(256, seed=11)
+    res = {}
+    for fast in ("1", "0"):
+        with _env(WW_TRAIN_KERNEL="tc", WW_TRAIN_FAST=fast):
+            net, tr = _trainer(ww, sd)
+            losses = []
+            for s in range(4):
+                x, y = _batch(48, 1000 + s)
+                loss, _ = tr.train_step(x, y)
+                losses.append(loss.item())
+            res[fast] = (losses, {k: v.cpu().numpy().copy() for k, v in net.state_dict().items()})
+    assert res["1"][0] == res["0"][0], (res["1"][0], res["0"][0])
+    for k, v in res["0"][1].items():
+        assert np.array_equal(res["1"][1][k], v), k
+
+
+def test_training_with_tensor_core_kernels_learns(ww):
+    """A separable toy problem: 30 steps bring the loss down like the exact kernels do."""
+    sd = R.seeded_state_dict(64, seed=3)
+    rng = np.random.default_rng(0)
+    y_np = rng.integers(0, 2, 64)
+    x_np = (rng.standard_normal((64, 1, 80, 32)) * 5 - 40).astype(np.float32)
+    x_np[y_np == 1, :, 20:40, :] += 25.0
+    x, y = torch.from_numpy(x_np).cuda(), torch.from_numpy(y_np.astype(np.int64)).cuda()
+    final = {}
+    for kern in ("fp32", "tc"):
+        with _env(WW_TRAIN_KERNEL=kern):
+            net, tr = _trainer(ww, sd, hidden=64)
+            for _ in range(30):
+                loss, _ = tr.train_step(x, y)
+            final[kern] = loss.item()
+    print("loss after 30 steps", final)
+    assert final["tc"] < 0.45 and abs(final["tc"] - final["fp32"]) < 0.05 * max(final["fp32"], 0.05), final

@@ -150,6 +150,7 @@ int free_all(ww_ctx* c) {
     float* bufs[] = {t.grad, t.m, t.v, t.wflip3, t.wflip2, t.part, t.loss, t.act1, t.act2, t.act3, t.dact2, t.dact1, t.pooled,
                      t.dpooled, t.gates, t.hbuf, t.dh, t.logits, t.dlogits, t.loss_row};
     for (float* b : bufs) cudaFree(b);
+    ww_train_tc_free(c);
   }
   cudaFree(c->d_w1_split); cudaFree(c->d_w2_split); cudaFree(c->d_w3_split); cudaFree(c->ws_logmel_pad);
   cudaFree(c->ws_clips); cudaFree(c->ws_logmel); cudaFree(c->ws_act1); cudaFree(c->ws_act2);
@@ -334,6 +335,7 @@ int ww_set_weights(ww_ctx* c, const char* name, const float* src, const int64_t*
   WW_CHECK(c, cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDefault));
   c->w_shape[name] = want;
   c->weights_dirty = true;
+  c->weights_version++;
   return WW_OK;
 }
 

@@ -48,6 +48,7 @@ struct Conv12Params {
   const __half* w2s;              // conv2 weights * 2^k2, stacked hi/lo
   __half* act2;                   // [B][8 planes (chunks of 8 channels)][npix][8 fp16]
   uint8_t* act2_8;                // [B][4 planes (chunks of 16 channels)][npix][16 e4m3]: operand of conv3's W_lo pass
+  __half* act1;                   // training only (else null): [B][4 planes][npix][8 fp16] copy of conv1's output
   float inv_s1, inv_s2;           // accumulator -> stored activation: 2^-k(weights) x activation scale (b1 / b2 carry the same scale)
   float r8;                       // e4m3 copy of act2 = fp16 copy x r8 (a power of two <= 1)
   int B;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     uint32_t g1 = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int tp = item % items_per_clip;
+      const int b = item / items_per_clip, tp = item - b * items_per_clip;
       const int pbase = 256 * tp - 1 - g.P - 1;
       const int buf = it & 1;
       mbar_wait(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
@@ -277,7 +278,11 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             for (int e = 0; e < 8; ++e)
               o[e] = fmaf(__uint_as_float(r0[k2 * 8 + e]) + __uint_as_float(r1[k2 * 8 + e]), inv_s,
                           half ? p.b1[16 + k2 * 8 + e] : p.b1[k2 * 8 + e]);
-            *reinterpret_cast<uint4*>(ab + ((size_t)(half * 2 + k2) * g.nsl2 + l) * 16) = cvt8_relu(o, ok);
+            const uint4 u = cvt8_relu(o, ok);
+            *reinterpret_cast<uint4*>(ab + ((size_t)(half * 2 + k2) * g.nsl2 + l) * 16) = u;
+            // training: the item's own 256 pixels (plane slots 256 tp .. 256 tp + 255) also go to HBM for the backward pass
+            if (p.act1 && l > g.P && l < g.P + 257)
+              reinterpret_cast<uint4*>(p.act1)[((size_t)b * 4 + half * 2 + k2) * g.npix + 256 * tp + l - (g.P + 1)] = u;
           }
         }
       }
@@ -809,7 +814,7 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   // stored act1 = true x act1_scale, stored act2 (fp16) = true x act2_scale, e4m3 copy = fp16 copy x 2^-act2_lo_shift
   for (int i = 0; i < 32; ++i) p.b1[i] = c->h_b1[i] * c->act1_scale;
   for (int i = 0; i < 64; ++i) p.b2[i] = c->h_b2[i] * c->act2_scale;
-  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8;
+  p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.act1 = c->tc_act1_out;
   p.inv_s1 = c->w1_inv_scale * c->act1_scale;
   p.inv_s2 = c->w2_inv_scale / c->act1_scale * c->act2_scale;
   p.r8 = ldexpf(1.0f, -c->act2_lo_shift);
@@ -824,7 +829,7 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   // opt-in (WW_CONV12_PAIR=1): measured SLOWER than the single-CTA kernel (20.8 vs 12.1 ms per 65,536 clips): with real,
   // changing operands an M = 256, N = 128 pair instruction takes ~160 cycles (the same-address burst of
   // tools/umma_cta2_check.cu ran at 64): the peer's half of B arrives over the SM-to-SM path in 128-byte SWIZZLE_NONE granules
-  const bool pair = c->cfg.conv_mode != WW_CONV_FP16 && pair_env && pair_env[0] == '1' && c->sm_count >= 2;
+  const bool pair = !c->tc_act1_out && c->cfg.conv_mode != WW_CONV_FP16 && pair_env && pair_env[0] == '1' && c->sm_count >= 2;
   {
     ProfScope prof(c, WW_STAGE_CONV12, st);
     if (pair) {

@@ -54,12 +54,13 @@ struct Conv3Params {
   const float* b3;                // [128]
   const uint32_t* mask;           // [T3][4] validity bits of the 128 pixels of each tile
   float* pool_part;               // [B][T3][128]: one partial sum per tile
+  uint32_t* relu_bits;            // BITS (training forward): [B][T3][4][128] bit r of word (t, k, ch) = output > 0 at pixel 32 k + r of tile t
   int B;
   Geom g;
   long long* trace;               // debug (WW_TC_TRACE=1): per-group role timestamps of CTA 0
 };
 
-template <int NPASS>
+template <int NPASS, bool BITS>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
@@ -282,14 +283,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_kernel(Conv3Params p) {
             tmem_ld32_nowait(taddr + cp * 64 + 32, r1);
             tmem_ld_wait();
             float s0 = 0.0f, s1 = 0.0f;
+            uint32_t pos0 = 0u, pos1 = 0u;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
               const float v0 = fmaxf(fmaf(__uint_as_float(r0[r]), inv_s, bias), 0.0f);
               const float v1 = fmaxf(fmaf(__uint_as_float(r1[r]), inv_s, bias), 0.0f);
               s0 += (mw[cp * 2] >> r) & 1u ? v0 : 0.0f;
               s1 += (mw[cp * 2 + 1] >> r) & 1u ? v1 : 0.0f;
+              if (BITS) { pos0 |= (v0 > 0.0f ? 1u : 0u) << r; pos1 |= (v1 > 0.0f ? 1u : 0u) << r; }
             }
             sum += s0 + s1;
+            if (BITS) {      // the ReLU derivative of the backward pass (padding pixels: 0)
+              uint32_t* rb = p.relu_bits + (((size_t)b * g.T3 + t) * 4 + cp * 2) * 128 + ch;
+              rb[0] = pos0 & mw[cp * 2];
+              rb[128] = pos1 & mw[cp * 2 + 1];
+            }
           }
           // one partial per (clip, tile, channel): a clip's mean does not depend on how its tiles fell into groups
           p.pool_part[((size_t)b * g.T3 + t) * 128 + ch] = sum;
@@ -372,13 +380,15 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   }
   static size_t conf = 0;
   if (smem > conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
   Conv3Params p;
   p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.w3s = reinterpret_cast<const unsigned char*>(c->d_w3_split); p.inv_scale = c->w3_inv_scale / c->act2_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;
-  p.pool_part = c->pool_cur; p.B = B; p.g = g;
+  p.pool_part = c->pool_cur; p.relu_bits = c->tc_relu_bits; p.B = B; p.g = g;
   static long long* d_trace = nullptr;
   const bool tracing = getenv("WW_TC_TRACE") != nullptr;
   if (tracing && !d_trace) { cudaMalloc((void**)&d_trace, 48 * 16 * 8); }
@@ -387,8 +397,12 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
   const int n_items = (int)(((long long)B * g.T3 + g.G - 1) / g.G);
   const int grid = std::min(c->sm_count, n_items);
   ProfScope prof(c, WW_STAGE_CONV3, st);
-  if (c->cfg.conv_mode == WW_CONV_FP16) conv3_kernel<1><<<grid, C3_THREADS, smem, st>>>(p);
-  else conv3_kernel<2><<<grid, C3_THREADS, smem, st>>>(p);
+  const bool fp16 = c->cfg.conv_mode == WW_CONV_FP16;
+  if (p.relu_bits) {
+    if (fp16) conv3_kernel<1, true><<<grid, C3_THREADS, smem, st>>>(p);
+    else conv3_kernel<2, true><<<grid, C3_THREADS, smem, st>>>(p);
+  } else if (fp16) conv3_kernel<1, false><<<grid, C3_THREADS, smem, st>>>(p);
+  else conv3_kernel<2, false><<<grid, C3_THREADS, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   if (tracing) {
     long long h[48 * 16];

@@ -64,7 +64,11 @@ struct TrainState {
   int64_t n_flat = 0, step = 0;
   float *grad = nullptr, *m = nullptr, *v = nullptr;
   float *wflip3 = nullptr, *wflip2 = nullptr, *part = nullptr, *loss = nullptr;
-  int cap = 0;
+  void* tc = nullptr;               // tensor-core backward state (train_tc.cu)
+  uint64_t tc_version = 0;          // weights_version its operand forms were built from
+  bool tc_last = false, fast_pending = false;   // last backward ran the tensor-core kernels; last apply rebuilt their forms on the device
+  int fast_steps = 0;               // device-side rebuilds since the last host-side preparation
+  int cap = 0, cap32 = 0;           // clips the head buffers / the fp32 conv activations are sized for
   float *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *dact2 = nullptr, *dact1 = nullptr;
   float *pooled = nullptr, *dpooled = nullptr, *gates = nullptr, *hbuf = nullptr, *dh = nullptr;
   float *logits = nullptr, *dlogits = nullptr, *loss_row = nullptr;
@@ -110,6 +114,7 @@ struct ww_ctx {
   std::map<std::string, float*> w;          // name -> device fp32 copy
   std::map<std::string, std::vector<int64_t>> w_shape;
   bool weights_dirty = true;
+  uint64_t weights_version = 1;     // bumped wherever weights_dirty is set (prepared forms remember the version they were built from)
   // prepared forms
   float* d_convw_t[3] = {nullptr, nullptr, nullptr};   // [Cin][9][Cout] fp32 (fp32 conv path, conv1 everywhere)
   float* d_head_wt[8] = {};                            // per LSTM layer: [K][3H] gate-interleaved (i,g,o), fp32
@@ -132,6 +137,8 @@ struct ww_ctx {
   float* ws_act2 = nullptr;      // fp32 path: [chunk][64][H][W]
   __half* ws_act2_h = nullptr;   // tc path: [chunk][8 channel chunks][NPIX][8] fp16
   uint8_t* ws_act2_8 = nullptr;  // tc path: [chunk][4 channel chunks][NPIX][16] e4m3 (operand of the W_lo pass)
+  __half* tc_act1_out = nullptr;      // training forward only: conv12 also stores conv1's output planes here (else null)
+  uint32_t* tc_relu_bits = nullptr;   // training forward only: conv3 also stores the sign bits of its output here (else null)
   float* ws_pool_part = nullptr; // [pool_cap_clips][n_part][128]: conv3 partial sums of the whole batch of a call
   float* pool_cur = nullptr;     // where the current chunk's conv launch writes its partials
   float* ws_h[2] = {nullptr, nullptr};   // [pool_cap_clips][hidden]: head layer outputs (ping-pong)
@@ -208,3 +215,12 @@ int ww_prepare_weights(ww_ctx* c, cudaStream_t st);
 int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t st);
 size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c);
 int ww_conv_tc_groups(const ww_ctx* c);
+// training step, conv stack on the tensor cores (train_tc.cu)
+bool ww_train_tc_supported(const ww_ctx* c);
+int ww_train_tc_prepare(ww_ctx* c);
+int ww_train_tc_forward(ww_ctx* c, const float* x, int B, float* pooled, cudaStream_t st);
+int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3,
+                         float* gb3, cudaStream_t st);
+void ww_train_tc_free(ww_ctx* c);
+int ww_train_tc_repack(ww_ctx* c, cudaStream_t st);      // after an optimiser step: operand forms rebuilt on the device
+int ww_train_tc_sync_biases(ww_ctx* c);                  // before the next forward: conv biases -> host copies (kernel parameters)

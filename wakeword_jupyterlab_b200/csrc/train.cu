@@ -16,6 +16,7 @@
 #include "ctx.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <math.h>
 #include <algorithm>
 
@@ -28,18 +29,26 @@ int ww_train_conv_backward(ww_ctx* c, const float* x, int B, const float* act1, 
 namespace {
 
 constexpr int kSlices = 64;
+constexpr int kFastSteps = 64;      // optimiser steps between two host-side weight preparations (tensor-core training loop)
+constexpr int64_t kPartFloats = (int64_t)kSlices * 128 * 64 * 9;      // TrainState::part: conv partial sums / split-K scratch
 
 // C[m][n] (+)= sum_k A(m,k) * B(k,n) with arbitrary element strides; 64x64 tile, 16-wide k steps, 4x4 per thread
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                             const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                             float* __restrict__ C, int64_t scm, int64_t scn, int M,
-                                                            int N, int K, const float* __restrict__ bias_n) {
+                                                            int N, int K, const float* __restrict__ bias_n, int k_slice,
+                                                            int64_t c_slice) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K: slice z sums k in [z k_slice, (z + 1) k_slice) into its own dense [M][N] block of C (scratch), which
+  // reduce_k_slices_kernel adds up in fixed order
+  const int k_lo = blockIdx.z * k_slice;
+  K = min(K, k_lo + k_slice);
+  C += (int64_t)blockIdx.z * c_slice;
+  for (int k0 = k_lo; k0 < K; k0 += 16) {
     __syncthreads();
     for (int i = tid; i < 16 * 64; i += 256) {
       const int k = i & 15, m = i >> 4;
@@ -103,14 +112,33 @@ __global__ void lstm_cell_bwd_kernel(float* __restrict__ gates, const float* __r
   g[3 * H + j] = d_o * o * (1.0f - o);
 }
 
-// y[n] = sum_m X[m][n]  (column sums, one thread per column chunk; M up to a few thousand)
-__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ y, float* __restrict__ y2, int M, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// C[m scm + n scn] = sum_z part[z][m][n] (+ bias[n]): the fixed-order reduction of a split-K product
+__global__ void reduce_k_slices_kernel(const float* __restrict__ part, int slices, float* __restrict__ C, int64_t scm, int64_t scn,
+                                       int M, int N, const float* __restrict__ bias_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
   float s = 0.0f;
-  for (int m = 0; m < M; ++m) s += X[(int64_t)m * N + n];
-  y[n] = s;
-  if (y2) y2[n] = s;
+  for (int z = 0; z < slices; ++z) s += part[(int64_t)z * M * N + i];
+  const int m = i / N, n = i - m * N;
+  C[(int64_t)m * scm + (int64_t)n * scn] = s + (bias_n ? bias_n[n] : 0.0f);
+}
+
+// y[n] = sum_m X[m][n]: block = 32 columns x 32 row lanes (each sums rows r, r + 32, ..), then a shared-memory tree
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ X, float* __restrict__ y, float* __restrict__ y2,
+                                                      int M, int N) {
+  __shared__ float red[32][33];
+  const int n = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y;
+  float s = 0.0f;
+  if (n < N)
+    for (int m = r; m < M; m += 32) s += X[(int64_t)m * N + n];
+  red[r][threadIdx.x] = s;
+  __syncthreads();
+  if (r == 0 && n < N) {
+    float t = 0.0f;
+    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
+    y[n] = t;
+    if (y2) y2[n] = t;
+  }
 }
 
 // per-row softmax cross entropy: loss_row[b], dlogits[b][c] = (softmax - onehot) / B
@@ -140,26 +168,51 @@ __global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, 
   if (threadIdx.x == 0) out[0] = red[0] / (float)n;
 }
 
-// torch.optim.Adam (single-tensor path) with coupled weight decay, in its order of operations
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                            float grad_scale) {
+// torch.optim.Adam (single-tensor path) with coupled weight decay, in its order of operations; ONE launch walks the flat
+// gradient / moment buffers and finds each element's parameter tensor in a table (tab: n_tensors x {offset, count}).
+struct AdamTable { float* ptr[48]; int64_t off[48]; int64_t cnt[48]; int n; };
+
+__global__ void adam_kernel(const __grid_constant__ AdamTable tab, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n_flat, float lr, float b1, float b2, float eps, float wd, float bc1,
+                            float bc2_sqrt, float grad_scale) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float grad = fmaf(wd, p[i], g[i] * grad_scale);
+  if (i >= n_flat) return;
+  int k = 0;
+  while (k + 1 < tab.n && i >= tab.off[k + 1]) ++k;
+  const int64_t j = i - tab.off[k];
+  if (j >= tab.cnt[k]) return;                                         // alignment padding between tensors
+  float* p = tab.ptr[k] + j;
+  const float grad = fmaf(wd, *p, g[i] * grad_scale);
   const float mi = m[i] + (grad - m[i]) * (1.0f - b1);                 // exp_avg.lerp_(grad, 1 - beta1)
   const float vi = fmaf(1.0f - b2, grad * grad, v[i] * b2);            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  p[i] = p[i] - (lr / bc1) * (mi / denom);
+  *p = *p - (lr / bc1) * (mi / denom);
 }
 
 // scatter the i, g, o rows of a [4H][K] gradient and zero the f rows: handled by computing full [4H][K] (f rows of dgates are 0)
 
 int sgemm(ww_ctx* c, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
-          int64_t scm, int64_t scn, int M, int N, int K, const float* bias, cudaStream_t st) {
+          int64_t scm, int64_t scn, int M, int N, int K, const float* bias, cudaStream_t st, float* scratch = nullptr,
+          int64_t scratch_floats = 0) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, scm, scn, M, N, K, bias);
+  // few output tiles and a long K (the weight gradients: K = batch): split K over blockIdx.z into the scratch buffer
+  const int tiles = (int)(grid.x * grid.y);
+  int slices = 1;
+  if (scratch && K >= 512 && tiles < 2 * c->sm_count) {
+    slices = std::min({(2 * c->sm_count + tiles - 1) / tiles, K / 128, 64});
+    while (slices > 1 && (int64_t)slices * M * N > scratch_floats) --slices;
+  }
+  if (slices <= 1) {
+    sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, scm, scn, M, N, K, bias, K, 0);
+    WW_LAUNCH_CHECK(c);
+    return WW_OK;
+  }
+  const int k_slice = (((K + slices - 1) / slices) + 15) & ~15;
+  grid.z = (K + k_slice - 1) / k_slice;
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, scratch, N, 1, M, N, K, nullptr, k_slice, (int64_t)M * N);
+  WW_LAUNCH_CHECK(c);
+  reduce_k_slices_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(scratch, (int)grid.z, C, scm, scn, M, N, bias);
   WW_LAUNCH_CHECK(c);
   return WW_OK;
 }
@@ -175,7 +228,7 @@ std::vector<std::string> param_order(const ww_ctx* c) {
   return r;
 }
 
-int ensure_train(ww_ctx* c, int B) {
+int ensure_train(ww_ctx* c, int B, bool fp32_conv = false) {
   TrainState& t = c->train;
   const int H = c->cfg.n_mels, W = c->W, HW = H * W, Hd = c->cfg.hidden_size, L = c->cfg.num_layers, C = c->cfg.num_classes;
   if (t.names.empty()) {
@@ -201,15 +254,9 @@ int ensure_train(ww_ctx* c, int B) {
     WW_CHECK(c, cudaMalloc((void**)&t.loss, 4));
   }
   if (B > t.cap) {
-    float** bufs[] = {&t.act1, &t.act2, &t.act3, &t.dact2, &t.dact1, &t.pooled, &t.dpooled, &t.gates, &t.hbuf, &t.dh,
-                      &t.logits, &t.dlogits, &t.loss_row};
+    float** bufs[] = {&t.pooled, &t.dpooled, &t.gates, &t.hbuf, &t.dh, &t.logits, &t.dlogits, &t.loss_row};
     for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
     const size_t n = (size_t)B;
-    WW_CHECK(c, cudaMalloc((void**)&t.act1, n * 32 * HW * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t.act2, n * 64 * HW * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t.act3, n * 128 * HW * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t.dact2, n * 64 * HW * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t.dact1, n * 32 * HW * 4));
     WW_CHECK(c, cudaMalloc((void**)&t.pooled, n * 128 * 4));
     WW_CHECK(c, cudaMalloc((void**)&t.dpooled, n * std::max(128, Hd) * 4));
     WW_CHECK(c, cudaMalloc((void**)&t.gates, n * L * 4 * Hd * 4));
@@ -219,6 +266,17 @@ int ensure_train(ww_ctx* c, int B) {
     WW_CHECK(c, cudaMalloc((void**)&t.dlogits, n * C * 4));
     WW_CHECK(c, cudaMalloc((void**)&t.loss_row, n * 4));
     t.cap = B;
+  }
+  if (fp32_conv && B > t.cap32) {       // full fp32 activations: only the exact CUDA-core path keeps them
+    float** bufs[] = {&t.act1, &t.act2, &t.act3, &t.dact2, &t.dact1};
+    for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
+    const size_t n = (size_t)B;
+    WW_CHECK(c, cudaMalloc((void**)&t.act1, n * 32 * HW * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t.act2, n * 64 * HW * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t.act3, n * 128 * HW * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t.dact2, n * 64 * HW * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t.dact1, n * 32 * HW * 4));
+    t.cap32 = B;
   }
   return WW_OK;
 }
@@ -319,20 +377,40 @@ int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, c
   if (!c || !x || !labels || B <= 0) return WW_ERR_INVALID;
   DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ww_prepare_weights(c, st);
-  if (rc) return rc;
-  if ((rc = ensure_train(c, B))) return rc;
+  // conv stack: tcgen05 kernels (train_tc.cu) unless the context computes in exact fp32 or WW_TRAIN_KERNEL=fp32 asks for it
+  const char* kern = getenv("WW_TRAIN_KERNEL");
+  const bool tc = ww_train_tc_supported(c) && !(kern && kern[0] == 'f');
   TrainState& t = c->train;
+  int rc;
+  if (tc && t.fast_pending && t.tc_version == c->weights_version) {
+    // the last ww_train_apply rebuilt every operand form this step reads ON THE DEVICE (ww_train_tc_repack): no host work
+    // except the conv biases, which travel as kernel parameters
+    if ((rc = ww_train_tc_sync_biases(c))) return rc;
+  } else {
+    if ((rc = ww_prepare_weights(c, st))) return rc;
+    if (tc && t.tc_version != c->weights_version) {
+      WW_CHECK(c, cudaStreamSynchronize(st));
+      if ((rc = ww_train_tc_prepare(c))) return rc;
+      t.tc_version = c->weights_version;
+      t.fast_steps = 0;
+    }
+  }
+  t.tc_last = tc;
+  if ((rc = ensure_train(c, B, !tc))) return rc;
   const int Hd = c->cfg.hidden_size, L = c->cfg.num_layers, C = c->cfg.num_classes;
   auto G = [&](const std::string& n) { return t.grad + t.offset[n]; };
-  flip_weights_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], t.wflip3, 128, 64);
-  WW_LAUNCH_CHECK(c);
-  flip_weights_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], t.wflip2, 64, 32);
-  WW_LAUNCH_CHECK(c);
+  if (!tc) {
+    flip_weights_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], t.wflip3, 128, 64);
+    WW_LAUNCH_CHECK(c);
+    flip_weights_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], t.wflip2, 64, 32);
+    WW_LAUNCH_CHECK(c);
+  }
   WW_CHECK(c, cudaMemsetAsync(t.grad, 0, t.n_flat * 4, st));                      // optimizer.zero_grad()
 
   // ---- forward (train mode)
-  if ((rc = ww_train_conv_forward(c, x, B, t.act1, t.act2, t.act3, t.pooled, st))) return rc;
+  if (tc) rc = ww_train_tc_forward(c, x, B, t.pooled, st);
+  else rc = ww_train_conv_forward(c, x, B, t.act1, t.act2, t.act3, t.pooled, st);
+  if (rc) return rc;
   const float* xin = t.pooled;
   int K = 128;
   for (int l = 0; l < L; ++l) {
@@ -357,8 +435,8 @@ int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, c
   if (logits_out) WW_CHECK(c, cudaMemcpyAsync(logits_out, t.logits, (size_t)B * C * 4, cudaMemcpyDefault, st));
 
   // ---- backward: fc
-  if ((rc = sgemm(c, t.dlogits, 1, C, xin, Hd, 1, G("fc.weight"), Hd, 1, C, Hd, B, nullptr, st))) return rc;   // dW = dlogits^T h
-  colsum_kernel<<<1, 32, 0, st>>>(t.dlogits, G("fc.bias"), nullptr, B, C);
+  if ((rc = sgemm(c, t.dlogits, 1, C, xin, Hd, 1, G("fc.weight"), Hd, 1, C, Hd, B, nullptr, st, t.part, kPartFloats))) return rc;   // dW = dlogits^T h
+  colsum_kernel<<<1, dim3(32, 32), 0, st>>>(t.dlogits, G("fc.bias"), nullptr, B, C);
   WW_LAUNCH_CHECK(c);
   float* dh = t.dh;
   if ((rc = sgemm(c, t.dlogits, C, 1, c->w["fc.weight"], Hd, 1, dh, Hd, 1, B, Hd, C, nullptr, st))) return rc;  // dh = dlogits W
@@ -372,14 +450,18 @@ int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, c
     lstm_cell_bwd_kernel<<<(int)(((int64_t)B * Hd + 255) / 256), 256, 0, st>>>(gates, dh, drop, B, Hd);
     WW_LAUNCH_CHECK(c);
     // dW_ih [4H][K] = dgates^T inp ; db_ih = db_hh = colsum(dgates) ; d_inp [B][K] = dgates W_ih
-    if ((rc = sgemm(c, gates, 1, 4 * Hd, inp, Kin, 1, G("lstm.weight_ih_l" + s), Kin, 1, 4 * Hd, Kin, B, nullptr, st))) return rc;
-    colsum_kernel<<<(4 * Hd + 127) / 128, 128, 0, st>>>(gates, G("lstm.bias_ih_l" + s), G("lstm.bias_hh_l" + s), B, 4 * Hd);
+    if ((rc = sgemm(c, gates, 1, 4 * Hd, inp, Kin, 1, G("lstm.weight_ih_l" + s), Kin, 1, 4 * Hd, Kin, B, nullptr, st, t.part,
+                    kPartFloats))) return rc;
+    colsum_kernel<<<(4 * Hd + 31) / 32, dim3(32, 32), 0, st>>>(gates, G("lstm.bias_ih_l" + s), G("lstm.bias_hh_l" + s), B, 4 * Hd);
     WW_LAUNCH_CHECK(c);
     float* dnext = (l == 0) ? t.dpooled : (dh == t.dh ? t.dh + (size_t)B * Hd : t.dh);
     if ((rc = sgemm(c, gates, 4 * Hd, 1, c->w["lstm.weight_ih_l" + s], Kin, 1, dnext, Kin, 1, B, Kin, 4 * Hd, nullptr, st))) return rc;
     dh = dnext;
   }
   // ---- backward: conv stack
+  if (tc)
+    return ww_train_tc_backward(c, B, t.dpooled, G("conv1.weight"), G("conv1.bias"), G("conv2.weight"), G("conv2.bias"),
+                                G("conv3.weight"), G("conv3.bias"), st);
   return ww_train_conv_backward(c, x, B, t.act1, t.act2, t.act3, t.dpooled, t.dact2, t.dact1, t.wflip3, t.wflip2,
                                 G("conv1.weight"), G("conv1.bias"), G("conv2.weight"), G("conv2.bias"),
                                 G("conv3.weight"), G("conv3.bias"), t.part, kSlices, st);
@@ -409,13 +491,26 @@ int ww_train_apply(ww_ctx* c, float lr, float beta1, float beta2, float eps, flo
   // bias corrections in double, like torch.optim.Adam's Python-side scalars
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)t.step));
   const double bc2 = 1.0 - pow((double)beta2, (double)t.step);
-  for (const std::string& n : t.names) {
-    const int64_t cnt = t.count[n], off = t.offset[n];
-    adam_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(c->w[n], t.grad + off, t.m + off, t.v + off, cnt, lr, beta1, beta2,
-                                                          eps, weight_decay, bc1, (float)sqrt(bc2), grad_scale);
-    WW_LAUNCH_CHECK(c);
-  }
+  AdamTable tab;
+  tab.n = (int)t.names.size();
+  if (tab.n > 48) { c->set_error("ww_train_apply: too many parameter tensors"); return WW_ERR_INVALID; }
+  for (int k = 0; k < tab.n; ++k) { tab.ptr[k] = c->w[t.names[k]]; tab.off[k] = t.offset[t.names[k]]; tab.cnt[k] = t.count[t.names[k]]; }
+  adam_kernel<<<(int)((t.n_flat + 255) / 256), 256, 0, st>>>(tab, t.grad, t.m, t.v, t.n_flat, lr, beta1, beta2, eps, weight_decay,
+                                                             bc1, (float)sqrt(bc2), grad_scale);
+  WW_LAUNCH_CHECK(c);
+  c->weights_version++;
   c->weights_dirty = true;      // prepared (transposed / split) forms are rebuilt at the next forward
+  // training loop on the tensor-core kernels: rebuild the forms the NEXT step reads right here, on the device, with the
+  // power-of-two scales of the last host-side preparation (a full preparation is redone every kFastSteps steps, long before
+  // the weights can drift out of the scales' 8x headroom)
+  t.fast_pending = false;
+  const char* fast_env = getenv("WW_TRAIN_FAST");       // WW_TRAIN_FAST=0: host-side preparation every step (A/B, tests)
+  if (t.tc_last && t.tc_version + 1 == c->weights_version && t.fast_steps < kFastSteps && !(fast_env && fast_env[0] == '0')) {
+    if ((rc = ww_train_tc_repack(c, st))) return rc;
+    t.tc_version = c->weights_version;
+    t.fast_steps++;
+    t.fast_pending = true;
+  }
   if (!c->apply_event) WW_CHECK(c, cudaEventCreateWithFlags(&c->apply_event, cudaEventDisableTiming));
   WW_CHECK(c, cudaEventRecord(c->apply_event, st));     // ww_get_weights / ww_train_get_moments wait for it
   return WW_OK;

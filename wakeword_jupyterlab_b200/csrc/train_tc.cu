@@ -1,0 +1,911 @@
+// Backward pass of the conv stack on tcgen05 / TMEM  (sm_100a; SURVEY.md section 8 row a12, BASELINE config 5)
+//
+// Replaces what loss.backward() does below the pooling layer in WakewordTrainer.train_epoch
+// (/root/reference/wakeword_training_script.py:247-257) for the conv stack of WakewordModel (:170-173): the weight, bias
+// and data gradients of conv3 / conv2 / conv1.  conv_fp32.cu holds the exact fp32 CUDA-core form (WW_CONV_FP32, or
+// WW_TRAIN_KERNEL=fp32); this file is the tensor-core form, 1.42 GFLOP per clip.
+//
+// Forward (train mode) = the scoring kernels (conv12_tc.cu, conv3_tc.cu) with two extra outputs: conv1's activation
+// planes and ONE BIT per conv3 output (its sign).  conv3's activation is never stored: after the mean pool its gradient
+// is dY3[b][co][pixel] = (out > 0) * dpooled[b][co] / HW, a per-(clip, channel) constant times that bit, so both kernels
+// that consume dY3 rebuild their operand tiles in shared memory from 43 KB of bits per clip instead of reading 1.4 MB.
+//
+// All tensors keep the forward's layout: zero-padded pixel-linear planes [chunk of 8 channels][slot][8 x fp16]
+// (tc_common.cuh), slot = padded pixel index + 1.  One plane set serves every GEMM of the backward pass as a *view*:
+//   * data gradient  dX[pixel, ci] = sum_{tap, co} dY[pixel - tap offset, co] W[co, ci, tap]      (dgrad_kernel)
+//       A = dY planes, K-major (rows = pixels, the 3x3 tap is a start-address offset), M = 128 pixels;
+//       B = flipped weights [tap][co chunk][ci][8], fp16 hi and lo stacked along N (one N = 2 Cin instruction does both
+//       passes); epilogue (thread = pixel): (hi + lo) * 2^-k, ReLU derivative from the forward activation planes,
+//       fp16, 16-byte plane stores (512 contiguous bytes per warp);
+//   * weight gradient  dW[co, ci, tap] = sum_pixels dY[co, pixel] X[ci, pixel + tap offset]          (wgrad_kernel)
+//       K = pixels: the SAME planes read MN-major (8 channels contiguous per slot, LBO = 8 slots, SBO = one plane); the tap
+//       is again a start-address offset of the X window; 9 taps = 9 accumulators of Cin columns that stay in TMEM for
+//       the whole launch (one drain per CTA, then a fixed-order reduction over CTAs: deterministic);
+//       a constant "ones" plane appended to X makes the bias gradient column Cin of the centre tap.
+//       conv3 (128 x 64 x 9 = 576 columns > 512): CTAs of type 0 take taps 0-4, type 1 taps 5-8, in the ratio 5 : 4.
+// Precision (tolerances of tests/test_train_gpu.py): operands whose rounding errors are independent from pixel to pixel
+// (activations, dY2, dY1) are single fp16 values - the errors average out over the >= 12,800 pixels every weight gradient
+// sums; operands whose error would be the same at every pixel are split fp16 hi + lo: the weights of the data gradients
+// and the per-(clip, channel) constant of dY3 in the conv3 weight gradient.  Gradient magnitudes (1e-10 and below) are
+// brought into fp16's range by one power-of-two scale found on the device from max |dpooled|, and by static
+// power-of-two bounds (L1 norms of the weights) for dY2 and dY1; every scale is undone in fp32 in the reductions.
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+using namespace tc;
+
+namespace {
+
+constexpr uint32_t kAMn = 1u << 15, kBMn = 1u << 16;      // instruction-descriptor bits: A / B operand is MN-major
+
+// ---------------------------------------------------------------------------------------------------------------
+// small kernels
+// pooled[b][c] = sum_t part[b][t][c] / HW   (finishes conv3_kernel's per-tile partial sums)
+__global__ void pooled_mean_kernel(const float* __restrict__ part, float* __restrict__ pooled, int B, int T3, float inv_hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i >> 7, ch = i & 127;
+  float s = 0.0f;
+  for (int t = 0; t < T3; ++t) s += part[((size_t)b * T3 + t) * 128 + ch];
+  pooled[i] = s * inv_hw;
+}
+
+// gs[0] = 2^k with max |dpooled| / HW * 2^k in [2^13, 2^14), gs[1] = 2^-k
+__global__ void __launch_bounds__(1024) grad_scale_kernel(const float* __restrict__ dpooled, int n, float inv_hw, float* __restrict__ gs) {
+  __shared__ float red[32];
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(dpooled[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, red[i]);
+    const float a = m * inv_hw;
+    float sc = 1.0f;
+    if (a > 0.0f && isfinite(a)) {
+      int e;
+      frexpf(a, &e);                              // a = f 2^e, f in [0.5, 1)
+      sc = ldexpf(1.0f, min(max(14 - e, -100), 100));
+    }
+    gs[0] = sc;
+    gs[1] = 1.0f / sc;
+  }
+}
+
+// sq[b][0][c] = fp16(s), sq[b][1][c] = fp16(s - hi), s = dpooled[b][c] / HW * gs[0]
+__global__ void dy3_scalars_kernel(const float* __restrict__ dpooled, const float* __restrict__ gs, float inv_hw,
+                                   __half* __restrict__ sq, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i >> 7, ch = i & 127;
+  const float s = dpooled[i] * inv_hw * gs[0];
+  const __half hi = __float2half_rn(s);
+  sq[((size_t)b * 2) * 128 + ch] = hi;
+  sq[((size_t)b * 2 + 1) * 128 + ch] = __float2half_rn(s - __half2float(hi));
+}
+
+// 8 fp16 values (one plane row) kept where the bit of their channel's word is set at position `sh`
+__device__ __forceinline__ uint4 select8(const uint4 v, const uint4 w0, const uint4 w1, int sh) {
+  const uint32_t m0 = 0u - ((w0.x >> sh) & 1u), m1 = 0u - ((w0.y >> sh) & 1u), m2 = 0u - ((w0.z >> sh) & 1u),
+                 m3 = 0u - ((w0.w >> sh) & 1u), m4 = 0u - ((w1.x >> sh) & 1u), m5 = 0u - ((w1.y >> sh) & 1u),
+                 m6 = 0u - ((w1.z >> sh) & 1u), m7 = 0u - ((w1.w >> sh) & 1u);
+  return make_uint4(v.x & ((m0 & 0xffffu) | (m1 & 0xffff0000u)), v.y & ((m2 & 0xffffu) | (m3 & 0xffff0000u)),
+                    v.z & ((m4 & 0xffffu) | (m5 & 0xffff0000u)), v.w & ((m6 & 0xffffu) | (m7 & 0xffff0000u)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient
+constexpr int WG_THREADS = 320;     // warp 0 loader, warp 1 MMA issuer, warps 2-9 dY3 tile builders; warps 2-5 drain TMEM at the end
+
+struct WgradParams {
+  const uint32_t* bits;     // A_BITS: [B][T3][4][128] sign bits of conv3's output (conv3_tc.cu)
+  const __half* sq;         // A_BITS: [B][2][128] fp16 hi / lo of dpooled / HW * 2^k
+  const __half* a_planes;   // !A_BITS: dY planes [B][MCH/8][npix][8]
+  const __half* b_planes;   // X planes [B][NCH/8][npix][8]
+  float* part;              // [grid][tl_cap][NCH + 16][128] fp32 partial sums (lane = co)
+  int B, n0, tsplit, tl_cap;   // CTAs [0, n0) take taps [0, tsplit), the others taps [tsplit, 9)
+  Geom g;
+};
+
+// Work unit = (clip b, tile t): the 128 dY slots P + 1 + 128 t .. (= conv3's output tile t) and the X window of
+// 128 + 2 P + 2 slots from slot 128 t: 8 K-steps of 16 pixels per tap.
+template <int MCH, int NCH, bool A_BITS>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
+  constexpr int NA = A_BITS ? 2 : 1;                       // dY operand copies (hi, lo)
+  constexpr int MP = MCH / 8, NP = NCH / 8, NPB = NP + 2, NS = NCH + 16;
+  constexpr int NSTG = A_BITS ? 2 : 3;
+  constexpr uint32_t A_BYTES = NA * 16 * 2048;             // always 16 planes per copy (M = 128); MCH = 64: the upper 8 stay zero
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geom g = p.g;
+  const uint32_t bsl = (uint32_t)((128 + 2 * g.P + 2 + 7) & ~7);
+  const uint32_t bpl = bsl * 16u;
+  const uint32_t stage_bytes = A_BYTES + NPB * bpl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTG * stage_bytes);
+  uint64_t* full = bars;              // [NSTG] bulk copies landed
+  uint64_t* afull = bars + 4;         // [NSTG] dY3 tile built (A_BITS)
+  uint64_t* empty = bars + 8;         // [NSTG] MMAs of the stage retired
+  uint64_t* done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NSTG; ++i) { mbar_init(full + i, 1); mbar_init(afull + i, 8); mbar_init(empty + i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  // zero everything once (unused A planes, the all-zero pad plane), and write the ones plane: channel 0 = 1.0 at every slot
+  for (uint32_t i = tid * 16u; i < NSTG * stage_bytes; i += WG_THREADS * 16u) {
+    const uint32_t off = i % stage_bytes;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (off >= A_BYTES + NP * bpl && off < A_BYTES + (NP + 1) * bpl) v.x = 0x3c00u;
+    *reinterpret_cast<uint4*>(smem + i) = v;
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int n_units = p.B * g.T3;
+  int j, nj, tap_lo, tap_hi;
+  if ((int)blockIdx.x < p.n0) { j = blockIdx.x; nj = p.n0; tap_lo = 0; tap_hi = p.tsplit; }
+  else { j = blockIdx.x - p.n0; nj = gridDim.x - p.n0; tap_lo = p.tsplit; tap_hi = 9; }
+  const int u_lo = (int)((long long)n_units * j / nj), u_hi = (int)((long long)n_units * (j + 1) / nj);
+
+  if (warp == 0) {
+    // ===================== loader (one thread)
+    if (lane == 0) {
+      int it = 0;
+      for (int u = u_lo; u < u_hi; ++u, ++it) {
+        const int st = it % NSTG;
+        mbar_wait(empty + st, ((it / NSTG) & 1) ^ 1, 70);
+        const int b = u / g.T3, t = u - b * g.T3;
+        unsigned char* sb = smem + st * stage_bytes;
+        mbar_arrive_expect_tx(full + st, NP * bpl + (A_BITS ? 0u : (uint32_t)MP * 2048u));
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl)
+          bulk_g2s(sb + A_BYTES + pl * bpl, p.b_planes + (((size_t)b * NP + pl) * g.npix + (size_t)128 * t) * 8, bpl, full + st);
+        if (!A_BITS) {
+#pragma unroll
+          for (int pl = 0; pl < MP; ++pl)
+            bulk_g2s(sb + pl * 2048, p.a_planes + (((size_t)b * MP + pl) * g.npix + (size_t)(g.P + 1 + 128 * t)) * 8, 2048, full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    const uint32_t idN = make_idesc(128, NCH) | kAMn | kBMn, idC = make_idesc(128, NCH + 16) | kAMn | kBMn;
+    const uint64_t a0 = make_desc(smem_u32(smem), 128, 2048);                // MN-major: LBO = 8-slot group, SBO = plane
+    const uint64_t b0 = make_desc(smem_u32(smem) + A_BYTES, 128, bpl);
+    int it = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++it) {
+      const int st = it % NSTG;
+      const uint32_t par = (it / NSTG) & 1;
+      mbar_wait(full + st, par, 71);
+      if (A_BITS) mbar_wait(afull + st, par, 72);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t as = a0 + (uint64_t)((st * stage_bytes) >> 4), bs = b0 + (uint64_t)((st * stage_bytes) >> 4);
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll 1
+          for (int tap = tap_lo; tap < tap_hi; ++tap) {
+            const int ty = tap / 3, tx = tap - 3 * ty;
+            const uint32_t off = (uint32_t)((g.P + 1) + (ty - 1) * g.P + (tx - 1) + ks * 16);
+            const uint32_t d = tmem_base + (uint32_t)(tap - tap_lo) * NS;
+            const uint32_t id = tap == 4 ? idC : idN;
+            umma_f16(d, as + (uint64_t)(ks * 16), bs + (uint64_t)off, id, (it | ks) != 0);
+            if (NA == 2) umma_f16(d, as + (uint64_t)(ks * 16 + ((16 * 2048) >> 4)), bs + (uint64_t)off, id, 1);
+          }
+        }
+        umma_commit(empty + st);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else if (A_BITS) {
+    // ===================== dY3 tile builders: warp w -> channel chunks 2w, 2w + 1; lane = slot within a 32-slot block
+    const int w = warp - 2;
+    int it = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++it) {
+      const int st = it % NSTG;
+      mbar_wait(empty + st, ((it / NSTG) & 1) ^ 1, 73);
+      const int b = u / g.T3, t = u - b * g.T3;
+      unsigned char* ast = smem + st * stage_bytes;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * w + cc;
+        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2) * 128 + 8 * c));
+        const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2 + 1) * 128 + 8 * c));
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+          const uint4* wp = reinterpret_cast<const uint4*>(p.bits + (((size_t)b * g.T3 + t) * 4 + blk) * 128 + 8 * c);
+          const uint4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          unsigned char* dst = ast + c * 2048 + (blk * 32 + lane) * 16;
+          *reinterpret_cast<uint4*>(dst) = select8(hq, w0, w1, lane);
+          *reinterpret_cast<uint4*>(dst + 16 * 2048) = select8(lq, w0, w1, lane);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(afull + st, lane);
+    }
+  }
+  if (warp >= 2 && warp < 6) {
+    // ===================== final drain: lane = output channel, columns = (tap, ci)
+    mbar_wait_relaxed(done, 0, 74);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* dst = p.part + (size_t)blockIdx.x * p.tl_cap * NS * 128 + q * 32 + lane;
+    const bool any = u_hi > u_lo;
+    for (int tl = 0; tl < tap_hi - tap_lo; ++tl)
+      for (int n0 = 0; n0 < NS; n0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + tl * NS + n0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[((size_t)tl * NS + n0 + k) * 128] = any ? __uint_as_float(r[k]) : 0.0f;
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// gw[co][ci][tap] = wfac * gs[1] * sum_cta part, gb[co] = bfac * gs[1] * sum_cta (column NCH of the centre tap); fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int grid, int n0, int tsplit, int tl_cap, int NS, int MCH,
+                                    int NCH, const float* __restrict__ gs, float wfac, float bfac, float* __restrict__ gw,
+                                    float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = MCH * NCH * 9;
+  if (i >= nw + MCH) return;
+  int co, ci, tap;
+  if (i < nw) { co = i % MCH; const int r = i / MCH; ci = r % NCH; tap = r / NCH; }
+  else { co = i - nw; ci = NCH; tap = 4; }
+  const int c_lo = tap < tsplit ? 0 : n0, c_hi = tap < tsplit ? n0 : grid, tl = tap < tsplit ? tap : tap - tsplit;
+  float s = 0.0f;
+  for (int c = c_lo; c < c_hi; ++c) s += part[(((size_t)c * tl_cap + tl) * NS + ci) * 128 + co];
+  if (i < nw) gw[((size_t)co * NCH + ci) * 9 + tap] = s * wfac * gs[1];
+  else gb[co] = s * bfac * gs[1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// data gradient
+constexpr int DG_THREADS = 14 * 32;   // warp 0 loader, warp 1 MMA issuer, warps 2-9 epilogue, warps 10-13 dY3 plane builders
+constexpr int DG_NSTW = 4;            // weight ring stages
+
+struct DgradParams {
+  const uint32_t* bits;          // A_BITS: sign bits of conv3's output
+  const __half* sq;              // A_BITS: [B][2][128] (hi used)
+  const __half* a_planes;        // !A_BITS: dY planes [B][KCH/8][npix][8]
+  const unsigned char* wst;      // weight stages [pair q][tap row tt]: [tl 3][kc 4][n' NT][8 fp16]
+  const __half* relu_planes;     // forward activation planes of the layer below [B][NOUT/8][npix][8]: ReLU derivative
+  __half* out;                   // dX planes [B][NOUT/8][npix][8]
+  float mult;                    // accumulator -> stored value
+  int B;
+  Geom g;
+};
+
+template <int NT>
+__host__ __device__ constexpr uint32_t dg_wstage_bytes() { return 3u * 4u * NT * 16u; }
+
+// Work item = group of G tape tiles (conv3_tc.cu's tape: clip b + 1 follows clip b at a period of 128 T3 slots).
+template <int KCH, int NOUT, int NPASS, bool A_BITS>
+__global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const DgradParams p) {
+  constexpr int NT = NOUT * NPASS, NQ = KCH / 32, OP = NOUT / 8;
+  constexpr uint32_t WST = dg_wstage_bytes<NT>();
+  constexpr int NBUF = (4 * NT <= 256) ? 2 : 1;          // accumulator sets in TMEM
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geom g = p.g;
+  const uint32_t plane_bytes = (uint32_t)g.nsl3 * 16u, abuf = 4u * plane_bytes;
+  unsigned char* a_s = smem;                               // [2 pair buffers][4 planes]
+  unsigned char* w_s = a_s + 2 * abuf;                     // [DG_NSTW][WST]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + DG_NSTW * WST);
+  uint64_t* a_full = bars;                // [2]
+  uint64_t* a_empty = bars + 2;           // [2]
+  uint64_t* w_full = bars + 4;            // [4]
+  uint64_t* w_empty = bars + 8;           // [4]
+  uint64_t* t_full = bars + 12;           // [2]
+  uint64_t* t_empty = bars + 14;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full + i, A_BITS ? 4 : 1); mbar_init(a_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8);
+    }
+    for (int i = 0; i < DG_NSTW; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int n_tiles = p.B * g.T3;
+  const int n_items = (n_tiles + g.G - 1) / g.G;
+  const int item_lo = (int)((long long)n_items * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+  auto item_tiles = [&](int item) { return min(g.G, n_tiles - item * g.G); };
+
+  if (warp == 0) {
+    // ===================== loader (one thread): dY planes of a 32-channel slice (when they exist in HBM) + weight ring
+    if (lane == 0) {
+      int it = 0;
+      uint32_t st = 0, wpar = 1;
+      for (int item = item_lo; item < item_hi; ++item, ++it) {
+        const int tau0 = item * g.G;
+        const int b = tau0 / g.T3, t0 = tau0 - b * g.T3, n_t = item_tiles(item);
+        const uint32_t nslots = (uint32_t)(n_t * 128 + 2 * g.P + 2);
+        uint32_t n1 = nslots, n2 = 0;
+        if (128u * t0 + nslots > 128u * g.T3 && b + 1 < p.B) { n1 = 128u * (g.T3 - t0); n2 = nslots - n1; }
+        for (int q = 0; q < NQ; ++q) {
+          const int f = it * NQ + q, ab = f & 1;
+          if (!A_BITS) {
+            mbar_wait(a_empty + ab, ((f >> 1) & 1) ^ 1, 80);
+            mbar_arrive_expect_tx(a_full + ab, 4u * nslots * 16u);
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) {
+              unsigned char* dst = a_s + ab * abuf + pl * plane_bytes;
+              const __half* src = p.a_planes + (((size_t)b * (KCH / 8) + 4 * q + pl) * g.npix + (size_t)t0 * 128) * 8;
+              bulk_g2s(dst, src, n1 * 16u, a_full + ab);
+              if (n2) bulk_g2s(dst + n1 * 16u, p.a_planes + (((size_t)(b + 1) * (KCH / 8) + 4 * q + pl) * g.npix) * 8, n2 * 16u, a_full + ab);
+            }
+          }
+          for (int tt = 0; tt < 3; ++tt) {
+            mbar_wait(w_empty + st, wpar, 81);
+            mbar_arrive_expect_tx(w_full + st, WST);
+            bulk_g2s(w_s + st * WST, p.wst + (size_t)(q * 3 + tt) * WST, WST, w_full + st);
+            if (++st == DG_NSTW) { st = 0; wpar ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    constexpr uint32_t idesc = make_idesc(128, NT);
+    const uint64_t adesc0 = make_desc(smem_u32(a_s), plane_bytes, 128);      // pixels: K-major, chunk-plane stride
+    const uint64_t wdesc0 = make_desc(smem_u32(w_s), NT * 16, 128);          // weights: [kc][n'][8]
+    const uint32_t plane_u = plane_bytes >> 4;
+    int it = 0;
+    uint32_t st = 0, wpar = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
+      const int n_t = item_tiles(item);
+      const int tb = it % NBUF;
+      mbar_wait(t_empty + tb, ((it / NBUF) & 1) ^ 1, 84);
+      for (int q = 0; q < NQ; ++q) {
+        const int f = it * NQ + q, ab = f & 1;
+        mbar_wait(a_full + ab, (f >> 1) & 1, 85);
+        for (int tt = 0; tt < 3; ++tt) {
+          mbar_wait(w_full + st, wpar, 86);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)((ab * abuf) >> 4);
+            const uint64_t wd = wdesc0 + (uint64_t)((st * WST) >> 4);
+#pragma unroll 1
+            for (int i = 0; i < n_t; ++i) {
+              const uint32_t d = tmem_base + tb * 256 + i * NT;
+#pragma unroll
+              for (int tl = 0; tl < 3; ++tl) {
+                const uint32_t row_off = (uint32_t)((g.P + 1) + (tt - 1) * g.P + (tl - 1) + i * 128);
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2)
+                  umma_f16(d, ad + (uint64_t)(2 * k2 * plane_u + row_off), wd + (uint64_t)(((tl * 4 + 2 * k2) * NT * 16) >> 4), idesc,
+                           (q | tt | tl | k2) != 0);
+              }
+            }
+            umma_commit(w_empty + st);
+            if (tt == 2) umma_commit(a_empty + ab);
+            if (tt == 2 && q == NQ - 1) umma_commit(t_full + tb);
+          }
+          __syncwarp();
+          if (++st == DG_NSTW) { st = 0; wpar ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== epilogue: lane = pixel, columns = output channels (hi | lo)
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    const float mult = p.mult;
+    int it = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
+      const int tau0 = item * g.G, n_t = item_tiles(item);
+      const int tb = it % NBUF;
+      mbar_wait_relaxed(t_full + tb, (it / NBUF) & 1, 87);
+      tc_fence_after();
+      for (int i = sub; i < n_t; i += 2) {
+        const int tau = tau0 + i;
+        const int b = tau / g.T3, t = tau - b * g.T3;
+        const size_t s = (size_t)(g.P + 1 + 128 * t + q * 32 + lane);                 // plane slot of this thread's pixel
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tb * 256 + i * NT;
+#pragma unroll
+        for (int c = 0; c < OP; c += 2) {
+          uint32_t rh[16], rl[16];
+          tmem_ld16_nowait(taddr + c * 8, rh);
+          if (NPASS == 2) tmem_ld16_nowait(taddr + NOUT + c * 8, rl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const size_t idx = ((size_t)b * OP + c + cc) * g.npix + s;
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.relu_planes) + idx);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = (__uint_as_float(rh[cc * 8 + e]) + (NPASS == 2 ? __uint_as_float(rl[cc * 8 + e]) : 0.0f)) * mult;
+            uint4 v = cvt8(o);
+            v.x &= ((a.x & 0xffffu) ? 0xffffu : 0u) | ((a.x >> 16) ? 0xffff0000u : 0u);
+            v.y &= ((a.y & 0xffffu) ? 0xffffu : 0u) | ((a.y >> 16) ? 0xffff0000u : 0u);
+            v.z &= ((a.z & 0xffffu) ? 0xffffu : 0u) | ((a.z >> 16) ? 0xffff0000u : 0u);
+            v.w &= ((a.w & 0xffffu) ? 0xffffu : 0u) | ((a.w >> 16) ? 0xffff0000u : 0u);
+            reinterpret_cast<uint4*>(p.out)[idx] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp(t_empty + tb, lane);
+    }
+  } else if (A_BITS) {
+    // ===================== dY3 plane builders: warp w -> plane w of the 32-channel slice; lane = slot.
+    // The sign bits of the clips of a launch form ONE bit stream per channel (clip b's 128 T3 bits, then clip b + 1's: the
+    // tape), so the window of a fill is at most 32 consecutive words: lane l fetches word l of the window once (8 channels =
+    // two 16-byte loads), and every slot then takes its word from the lane that holds it with shuffles.
+    const int w = warp - 10;
+    const int period = 128 * g.T3;
+    const int sh = g.P + 1, sa = sh >> 5, sb = sh & 31;        // slot s of a clip <-> bit s - (P + 1) of its stream
+    const long long n_words = (long long)p.B * (period >> 5);
+    const int bit = (lane - sb) & 31;
+    int it = 0;
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
+      const int tau0 = item * g.G;
+      const int b = tau0 / g.T3, t0 = tau0 - b * g.T3, n_t = item_tiles(item);
+      const int nslots = n_t * 128 + 2 * g.P + 2;
+      const long long w0 = (((long long)b * period + 128 * t0) >> 5) - sa - 1;      // first word of the window
+      // slots whose bit lies at or past the next clip's stream start take that clip's constants
+      const int next_from = period - 128 * t0 + sh;
+      for (int q = 0; q < NQ; ++q) {
+        const int f = it * NQ + q, ab = f & 1;
+        const int c = 4 * q + w;
+        uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+        const long long wi = w0 + lane;
+        if (wi >= 0 && wi < n_words) {
+          const uint4* wp = reinterpret_cast<const uint4*>(p.bits + (size_t)wi * 128 + 8 * c);
+          x0 = __ldg(wp); x1 = __ldg(wp + 1);
+        }
+        const uint4 hq0 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2) * 128 + 8 * c));
+        uint4 hq1 = make_uint4(0u, 0u, 0u, 0u);
+        if (b + 1 < p.B) hq1 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)(b + 1) * 2) * 128 + 8 * c));
+        mbar_wait(a_empty + ab, ((f >> 1) & 1) ^ 1, 83);
+        unsigned char* dst = a_s + ab * abuf + w * plane_bytes;
+        for (int k = 0; k * 32 < g.nsl3; ++k) {
+          const int i = 32 * k + lane;
+          const int src = k + (lane >= sb ? 1 : 0);             // window word that holds this slot's bit
+          uint4 a0, a1;
+          a0.x = __shfl_sync(0xffffffffu, x0.x, src); a0.y = __shfl_sync(0xffffffffu, x0.y, src);
+          a0.z = __shfl_sync(0xffffffffu, x0.z, src); a0.w = __shfl_sync(0xffffffffu, x0.w, src);
+          a1.x = __shfl_sync(0xffffffffu, x1.x, src); a1.y = __shfl_sync(0xffffffffu, x1.y, src);
+          a1.z = __shfl_sync(0xffffffffu, x1.z, src); a1.w = __shfl_sync(0xffffffffu, x1.w, src);
+          uint4 v = select8(i >= next_from ? hq1 : hq0, a0, a1, bit);
+          if (i >= nslots) v = make_uint4(0u, 0u, 0u, 0u);
+          if (i < g.nsl3) *reinterpret_cast<uint4*>(dst + (size_t)i * 16) = v;
+        }
+        fence_proxy_async();
+        mbar_arrive_warp(a_full + ab, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv1 weight / bias gradient on CUDA cores (1.5 MFLOP per clip): thread = (tap row ky, co) with its three taps in
+// registers (one 128-bit load of 8 dY values + 10 broadcast loads of x per 24 multiply-adds), 32 more threads = bias
+constexpr int W1_THREADS = 128, W1_OUT = 320, W1_PITCH = 136;
+
+__global__ void __launch_bounds__(W1_THREADS) wgrad1_kernel(const __half* __restrict__ dy1,     // [B][4][npix][8]
+                                                            const float* __restrict__ in_pad,   // [B][npix_in]
+                                                            float* __restrict__ part,           // [grid][320]
+                                                            int B, Geom g) {
+  __shared__ __align__(16) __half sdy[32][W1_PITCH];          // [co][slot]
+  __shared__ float sx[128 + 2 * 40 + 4];
+  const int tid = threadIdx.x;
+  const int ky = tid >> 5, co = tid & 31;
+  const int n_units = B * g.T3;
+  const int u_lo = (int)((long long)n_units * blockIdx.x / gridDim.x), u_hi = (int)((long long)n_units * (blockIdx.x + 1) / gridDim.x);
+  const int nx = 128 + 2 * g.P + 2;
+  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+  for (int u = u_lo; u < u_hi; ++u) {
+    const int b = u / g.T3, t = u - b * g.T3;
+    __syncthreads();
+    for (int i = tid; i < 512; i += W1_THREADS) {
+      const int pl = i >> 7, sl = i & 127;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy1) + ((size_t)b * 4 + pl) * g.npix + (g.P + 1 + 128 * t + sl));
+      const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sdy[8 * pl + e][sl] = __ushort_as_half((unsigned short)(vw[e >> 1] >> (16 * (e & 1))));
+    }
+    // dY slot P + 1 + 128 t + i pairs with x at padded index P + 128 t + i + (ky - 1) P + (kx - 1) = in_pad[lead + 128 t - 1 + i + ky P + kx]
+    for (int i = tid; i < nx; i += W1_THREADS) sx[i] = __ldg(in_pad + (size_t)b * g.npix_in + g.lead + 128 * t - 1 + i);
+    __syncthreads();
+    if (ky < 3) {
+      const float* xr = sx + ky * g.P;
+#pragma unroll 2
+      for (int i0 = 0; i0 < 128; i0 += 8) {
+        const uint4 d = *reinterpret_cast<const uint4*>(&sdy[co][i0]);
+        const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+        float xv[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xv[k] = xr[i0 + k];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dv = __half2float(__ushort_as_half((unsigned short)(dw[e >> 1] >> (16 * (e & 1)))));
+          acc0 = fmaf(dv, xv[e], acc0);
+          acc1 = fmaf(dv, xv[e + 1], acc1);
+          acc2 = fmaf(dv, xv[e + 2], acc2);
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int i0 = 0; i0 < 128; i0 += 8) {
+        const uint4 d = *reinterpret_cast<const uint4*>(&sdy[co][i0]);
+        const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc0 += __half2float(__ushort_as_half((unsigned short)(dw[e >> 1] >> (16 * (e & 1)))));
+      }
+    }
+  }
+  float* o = part + (size_t)blockIdx.x * W1_OUT;
+  if (ky < 3) { o[(ky * 3) * 32 + co] = acc0; o[(ky * 3 + 1) * 32 + co] = acc1; o[(ky * 3 + 2) * 32 + co] = acc2; }
+  else o[288 + co] = acc0;
+}
+
+__global__ void wgrad1_reduce_kernel(const float* __restrict__ part, int grid, const float* __restrict__ gs, float fac,
+                                     float* __restrict__ gw, float* __restrict__ gb) {
+  const int tid = threadIdx.x;            // 320 threads
+  float s = 0.0f;
+  for (int c = 0; c < grid; ++c) s += part[(size_t)c * W1_OUT + tid];
+  s *= fac * gs[1];
+  const int tap = tid >> 5, co = tid & 31;
+  if (tap < 9) gw[co * 9 + tap] = s;
+  else gb[co] = s;
+}
+
+constexpr int kDgradPass = 2;      // fp16 hi + lo weights in the data gradients (stacked along N)
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand forms rebuilt on the device after an optimiser step (same element formulas as the host-side preparations in
+// conv12_tc.cu / conv3_tc.cu / pack_dgrad_weights below, with the scales those fixed)
+__device__ __forceinline__ uint16_t d_f2h(float v) { return __half_as_ushort(__float2half_rn(v)); }
+__device__ __forceinline__ float d_h2f(uint16_t u) { return __half2float(__ushort_as_half(u)); }
+
+__global__ void repack_w1_kernel(const float* __restrict__ w, float sc, uint16_t* __restrict__ s) {       // [kc 4][n' 64][8]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * 32 * 8) return;
+  const int kc = i >> 8, n = (i >> 3) & 31, e = i & 7;
+  if (kc == 1 && e >= 2) return;
+  const float v = w[n * 9 + (kc == 1 ? 8 : e)] * sc;
+  const uint16_t hi = d_f2h(v);
+  s[(kc * 64 + n) * 8 + e] = hi;
+  s[(kc * 64 + 32 + n) * 8 + e] = d_f2h(v - d_h2f(hi));
+}
+__global__ void repack_w2_kernel(const float* __restrict__ w, float sc, uint16_t* __restrict__ s) {       // [tap][kc 4][n' 128][8]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 32 * 9) return;
+  const int n = i / 288, r = i - n * 288, ci = r / 9, tap = r - ci * 9;
+  const float v = w[i] * sc;
+  const uint16_t hi = d_f2h(v);
+  const size_t base = ((size_t)tap * 4 + (ci >> 3)) * 128;
+  s[(base + n) * 8 + (ci & 7)] = hi;
+  s[(base + 64 + n) * 8 + (ci & 7)] = d_f2h(v - d_h2f(hi));
+}
+__global__ void repack_w3_kernel(const float* __restrict__ w, float sc, int lo_shift, unsigned char* __restrict__ s) {   // conv3 stages
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 64 * 9) return;
+  const int n = i / 576, r = i - n * 576, ci = r / 9, tap = r - ci * 9;
+  const float v = w[i] * sc;
+  const uint16_t hi = d_f2h(v);
+  const int pr = ci >> 5, c32 = ci & 31, tt = tap / 3, tl = tap - 3 * tt;
+  unsigned char* stg = s + (size_t)(pr * 3 + tt) * C3_STAGE_BYTES;
+  *reinterpret_cast<uint16_t*>(stg + (size_t)(c32 >> 4) * C3_PART_BYTES + (((size_t)tl * 2 + ((c32 >> 3) & 1)) * 128 + n) * 16 + (c32 & 7) * 2) = hi;
+  stg[(size_t)2 * C3_PART_BYTES + (((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] =
+      (unsigned char)__nv_cvt_float_to_fp8(ldexpf(v - d_h2f(hi), lo_shift), __NV_SATFINITE, __NV_E4M3);
+}
+__global__ void repack_dgrad_kernel(const float* __restrict__ w, int COUT, int CIN, float sc, uint16_t* __restrict__ s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= COUT * CIN * 9) return;
+  const int co = i / (CIN * 9), r = i - co * CIN * 9, n = r / 9, tap = r - n * 9;
+  const int tt = 2 - tap / 3, tl = 2 - tap % 3, q = co >> 5, kc = (co & 31) >> 3, e = co & 7, NT = CIN * kDgradPass;
+  const float v = w[i] * sc;
+  const uint16_t hi = d_f2h(v);
+  const size_t base = ((((size_t)(q * 3 + tt) * 3 + tl) * 4 + kc) * NT) * 8;
+  s[base + (size_t)n * 8 + e] = hi;
+  if (kDgradPass == 2) s[base + (size_t)(CIN + n) * 8 + e] = d_f2h(v - d_h2f(hi));
+}
+__global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+struct TcTrain {
+  int cap = 0;
+  float* in_pad = nullptr;
+  __half *act1 = nullptr, *act2 = nullptr, *dact2 = nullptr, *dact1 = nullptr, *sq = nullptr;
+  uint8_t* act2_8 = nullptr;
+  uint32_t* bits = nullptr;
+  float *pool_part = nullptr, *gs = nullptr, *part = nullptr, *part1 = nullptr;
+  unsigned char *wd3 = nullptr, *wd2 = nullptr;       // data-gradient weight stages
+  float mult3 = 1.0f, mult2 = 1.0f;                   // dgrad epilogue multipliers
+  int k2 = 0, k1 = 0;                                 // stored dY2 = true * gs * 2^-k2, stored dY1 = true * gs * 2^-(k2 + k1)
+  float sc3 = 1.0f, sc2 = 1.0f;                       // weight scales baked into wd3 / wd2 and mult3 / mult2
+  float* h_bias = nullptr;                            // pinned: conv1 / conv2 biases after the last optimiser step
+  cudaEvent_t bias_ev = nullptr;
+  int grid = 0;
+  bool conf = false;                                  // dynamic shared-memory attributes set on this context's device
+};
+
+
+template <int KCH, int NOUT>
+size_t dgrad_smem(const Geom& g) {
+  return (size_t)2 * 4 * g.nsl3 * 16 + (size_t)DG_NSTW * dg_wstage_bytes<NOUT * kDgradPass>() + 32 * 8 + 64;
+}
+template <int NCH, bool A_BITS>
+size_t wgrad_smem(const Geom& g) {
+  const size_t bsl = (size_t)((128 + 2 * g.P + 2 + 7) & ~7);
+  return (size_t)(A_BITS ? 2 : 3) * ((A_BITS ? 2 : 1) * 16 * 2048 + (NCH / 8 + 2) * bsl * 16) + 32 * 8 + 64;
+}
+
+// flipped / transposed weights of a data gradient as fp16 hi | lo stacked along N, in stage order [q][tt][tl][kc][n'][8]:
+// k channel = forward output channel, n = forward input channel, tap (tt, tl) <-> forward tap (2 - tt, 2 - tl)
+void pack_dgrad_weights(const std::vector<float>& w, int COUT, int CIN, float sc, std::vector<uint16_t>& s) {
+  const int NT = CIN * kDgradPass, NQ = COUT / 32;
+  s.assign((size_t)NQ * 3 * 3 * 4 * NT * 8, 0);
+  for (int q = 0; q < NQ; ++q)
+    for (int tt = 0; tt < 3; ++tt)
+      for (int tl = 0; tl < 3; ++tl)
+        for (int kc = 0; kc < 4; ++kc)
+          for (int n = 0; n < CIN; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int co = 32 * q + 8 * kc + e;
+              const float v = w[((size_t)co * CIN + n) * 9 + (2 - tt) * 3 + (2 - tl)] * sc;
+              const uint16_t hi = f2h(v);
+              const size_t base = ((((size_t)(q * 3 + tt) * 3 + tl) * 4 + kc) * NT) * 8;
+              s[base + (size_t)n * 8 + e] = hi;
+              if (kDgradPass == 2) s[base + (size_t)(CIN + n) * 8 + e] = f2h(v - h2f(hi));
+            }
+}
+
+// smallest k with 2^k >= max over input channels of sum_{co, tap} |w|: |dX| <= 2^k max |dY|
+int l1_shift(const std::vector<float>& w, int COUT, int CIN) {
+  double m = 0.0;
+  for (int ci = 0; ci < CIN; ++ci) {
+    double s = 0.0;
+    for (int co = 0; co < COUT; ++co)
+      for (int k = 0; k < 9; ++k) s += fabs((double)w[((size_t)co * CIN + ci) * 9 + k]);
+    m = std::max(m, s);
+  }
+  int k = 0;
+  if (!(m > 0.0) || !std::isfinite(m)) return 0;
+  while (ldexp(1.0, k) < m && k < 60) ++k;
+  while (k > -60 && ldexp(1.0, k - 1) >= m) --k;
+  return k;
+}
+
+}  // namespace
+
+bool ww_train_tc_supported(const ww_ctx* c) {
+  if (c->cfg.conv_mode == WW_CONV_FP32) return false;
+  const Geom g = make_geom(c);
+  if (g.G < 1 || 2 * g.P + 2 + 128 > 4096) return false;
+  if (128 + 2 * g.P + 2 > 128 + 2 * 40 + 4) return false;                  // wgrad1_kernel's x window
+  if ((g.nsl3 + 31) / 32 + 1 > 32) return false;                           // dgrad_kernel's bit window: one word per lane
+  return dgrad_smem<128, 64>(g) <= 227 * 1024 && wgrad_smem<64, true>(g) <= 227 * 1024 && conv3_smem_bytes(g.nsl3, g.nst3) <= 227 * 1024;
+}
+
+void ww_train_tc_free(ww_ctx* c) {
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  if (!t) return;
+  void* bufs[] = {t->in_pad, t->act1, t->act2, t->dact2, t->dact1, t->sq, t->act2_8, t->bits, t->pool_part, t->gs, t->part, t->part1,
+                  t->wd3, t->wd2};
+  for (void* b : bufs) cudaFree(b);
+  if (t->h_bias) cudaFreeHost(t->h_bias);
+  if (t->bias_ev) cudaEventDestroy(t->bias_ev);
+  delete t;
+  c->train.tc = nullptr;
+}
+
+static int ensure_tc(ww_ctx* c, int B, const Geom& g) {
+  if (!c->train.tc) c->train.tc = new TcTrain();
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  if (!t->gs) {
+    t->grid = c->sm_count;
+    WW_CHECK(c, cudaMalloc((void**)&t->gs, 2 * sizeof(float)));
+    WW_CHECK(c, cudaMalloc((void**)&t->part, (size_t)t->grid * 9 * (32 + 16) * 128 * 4 + (size_t)t->grid * 5 * (64 + 16) * 128 * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t->part1, (size_t)t->grid * 8 * W1_OUT * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t->wd3, (size_t)4 * 3 * dg_wstage_bytes<64 * kDgradPass>()));
+    WW_CHECK(c, cudaMalloc((void**)&t->wd2, (size_t)2 * 3 * dg_wstage_bytes<32 * kDgradPass>()));
+  }
+  if (B > t->cap) {
+    void* bufs[] = {t->in_pad, t->act1, t->act2, t->dact2, t->dact1, t->sq, t->act2_8, t->bits, t->pool_part};
+    for (void* b : bufs) cudaFree(b);
+    const size_t n = (size_t)B, pl = (size_t)g.npix * 16;
+    WW_CHECK(c, cudaMalloc((void**)&t->in_pad, n * g.npix_in * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t->act1, n * 4 * pl));
+    WW_CHECK(c, cudaMalloc((void**)&t->act2, n * 8 * pl));
+    WW_CHECK(c, cudaMalloc((void**)&t->act2_8, n * 4 * pl));
+    WW_CHECK(c, cudaMalloc((void**)&t->dact2, n * 8 * pl));
+    WW_CHECK(c, cudaMalloc((void**)&t->dact1, n * 4 * pl));
+    WW_CHECK(c, cudaMalloc((void**)&t->bits, n * g.T3 * 4 * 128 * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t->sq, n * 2 * 128 * 2));
+    WW_CHECK(c, cudaMalloc((void**)&t->pool_part, n * g.T3 * 128 * 4));
+    // padding of the input image and the plane slots no kernel writes stay zero
+    WW_CHECK(c, cudaMemset(t->in_pad, 0, n * g.npix_in * 4));
+    WW_CHECK(c, cudaMemset(t->dact2, 0, n * 8 * pl));
+    WW_CHECK(c, cudaMemset(t->dact1, 0, n * 4 * pl));
+    t->cap = B;
+  }
+  return WW_OK;
+}
+
+// weights changed (every optimiser step): data-gradient operand forms + the static scale bounds
+int ww_train_tc_prepare(ww_ctx* c) {
+  if (!c->train.tc) c->train.tc = new TcTrain();
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  const Geom g = make_geom(c);
+  int rc = ensure_tc(c, 0, g);
+  if (rc) return rc;
+  std::vector<float> w3((size_t)128 * 64 * 9), w2((size_t)64 * 32 * 9);
+  WW_CHECK(c, cudaMemcpy(w3.data(), c->w["conv3.weight"], w3.size() * 4, cudaMemcpyDeviceToHost));
+  WW_CHECK(c, cudaMemcpy(w2.data(), c->w["conv2.weight"], w2.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint16_t> s;
+  const float sc3 = weight_scale(w3), sc2 = weight_scale(w2);
+  pack_dgrad_weights(w3, 128, 64, sc3, s);
+  WW_CHECK(c, cudaMemcpy(t->wd3, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+  pack_dgrad_weights(w2, 64, 32, sc2, s);
+  WW_CHECK(c, cudaMemcpy(t->wd2, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+  t->k2 = l1_shift(w3, 128, 64);
+  t->k1 = l1_shift(w2, 64, 32);
+  t->mult3 = ldexpf(1.0f, -t->k2) / sc3;
+  t->mult2 = ldexpf(1.0f, -t->k1) / sc2;
+  t->sc3 = sc3; t->sc2 = sc2;
+  return WW_OK;
+}
+
+// forward of the conv stack in train mode: x [B][1][H][W] -> pooled [B][128]; keeps act1 / act2 planes and conv3's sign bits
+int ww_train_tc_forward(ww_ctx* c, const float* x, int B, float* pooled, cudaStream_t st) {
+  const Geom g = make_geom(c);
+  int rc = ensure_tc(c, B, g);
+  if (rc) return rc;
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  if ((rc = ww_launch_pad_logmel(c, x, t->in_pad, B, st))) return rc;
+  // the scoring kernels write into this call's buffers instead of the chunk workspace
+  __half* s_act2 = c->ws_act2_h; uint8_t* s_act2_8 = c->ws_act2_8; float* s_pool = c->pool_cur; const int s_np = c->n_pool_part;
+  c->ws_act2_h = t->act2; c->ws_act2_8 = t->act2_8; c->pool_cur = t->pool_part;
+  c->tc_act1_out = t->act1; c->tc_relu_bits = t->bits;
+  rc = ww_launch_conv12_tc(c, t->in_pad, B, g, st);
+  if (!rc) rc = ww_launch_conv3_tc(c, B, g, st);
+  c->ws_act2_h = s_act2; c->ws_act2_8 = s_act2_8; c->pool_cur = s_pool; c->n_pool_part = s_np;
+  c->tc_act1_out = nullptr; c->tc_relu_bits = nullptr;
+  if (rc) return rc;
+  pooled_mean_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(t->pool_part, pooled, B, g.T3, 1.0f / (float)(g.H * g.W));
+  WW_LAUNCH_CHECK(c);
+  return WW_OK;
+}
+
+// backward of the conv stack: dpooled [B][128] -> the six conv gradients
+int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3,
+                         float* gb3, cudaStream_t st) {
+  const Geom g = make_geom(c);
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  const float inv_hw = 1.0f / (float)(g.H * g.W);
+  const int grid = t->grid;
+  if (!t->conf) {
+    WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<64, true>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<64, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<32, false>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<128, 64, kDgradPass, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<128, 64>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<64, 32, kDgradPass, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<64, 32>(g)));
+    t->conf = true;
+  }
+  grad_scale_kernel<<<1, 1024, 0, st>>>(dpooled, B * 128, inv_hw, t->gs);
+  WW_LAUNCH_CHECK(c);
+  dy3_scalars_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(dpooled, t->gs, inv_hw, t->sq, B);
+  WW_LAUNCH_CHECK(c);
+  float* part3 = t->part;
+  float* part2 = t->part + (size_t)grid * 5 * (64 + 16) * 128;
+  // ---- conv3: weight + bias gradient (dY3 from bits x act2), data gradient -> dY2
+  {
+    WgradParams p{};
+    p.bits = t->bits; p.sq = t->sq; p.a_planes = nullptr; p.b_planes = t->act2; p.part = part3;
+    p.B = B; p.tsplit = 5; p.tl_cap = 5; p.g = g;
+    p.n0 = std::min(grid - 1, std::max(1, (grid * 5 + 4) / 9));
+    wgrad_kernel<128, 64, true><<<grid, WG_THREADS, wgrad_smem<64, true>(g), st>>>(p);
+    WW_LAUNCH_CHECK(c);
+    const int n = 128 * 64 * 9 + 128;
+    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part3, grid, p.n0, 5, 5, 64 + 16, 128, 64, t->gs, 1.0f / c->act2_scale, 1.0f,
+                                                         gw3, gb3);
+    WW_LAUNCH_CHECK(c);
+  }
+  const int n_items = (int)(((long long)B * g.T3 + g.G - 1) / g.G);
+  {
+    DgradParams p{};
+    p.bits = t->bits; p.sq = t->sq; p.a_planes = nullptr; p.wst = t->wd3; p.relu_planes = t->act2; p.out = t->dact2;
+    p.mult = t->mult3; p.B = B; p.g = g;
+    dgrad_kernel<128, 64, kDgradPass, true><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<128, 64>(g), st>>>(p);
+    WW_LAUNCH_CHECK(c);
+  }
+  // ---- conv2: weight + bias gradient (dY2 x act1), data gradient -> dY1
+  {
+    WgradParams p{};
+    p.a_planes = t->dact2; p.b_planes = t->act1; p.part = part2;
+    p.B = B; p.tsplit = 9; p.tl_cap = 9; p.n0 = grid; p.g = g;
+    wgrad_kernel<64, 32, false><<<grid, WG_THREADS, wgrad_smem<32, false>(g), st>>>(p);
+    WW_LAUNCH_CHECK(c);
+    const int n = 64 * 32 * 9 + 64;
+    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part2, grid, grid, 9, 9, 32 + 16, 64, 32, t->gs,
+                                                         ldexpf(1.0f, t->k2) / c->act1_scale, ldexpf(1.0f, t->k2), gw2, gb2);
+    WW_LAUNCH_CHECK(c);
+  }
+  {
+    DgradParams p{};
+    p.a_planes = t->dact2; p.wst = t->wd2; p.relu_planes = t->act1; p.out = t->dact1;
+    p.mult = t->mult2; p.B = B; p.g = g;
+    dgrad_kernel<64, 32, kDgradPass, false><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<64, 32>(g), st>>>(p);
+    WW_LAUNCH_CHECK(c);
+  }
+  // ---- conv1: weight + bias gradient (dY1 x input image)
+  {
+    const int g1 = grid * 8;
+    wgrad1_kernel<<<g1, W1_THREADS, 0, st>>>(t->dact1, t->in_pad, t->part1, B, g);
+    WW_LAUNCH_CHECK(c);
+    wgrad1_reduce_kernel<<<1, W1_OUT, 0, st>>>(t->part1, g1, t->gs, ldexpf(1.0f, t->k2 + t->k1), gw1, gb1);
+    WW_LAUNCH_CHECK(c);
+  }
+  return WW_OK;
+}
+
+// After an optimiser step (weights changed on the device): every operand form the next training step reads, rebuilt by
+// kernels on `st` with the scales of the last host-side preparation.
+int ww_train_tc_repack(ww_ctx* c, cudaStream_t st) {
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  if (!t || !c->d_w1_split || !c->d_w2_split || !c->d_w3_split) { c->set_error("ww_train_tc_repack: nothing prepared yet"); return WW_ERR_INVALID; }
+  repack_w1_kernel<<<3, 256, 0, st>>>(c->w["conv1.weight"], 1.0f / c->w1_inv_scale, reinterpret_cast<uint16_t*>(c->d_w1_split));
+  WW_LAUNCH_CHECK(c);
+  repack_w2_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], 1.0f / c->w2_inv_scale, reinterpret_cast<uint16_t*>(c->d_w2_split));
+  WW_LAUNCH_CHECK(c);
+  repack_w3_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], 1.0f / c->w3_inv_scale, c->act2_lo_shift,
+                                                               reinterpret_cast<unsigned char*>(c->d_w3_split));
+  WW_LAUNCH_CHECK(c);
+  repack_dgrad_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], 128, 64, t->sc3, reinterpret_cast<uint16_t*>(t->wd3));
+  WW_LAUNCH_CHECK(c);
+  repack_dgrad_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], 64, 32, t->sc2, reinterpret_cast<uint16_t*>(t->wd2));
+  WW_LAUNCH_CHECK(c);
+  const int H4 = 4 * c->cfg.hidden_size;
+  for (int l = 0; l < c->cfg.num_layers; ++l) {
+    const std::string s = std::to_string(l);
+    bias_sum_kernel<<<(H4 + 255) / 256, 256, 0, st>>>(c->w["lstm.bias_ih_l" + s], c->w["lstm.bias_hh_l" + s], c->d_bias_sum[l], H4);
+    WW_LAUNCH_CHECK(c);
+  }
+  if (!t->h_bias) WW_CHECK(c, cudaMallocHost((void**)&t->h_bias, 96 * sizeof(float)));
+  if (!t->bias_ev) WW_CHECK(c, cudaEventCreateWithFlags(&t->bias_ev, cudaEventDisableTiming));
+  WW_CHECK(c, cudaMemcpyAsync(t->h_bias, c->w["conv1.bias"], 32 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  WW_CHECK(c, cudaMemcpyAsync(t->h_bias + 32, c->w["conv2.bias"], 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  WW_CHECK(c, cudaEventRecord(t->bias_ev, st));
+  return WW_OK;
+}
+
+int ww_train_tc_sync_biases(ww_ctx* c) {
+  TcTrain* t = static_cast<TcTrain*>(c->train.tc);
+  if (!t || !t->bias_ev) { c->set_error("ww_train_tc_sync_biases: no pending repack"); return WW_ERR_INVALID; }
+  WW_CHECK(c, cudaEventSynchronize(t->bias_ev));
+  c->h_b1.assign(t->h_bias, t->h_bias + 32);
+  c->h_b2.assign(t->h_bias + 32, t->h_bias + 96);
+  return WW_OK;
+}
