@@ -298,16 +298,22 @@ def measure_train(ww, dev, rank, world, steps, warmup, barrier, max_over_ranks, 
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool(torch.equal(lo, hi))
     flop = 1.419e9 * B
+    # which backward kernels ran: the tensor-core ones (train_tc.cu) unless WW_TRAIN_KERNEL=fp32 / an fp32 context
+    kern = "fp32" if os.environ.get("WW_TRAIN_KERNEL", "tc").startswith("f") else "tcgen05"
+    train_dtype = "f32" if kern == "fp32" else "f16 hi+lo split products, f32 accumulate (weights, Adam, head: f32)"
+    note = ("exact fp32 on CUDA cores (conv_fp32.cu)" if kern == "fp32" else
+            "conv stack forward + weight / data gradients on tcgen05 (train_tc.cu); FLOP = 1.419 GFLOP per clip of useful work")
     return {"metric": "clips_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "clips/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": train_dtype, "data": "synthetic",
             "config": {"workload": "config5: CNN+LSTM training step (fwd+bwd+Adam), on-GPU features",
+                       "backward_kernels": kern,
                        "clips_per_gpu": B, "allreduce": "nccl sum of the flat fp32 gradient buffer" if world > 1 else "none",
                        "loss": float(loss.item()), "replicas_in_sync": in_sync},
             "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "note": "fp32 on CUDA cores (exact); tcgen05 dgrad/wgrad is not built yet"}}
+                         "note": note}}
 
 
 def measure_stream(ww, dev, rank, world, steps, warmup, barrier, max_over_ranks, conv_mode):

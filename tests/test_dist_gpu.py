@@ -112,11 +112,15 @@ def _worker(rank, world, port, uid_path, out_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_data_parallel_training_step_two_ranks(tmp_path):
+@pytest.mark.parametrize("kernel", ["fp32", "tc"])
+def test_data_parallel_training_step_two_ranks(tmp_path, monkeypatch, kernel):
     import torch.multiprocessing as mp
+    monkeypatch.setenv("WW_TRAIN_KERNEL", kernel)          # inherited by the spawned ranks
     out = str(tmp_path / "res.npy")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path / "uid"), out), nprocs=2, join=True)
     c_vs_py, dp_vs_full, equal = np.load(out)
     assert equal == 1.0                      # both replicas hold the same weights after the all-reduced steps
     assert c_vs_py < 1e-7                    # ww_train_step(nccl_comm) == backward + torch all-reduce + apply
-    assert dp_vs_full < 2e-6                 # two half batches averaged == one full batch (fp32 summation order only)
+    # two half batches averaged == one full batch: fp32 summation order only for the exact kernels; the tensor-core kernels
+    # scale their fp16 operands per batch (train_tc.cu), so the half-batch and full-batch roundings differ (2 steps at lr 1e-3)
+    assert dp_vs_full < (2e-6 if kernel == "fp32" else 2e-4)

@@ -89,19 +89,31 @@ def test_tensor_core_gradients_vs_float64_autograd(ww, B):
 
 
 def test_tensor_core_and_fp32_kernels_agree(ww):
-    """Same inputs through both backward kernels of the library: the tensor-core result sits inside the same band."""
+    """Same batch through both backward kernels of the library.  A batch gradient is a sum of per-clip gradients of both
+    signs, so the yardstick is the un-cancelled magnitude: the mean over the clips of max |per-clip gradient| (each clip run
+    alone through the exact kernels)."""
     sd = R.seeded_state_dict(256, seed=5)
-    x, y = _batch(33, 7)
+    B = 12
+    x, y = _batch(B, 7)
     out = {}
     for kern in ("fp32", "tc"):
         with _env(WW_TRAIN_KERNEL=kern):
             net, tr = _trainer(ww, sd)
             loss, _ = tr.train_step(x, y)
             out[kern] = (loss.item(), {k: v.cpu().numpy().copy() for k, v in tr.gradients(net.engine()).items()})
+    scale = {k: 0.0 for k in out["fp32"][1]}
+    with _env(WW_TRAIN_KERNEL="fp32"):
+        net, tr = _trainer(ww, sd)
+        for b in range(B):
+            tr.train_step(x[b:b + 1], y[b:b + 1])
+            for k, v in tr.gradients(net.engine()).items():
+                scale[k] += float(v.abs().max().item()) / B
+            net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     assert abs(out["tc"][0] - out["fp32"][0]) < 1e-5 * abs(out["fp32"][0])
     for name, r in out["fp32"][1].items():
-        if np.abs(r).max() > 0.0:
-            assert _rel(out["tc"][1][name], r) < (CONV_TOL if name.startswith("conv") else HEAD_TOL), name
+        if scale[name] > 0.0:
+            err = float(np.abs(out["tc"][1][name] - r).max()) / scale[name]
+            assert err < (CONV_TOL if name.startswith("conv") else HEAD_TOL), (name, err)
 
 
 def test_device_side_repack_equals_host_side_preparation(ww):
@@ -124,19 +136,23 @@ def test_device_side_repack_equals_host_side_preparation(ww):
 
 
 def test_training_with_tensor_core_kernels_learns(ww):
-    """A separable toy problem: 30 steps bring the loss down like the exact kernels do."""
+    """A separable toy problem at lr = 1e-3 (ten times the reference's default): the loss collapses with both backward
+    kernels, at the same step within a few.  (tests/probes/train_curve_probe3.py: five seeds, both kernels; at lr = 3e-3 the
+    tensor-core curves jitter more on the way down and end at the same loss.)"""
     sd = R.seeded_state_dict(64, seed=3)
     rng = np.random.default_rng(0)
     y_np = rng.integers(0, 2, 64)
     x_np = (rng.standard_normal((64, 1, 80, 32)) * 5 - 40).astype(np.float32)
     x_np[y_np == 1, :, 20:40, :] += 25.0
     x, y = torch.from_numpy(x_np).cuda(), torch.from_numpy(y_np.astype(np.int64)).cuda()
-    final = {}
+    curves = {}
     for kern in ("fp32", "tc"):
         with _env(WW_TRAIN_KERNEL=kern):
             net, tr = _trainer(ww, sd, hidden=64)
-            for _ in range(30):
-                loss, _ = tr.train_step(x, y)
-            final[kern] = loss.item()
-    print("loss after 30 steps", final)
-    assert final["tc"] < 0.45 and abs(final["tc"] - final["fp32"]) < 0.05 * max(final["fp32"], 0.05), final
+            tr.lr = 1e-3
+            curves[kern] = np.array([tr.train_step(x, y)[0].item() for _ in range(80)])
+    first = {k: int(np.argmax(v < 0.1)) for k, v in curves.items()}
+    print("first step below 0.1:", first, "final:", {k: float(v[-1]) for k, v in curves.items()})
+    assert all((v < 0.1).any() for v in curves.values()), first
+    assert abs(first["tc"] - first["fp32"]) <= 8, first
+    assert curves["tc"][-1] < 0.05 and curves["fp32"][-1] < 0.05

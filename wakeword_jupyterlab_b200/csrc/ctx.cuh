@@ -68,6 +68,7 @@ struct TrainState {
   uint64_t tc_version = 0;          // weights_version its operand forms were built from
   bool tc_last = false, fast_pending = false;   // last backward ran the tensor-core kernels; last apply rebuilt their forms on the device
   int fast_steps = 0;               // device-side rebuilds since the last host-side preparation
+  float fast_drift = 0.0f, fast_room = 0.0f;    // bound on how far a weight has moved since then / how far it may (half the smallest layer maximum)
   int cap = 0, cap32 = 0;           // clips the head buffers / the fp32 conv activations are sized for
   float *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *dact2 = nullptr, *dact1 = nullptr;
   float *pooled = nullptr, *dpooled = nullptr, *gates = nullptr, *hbuf = nullptr, *dh = nullptr;

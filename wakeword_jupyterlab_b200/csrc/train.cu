@@ -393,6 +393,7 @@ int ww_train_backward(ww_ctx* c, const float* x, const int64_t* labels, int B, c
       if ((rc = ww_train_tc_prepare(c))) return rc;
       t.tc_version = c->weights_version;
       t.fast_steps = 0;
+      t.fast_drift = 0.0f;
     }
   }
   t.tc_last = tc;
@@ -501,11 +502,14 @@ int ww_train_apply(ww_ctx* c, float lr, float beta1, float beta2, float eps, flo
   c->weights_version++;
   c->weights_dirty = true;      // prepared (transposed / split) forms are rebuilt at the next forward
   // training loop on the tensor-core kernels: rebuild the forms the NEXT step reads right here, on the device, with the
-  // power-of-two scales of the last host-side preparation (a full preparation is redone every kFastSteps steps, long before
-  // the weights can drift out of the scales' 8x headroom)
+  // power-of-two scales of the last host-side preparation.  Those leave 8x headroom above the largest weight of a layer; a
+  // full preparation is redone every kFastSteps steps, or earlier when the steps taken since (Adam moves a weight by at
+  // most ~4 lr per step) could have grown the smallest layer maximum by half.
   t.fast_pending = false;
+  t.fast_drift += 4.0f * fabsf(lr);
   const char* fast_env = getenv("WW_TRAIN_FAST");       // WW_TRAIN_FAST=0: host-side preparation every step (A/B, tests)
-  if (t.tc_last && t.tc_version + 1 == c->weights_version && t.fast_steps < kFastSteps && !(fast_env && fast_env[0] == '0')) {
+  if (t.tc_last && t.tc_version + 1 == c->weights_version && t.fast_steps < kFastSteps && t.fast_drift < t.fast_room &&
+      !(fast_env && fast_env[0] == '0')) {
     if ((rc = ww_train_tc_repack(c, st))) return rc;
     t.tc_version = c->weights_version;
     t.fast_steps++;

@@ -75,16 +75,39 @@ __global__ void __launch_bounds__(1024) grad_scale_kernel(const float* __restric
   }
 }
 
-// sq[b][0][c] = fp16(s), sq[b][1][c] = fp16(s - hi), s = dpooled[b][c] / HW * gs[0]
+// Per (clip, channel) constant of dY3, s = dpooled[b][c] / HW * gs[0], as fp16 operands:
+//   sq[b][0][c] = round-to-nearest(s)                      (data gradient)
+//   sq[b][1][c], sq[b][2][c] = s rounded down / up, pat[b][c] = 32-slot pattern with round(32 f) bits set evenly,
+//   f = (s - down) / (up - down)                            (weight gradient: slot r of a block takes `up` where its
+//   pattern bit is set, so the value averaged over the ~1,300 active pixels of a channel is s to 2^-17 instead of 2^-12 -
+//   the rounding error of a constant would otherwise be the same at every pixel and survive the sum)
 __global__ void dy3_scalars_kernel(const float* __restrict__ dpooled, const float* __restrict__ gs, float inv_hw,
-                                   __half* __restrict__ sq, int B) {
+                                   __half* __restrict__ sq, uint32_t* __restrict__ pat, int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 128) return;
   const int b = i >> 7, ch = i & 127;
   const float s = dpooled[i] * inv_hw * gs[0];
-  const __half hi = __float2half_rn(s);
-  sq[((size_t)b * 2) * 128 + ch] = hi;
-  sq[((size_t)b * 2 + 1) * 128 + ch] = __float2half_rn(s - __half2float(hi));
+  const __half dn = __float2half_rd(s), up = __float2half_ru(s);
+  sq[((size_t)b * 3) * 128 + ch] = __float2half_rn(s);
+  sq[((size_t)b * 3 + 1) * 128 + ch] = dn;
+  sq[((size_t)b * 3 + 2) * 128 + ch] = up;
+  const float fd = __half2float(dn), fu = __half2float(up);
+  const int k = fu > fd ? (int)rintf(32.0f * (s - fd) / (fu - fd)) : 0;
+  uint32_t w = 0u;
+  for (int r = 0; r < 32; ++r)
+    if (((r * k) & 31) < k) w |= 1u << r;
+  pat[i] = w;
+}
+
+// one plane row (8 fp16): channel j takes up[j] where its pattern word has bit `shp` set, else dn[j]; zero where its sign
+// word has bit `shm` clear
+__device__ __forceinline__ uint4 select8_dither(const uint4 dn, const uint4 up, const uint4 p0, const uint4 p1, const uint4 w0,
+                                                const uint4 w1, int shp, int shm) {
+  auto pair = [](uint32_t a, uint32_t b, int sh) { return ((0u - ((a >> sh) & 1u)) & 0xffffu) | ((0u - ((b >> sh) & 1u)) & 0xffff0000u); };
+  const uint32_t pm0 = pair(p0.x, p0.y, shp), pm1 = pair(p0.z, p0.w, shp), pm2 = pair(p1.x, p1.y, shp), pm3 = pair(p1.z, p1.w, shp);
+  const uint32_t mm0 = pair(w0.x, w0.y, shm), mm1 = pair(w0.z, w0.w, shm), mm2 = pair(w1.x, w1.y, shm), mm3 = pair(w1.z, w1.w, shm);
+  return make_uint4(((dn.x & ~pm0) | (up.x & pm0)) & mm0, ((dn.y & ~pm1) | (up.y & pm1)) & mm1,
+                    ((dn.z & ~pm2) | (up.z & pm2)) & mm2, ((dn.w & ~pm3) | (up.w & pm3)) & mm3);
 }
 
 // 8 fp16 values (one plane row) kept where the bit of their channel's word is set at position `sh`
@@ -98,11 +121,16 @@ __device__ __forceinline__ uint4 select8(const uint4 v, const uint4 w0, const ui
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight gradient
-constexpr int WG_THREADS = 320;     // warp 0 loader, warp 1 MMA issuer, warps 2-9 dY3 tile builders; warps 2-5 drain TMEM at the end
+constexpr int WG_THREADS = 320;     // warp 0 loader, warp 1 MMA issuer, warps 2-9 operand builders; warps 2-5 drain TMEM at the end
 
-struct WgradParams {
+// Form 1 (conv3: the dY3 tile built from sign bits, hi + lo copies): one instruction per (tap, copy), the tap a start-address
+// offset of the bulk-loaded X window; 128 dY slots per stage.  576 accumulator columns > 512: CTAs of type 0 take taps 0-4,
+// type 1 taps 5-8, in the ratio 5 : 4.  (Form 2 below issues a third of the instructions, but its extra shared-memory
+// copies and shorter stages lose against this form when the tile builders already write 64 KB per stage: 5.9 vs 2.65 ms.)
+struct WgradTapParams {
   const uint32_t* bits;     // A_BITS: [B][T3][4][128] sign bits of conv3's output (conv3_tc.cu)
-  const __half* sq;         // A_BITS: [B][2][128] fp16 hi / lo of dpooled / HW * 2^k
+  const __half* sq;         // A_BITS: [B][3][128] fp16 nearest / down / up of dpooled / HW * 2^k (dy3_scalars_kernel)
+  const uint32_t* pat;      // A_BITS: [B][128] dither patterns
   const __half* a_planes;   // !A_BITS: dY planes [B][MCH/8][npix][8]
   const __half* b_planes;   // X planes [B][NCH/8][npix][8]
   float* part;              // [grid][tl_cap][NCH + 16][128] fp32 partial sums (lane = co)
@@ -113,10 +141,10 @@ struct WgradParams {
 // Work unit = (clip b, tile t): the 128 dY slots P + 1 + 128 t .. (= conv3's output tile t) and the X window of
 // 128 + 2 P + 2 slots from slot 128 t: 8 K-steps of 16 pixels per tap.
 template <int MCH, int NCH, bool A_BITS>
-__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
-  constexpr int NA = A_BITS ? 2 : 1;                       // dY operand copies (hi, lo)
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTapParams p) {
+  constexpr int NA = 1;                                    // one dY operand copy (the conv3 constants are dithered, see dy3_scalars_kernel)
   constexpr int MP = MCH / 8, NP = NCH / 8, NPB = NP + 2, NS = NCH + 16;
-  constexpr int NSTG = A_BITS ? 2 : 3;
+  constexpr int NSTG = 3;
   constexpr uint32_t A_BYTES = NA * 16 * 2048;             // always 16 planes per copy (M = 128); MCH = 64: the upper 8 stay zero
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
@@ -220,15 +248,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * w + cc;
-        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2) * 128 + 8 * c));
-        const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2 + 1) * 128 + 8 * c));
+        const uint4 dnq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 3 + 1) * 128 + 8 * c));
+        const uint4 upq = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 3 + 2) * 128 + 8 * c));
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(p.pat + (size_t)b * 128 + 8 * c));
+        const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(p.pat + (size_t)b * 128 + 8 * c) + 1);
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) {
           const uint4* wp = reinterpret_cast<const uint4*>(p.bits + (((size_t)b * g.T3 + t) * 4 + blk) * 128 + 8 * c);
           const uint4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-          unsigned char* dst = ast + c * 2048 + (blk * 32 + lane) * 16;
-          *reinterpret_cast<uint4*>(dst) = select8(hq, w0, w1, lane);
-          *reinterpret_cast<uint4*>(dst + 16 * 2048) = select8(lq, w0, w1, lane);
+          // the pattern is rotated from block to block (and the image pitch P = W + 1 slides it across the frames)
+          *reinterpret_cast<uint4*>(ast + c * 2048 + (blk * 32 + lane) * 16) =
+              select8_dither(dnq, upq, p0, p1, w0, w1, (lane + 7 * (4 * t + blk)) & 31, lane);
         }
       }
       fence_proxy_async();
@@ -257,7 +287,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
 }
 
 // gw[co][ci][tap] = wfac * gs[1] * sum_cta part, gb[co] = bfac * gs[1] * sum_cta (column NCH of the centre tap); fixed order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int grid, int n0, int tsplit, int tl_cap, int NS, int MCH,
+__global__ void wgrad_tap_reduce_kernel(const float* __restrict__ part, int grid, int n0, int tsplit, int tl_cap, int NS, int MCH,
                                     int NCH, const float* __restrict__ gs, float wfac, float bfac, float* __restrict__ gw,
                                     float* __restrict__ gb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,6 +303,178 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int grid, in
   else gb[co] = s * bfac * gs[1];
 }
 
+// Form 2 (conv2: both operands exist as planes in HBM)
+struct WgradParams {
+  const __half* a_planes;   // dY planes [B][MCH/8][npix][8]
+  const __half* b_planes;   // X planes [B][NCH/8][npix][8]
+  float* part;              // [grid][3][3 NCH + 16][128] fp32 partial sums (lane = co)
+  int B, n0, ky_split;      // CTAs [0, n0) take tap rows [0, ky_split), the others [ky_split, 3)
+  Geom g;
+};
+
+// An M = 128 instruction costs 64 cycles whatever its N <= 128, so the three taps of a tap row are ONE instruction:
+// the X window sits in shared memory three times, copy kx shifted by kx slots (made by the builder warps from the
+// bulk-loaded copy 0), the copies stacked along N: D[co, (kx, ci)] += dY[co, 16 slots] * [X_0 ; X_1 ; X_2], with the tap row
+// ky a start-address offset of ky * P slots common to the copies.  Two constant planes after copy 2 (channel 0 = 1) give the
+// bias gradient as column 3 NCH of tap row 1.  Work unit = KSL dY slots of one clip (from slot P + 1 + KSL v, v = unit of the
+// clip) and the X window of KSL + 2 P + 2 slots from slot KSL v.
+template <int MCH, int NCH>
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
+  constexpr int MP = MCH / 8, NP = NCH / 8, NPB = 3 * NP + 2, NS = 3 * NCH + 16;
+  constexpr int KSL = 128, KST = KSL / 16;
+  constexpr int NSTG = 2;
+  constexpr uint32_t APL = KSL * 16;                       // one dY plane of a stage
+  constexpr uint32_t A_BYTES = 16 * APL;              // always 16 planes per copy (M = 128); MCH = 64: the upper 8 stay zero
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geom g = p.g;
+  const uint32_t bsl = (uint32_t)(KSL + 2 * g.P + 2);
+  const uint32_t bpl = bsl * 16u;
+  const uint32_t stage_bytes = A_BYTES + NPB * bpl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((NSTG * stage_bytes + 127u) & ~127u));
+  uint64_t* full = bars;              // [NSTG] bulk copies landed
+  uint64_t* afull = bars + 4;         // [NSTG] builder warps done (shifted X copies)
+  uint64_t* empty = bars + 8;         // [NSTG] MMAs of the stage retired
+  uint64_t* done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NSTG; ++i) { mbar_init(full + i, 1); mbar_init(afull + i, 8); mbar_init(empty + i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  // zero everything once (unused dY planes, the all-zero pad plane), and write the ones plane: channel 0 = 1.0 at every slot
+  for (uint32_t i = tid * 16u; i < NSTG * stage_bytes; i += WG_THREADS * 16u) {
+    const uint32_t off = i % stage_bytes;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (off >= A_BYTES + 3 * NP * bpl && off < A_BYTES + (3 * NP + 1) * bpl) v.x = 0x3c00u;
+    *reinterpret_cast<uint4*>(smem + i) = v;
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int upc = 128 * g.T3 / KSL;                         // units per clip
+  const int n_units = p.B * upc;
+  int j, nj, ky_lo, ky_hi;
+  if ((int)blockIdx.x < p.n0) { j = blockIdx.x; nj = p.n0; ky_lo = 0; ky_hi = p.ky_split; }
+  else { j = blockIdx.x - p.n0; nj = gridDim.x - p.n0; ky_lo = p.ky_split; ky_hi = 3; }
+  const int u_lo = (int)((long long)n_units * j / nj), u_hi = (int)((long long)n_units * (j + 1) / nj);
+
+  if (warp == 0) {
+    // ===================== loader (one thread): X window (copy 0) and, when they exist in HBM, the dY planes
+    if (lane == 0) {
+      int it = 0;
+      for (int u = u_lo; u < u_hi; ++u, ++it) {
+        const int st = it % NSTG;
+        mbar_wait(empty + st, ((it / NSTG) & 1) ^ 1, 70);
+        const int b = u / upc, v = u - b * upc;
+        unsigned char* sb = smem + st * stage_bytes;
+        mbar_arrive_expect_tx(full + st, NP * bpl + (uint32_t)MP * APL);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl)
+          bulk_g2s(sb + A_BYTES + pl * bpl, p.b_planes + (((size_t)b * NP + pl) * g.npix + (size_t)KSL * v) * 8, bpl, full + st);
+#pragma unroll
+        for (int pl = 0; pl < MP; ++pl)
+          bulk_g2s(sb + pl * APL, p.a_planes + (((size_t)b * MP + pl) * g.npix + (size_t)(g.P + 1 + KSL * v)) * 8, APL, full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    const uint32_t idN = make_idesc(128, 3 * NCH) | kAMn | kBMn, idC = make_idesc(128, 3 * NCH + 16) | kAMn | kBMn;
+    const uint64_t a0 = make_desc(smem_u32(smem), 128, APL);                 // MN-major: LBO = 8-slot group, SBO = plane
+    const uint64_t b0 = make_desc(smem_u32(smem) + A_BYTES, 128, bpl);
+    int it = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++it) {
+      const int st = it % NSTG;
+      const uint32_t par = (it / NSTG) & 1;
+      mbar_wait(full + st, par, 71);
+      mbar_wait(afull + st, par, 72);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t as = a0 + (uint64_t)((st * stage_bytes) >> 4), bs = b0 + (uint64_t)((st * stage_bytes) >> 4);
+#pragma unroll 1
+        for (int ks = 0; ks < KST; ++ks) {
+#pragma unroll 1
+          for (int ky = ky_lo; ky < ky_hi; ++ky) {
+            const uint32_t off = (uint32_t)(ky * g.P + ks * 16);
+            const uint32_t d = tmem_base + (uint32_t)(ky - ky_lo) * NS;
+            const uint32_t id = ky == 1 ? idC : idN;
+            umma_f16(d, as + (uint64_t)(ks * 16), bs + (uint64_t)off, id, (it | ks) != 0);
+          }
+        }
+        umma_commit(empty + st);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  } else {
+    // ===================== operand builders (8 warps): the shifted copies 1 and 2 of the X window
+    const int bt = tid - 64;
+    int it = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++it) {
+      const int st = it % NSTG;
+      const uint32_t par = (it / NSTG) & 1;
+      unsigned char* ast = smem + st * stage_bytes;
+      mbar_wait(full + st, par, 75);
+      unsigned char* bst = ast + A_BYTES;
+      {
+        // plane pl of copy 0 -> the same plane of copies 1 and 2, one and two slots earlier (256 / NP threads per plane)
+        constexpr uint32_t TPP = 256 / NP;
+        const uint32_t pl = (uint32_t)bt / TPP;
+        unsigned char* src = bst + pl * bpl;
+        for (uint32_t i = (uint32_t)bt % TPP + 1; i < bsl; i += TPP) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + i * 16u);
+          *reinterpret_cast<uint4*>(src + (size_t)NP * bpl + (i - 1) * 16u) = v;
+          if (i >= 2) *reinterpret_cast<uint4*>(src + (size_t)2 * NP * bpl + (i - 2) * 16u) = v;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(afull + st, lane);
+    }
+  }
+  if (warp >= 2 && warp < 6) {
+    // ===================== final drain: lane = output channel, columns = (tap row, kx, ci)
+    mbar_wait_relaxed(done, 0, 74);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* dst = p.part + (size_t)blockIdx.x * 3 * NS * 128 + q * 32 + lane;
+    const bool any = u_hi > u_lo;
+    for (int kl = 0; kl < ky_hi - ky_lo; ++kl)
+      for (int n0 = 0; n0 < NS; n0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + kl * NS + n0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[((size_t)kl * NS + n0 + k) * 128] = any ? __uint_as_float(r[k]) : 0.0f;
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// gw[co][ci][tap] = wfac * gs[1] * sum_cta part, gb[co] = bfac * gs[1] * sum_cta (column 3 NCH of tap row 1); fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int grid, int n0, int ky_split, int MCH, int NCH,
+                                    const float* __restrict__ gs, float wfac, float bfac, float* __restrict__ gw,
+                                    float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = MCH * NCH * 9, NS = 3 * NCH + 16;
+  if (i >= nw + MCH) return;
+  int co, col, ky, tap = 4;
+  if (i < nw) { co = i % MCH; const int r = i / MCH; const int ci = r % NCH; tap = r / NCH; ky = tap / 3; col = (tap - 3 * ky) * NCH + ci; }
+  else { co = i - nw; ky = 1; col = 3 * NCH; }
+  const int c_lo = ky < ky_split ? 0 : n0, c_hi = ky < ky_split ? n0 : grid, kl = ky < ky_split ? ky : ky - ky_split;
+  float s = 0.0f;
+  for (int c = c_lo; c < c_hi; ++c) s += part[(((size_t)c * 3 + kl) * NS + col) * 128 + co];
+  if (i < nw) gw[((size_t)co * NCH + (col % NCH)) * 9 + tap] = s * wfac * gs[1];
+  else gb[co] = s * bfac * gs[1];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // data gradient
 constexpr int DG_THREADS = 14 * 32;   // warp 0 loader, warp 1 MMA issuer, warps 2-9 epilogue, warps 10-13 dY3 plane builders
@@ -280,7 +482,7 @@ constexpr int DG_NSTW = 4;            // weight ring stages
 
 struct DgradParams {
   const uint32_t* bits;          // A_BITS: sign bits of conv3's output
-  const __half* sq;              // A_BITS: [B][2][128] (hi used)
+  const __half* sq;              // A_BITS: [B][3][128] (round-to-nearest row used)
   const __half* a_planes;        // !A_BITS: dY planes [B][KCH/8][npix][8]
   const unsigned char* wst;      // weight stages [pair q][tap row tt]: [tl 3][kc 4][n' NT][8 fp16]
   const __half* relu_planes;     // forward activation planes of the layer below [B][NOUT/8][npix][8]: ReLU derivative
@@ -477,9 +679,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_kernel(const DgradParams 
           const uint4* wp = reinterpret_cast<const uint4*>(p.bits + (size_t)wi * 128 + 8 * c);
           x0 = __ldg(wp); x1 = __ldg(wp + 1);
         }
-        const uint4 hq0 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 2) * 128 + 8 * c));
+        const uint4 hq0 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)b * 3) * 128 + 8 * c));
         uint4 hq1 = make_uint4(0u, 0u, 0u, 0u);
-        if (b + 1 < p.B) hq1 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)(b + 1) * 2) * 128 + 8 * c));
+        if (b + 1 < p.B) hq1 = __ldg(reinterpret_cast<const uint4*>(p.sq + ((size_t)(b + 1) * 3) * 128 + 8 * c));
         mbar_wait(a_empty + ab, ((f >> 1) & 1) ^ 1, 83);
         unsigned char* dst = a_s + ab * abuf + w * plane_bytes;
         for (int k = 0; k * 32 < g.nsl3; ++k) {
@@ -577,7 +779,11 @@ __global__ void wgrad1_reduce_kernel(const float* __restrict__ part, int grid, c
   else gb[co] = s;
 }
 
-constexpr int kDgradPass = 2;      // fp16 hi + lo weights in the data gradients (stacked along N)
+// Weight operand of the data gradients: fp16 hi only (1) or hi | lo stacked along N (2).  An M = 128 instruction costs 64
+// cycles for any N <= 128, so conv2's lo half (N = 64) is free; conv3's (N = 128) would fill all 512 TMEM columns with one
+// item's accumulators and serialise the epilogue with the next item's instructions.  The weight rounding it would remove
+// (2^-12 per weight, 1,152 weights per sum: ~1e-5) is far below the ReLU-branch noise of the activations (~1e-3).
+constexpr int kPass3 = 1, kPass2 = 2;
 
 // ---------------------------------------------------------------------------------------------------------------
 // operand forms rebuilt on the device after an optimiser step (same element formulas as the host-side preparations in
@@ -617,16 +823,16 @@ __global__ void repack_w3_kernel(const float* __restrict__ w, float sc, int lo_s
   stg[(size_t)2 * C3_PART_BYTES + (((size_t)tl * 2 + (c32 >> 4)) * 128 + n) * 16 + (c32 & 15)] =
       (unsigned char)__nv_cvt_float_to_fp8(ldexpf(v - d_h2f(hi), lo_shift), __NV_SATFINITE, __NV_E4M3);
 }
-__global__ void repack_dgrad_kernel(const float* __restrict__ w, int COUT, int CIN, float sc, uint16_t* __restrict__ s) {
+__global__ void repack_dgrad_kernel(const float* __restrict__ w, int COUT, int CIN, int npass, float sc, uint16_t* __restrict__ s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= COUT * CIN * 9) return;
   const int co = i / (CIN * 9), r = i - co * CIN * 9, n = r / 9, tap = r - n * 9;
-  const int tt = 2 - tap / 3, tl = 2 - tap % 3, q = co >> 5, kc = (co & 31) >> 3, e = co & 7, NT = CIN * kDgradPass;
+  const int tt = 2 - tap / 3, tl = 2 - tap % 3, q = co >> 5, kc = (co & 31) >> 3, e = co & 7, NT = CIN * npass;
   const float v = w[i] * sc;
   const uint16_t hi = d_f2h(v);
   const size_t base = ((((size_t)(q * 3 + tt) * 3 + tl) * 4 + kc) * NT) * 8;
   s[base + (size_t)n * 8 + e] = hi;
-  if (kDgradPass == 2) s[base + (size_t)(CIN + n) * 8 + e] = d_f2h(v - d_h2f(hi));
+  if (npass == 2) s[base + (size_t)(CIN + n) * 8 + e] = d_f2h(v - d_h2f(hi));
 }
 __global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -640,7 +846,7 @@ struct TcTrain {
   float* in_pad = nullptr;
   __half *act1 = nullptr, *act2 = nullptr, *dact2 = nullptr, *dact1 = nullptr, *sq = nullptr;
   uint8_t* act2_8 = nullptr;
-  uint32_t* bits = nullptr;
+  uint32_t *bits = nullptr, *pat = nullptr;
   float *pool_part = nullptr, *gs = nullptr, *part = nullptr, *part1 = nullptr;
   unsigned char *wd3 = nullptr, *wd2 = nullptr;       // data-gradient weight stages
   float mult3 = 1.0f, mult2 = 1.0f;                   // dgrad epilogue multipliers
@@ -653,20 +859,25 @@ struct TcTrain {
 };
 
 
-template <int KCH, int NOUT>
+template <int NT>
 size_t dgrad_smem(const Geom& g) {
-  return (size_t)2 * 4 * g.nsl3 * 16 + (size_t)DG_NSTW * dg_wstage_bytes<NOUT * kDgradPass>() + 32 * 8 + 64;
+  return (size_t)2 * 4 * g.nsl3 * 16 + (size_t)DG_NSTW * dg_wstage_bytes<NT>() + 32 * 8 + 64;
 }
 template <int NCH, bool A_BITS>
-size_t wgrad_smem(const Geom& g) {
+size_t wgrad_tap_smem(const Geom& g) {
   const size_t bsl = (size_t)((128 + 2 * g.P + 2 + 7) & ~7);
-  return (size_t)(A_BITS ? 2 : 3) * ((A_BITS ? 2 : 1) * 16 * 2048 + (NCH / 8 + 2) * bsl * 16) + 32 * 8 + 64;
+  return (size_t)3 * (16 * 2048 + (NCH / 8 + 2) * bsl * 16) + 32 * 8 + 64;
+}
+template <int NCH>
+size_t wgrad_smem(const Geom& g) {
+  const size_t ksl = 128, bsl = ksl + 2 * g.P + 2;
+  return (size_t)2 * (16 * ksl * 16 + (3 * NCH / 8 + 2) * bsl * 16) + 128 + 32 * 8 + 64;
 }
 
 // flipped / transposed weights of a data gradient as fp16 hi | lo stacked along N, in stage order [q][tt][tl][kc][n'][8]:
 // k channel = forward output channel, n = forward input channel, tap (tt, tl) <-> forward tap (2 - tt, 2 - tl)
-void pack_dgrad_weights(const std::vector<float>& w, int COUT, int CIN, float sc, std::vector<uint16_t>& s) {
-  const int NT = CIN * kDgradPass, NQ = COUT / 32;
+void pack_dgrad_weights(const std::vector<float>& w, int COUT, int CIN, int npass, float sc, std::vector<uint16_t>& s) {
+  const int NT = CIN * npass, NQ = COUT / 32;
   s.assign((size_t)NQ * 3 * 3 * 4 * NT * 8, 0);
   for (int q = 0; q < NQ; ++q)
     for (int tt = 0; tt < 3; ++tt)
@@ -679,7 +890,7 @@ void pack_dgrad_weights(const std::vector<float>& w, int COUT, int CIN, float sc
               const uint16_t hi = f2h(v);
               const size_t base = ((((size_t)(q * 3 + tt) * 3 + tl) * 4 + kc) * NT) * 8;
               s[base + (size_t)n * 8 + e] = hi;
-              if (kDgradPass == 2) s[base + (size_t)(CIN + n) * 8 + e] = f2h(v - h2f(hi));
+              if (npass == 2) s[base + (size_t)(CIN + n) * 8 + e] = f2h(v - h2f(hi));
             }
 }
 
@@ -707,14 +918,14 @@ bool ww_train_tc_supported(const ww_ctx* c) {
   if (g.G < 1 || 2 * g.P + 2 + 128 > 4096) return false;
   if (128 + 2 * g.P + 2 > 128 + 2 * 40 + 4) return false;                  // wgrad1_kernel's x window
   if ((g.nsl3 + 31) / 32 + 1 > 32) return false;                           // dgrad_kernel's bit window: one word per lane
-  return dgrad_smem<128, 64>(g) <= 227 * 1024 && wgrad_smem<64, true>(g) <= 227 * 1024 && conv3_smem_bytes(g.nsl3, g.nst3) <= 227 * 1024;
+  return dgrad_smem<64 * kPass3>(g) <= 227 * 1024 && wgrad_tap_smem<64, true>(g) <= 227 * 1024 && conv3_smem_bytes(g.nsl3, g.nst3) <= 227 * 1024;
 }
 
 void ww_train_tc_free(ww_ctx* c) {
   TcTrain* t = static_cast<TcTrain*>(c->train.tc);
   if (!t) return;
   void* bufs[] = {t->in_pad, t->act1, t->act2, t->dact2, t->dact1, t->sq, t->act2_8, t->bits, t->pool_part, t->gs, t->part, t->part1,
-                  t->wd3, t->wd2};
+                  t->wd3, t->wd2, t->pat};
   for (void* b : bufs) cudaFree(b);
   if (t->h_bias) cudaFreeHost(t->h_bias);
   if (t->bias_ev) cudaEventDestroy(t->bias_ev);
@@ -728,13 +939,13 @@ static int ensure_tc(ww_ctx* c, int B, const Geom& g) {
   if (!t->gs) {
     t->grid = c->sm_count;
     WW_CHECK(c, cudaMalloc((void**)&t->gs, 2 * sizeof(float)));
-    WW_CHECK(c, cudaMalloc((void**)&t->part, (size_t)t->grid * 9 * (32 + 16) * 128 * 4 + (size_t)t->grid * 5 * (64 + 16) * 128 * 4));
+    WW_CHECK(c, cudaMalloc((void**)&t->part, (size_t)t->grid * 3 * (3 * 32 + 16) * 128 * 4 + (size_t)t->grid * 5 * (64 + 16) * 128 * 4));
     WW_CHECK(c, cudaMalloc((void**)&t->part1, (size_t)t->grid * 8 * W1_OUT * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t->wd3, (size_t)4 * 3 * dg_wstage_bytes<64 * kDgradPass>()));
-    WW_CHECK(c, cudaMalloc((void**)&t->wd2, (size_t)2 * 3 * dg_wstage_bytes<32 * kDgradPass>()));
+    WW_CHECK(c, cudaMalloc((void**)&t->wd3, (size_t)4 * 3 * dg_wstage_bytes<64 * kPass3>()));
+    WW_CHECK(c, cudaMalloc((void**)&t->wd2, (size_t)2 * 3 * dg_wstage_bytes<32 * kPass2>()));
   }
   if (B > t->cap) {
-    void* bufs[] = {t->in_pad, t->act1, t->act2, t->dact2, t->dact1, t->sq, t->act2_8, t->bits, t->pool_part};
+    void* bufs[] = {t->in_pad, t->act1, t->act2, t->dact2, t->dact1, t->sq, t->act2_8, t->bits, t->pool_part, t->pat};
     for (void* b : bufs) cudaFree(b);
     const size_t n = (size_t)B, pl = (size_t)g.npix * 16;
     WW_CHECK(c, cudaMalloc((void**)&t->in_pad, n * g.npix_in * 4));
@@ -744,7 +955,8 @@ static int ensure_tc(ww_ctx* c, int B, const Geom& g) {
     WW_CHECK(c, cudaMalloc((void**)&t->dact2, n * 8 * pl));
     WW_CHECK(c, cudaMalloc((void**)&t->dact1, n * 4 * pl));
     WW_CHECK(c, cudaMalloc((void**)&t->bits, n * g.T3 * 4 * 128 * 4));
-    WW_CHECK(c, cudaMalloc((void**)&t->sq, n * 2 * 128 * 2));
+    WW_CHECK(c, cudaMalloc((void**)&t->sq, n * 3 * 128 * 2));
+    WW_CHECK(c, cudaMalloc((void**)&t->pat, n * 128 * 4));
     WW_CHECK(c, cudaMalloc((void**)&t->pool_part, n * g.T3 * 128 * 4));
     // padding of the input image and the plane slots no kernel writes stay zero
     WW_CHECK(c, cudaMemset(t->in_pad, 0, n * g.npix_in * 4));
@@ -767,15 +979,25 @@ int ww_train_tc_prepare(ww_ctx* c) {
   WW_CHECK(c, cudaMemcpy(w2.data(), c->w["conv2.weight"], w2.size() * 4, cudaMemcpyDeviceToHost));
   std::vector<uint16_t> s;
   const float sc3 = weight_scale(w3), sc2 = weight_scale(w2);
-  pack_dgrad_weights(w3, 128, 64, sc3, s);
+  pack_dgrad_weights(w3, 128, 64, kPass3, sc3, s);
   WW_CHECK(c, cudaMemcpy(t->wd3, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
-  pack_dgrad_weights(w2, 64, 32, sc2, s);
+  pack_dgrad_weights(w2, 64, 32, kPass2, sc2, s);
   WW_CHECK(c, cudaMemcpy(t->wd2, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
   t->k2 = l1_shift(w3, 128, 64);
   t->k1 = l1_shift(w2, 64, 32);
   t->mult3 = ldexpf(1.0f, -t->k2) / sc3;
   t->mult2 = ldexpf(1.0f, -t->k1) / sc2;
   t->sc3 = sc3; t->sc2 = sc2;
+  // the device-side rebuilds keep these scales while the weights move: remember how far they may (train.cu)
+  std::vector<float> w1((size_t)32 * 9);
+  WW_CHECK(c, cudaMemcpy(w1.data(), c->w["conv1.weight"], w1.size() * 4, cudaMemcpyDeviceToHost));
+  float mins = 1e30f;
+  for (const std::vector<float>* w : {&w1, &w2, &w3}) {
+    float m = 0.0f;
+    for (float v : *w) m = std::max(m, fabsf(v));
+    mins = std::min(mins, m);
+  }
+  c->train.fast_room = 0.5f * mins;
   return WW_OK;
 }
 
@@ -808,29 +1030,29 @@ int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, flo
   const float inv_hw = 1.0f / (float)(g.H * g.W);
   const int grid = t->grid;
   if (!t->conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<64, true>(g)));
-    WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<64, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<32, false>(g)));
-    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<128, 64, kDgradPass, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<128, 64>(g)));
-    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<64, 32, kDgradPass, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<64, 32>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(wgrad_tap_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tap_smem<64, true>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<32>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<128, 64, kPass3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<64 * kPass3>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<64, 32, kPass2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<32 * kPass2>(g)));
     t->conf = true;
   }
   grad_scale_kernel<<<1, 1024, 0, st>>>(dpooled, B * 128, inv_hw, t->gs);
   WW_LAUNCH_CHECK(c);
-  dy3_scalars_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(dpooled, t->gs, inv_hw, t->sq, B);
+  dy3_scalars_kernel<<<(B * 128 + 255) / 256, 256, 0, st>>>(dpooled, t->gs, inv_hw, t->sq, t->pat, B);
   WW_LAUNCH_CHECK(c);
   float* part3 = t->part;
   float* part2 = t->part + (size_t)grid * 5 * (64 + 16) * 128;
   // ---- conv3: weight + bias gradient (dY3 from bits x act2), data gradient -> dY2
   {
-    WgradParams p{};
-    p.bits = t->bits; p.sq = t->sq; p.a_planes = nullptr; p.b_planes = t->act2; p.part = part3;
+    WgradTapParams p{};
+    p.bits = t->bits; p.sq = t->sq; p.pat = t->pat; p.a_planes = nullptr; p.b_planes = t->act2; p.part = part3;
     p.B = B; p.tsplit = 5; p.tl_cap = 5; p.g = g;
     p.n0 = std::min(grid - 1, std::max(1, (grid * 5 + 4) / 9));
-    wgrad_kernel<128, 64, true><<<grid, WG_THREADS, wgrad_smem<64, true>(g), st>>>(p);
+    wgrad_tap_kernel<128, 64, true><<<grid, WG_THREADS, wgrad_tap_smem<64, true>(g), st>>>(p);
     WW_LAUNCH_CHECK(c);
     const int n = 128 * 64 * 9 + 128;
-    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part3, grid, p.n0, 5, 5, 64 + 16, 128, 64, t->gs, 1.0f / c->act2_scale, 1.0f,
-                                                         gw3, gb3);
+    wgrad_tap_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part3, grid, p.n0, 5, 5, 64 + 16, 128, 64, t->gs, 1.0f / c->act2_scale, 1.0f,
+                                                             gw3, gb3);
     WW_LAUNCH_CHECK(c);
   }
   const int n_items = (int)(((long long)B * g.T3 + g.G - 1) / g.G);
@@ -838,26 +1060,26 @@ int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, flo
     DgradParams p{};
     p.bits = t->bits; p.sq = t->sq; p.a_planes = nullptr; p.wst = t->wd3; p.relu_planes = t->act2; p.out = t->dact2;
     p.mult = t->mult3; p.B = B; p.g = g;
-    dgrad_kernel<128, 64, kDgradPass, true><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<128, 64>(g), st>>>(p);
+    dgrad_kernel<128, 64, kPass3, true><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<64 * kPass3>(g), st>>>(p);
     WW_LAUNCH_CHECK(c);
   }
   // ---- conv2: weight + bias gradient (dY2 x act1), data gradient -> dY1
   {
     WgradParams p{};
     p.a_planes = t->dact2; p.b_planes = t->act1; p.part = part2;
-    p.B = B; p.tsplit = 9; p.tl_cap = 9; p.n0 = grid; p.g = g;
-    wgrad_kernel<64, 32, false><<<grid, WG_THREADS, wgrad_smem<32, false>(g), st>>>(p);
+    p.B = B; p.ky_split = 3; p.n0 = grid; p.g = g;
+    wgrad_kernel<64, 32><<<grid, WG_THREADS, wgrad_smem<32>(g), st>>>(p);
     WW_LAUNCH_CHECK(c);
     const int n = 64 * 32 * 9 + 64;
-    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part2, grid, grid, 9, 9, 32 + 16, 64, 32, t->gs,
-                                                         ldexpf(1.0f, t->k2) / c->act1_scale, ldexpf(1.0f, t->k2), gw2, gb2);
+    wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part2, grid, grid, 3, 64, 32, t->gs, ldexpf(1.0f, t->k2) / c->act1_scale,
+                                                         ldexpf(1.0f, t->k2), gw2, gb2);
     WW_LAUNCH_CHECK(c);
   }
   {
     DgradParams p{};
     p.a_planes = t->dact2; p.wst = t->wd2; p.relu_planes = t->act1; p.out = t->dact1;
     p.mult = t->mult2; p.B = B; p.g = g;
-    dgrad_kernel<64, 32, kDgradPass, false><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<64, 32>(g), st>>>(p);
+    dgrad_kernel<64, 32, kPass2, false><<<std::min(grid, n_items), DG_THREADS, dgrad_smem<32 * kPass2>(g), st>>>(p);
     WW_LAUNCH_CHECK(c);
   }
   // ---- conv1: weight + bias gradient (dY1 x input image)
@@ -883,9 +1105,9 @@ int ww_train_tc_repack(ww_ctx* c, cudaStream_t st) {
   repack_w3_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], 1.0f / c->w3_inv_scale, c->act2_lo_shift,
                                                                reinterpret_cast<unsigned char*>(c->d_w3_split));
   WW_LAUNCH_CHECK(c);
-  repack_dgrad_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], 128, 64, t->sc3, reinterpret_cast<uint16_t*>(t->wd3));
+  repack_dgrad_kernel<<<(128 * 64 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv3.weight"], 128, 64, kPass3, t->sc3, reinterpret_cast<uint16_t*>(t->wd3));
   WW_LAUNCH_CHECK(c);
-  repack_dgrad_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], 64, 32, t->sc2, reinterpret_cast<uint16_t*>(t->wd2));
+  repack_dgrad_kernel<<<(64 * 32 * 9 + 255) / 256, 256, 0, st>>>(c->w["conv2.weight"], 64, 32, kPass2, t->sc2, reinterpret_cast<uint16_t*>(t->wd2));
   WW_LAUNCH_CHECK(c);
   const int H4 = 4 * c->cfg.hidden_size;
   for (int l = 0; l < c->cfg.num_layers; ++l) {
