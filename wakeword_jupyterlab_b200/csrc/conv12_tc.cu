@@ -72,7 +72,7 @@ __device__ __forceinline__ uint4 cvt8_relu(const float* v, bool ok) {
 __device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
 __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
 
-template <int NPASS>
+template <int NPASS, bool ACT1>
 __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_constant__ Conv12Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
     uint32_t g1 = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int b = item / items_per_clip, tp = item - b * items_per_clip;
+      const int tp = item % items_per_clip;
+      const int b = ACT1 ? item / items_per_clip : 0;
       const int pbase = 256 * tp - 1 - g.P - 1;
       const int buf = it & 1;
       mbar_wait(a2_empty + buf, ((it >> 1) & 1) ^ 1, 50);
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(C12_THREADS, 1) conv12_kernel(const __grid_con
             const uint4 u = cvt8_relu(o, ok);
             *reinterpret_cast<uint4*>(ab + ((size_t)(half * 2 + k2) * g.nsl2 + l) * 16) = u;
             // training: the item's own 256 pixels (plane slots 256 tp .. 256 tp + 255) also go to HBM for the backward pass
-            if (p.act1 && l > g.P && l < g.P + 257)
+            if (ACT1 && l > g.P && l < g.P + 257)
               reinterpret_cast<uint4*>(p.act1)[((size_t)b * 4 + half * 2 + k2) * g.npix + 256 * tp + l - (g.P + 1)] = u;
           }
         }
@@ -805,8 +806,10 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
   }
   static size_t conf = 0;
   if (smem > conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
   Conv12Params p;
@@ -839,8 +842,11 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
       const int n_items = B * (g.T2 / 2);
       const int pgrid = std::max(2, std::min(c->sm_count & ~1, ((n_items + 1) / 2) * 2));
       conv12_pair_kernel<<<pgrid, C12_THREADS, psmem, st>>>(p);
-    } else if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1><<<grid, C12_THREADS, smem, st>>>(p);
-    else conv12_kernel<2><<<grid, C12_THREADS, smem, st>>>(p);
+    } else if (p.act1) {      // training forward: conv1's output planes also go to HBM
+      if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1, true><<<grid, C12_THREADS, smem, st>>>(p);
+      else conv12_kernel<2, true><<<grid, C12_THREADS, smem, st>>>(p);
+    } else if (c->cfg.conv_mode == WW_CONV_FP16) conv12_kernel<1, false><<<grid, C12_THREADS, smem, st>>>(p);
+    else conv12_kernel<2, false><<<grid, C12_THREADS, smem, st>>>(p);
     WW_LAUNCH_CHECK(c);
   }
   if (tracing) {

@@ -14,21 +14,24 @@
 // (tc_common.cuh), slot = padded pixel index + 1.  One plane set serves every GEMM of the backward pass as a *view*:
 //   * data gradient  dX[pixel, ci] = sum_{tap, co} dY[pixel - tap offset, co] W[co, ci, tap]      (dgrad_kernel)
 //       A = dY planes, K-major (rows = pixels, the 3x3 tap is a start-address offset), M = 128 pixels;
-//       B = flipped weights [tap][co chunk][ci][8], fp16 hi and lo stacked along N (one N = 2 Cin instruction does both
-//       passes); epilogue (thread = pixel): (hi + lo) * 2^-k, ReLU derivative from the forward activation planes,
-//       fp16, 16-byte plane stores (512 contiguous bytes per warp);
-//   * weight gradient  dW[co, ci, tap] = sum_pixels dY[co, pixel] X[ci, pixel + tap offset]          (wgrad_kernel)
+//       B = flipped weights [tap][co chunk][ci][8] (conv2: fp16 hi and lo stacked along N, one instruction does both);
+//       epilogue (thread = pixel): x 2^-k, ReLU derivative from the forward activation planes, fp16, 16-byte plane
+//       stores (512 contiguous bytes per warp);
+//   * weight gradient  dW[co, ci, tap] = sum_pixels dY[co, pixel] X[ci, pixel + tap offset]   (wgrad_tap_kernel, wgrad_kernel)
 //       K = pixels: the SAME planes read MN-major (8 channels contiguous per slot, LBO = 8 slots, SBO = one plane); the tap
-//       is again a start-address offset of the X window; 9 taps = 9 accumulators of Cin columns that stay in TMEM for
-//       the whole launch (one drain per CTA, then a fixed-order reduction over CTAs: deterministic);
-//       a constant "ones" plane appended to X makes the bias gradient column Cin of the centre tap.
-//       conv3 (128 x 64 x 9 = 576 columns > 512): CTAs of type 0 take taps 0-4, type 1 taps 5-8, in the ratio 5 : 4.
-// Precision (tolerances of tests/test_train_gpu.py): operands whose rounding errors are independent from pixel to pixel
+//       is again a start-address offset of the X window; the accumulators stay in TMEM for the whole launch (one drain per
+//       CTA, then a fixed-order reduction over CTAs: deterministic); a constant "ones" plane appended to X makes the bias
+//       gradient one more accumulator column.
+// An M = 128 tcgen05.mma costs 64 cycles whatever its N <= 128, which shapes every kernel here.
+// Precision (tolerances of tests/test_train_tc_gpu.py): operands whose rounding errors are independent from pixel to pixel
 // (activations, dY2, dY1) are single fp16 values - the errors average out over the >= 12,800 pixels every weight gradient
-// sums; operands whose error would be the same at every pixel are split fp16 hi + lo: the weights of the data gradients
-// and the per-(clip, channel) constant of dY3 in the conv3 weight gradient.  Gradient magnitudes (1e-10 and below) are
+// sums; the per-(clip, channel) constant of dY3, whose rounding error would be the same at every pixel, is dithered between
+// its two fp16 neighbours in the conv3 weight gradient (dy3_scalars_kernel).  Gradient magnitudes (1e-10 and below) are
 // brought into fp16's range by one power-of-two scale found on the device from max |dpooled|, and by static
 // power-of-two bounds (L1 norms of the weights) for dY2 and dY1; every scale is undone in fp32 in the reductions.
+// What limits the accuracy is the forward: fp16 activations put ~2e-4 relative error on each conv output, so the few
+// outputs closer than that to zero take the other ReLU branch than in exact arithmetic: conv gradients match float64
+// autograd to ~1e-3 of the tensor maximum (the class of the reference's own TF32 GPU training), loss and head gradients to 1e-5.
 #include "tc_common.cuh"
 
 #include <algorithm>
