@@ -88,6 +88,32 @@ def test_tensor_core_gradients_vs_float64_autograd(ww, B):
         assert v < (CONV_TOL if name.startswith("conv") else HEAD_TOL), (name, v)
 
 
+@pytest.mark.parametrize("W", [20, 33])
+def test_tensor_core_gradients_other_widths(ww, W):
+    """Image widths other than the preset's 32 frames (pitch P = W + 1 changes every tap offset, tile count and tape period)."""
+    sd = R.seeded_state_dict(256, seed=4)
+    rng = np.random.default_rng(W)
+    B = 9
+    x = torch.from_numpy((rng.standard_normal((B, 1, 80, W)) * 15 - 40).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.integers(0, 2, B).astype(np.int64)).cuda()
+    with _env(WW_TRAIN_KERNEL="tc"):
+        net, tr = _trainer(ww, sd)
+        loss, _ = tr.train_step(x, y)
+        grads = {k: v.cpu().numpy().copy() for k, v in tr.gradients(net.engine(width=W)).items()}
+    ref_loss, ref = _autograd_reference(sd, x, y)
+    assert abs(loss.item() - ref_loss) < 1e-5 * abs(ref_loss)
+    # yardstick: the un-cancelled magnitude (a batch gradient is a sum of per-clip gradients of both signs)
+    scale = {k: 0.0 for k in ref}
+    for b in range(B):
+        _, gb = _autograd_reference(sd, x[b:b + 1], y[b:b + 1])
+        for k, v in gb.items():
+            scale[k] += float(np.abs(v).max()) / B
+    for name, r in ref.items():
+        if scale[name] > 0.0:
+            err = float(np.abs(grads[name] - r).max()) / scale[name]
+            assert err < (CONV_TOL if name.startswith("conv") else HEAD_TOL), (name, err)
+
+
 def test_tensor_core_and_fp32_kernels_agree(ww):
     """Same batch through both backward kernels of the library.  A batch gradient is a sum of per-clip gradients of both
     signs, so the yardstick is the un-cancelled magnitude: the mean over the clips of max |per-clip gradient| (each clip run

@@ -325,9 +325,11 @@ template <int MCH, int NCH>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
   constexpr int MP = MCH / 8, NP = NCH / 8, NPB = 3 * NP + 2, NS = 3 * NCH + 16;
   constexpr int KSL = 128, KST = KSL / 16;
-  constexpr int NSTG = 2;
+  constexpr int NSTG = 3;
   constexpr uint32_t APL = KSL * 16;                       // one dY plane of a stage
-  constexpr uint32_t A_BYTES = 16 * APL;              // always 16 planes per copy (M = 128); MCH = 64: the upper 8 stay zero
+  // M = 128 instructions with MCH = 64 real dY planes: rows 64-127 read the 8 "planes" that follow, i.e. the start of the X
+  // window (finite fp16 data), and fill accumulator lanes 64-127 that nobody reads
+  constexpr uint32_t A_BYTES = MP * APL;
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
   const uint32_t bsl = (uint32_t)(KSL + 2 * g.P + 2);
@@ -346,7 +348,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  // zero everything once (unused dY planes, the all-zero pad plane), and write the ones plane: channel 0 = 1.0 at every slot
+  // zero everything once (the all-zero pad plane; finite values wherever an instruction may read before the first load),
+  // and write the ones plane: channel 0 = 1.0 at every slot
   for (uint32_t i = tid * 16u; i < NSTG * stage_bytes; i += WG_THREADS * 16u) {
     const uint32_t off = i % stage_bytes;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -874,7 +877,7 @@ size_t wgrad_tap_smem(const Geom& g) {
 template <int NCH>
 size_t wgrad_smem(const Geom& g) {
   const size_t ksl = 128, bsl = ksl + 2 * g.P + 2;
-  return (size_t)2 * (16 * ksl * 16 + (3 * NCH / 8 + 2) * bsl * 16) + 128 + 32 * 8 + 64;
+  return (size_t)3 * (8 * ksl * 16 + (3 * NCH / 8 + 2) * bsl * 16) + 128 + 32 * 8 + 64;
 }
 
 // flipped / transposed weights of a data gradient as fp16 hi | lo stacked along N, in stage order [q][tt][tl][kc][n'][8]:
