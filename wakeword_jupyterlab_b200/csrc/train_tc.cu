@@ -126,15 +126,15 @@ __device__ __forceinline__ uint4 select8(const uint4 v, const uint4 w0, const ui
 // weight gradient
 constexpr int WG_THREADS = 320;     // warp 0 loader, warp 1 MMA issuer, warps 2-9 operand builders; warps 2-5 drain TMEM at the end
 
-// Form 1 (conv3: the dY3 tile built from sign bits, hi + lo copies): one instruction per (tap, copy), the tap a start-address
-// offset of the bulk-loaded X window; 128 dY slots per stage.  576 accumulator columns > 512: CTAs of type 0 take taps 0-4,
-// type 1 taps 5-8, in the ratio 5 : 4.  (Form 2 below issues a third of the instructions, but its extra shared-memory
-// copies and shorter stages lose against this form when the tile builders already write 64 KB per stage: 5.9 vs 2.65 ms.)
+// Form 1 (conv3: the dY3 tile is built in shared memory from the sign bits): one instruction per tap, the tap a
+// start-address offset of the bulk-loaded X window; 128 dY slots per stage.  576 accumulator columns > 512: CTAs of type 0
+// take taps 0-4, type 1 taps 5-8, in the ratio 5 : 4.  (Form 2 below issues a third of the instructions, but its extra
+// shared-memory copies and shorter stages lose against this form when the tile builders already write the dY tile of every
+// stage: 5.9 vs 2.65 ms, measured with a two-copy hi / lo tile.)
 struct WgradTapParams {
-  const uint32_t* bits;     // A_BITS: [B][T3][4][128] sign bits of conv3's output (conv3_tc.cu)
-  const __half* sq;         // A_BITS: [B][3][128] fp16 nearest / down / up of dpooled / HW * 2^k (dy3_scalars_kernel)
-  const uint32_t* pat;      // A_BITS: [B][128] dither patterns
-  const __half* a_planes;   // !A_BITS: dY planes [B][MCH/8][npix][8]
+  const uint32_t* bits;     // [B][T3][4][128] sign bits of conv3's output (conv3_tc.cu)
+  const __half* sq;         // [B][3][128] fp16 nearest / down / up of dpooled / HW * 2^k (dy3_scalars_kernel)
+  const uint32_t* pat;      // [B][128] dither patterns
   const __half* b_planes;   // X planes [B][NCH/8][npix][8]
   float* part;              // [grid][tl_cap][NCH + 16][128] fp32 partial sums (lane = co)
   int B, n0, tsplit, tl_cap;   // CTAs [0, n0) take taps [0, tsplit), the others taps [tsplit, 9)
@@ -143,20 +143,20 @@ struct WgradTapParams {
 
 // Work unit = (clip b, tile t): the 128 dY slots P + 1 + 128 t .. (= conv3's output tile t) and the X window of
 // 128 + 2 P + 2 slots from slot 128 t: 8 K-steps of 16 pixels per tap.
-template <int MCH, int NCH, bool A_BITS>
+template <int MCH, int NCH>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTapParams p) {
-  constexpr int NA = 1;                                    // one dY operand copy (the conv3 constants are dithered, see dy3_scalars_kernel)
-  constexpr int MP = MCH / 8, NP = NCH / 8, NPB = NP + 2, NS = NCH + 16;
+  static_assert(MCH == 128, "the tile builders fill all 16 channel chunks of an M = 128 operand");
+  constexpr int NP = NCH / 8, NPB = NP + 2, NS = NCH + 16;
   constexpr int NSTG = 3;
-  constexpr uint32_t A_BYTES = NA * 16 * 2048;             // always 16 planes per copy (M = 128); MCH = 64: the upper 8 stay zero
+  constexpr uint32_t A_BYTES = 16 * 2048;                  // the dY3 tile: 16 channel chunks x 128 slots (one copy: the constants are dithered)
   extern __shared__ __align__(128) unsigned char smem[];
   const Geom g = p.g;
-  const uint32_t bsl = (uint32_t)((128 + 2 * g.P + 2 + 7) & ~7);
+  const uint32_t bsl = (uint32_t)(128 + 2 * g.P + 2);          // exactly what the taps reach: the last window of a clip ends at its last plane slot
   const uint32_t bpl = bsl * 16u;
   const uint32_t stage_bytes = A_BYTES + NPB * bpl;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTG * stage_bytes);
   uint64_t* full = bars;              // [NSTG] bulk copies landed
-  uint64_t* afull = bars + 4;         // [NSTG] dY3 tile built (A_BITS)
+  uint64_t* afull = bars + 4;         // [NSTG] dY3 tile built
   uint64_t* empty = bars + 8;         // [NSTG] MMAs of the stage retired
   uint64_t* done = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
@@ -196,15 +196,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTap
         mbar_wait(empty + st, ((it / NSTG) & 1) ^ 1, 70);
         const int b = u / g.T3, t = u - b * g.T3;
         unsigned char* sb = smem + st * stage_bytes;
-        mbar_arrive_expect_tx(full + st, NP * bpl + (A_BITS ? 0u : (uint32_t)MP * 2048u));
+        mbar_arrive_expect_tx(full + st, NP * bpl);
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl)
           bulk_g2s(sb + A_BYTES + pl * bpl, p.b_planes + (((size_t)b * NP + pl) * g.npix + (size_t)128 * t) * 8, bpl, full + st);
-        if (!A_BITS) {
-#pragma unroll
-          for (int pl = 0; pl < MP; ++pl)
-            bulk_g2s(sb + pl * 2048, p.a_planes + (((size_t)b * MP + pl) * g.npix + (size_t)(g.P + 1 + 128 * t)) * 8, 2048, full + st);
-        }
       }
     }
   } else if (warp == 1) {
@@ -217,7 +212,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTap
       const int st = it % NSTG;
       const uint32_t par = (it / NSTG) & 1;
       mbar_wait(full + st, par, 71);
-      if (A_BITS) mbar_wait(afull + st, par, 72);
+      mbar_wait(afull + st, par, 72);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t as = a0 + (uint64_t)((st * stage_bytes) >> 4), bs = b0 + (uint64_t)((st * stage_bytes) >> 4);
@@ -230,7 +225,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTap
             const uint32_t d = tmem_base + (uint32_t)(tap - tap_lo) * NS;
             const uint32_t id = tap == 4 ? idC : idN;
             umma_f16(d, as + (uint64_t)(ks * 16), bs + (uint64_t)off, id, (it | ks) != 0);
-            if (NA == 2) umma_f16(d, as + (uint64_t)(ks * 16 + ((16 * 2048) >> 4)), bs + (uint64_t)off, id, 1);
           }
         }
         umma_commit(empty + st);
@@ -239,7 +233,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tap_kernel(const WgradTap
     }
     if (elect_one()) umma_commit(done);
     __syncwarp();
-  } else if (A_BITS) {
+  } else {
     // ===================== dY3 tile builders: warp w -> channel chunks 2w, 2w + 1; lane = slot within a 32-slot block
     const int w = warp - 2;
     int it = 0;
@@ -869,9 +863,9 @@ template <int NT>
 size_t dgrad_smem(const Geom& g) {
   return (size_t)2 * 4 * g.nsl3 * 16 + (size_t)DG_NSTW * dg_wstage_bytes<NT>() + 32 * 8 + 64;
 }
-template <int NCH, bool A_BITS>
+template <int NCH>
 size_t wgrad_tap_smem(const Geom& g) {
-  const size_t bsl = (size_t)((128 + 2 * g.P + 2 + 7) & ~7);
+  const size_t bsl = (size_t)(128 + 2 * g.P + 2);
   return (size_t)3 * (16 * 2048 + (NCH / 8 + 2) * bsl * 16) + 32 * 8 + 64;
 }
 template <int NCH>
@@ -924,7 +918,7 @@ bool ww_train_tc_supported(const ww_ctx* c) {
   if (g.G < 1 || 2 * g.P + 2 + 128 > 4096) return false;
   if (128 + 2 * g.P + 2 > 128 + 2 * 40 + 4) return false;                  // wgrad1_kernel's x window
   if ((g.nsl3 + 31) / 32 + 1 > 32) return false;                           // dgrad_kernel's bit window: one word per lane
-  return dgrad_smem<64 * kPass3>(g) <= 227 * 1024 && wgrad_tap_smem<64, true>(g) <= 227 * 1024 && conv3_smem_bytes(g.nsl3, g.nst3) <= 227 * 1024;
+  return dgrad_smem<64 * kPass3>(g) <= 227 * 1024 && wgrad_tap_smem<64>(g) <= 227 * 1024 && conv3_smem_bytes(g.nsl3, g.nst3) <= 227 * 1024;
 }
 
 void ww_train_tc_free(ww_ctx* c) {
@@ -1036,7 +1030,7 @@ int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, flo
   const float inv_hw = 1.0f / (float)(g.H * g.W);
   const int grid = t->grid;
   if (!t->conf) {
-    WW_CHECK(c, cudaFuncSetAttribute(wgrad_tap_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tap_smem<64, true>(g)));
+    WW_CHECK(c, cudaFuncSetAttribute(wgrad_tap_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tap_smem<64>(g)));
     WW_CHECK(c, cudaFuncSetAttribute(wgrad_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem<32>(g)));
     WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<128, 64, kPass3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<64 * kPass3>(g)));
     WW_CHECK(c, cudaFuncSetAttribute(dgrad_kernel<64, 32, kPass2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_smem<32 * kPass2>(g)));
@@ -1051,10 +1045,10 @@ int ww_train_tc_backward(ww_ctx* c, int B, const float* dpooled, float* gw1, flo
   // ---- conv3: weight + bias gradient (dY3 from bits x act2), data gradient -> dY2
   {
     WgradTapParams p{};
-    p.bits = t->bits; p.sq = t->sq; p.pat = t->pat; p.a_planes = nullptr; p.b_planes = t->act2; p.part = part3;
+    p.bits = t->bits; p.sq = t->sq; p.pat = t->pat; p.b_planes = t->act2; p.part = part3;
     p.B = B; p.tsplit = 5; p.tl_cap = 5; p.g = g;
     p.n0 = std::min(grid - 1, std::max(1, (grid * 5 + 4) / 9));
-    wgrad_tap_kernel<128, 64, true><<<grid, WG_THREADS, wgrad_tap_smem<64, true>(g), st>>>(p);
+    wgrad_tap_kernel<128, 64><<<grid, WG_THREADS, wgrad_tap_smem<64>(g), st>>>(p);
     WW_LAUNCH_CHECK(c);
     const int n = 128 * 64 * 9 + 128;
     wgrad_tap_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part3, grid, p.n0, 5, 5, 64 + 16, 128, 64, t->gs, 1.0f / c->act2_scale, 1.0f,
