@@ -804,13 +804,12 @@ int ww_launch_conv12_tc(ww_ctx* c, const float* in_pad, int B, const Geom& g, cu
     c->set_error("conv12_tc: frame count too large for the shared-memory tiles (use WW_CONV_FP32)");
     return WW_ERR_INVALID;
   }
-  static size_t conf = 0;
-  if (smem > conf) {
+  if (smem > c->c12_smem_conf) {      // per context (= per device), not per process
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv12_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conf = smem;
+    c->c12_smem_conf = smem;
   }
   Conv12Params p;
   p.in_pad = in_pad; p.w1s = c->d_w1_split; p.w2s = c->d_w2_split;

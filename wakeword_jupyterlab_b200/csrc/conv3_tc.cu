@@ -378,13 +378,12 @@ int ww_launch_conv3_tc(ww_ctx* c, int B, const Geom& g, cudaStream_t st) {
     c->set_error("conv3_tc: frame count too large for the shared-memory tiles (use WW_CONV_FP32)");
     return WW_ERR_INVALID;
   }
-  static size_t conf = 0;
-  if (smem > conf) {
+  if (smem > c->c3_smem_conf) {      // per context (= per device), not per process
     WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WW_CHECK(c, cudaFuncSetAttribute(conv3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conf = smem;
+    c->c3_smem_conf = smem;
   }
   Conv3Params p;
   p.act2 = c->ws_act2_h; p.act2_8 = c->ws_act2_8; p.w3s = reinterpret_cast<const unsigned char*>(c->d_w3_split); p.inv_scale = c->w3_inv_scale / c->act2_scale; p.b3 = c->w["conv3.bias"]; p.mask = c->d_tc_mask;

@@ -128,6 +128,7 @@ struct ww_ctx {
   __half* d_w1_split = nullptr;                        // conv1 weights * 2^k, fp16 hi/lo, K = 9 padded to 16, twice
   float w1_inv_scale = 1.0f, w2_inv_scale = 1.0f, w3_inv_scale = 1.0f;      // 2^-k per layer
   float act1_scale = 1.0f, act2_scale = 1.0f;                               // power-of-two scales of the stored fp16 activations
+  size_t c12_smem_conf = 0, c3_smem_conf = 0;   // dynamic shared-memory opt-in already made for this context's device
   int act2_lo_shift = 0;                                                    // e4m3 copy of act2 = fp16 copy x 2^-shift (conv12_tc.cu)
 
   // ---- workspaces (chunk clips)
