@@ -142,6 +142,29 @@ def test_tensor_core_and_fp32_kernels_agree(ww):
             assert err < (CONV_TOL if name.startswith("conv") else HEAD_TOL), (name, err)
 
 
+def test_tensor_core_training_in_fast_conv_mode(ww):
+    """conv_mode = "fp16" (single-pass forward kernels): the train-mode variants of those kernels (conv1 planes, conv3 sign
+    bits) feed the same backward kernels."""
+    sd = R.seeded_state_dict(256, seed=6)
+    x, y = _batch(7, 21)
+    with _env(WW_TRAIN_KERNEL="tc"):
+        net, tr = _trainer(ww, sd)
+        net.conv_mode = "fp16"
+        loss, _ = tr.train_step(x, y)
+        grads = {k: v.cpu().numpy().copy() for k, v in tr.gradients(net.engine()).items()}
+    ref_loss, ref = _autograd_reference(sd, x, y)
+    assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
+    scale = {k: 0.0 for k in ref}
+    for b in range(7):
+        _, gb = _autograd_reference(sd, x[b:b + 1], y[b:b + 1])
+        for k, v in gb.items():
+            scale[k] += float(np.abs(v).max()) / 7
+    for name, r in ref.items():
+        if scale[name] > 0.0:
+            err = float(np.abs(grads[name] - r).max()) / scale[name]
+            assert err < (CONV_TOL if name.startswith("conv") else 3e-4), (name, err)
+
+
 def test_device_side_repack_equals_host_side_preparation(ww):
     """After an optimiser step the operand forms are rebuilt by kernels (ww_train_tc_repack); the same steps with the
     host-side preparation (WW_TRAIN_FAST=0) must give the same weights bit for bit."""
