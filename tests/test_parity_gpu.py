@@ -184,6 +184,34 @@ def test_augment_pipelined_over_many_clips(ww):
         assert np.array_equal(eng.augment(clips[sl], ps, noise_bank=bank).cpu().numpy(), out[sl])
 
 
+def test_augment_pipelined_roles_match_lockstep_kernel(ww, monkeypatch):
+    """The default augment kernel (conditioning / gather roles on different clips, named-barrier hand-over) against the
+    one-clip-per-CTA lock-step kernel (WW_AUGMENT_KERNEL=lockstep): same per-element arithmetic, block sums over 16 instead
+    of 32 warps -> 1e-6; clips that only shift / normalise are bit-identical.  Includes a batch where some CTAs get one clip
+    and some two (odd pipeline depths) and every flag combination."""
+    n = 333
+    clips = np.tile(R.make_clips(37, seed=7), (9, 1))
+    bank = R.make_noise_bank()
+    p = R.draw_aug_params(n, seed=11)
+    flags = p.flags.copy()
+    combos = [0, A.F_SHIFT, A.F_SPEED, A.F_NOISE, A.F_SHIFT | A.F_NOISE, A.F_SPEED | A.F_NOISE, A.F_SHIFT | A.F_SPEED]
+    for i, f in enumerate(combos * 8):
+        flags[i] = f | (flags[i] & ~np.uint32(A.F_SHIFT | A.F_SPEED | A.F_NOISE))
+    p = A.AugParams(flags, p.shift, p.rs_orig, p.rs_new, p.crop_off, p.noise_idx, p.noise_off, p.snr_db, p.gain)
+    eng = ww.get_engine()
+    got = eng.augment(clips, _aug_to_ww(ww, p), noise_bank=bank).cpu().numpy()
+    monkeypatch.setenv("WW_AUGMENT_KERNEL", "lockstep")
+    old = eng.augment(clips, _aug_to_ww(ww, p), noise_bank=bank).cpu().numpy()
+    monkeypatch.delenv("WW_AUGMENT_KERNEL")
+    assert np.isfinite(got).all()
+    assert np.abs(got - old).max() < 1e-6
+    exact = (flags & (A.F_SPEED | A.F_NOISE)) == 0
+    assert exact.any() and np.array_equal(got[exact], old[exact])
+    ref = A.augment_batch(clips[:56], bank, A.AugParams(*[getattr(p, f)[:56] for f in (
+        "flags", "shift", "rs_orig", "rs_new", "crop_off", "noise_idx", "noise_off", "snr_db", "gain")]))
+    assert np.abs(got[:56] - ref).max() < 5e-5
+
+
 def test_int16_pcm_inputs_match_fp32_of_the_same_samples(ww):
     """int16 PCM in = the fp32 entries fed with s / 32768 (what librosa.load returns)."""
     n = 200

@@ -25,6 +25,8 @@
 #include "ctx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -463,6 +465,300 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
   cp_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Pipelined form (default).  The lock-step kernel above keeps every warp in the same phase between block barriers: the
+// gather saturates the shared-memory port while the issue slots idle, the element-wise passes do the opposite (ncu: LSU
+// data pipe 54 %, issue 47 %).  Here the CTA is two ROLES of 512 threads that work on DIFFERENT clips:
+//   C (conditioning, warps 0-15): loads clip k + 1 from HBM, peak-normalises it, stores it ROLLED into src[(k + 1) & 1]
+//     with the zero pads of the fixed-phase gather around it, copies its polyphase table; then takes the gathered clip k out
+//     of `res` into registers (32 samples per thread) and runs noise mix / gain / peak normalise / store on it;
+//   G (gather, warps 16-31): res[i] = sum_k taps[ph][k] * src[k & 1][x0(i) + k] for clip k, nothing else: one LDS + one FMA
+//     per tap, its tap row in registers (fixed-phase ownership as above, S = n * floor(512 / n)).
+// so the port-bound gather of one clip runs under the issue-bound passes of its neighbours.  The roles meet at named
+// barriers in producer / consumer form (bar.arrive by the producer, bar.sync by the consumer, 1024 = both roles):
+// src_full[2], src_empty[2], res_full, res_empty.  Arithmetic per element is the lock-step kernel's (same normalise,
+// same tap order, same mix); the block sums are taken over 16 warps instead of 32 (1e-7 relative on the noise scalars).
+// The RMS values "re-measured after scaling" (audiolib.py:60,65) are taken as scale^2 x the sums already known instead of a
+// second pass over registers (mathematically equal; 1e-7 relative).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRole = 512;            // threads per role
+constexpr int kPerC = 32;             // samples per conditioning thread: n_samples <= kRole * kPerC
+enum { BAR_C = 1, BAR_SRC_FULL = 2, BAR_SRC_EMPTY = 4, BAR_RES_FULL = 6, BAR_RES_EMPTY = 7 };
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// reductions over the conditioning role (16 warps); every call site has its own scratch row (see block_reduce2)
+__device__ __forceinline__ float role_max_nonneg(float v, float* red, int t) {
+  const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+  if ((t & 31) == 0) red[t >> 5] = __uint_as_float(w);
+  bar_sync(BAR_C, kRole);
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(red[t & 15])));
+}
+__device__ __forceinline__ void role_sum2(float& a, float& b, float* red, int t) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((t & 31) == 0) { red[t >> 5] = a; red[16 + (t >> 5)] = b; }
+  bar_sync(BAR_C, kRole);
+  float ra = red[t & 15], rb = red[16 + (t & 15)];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rb += __shfl_xor_sync(0xffffffffu, rb, o); }
+  a = ra; b = rb;
+}
+
+// gather role, fixed phase: thread t < S owns the outputs t + m S (see gather_fixed_phase)
+template <int NZ4>
+__device__ __forceinline__ void gather_role(const float* __restrict__ xr, const float* __restrict__ tbl, int pitch,
+                                            const RsDesc& d, int crop, int out_len, int N, int S, int t,
+                                            float* __restrict__ res) {
+  const int* lo_t = reinterpret_cast<const int*>(tbl + d.n * pitch);
+  const int j0 = t + crop;
+  const int qq0 = j0 / d.n, ph = j0 - qq0 * d.n;
+  float w[4 * NZ4];
+  const float4* kr4 = reinterpret_cast<const float4*>(tbl + ph * pitch);
+#pragma unroll
+  for (int k4 = 0; k4 < NZ4; ++k4) {
+    const float4 v = kr4[k4];
+    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+  }
+  const float* sp = xr + (qq0 * d.o - d.width + lo_t[ph]);
+  const int xstep = (S / d.n) * d.o;
+  // outputs past the resampled length read the leading zero pad instead (4 NZ4 <= 24 < kPad): no branch
+  const int i_end = min(N, out_len - crop);             // first output that has no source
+#pragma unroll 2
+  for (int i = t; i < N; i += S) {
+    const float* sq = (i < i_end) ? sp : xr - kPad;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < NZ4; ++k4) {
+      acc0 = fmaf(w[4 * k4], sq[4 * k4], acc0);
+      acc1 = fmaf(w[4 * k4 + 1], sq[4 * k4 + 1], acc1);
+      acc0 = fmaf(w[4 * k4 + 2], sq[4 * k4 + 2], acc0);
+      acc1 = fmaf(w[4 * k4 + 3], sq[4 * k4 + 3], acc1);
+    }
+    res[i] = acc0 + acc1;
+    sp += xstep;
+  }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red3[3][32];
+  __shared__ ClipPrm prm[2];
+  const int tid = threadIdx.x;
+  const int N = p.N;
+  const int NP = (N + 7) & ~7;
+  const int SP = NP + 2 * kPad;
+  float* src0 = reinterpret_cast<float*>(smem_raw) + kPad;      // src[s] = src0 + s SP, kPad zeros on either side
+  float* res = src0 - kPad + 2 * SP;                            // [NP]
+  float* tbl0 = res + NP;                                       // [2][kTblWords]
+  for (int k = tid; k < 2 * (2 * kPad + NP - N); k += 2 * kRole) {
+    float* base = src0 + (k & 1) * SP;
+    const int r = k >> 1;
+    base[r < kPad ? r - kPad : N + (r - kPad)] = 0.0f;
+  }
+  __syncthreads();
+  const int K = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // clips of this CTA
+
+  if (tid >= kRole) {
+    // ================================================= gather role
+    const int t = tid - kRole;
+    for (int k = 0; k < K; ++k) {
+      const int s = k & 1;
+      bar_sync(BAR_SRC_FULL + s, 2 * kRole);
+      if (k >= 1) bar_sync(BAR_RES_EMPTY, 2 * kRole);
+      const ClipPrm& q = prm[s];
+      const uint32_t flags = q.flags;
+      const float* cur = src0 + s * SP;
+      const float* tbl = tbl0 + s * kTblWords;
+      if (!(flags & WW_AUG_SPEED)) {
+        for (int i = t; i < N; i += kRole) res[i] = cur[i];      // the roll happened on the way in: bit-exact copy
+      } else if (q.rs < 0) {
+        for (int i = t; i < N; i += kRole) res[i] = __int_as_float(0x7fc00000);     // loud: NaN clip
+      } else {
+        const RsDesc d = q.d;
+        const int pitch = d.nz + ((d.nz & 4) ? 0 : 4);
+        const int tbl_words = d.n * pitch + 2 * d.n;
+        const bool in_smem = tbl_words <= kTblWords;
+        const int out_len = (d.n * N + d.o - 1) / d.o;                               // ceil(n*N/o), < 2^31
+        const int crop = (out_len > N) ? q.crop : 0;
+        const bool fixed = in_smem && d.n <= kRole && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
+        if (fixed) {
+          const int S = d.n * (kRole / d.n);
+          if (t < S) {
+            switch (d.nz >> 2) {
+              case 4: gather_role<4>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
+              case 5: gather_role<5>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
+              default: gather_role<6>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
+            }
+          }
+        } else {
+          // rare fallback (very long tap rows / tables that do not fit): generic phase decomposition, taps from global
+          const float* kern = in_smem ? tbl : p.rs_kern + d.offset;
+          const int* lo_t = reinterpret_cast<const int*>(kern + d.n * pitch);
+          const int* cnt_t = lo_t + d.n;
+#pragma unroll 1
+          for (int i = t; i < N; i += kRole) {
+            float acc = 0.0f;
+            const int j = i + crop;
+            if (j < out_len) {
+              const int qq = j / d.n, ph = j - qq * d.n;
+              const int x0 = qq * d.o - d.width + lo_t[ph];
+              const float* kr = kern + ph * pitch;
+              const int k0 = x0 < 0 ? -x0 : 0;
+              const int k1 = min(cnt_t[ph], N - x0);
+              for (int kk = k0; kk < k1; ++kk) acc = fmaf(kr[kk], cur[x0 + kk], acc);
+            }
+            res[i] = acc;
+          }
+        }
+      }
+      bar_arrive(BAR_RES_FULL, 2 * kRole);
+      if (k + 2 < K) bar_arrive(BAR_SRC_EMPTY + s, 2 * kRole);
+    }
+    return;
+  }
+
+  // =================================================== conditioning role
+  const int t = tid;
+  // clip j of this CTA -> src[j & 1], prm[j & 1], tbl[j & 1]
+  auto prep = [&](int j) {
+    const int s = j & 1;
+    const int b = (int)blockIdx.x + j * (int)gridDim.x;
+    if (j >= 2) bar_sync(BAR_SRC_EMPTY + s, 2 * kRole);
+    const TIn* __restrict__ x = static_cast<const TIn*>(p.clips) + (int64_t)b * N;
+    float o[kPerC];
+#pragma unroll
+    for (int e = 0; e < kPerC; ++e) {
+      const int i = t + e * kRole;
+      o[e] = (i < N) ? cvt_in(__ldg(x + i)) : 0.0f;
+    }
+    const uint32_t flags = __ldg(p.a.flags + b);
+    if (t < 32) {
+      // scalars of the clip (lane 0) and parallel search of the prepared resample ratios (whole warp), loads in flight
+      ClipPrm& q = prm[s];
+      if (t == 0) {
+        q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
+        q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
+      }
+      __syncwarp();
+      if (flags & WW_AUG_SPEED) {
+        const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+        for (int i = t; i < p.n_rs; i += 32)
+          if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
+      }
+    }
+    float m = 0.0f;
+#pragma unroll
+    for (int e = 0; e < kPerC; ++e) m = fmaxf(m, fabsf(o[e]));
+    m = role_max_nonneg(m, red3[0], t);                 // also publishes prm[s] to the role
+    const bool inexact = (flags & (WW_AUG_SPEED | WW_AUG_NOISE)) != 0;
+    if ((flags & WW_AUG_NORM_IN) && m > 0.0f) {
+      const ClipDiv dv = make_clip_div(m);
+      if (inexact && dv.fast) {
+#pragma unroll
+        for (int e = 0; e < kPerC; ++e) o[e] = dv.approx(o[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < kPerC; ++e) o[e] = dv(o[e]);
+      }
+    }
+    int sh = (flags & WW_AUG_SHIFT) ? prm[s].shift % N : 0;
+    if (sh < 0) sh += N;
+    float* cur = src0 + s * SP;
+    int dpos = t + sh;                                  // rolled[(i + shift) mod N] = in[i]
+    if (dpos >= N) dpos -= N;
+#pragma unroll
+    for (int e = 0; e < kPerC; ++e) {
+      const int i = t + e * kRole;
+      if (i < N) cur[dpos] = o[e];
+      dpos += kRole;
+      if (dpos >= N) dpos -= N;
+    }
+    if ((flags & WW_AUG_SPEED) && prm[s].rs >= 0) {
+      const RsDesc& d = prm[s].d;
+      const int pitch = d.nz + ((d.nz & 4) ? 0 : 4);
+      const int tbl_words = d.n * pitch + 2 * d.n;
+      if (tbl_words <= kTblWords) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.rs_kern + d.offset);    // offset and size are whole float4s
+        float4* t4 = reinterpret_cast<float4*>(tbl0 + s * kTblWords);
+        for (int i = t; i < (tbl_words + 3) >> 2; i += kRole) t4[i] = __ldg(g4 + i);
+      }
+    }
+    bar_arrive(BAR_SRC_FULL + s, 2 * kRole);
+  };
+
+  prep(0);
+  for (int k = 0; k < K; ++k) {
+    if (k + 1 < K) prep(k + 1);
+    const int b = (int)blockIdx.x + k * (int)gridDim.x;
+    bar_sync(BAR_RES_FULL, 2 * kRole);
+    float o[kPerC];
+#pragma unroll
+    for (int e = 0; e < kPerC; ++e) {
+      const int i = t + e * kRole;
+      o[e] = (i < N) ? res[i] : 0.0f;
+    }
+    if (k + 1 < K) bar_arrive(BAR_RES_EMPTY, 2 * kRole);
+    const ClipPrm& q = prm[k & 1];
+    const uint32_t flags = q.flags;
+    const bool inexact = (flags & (WW_AUG_SPEED | WW_AUG_NOISE)) != 0;
+    if (flags & WW_AUG_NOISE) {
+      const float* __restrict__ nb = p.bank + (int64_t)q.noise_idx * p.bank_len + q.noise_off;
+      const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
+      float sc = 0.0f, sn = 0.0f;
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) {
+        const int i = t + e * kRole;
+        const float n = (i < N) ? __ldg(nb + i) : 0.0f;
+        sc = fmaf(o[e], o[e], sc);
+        sn = fmaf(n, n, sn);
+      }
+      role_sum2(sc, sn, red3[1], t);
+      const float inv_n = 1.0f / (float)N;
+      const float scalarclean = target * rsqrtf(sc * inv_n), scalarnoise = target * rsqrtf(sn * inv_n);
+      // the reference re-measures both RMS values after scaling (audiolib.py:60,65): sum (a x)^2 = a^2 sum x^2
+      const float sc2 = sc * scalarclean * scalarclean, sn2 = sn * scalarnoise * scalarnoise;
+      // noisescalar = sqrt(rmsclean / 10^(snr/20) / rmsnoise), audiolib.py:68 (sqrt quirk kept)
+      const float noisescalar = rsqrtf(rsqrtf(__fdividef(sc2, sn2))) * exp2f(q.snr * -0.0830482023721841f);
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) {
+        const int i = t + e * kRole;
+        const float n = (i < N) ? __ldg(nb + i) : 0.0f;
+        o[e] = fmaf(n * scalarnoise, noisescalar, o[e] * scalarclean);
+      }
+    }
+    if (flags & WW_AUG_GAIN) {
+      const float g = q.gain;
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) o[e] *= g;
+    }
+    if (flags & WW_AUG_NORM_OUT) {
+      float mo = 0.0f;
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) mo = fmaxf(mo, fabsf(o[e]));
+      mo = role_max_nonneg(mo, red3[2], t);
+      if (mo > 0.0f) {
+        const ClipDiv dv = make_clip_div(mo);
+        if (inexact && dv.fast) {
+#pragma unroll
+          for (int e = 0; e < kPerC; ++e) o[e] = dv.approx(o[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kPerC; ++e) o[e] = dv(o[e]);
+        }
+      }
+    }
+    float* __restrict__ dst = p.out + (int64_t)b * N;
+#pragma unroll
+    for (int e = 0; e < kPerC; ++e) {
+      const int i = t + e * kRole;
+      if (i < N) dst[i] = o[e];
+    }
+  }
+}
+
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* out) {
   float m = 0.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -493,14 +789,24 @@ int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaS
 template <typename TIn>
 static int launch_augment_t(ww_ctx* c, const AugKParams& p, cudaStream_t st) {
   const int NP = (p.N + 7) & ~7;
-  // stage x2 (+ pads when the fp32 stage doubles as the gather source) | float copy + pads (int16 input) | noise | table
-  const size_t smem = (sizeof(TIn) == 4 ? (size_t)2 * (NP + 2 * kPad) * 4 : (size_t)2 * NP * 2 + (size_t)(NP + 2 * kPad) * 4) +
-                      (size_t)NP * 4 + (size_t)kTblWords * 4;
-  // opt in on every launch: the attribute is per device, a process may drive several
-  WW_CHECK(c, cudaFuncSetAttribute(augment_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(c->sm_count, p.B);
+  const char* kern = getenv("WW_AUGMENT_KERNEL");        // "lockstep": the one-clip-per-CTA kernel (A/B runs, tests); read per call
+  if (kern && strcmp(kern, "lockstep") == 0) {
+    // stage x2 (+ pads when the fp32 stage doubles as the gather source) | float copy + pads (int16 input) | noise | table
+    const size_t smem = (sizeof(TIn) == 4 ? (size_t)2 * (NP + 2 * kPad) * 4 : (size_t)2 * NP * 2 + (size_t)(NP + 2 * kPad) * 4) +
+                        (size_t)NP * 4 + (size_t)kTblWords * 4;
+    // opt in on every launch: the attribute is per device, a process may drive several
+    WW_CHECK(c, cudaFuncSetAttribute(augment_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(c, WW_STAGE_AUGMENT, st);
+    augment_kernel<TIn><<<grid, kThreads, smem, st>>>(p);
+    WW_LAUNCH_CHECK(c);
+    return WW_OK;
+  }
+  // rolled source x2 (with pads) | gathered clip | polyphase table x2
+  const size_t smem = ((size_t)2 * (NP + 2 * kPad) + NP + 2 * kTblWords) * 4;
+  WW_CHECK(c, cudaFuncSetAttribute(augment_pipe_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(c, WW_STAGE_AUGMENT, st);
-  augment_kernel<TIn><<<grid, kThreads, smem, st>>>(p);
+  augment_pipe_kernel<TIn><<<grid, 2 * kRole, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
   return WW_OK;
 }
