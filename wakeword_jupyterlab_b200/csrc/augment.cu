@@ -25,6 +25,7 @@
 #include "ctx.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -481,9 +482,12 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
 // The RMS values "re-measured after scaling" (audiolib.py:60,65) are taken as scale^2 x the sums already known instead of a
 // second pass over registers (mathematically equal; 1e-7 relative).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kRole = 512;            // threads per role
+constexpr int kRole = 512;            // threads of the conditioning role
+constexpr int kRoleG = 256;           // threads of the gather role (port-bound: a few warps saturate it, and a short queue in front of
+                                      // the shared-memory port keeps the latency of the other role's accesses down)
+constexpr int kPipeThreads = kRole + kRoleG;
 constexpr int kPerC = 32;             // samples per conditioning thread: n_samples <= kRole * kPerC
-enum { BAR_C = 1, BAR_SRC_FULL = 2, BAR_SRC_EMPTY = 4, BAR_RES_FULL = 6, BAR_RES_EMPTY = 7 };
+enum { BAR_C = 1, BAR_SRC_FULL = 2, BAR_RES_FULL = 4, BAR_RES_EMPTY = 5 };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -501,6 +505,20 @@ __device__ __forceinline__ void role_sum2(float& a, float& b, float* red, int t)
   if ((t & 31) == 0) { red[t >> 5] = a; red[16 + (t >> 5)] = b; }
   bar_sync(BAR_C, kRole);
   float ra = red[t & 15], rb = red[16 + (t & 15)];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rb += __shfl_xor_sync(0xffffffffu, rb, o); }
+  a = ra; b = rb;
+}
+
+// max of a non-negative value and two sums in one barrier
+__device__ __forceinline__ void role_reduce3(float& m, float& a, float& b, float* red, int t) {
+  const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((t & 31) == 0) { red[t >> 5] = a; red[16 + (t >> 5)] = b; red[32 + (t >> 5)] = __uint_as_float(w); }
+  bar_sync(BAR_C, kRole);
+  float ra = red[t & 15], rb = red[16 + (t & 15)];
+  m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(red[32 + (t & 15)])));
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rb += __shfl_xor_sync(0xffffffffu, rb, o); }
   a = ra; b = rb;
@@ -541,11 +559,20 @@ __device__ __forceinline__ void gather_role(const float* __restrict__ xr, const 
   }
 }
 
+#ifdef WW_AUG_TRACE
+__device__ unsigned long long aug_trace[16];
+#define AUG_T(var) const long long var = clock64()
+#define AUG_ACC(slot, a, b) do { if (blockIdx.x == 0 && (tid == 0 || tid == kRole)) aug_trace[slot] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define AUG_T(var)
+#define AUG_ACC(slot, a, b)
+#endif
+
 template <typename TIn>
-__global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKParams p) {
+__global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const AugKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red3[3][32];
-  __shared__ ClipPrm prm[2];
+  __shared__ float red3[3][48];
+  __shared__ ClipPrm prm[4];                          // ring: clip j's scalars live from one clip before its conditioning to its store
   const int tid = threadIdx.x;
   const int N = p.N;
   const int NP = (N + 7) & ~7;
@@ -553,7 +580,7 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
   float* src0 = reinterpret_cast<float*>(smem_raw) + kPad;      // src[s] = src0 + s SP, kPad zeros on either side
   float* res = src0 - kPad + 2 * SP;                            // [NP]
   float* tbl0 = res + NP;                                       // [2][kTblWords]
-  for (int k = tid; k < 2 * (2 * kPad + NP - N); k += 2 * kRole) {
+  for (int k = tid; k < 2 * (2 * kPad + NP - N); k += kPipeThreads) {
     float* base = src0 + (k & 1) * SP;
     const int r = k >> 1;
     base[r < kPad ? r - kPad : N + (r - kPad)] = 0.0f;
@@ -566,16 +593,20 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
     const int t = tid - kRole;
     for (int k = 0; k < K; ++k) {
       const int s = k & 1;
-      bar_sync(BAR_SRC_FULL + s, 2 * kRole);
-      if (k >= 1) bar_sync(BAR_RES_EMPTY, 2 * kRole);
-      const ClipPrm& q = prm[s];
+      AUG_T(g0);
+      bar_sync(BAR_SRC_FULL + s, kPipeThreads);
+      AUG_T(g1);
+      if (k >= 1) bar_sync(BAR_RES_EMPTY, kPipeThreads);
+      AUG_T(g2);
+      AUG_ACC(0, g0, g1); AUG_ACC(1, g1, g2);
+      const ClipPrm& q = prm[k & 3];
       const uint32_t flags = q.flags;
       const float* cur = src0 + s * SP;
       const float* tbl = tbl0 + s * kTblWords;
       if (!(flags & WW_AUG_SPEED)) {
-        for (int i = t; i < N; i += kRole) res[i] = cur[i];      // the roll happened on the way in: bit-exact copy
+        for (int i = t; i < N; i += kRoleG) res[i] = cur[i];      // the roll happened on the way in: bit-exact copy
       } else if (q.rs < 0) {
-        for (int i = t; i < N; i += kRole) res[i] = __int_as_float(0x7fc00000);     // loud: NaN clip
+        for (int i = t; i < N; i += kRoleG) res[i] = __int_as_float(0x7fc00000);     // loud: NaN clip
       } else {
         const RsDesc d = q.d;
         const int pitch = d.nz + ((d.nz & 4) ? 0 : 4);
@@ -583,9 +614,9 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
         const bool in_smem = tbl_words <= kTblWords;
         const int out_len = (d.n * N + d.o - 1) / d.o;                               // ceil(n*N/o), < 2^31
         const int crop = (out_len > N) ? q.crop : 0;
-        const bool fixed = in_smem && d.n <= kRole && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
+        const bool fixed = in_smem && d.n <= kRoleG && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
         if (fixed) {
-          const int S = d.n * (kRole / d.n);
+          const int S = d.n * (kRoleG / d.n);
           if (t < S) {
             switch (d.nz >> 2) {
               case 4: gather_role<4>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
@@ -599,7 +630,7 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
           const int* lo_t = reinterpret_cast<const int*>(kern + d.n * pitch);
           const int* cnt_t = lo_t + d.n;
 #pragma unroll 1
-          for (int i = t; i < N; i += kRole) {
+          for (int i = t; i < N; i += kRoleG) {
             float acc = 0.0f;
             const int j = i + crop;
             if (j < out_len) {
@@ -614,48 +645,215 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
           }
         }
       }
-      bar_arrive(BAR_RES_FULL, 2 * kRole);
-      if (k + 2 < K) bar_arrive(BAR_SRC_EMPTY + s, 2 * kRole);
+      AUG_T(g3);
+      AUG_ACC(2, g2, g3);
+      bar_arrive(BAR_RES_FULL, kPipeThreads);
     }
     return;
   }
 
   // =================================================== conditioning role
   const int t = tid;
-  // clip j of this CTA -> src[j & 1], prm[j & 1], tbl[j & 1]
-  auto prep = [&](int j) {
-    const int s = j & 1;
+  const int nt = N - t;                                  // sample t + off exists  <=>  off < nt
+  const int esz = (int)sizeof(TIn);
+  // scalars of clip j -> prm[j & 3] (warp 0: lane 0 the plain fields, the warp the search of the prepared resample ratios).
+  // Fetched ONE CLIP AHEAD of prep(j), so nobody ever waits for this two-level chain of global loads.
+  auto fetch_scalars = [&](int j) {
     const int b = (int)blockIdx.x + j * (int)gridDim.x;
-    if (j >= 2) bar_sync(BAR_SRC_EMPTY + s, 2 * kRole);
-    const TIn* __restrict__ x = static_cast<const TIn*>(p.clips) + (int64_t)b * N;
-    float o[kPerC];
-#pragma unroll
-    for (int e = 0; e < kPerC; ++e) {
-      const int i = t + e * kRole;
-      o[e] = (i < N) ? cvt_in(__ldg(x + i)) : 0.0f;
-    }
+    ClipPrm& q = prm[j & 3];
     const uint32_t flags = __ldg(p.a.flags + b);
-    if (t < 32) {
-      // scalars of the clip (lane 0) and parallel search of the prepared resample ratios (whole warp), loads in flight
-      ClipPrm& q = prm[s];
-      if (t == 0) {
-        q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
-        q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
+    if (t == 0) {
+      q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
+      q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
+    }
+    __syncwarp();
+    if (flags & WW_AUG_SPEED) {
+      const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+      for (int i = t; i < p.n_rs; i += 32)
+        if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
+    }
+  };
+  auto clip_ptr = [&](int j) {
+    return static_cast<const TIn*>(p.clips) + (int64_t)((int)blockIdx.x + j * (int)gridDim.x) * N;
+  };
+  auto prefetch_clip = [&](int j) {                      // HBM -> L2, one 128-byte line per thread
+    const char* g = reinterpret_cast<const char*>(clip_ptr(j));
+    for (int l = t * 128; l < N * esz; l += kRole * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + l));
+  };
+  // sum of squares of the noise segment of a clip (thread partial): two batches of 16 loads
+  auto noise_sumsq = [&](const ClipPrm& q) {
+    const float* __restrict__ nb = p.bank + (int64_t)q.noise_idx * p.bank_len + q.noise_off + t;
+    float sn = 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float n[kPerC / 2];
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e) {
+        const int off = (h * (kPerC / 2) + e) * kRole;
+        n[e] = (off < nt) ? __ldg(nb + off) : 0.0f;
       }
-      __syncwarp();
-      if (flags & WW_AUG_SPEED) {
-        const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
-        for (int i = t; i < p.n_rs; i += 32)
-          if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e) sn = fmaf(n[e], n[e], sn);
+    }
+    return sn;
+  };
+
+  // ---- conditioning of clip j into src[j & 1], in batches of kPB samples per thread that are threaded through the
+  // finishing pass of clip j - 2 (issue a batch's loads, do something else, fold them into the peak and store them rolled):
+  // the two chains of global / shared-memory latencies overlap instead of adding up, and the gather role never waits for it
+  constexpr int kPB = 8;
+  float pb[kPB];
+  float m_prep = 0.0f;                                   // thread-partial peak of the clip being conditioned
+  const TIn* __restrict__ px = nullptr;                  // its samples (+ t)
+  float* pa = nullptr; float* pbw = nullptr; int lim = 0;  // rolled destination: element t + off -> pa[off], or pbw[off] from off >= lim on
+  auto prep_begin = [&](int j) {
+    const ClipPrm& qn = prm[j & 3];
+    px = clip_ptr(j) + t;
+    int sh = (qn.flags & WW_AUG_SHIFT) ? qn.shift % N : 0;
+    if (sh < 0) sh += N;
+    pa = src0 + (j & 1) * SP + t + sh;                   // rolled[(i + shift) mod N] = in[i]
+    pbw = pa - N;
+    lim = nt - sh;
+    m_prep = 0.0f;
+  };
+  auto prep_issue = [&](int bi) {
+#pragma unroll
+    for (int e = 0; e < kPB; ++e) {
+      const int off = (bi * kPB + e) * kRole;
+      pb[e] = (off < nt) ? cvt_in(__ldg(px + off)) : 0.0f;
+    }
+  };
+  auto prep_consume = [&](int bi) {
+#pragma unroll
+    for (int e = 0; e < kPB; ++e) {
+      const int off = (bi * kPB + e) * kRole;
+      m_prep = fmaxf(m_prep, fabsf(pb[e]));
+      if (off < nt) { float* d = (off >= lim) ? pbw : pa; d[off] = pb[e]; }
+    }
+  };
+  auto prep_end = [&](int j) {
+    const ClipPrm& qn = prm[j & 3];
+    if ((qn.flags & WW_AUG_SPEED) && qn.rs >= 0) {
+      const int pitch = qn.d.nz + ((qn.d.nz & 4) ? 0 : 4);
+      const int tbl_words = qn.d.n * pitch + 2 * qn.d.n;
+      if (tbl_words <= kTblWords) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.rs_kern + qn.d.offset);    // offset and size are whole float4s
+        float4* t4 = reinterpret_cast<float4*>(tbl0 + (j & 1) * kTblWords);
+        for (int i = t; i < (tbl_words + 3) >> 2; i += kRole) t4[i] = __ldg(g4 + i);
       }
     }
-    float m = 0.0f;
+    bar_arrive(BAR_SRC_FULL + (j & 1), kPipeThreads);
+    if (j + 1 < K) prefetch_clip(j + 1);
+    if (t < 32 && j + 1 < K && j >= 2) fetch_scalars(j + 1);     // published by the role-wide barriers before it is read
+  };
+  static_assert(kPerC == 4 * kPB, "four conditioning batches per clip");
+
+  if (t < 32) { fetch_scalars(0); if (K > 1) fetch_scalars(1); if (K > 2) fetch_scalars(2); }
+  bar_sync(BAR_C, kRole);
+  float m_in = 0.0f, m_mid = 0.0f;                       // thread-partial peaks of clip k (being finished) and clip k + 1
+  for (int j = 0; j < 2 && j < K; ++j) {                 // the first two clips: nothing to hide behind yet
+    prep_begin(j);
+    prep_issue(0); prep_consume(0); prep_issue(1); prep_consume(1); prep_issue(2); prep_consume(2); prep_issue(3); prep_consume(3);
+    prep_end(j);
+    if (j == 0) m_in = m_prep; else m_mid = m_prep;
+  }
+
+  float o[kPerC];
+  for (int k = 0; k < K; ++k) {
+    // ---------------- iteration k: finish clip k out of `res`; meanwhile condition clip k + 2 into src[k & 1], which the
+    // gather of clip k has just released (res_full(k) says so: no barrier of its own)
+    const int j = k + 2;
+    const bool do_prep = j < K;
+    const ClipPrm& q = prm[k & 3];
+    const uint32_t flags = q.flags;
+    AUG_T(c0);
+    // the noise energy of clip k does not depend on the gather: taken while the gather role is still busy with the clip
+    float sn = (flags & WW_AUG_NOISE) ? noise_sumsq(q) : 0.0f;
+    AUG_T(c1);
+    bar_sync(BAR_RES_FULL, kPipeThreads);
+    AUG_T(c2);
+    AUG_ACC(4, c0, c1); AUG_ACC(5, c1, c2);
 #pragma unroll
-    for (int e = 0; e < kPerC; ++e) m = fmaxf(m, fabsf(o[e]));
-    m = role_max_nonneg(m, red3[0], t);                 // also publishes prm[s] to the role
+    for (int e = 0; e < kPerC; ++e) o[e] = (e * kRole < nt) ? res[t + e * kRole] : 0.0f;
+    if (k + 1 < K) bar_arrive(BAR_RES_EMPTY, kPipeThreads);
+    AUG_T(c2a); AUG_ACC(8, c2, c2a);
+    if (do_prep) { prep_begin(j); prep_issue(0); }
     const bool inexact = (flags & (WW_AUG_SPEED | WW_AUG_NOISE)) != 0;
-    if ((flags & WW_AUG_NORM_IN) && m > 0.0f) {
-      const ClipDiv dv = make_clip_div(m);
+    const float* __restrict__ nb = p.bank + (int64_t)q.noise_idx * p.bank_len + q.noise_off + t;
+    // first half of the noise segment for the mix: requested before the reduction, consumed after it
+    float n[kPerC / 2];
+    if (flags & WW_AUG_NOISE) {
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e) n[e] = (e * kRole < nt) ? __ldg(nb + e * kRole) : 0.0f;
+    }
+    float sc = 0.0f, mred = 0.0f;
+    if (flags & (WW_AUG_NORM_IN | WW_AUG_NOISE)) {
+      // ONE reduction: peak of the raw clip (taken while it was conditioned), energy of the gathered clip, energy of the noise
+      if (flags & WW_AUG_NOISE) {
+#pragma unroll
+        for (int e = 0; e < kPerC; ++e) sc = fmaf(o[e], o[e], sc);
+      }
+      mred = m_in;
+      role_reduce3(mred, sc, sn, red3[1], t);
+    }
+    AUG_T(c2b); AUG_ACC(9, c2a, c2b);
+    if (do_prep) { prep_consume(0); prep_issue(1); }
+    if ((flags & WW_AUG_NORM_IN) && mred > 0.0f) {
+      const ClipDiv dv = make_clip_div(mred);
+      if (inexact && dv.fast) {
+#pragma unroll
+        for (int e = 0; e < kPerC; ++e) o[e] = dv.approx(o[e]);
+        sc *= dv.r * dv.r;                               // energy of the normalised clip
+      } else {
+#pragma unroll
+        for (int e = 0; e < kPerC; ++e) o[e] = dv(o[e]);
+        if (flags & WW_AUG_NOISE) {                      // IEEE-divide path on a noisy clip (peak with an all-ones significand): re-measure
+          sc = 0.0f;
+#pragma unroll
+          for (int e = 0; e < kPerC; ++e) sc = fmaf(o[e], o[e], sc);
+          float z = 0.0f;
+          role_sum2(sc, z, red3[0], t);
+        }
+      }
+    }
+    if (flags & WW_AUG_NOISE) {
+      const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
+      const float inv_n = 1.0f / (float)N;
+      const float scalarclean = target * rsqrtf(sc * inv_n), scalarnoise = target * rsqrtf(sn * inv_n);
+      // the reference re-measures both RMS values after scaling (audiolib.py:60,65): sum (a x)^2 = a^2 sum x^2
+      const float sc2 = sc * scalarclean * scalarclean, sn2 = sn * scalarnoise * scalarnoise;
+      // noisescalar = sqrt(rmsclean / 10^(snr/20) / rmsnoise), audiolib.py:68 (sqrt quirk kept)
+      const float noisescalar = rsqrtf(rsqrtf(__fdividef(sc2, sn2))) * exp2f(q.snr * -0.0830482023721841f);
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e) o[e] = fmaf(n[e] * scalarnoise, noisescalar, o[e] * scalarclean);
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e) {
+        const int off = (kPerC / 2 + e) * kRole;
+        n[e] = (off < nt) ? __ldg(nb + off) : 0.0f;
+      }
+      if (do_prep) { prep_consume(1); prep_issue(2); }
+#pragma unroll
+      for (int e = 0; e < kPerC / 2; ++e)
+        o[kPerC / 2 + e] = fmaf(n[e] * scalarnoise, noisescalar, o[kPerC / 2 + e] * scalarclean);
+    } else if (do_prep) {
+      prep_consume(1); prep_issue(2);
+    }
+    AUG_T(c2c); AUG_ACC(10, c2b, c2c);
+    if (flags & WW_AUG_GAIN) {
+      const float g = q.gain;
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) o[e] *= g;
+    }
+    float mo = 0.0f;
+    if (flags & WW_AUG_NORM_OUT) {
+#pragma unroll
+      for (int e = 0; e < kPerC; ++e) mo = fmaxf(mo, fabsf(o[e]));
+      mo = role_max_nonneg(mo, red3[2], t);
+    }
+    AUG_T(c2d); AUG_ACC(11, c2c, c2d);
+    if (do_prep) { prep_consume(2); prep_issue(3); }
+    if ((flags & WW_AUG_NORM_OUT) && mo > 0.0f) {
+      const ClipDiv dv = make_clip_div(mo);
       if (inexact && dv.fast) {
 #pragma unroll
         for (int e = 0; e < kPerC; ++e) o[e] = dv.approx(o[e]);
@@ -664,98 +862,14 @@ __global__ void __launch_bounds__(2 * kRole, 1) augment_pipe_kernel(const AugKPa
         for (int e = 0; e < kPerC; ++e) o[e] = dv(o[e]);
       }
     }
-    int sh = (flags & WW_AUG_SHIFT) ? prm[s].shift % N : 0;
-    if (sh < 0) sh += N;
-    float* cur = src0 + s * SP;
-    int dpos = t + sh;                                  // rolled[(i + shift) mod N] = in[i]
-    if (dpos >= N) dpos -= N;
+    float* __restrict__ dst = p.out + (int64_t)((int)blockIdx.x + k * (int)gridDim.x) * N + t;
 #pragma unroll
-    for (int e = 0; e < kPerC; ++e) {
-      const int i = t + e * kRole;
-      if (i < N) cur[dpos] = o[e];
-      dpos += kRole;
-      if (dpos >= N) dpos -= N;
-    }
-    if ((flags & WW_AUG_SPEED) && prm[s].rs >= 0) {
-      const RsDesc& d = prm[s].d;
-      const int pitch = d.nz + ((d.nz & 4) ? 0 : 4);
-      const int tbl_words = d.n * pitch + 2 * d.n;
-      if (tbl_words <= kTblWords) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.rs_kern + d.offset);    // offset and size are whole float4s
-        float4* t4 = reinterpret_cast<float4*>(tbl0 + s * kTblWords);
-        for (int i = t; i < (tbl_words + 3) >> 2; i += kRole) t4[i] = __ldg(g4 + i);
-      }
-    }
-    bar_arrive(BAR_SRC_FULL + s, 2 * kRole);
-  };
-
-  prep(0);
-  for (int k = 0; k < K; ++k) {
-    if (k + 1 < K) prep(k + 1);
-    const int b = (int)blockIdx.x + k * (int)gridDim.x;
-    bar_sync(BAR_RES_FULL, 2 * kRole);
-    float o[kPerC];
-#pragma unroll
-    for (int e = 0; e < kPerC; ++e) {
-      const int i = t + e * kRole;
-      o[e] = (i < N) ? res[i] : 0.0f;
-    }
-    if (k + 1 < K) bar_arrive(BAR_RES_EMPTY, 2 * kRole);
-    const ClipPrm& q = prm[k & 1];
-    const uint32_t flags = q.flags;
-    const bool inexact = (flags & (WW_AUG_SPEED | WW_AUG_NOISE)) != 0;
-    if (flags & WW_AUG_NOISE) {
-      const float* __restrict__ nb = p.bank + (int64_t)q.noise_idx * p.bank_len + q.noise_off;
-      const float target = 0.0562341325190349f;            // 10 ** (-25 / 20)
-      float sc = 0.0f, sn = 0.0f;
-#pragma unroll
-      for (int e = 0; e < kPerC; ++e) {
-        const int i = t + e * kRole;
-        const float n = (i < N) ? __ldg(nb + i) : 0.0f;
-        sc = fmaf(o[e], o[e], sc);
-        sn = fmaf(n, n, sn);
-      }
-      role_sum2(sc, sn, red3[1], t);
-      const float inv_n = 1.0f / (float)N;
-      const float scalarclean = target * rsqrtf(sc * inv_n), scalarnoise = target * rsqrtf(sn * inv_n);
-      // the reference re-measures both RMS values after scaling (audiolib.py:60,65): sum (a x)^2 = a^2 sum x^2
-      const float sc2 = sc * scalarclean * scalarclean, sn2 = sn * scalarnoise * scalarnoise;
-      // noisescalar = sqrt(rmsclean / 10^(snr/20) / rmsnoise), audiolib.py:68 (sqrt quirk kept)
-      const float noisescalar = rsqrtf(rsqrtf(__fdividef(sc2, sn2))) * exp2f(q.snr * -0.0830482023721841f);
-#pragma unroll
-      for (int e = 0; e < kPerC; ++e) {
-        const int i = t + e * kRole;
-        const float n = (i < N) ? __ldg(nb + i) : 0.0f;
-        o[e] = fmaf(n * scalarnoise, noisescalar, o[e] * scalarclean);
-      }
-    }
-    if (flags & WW_AUG_GAIN) {
-      const float g = q.gain;
-#pragma unroll
-      for (int e = 0; e < kPerC; ++e) o[e] *= g;
-    }
-    if (flags & WW_AUG_NORM_OUT) {
-      float mo = 0.0f;
-#pragma unroll
-      for (int e = 0; e < kPerC; ++e) mo = fmaxf(mo, fabsf(o[e]));
-      mo = role_max_nonneg(mo, red3[2], t);
-      if (mo > 0.0f) {
-        const ClipDiv dv = make_clip_div(mo);
-        if (inexact && dv.fast) {
-#pragma unroll
-          for (int e = 0; e < kPerC; ++e) o[e] = dv.approx(o[e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < kPerC; ++e) o[e] = dv(o[e]);
-        }
-      }
-    }
-    float* __restrict__ dst = p.out + (int64_t)b * N;
-#pragma unroll
-    for (int e = 0; e < kPerC; ++e) {
-      const int i = t + e * kRole;
-      if (i < N) dst[i] = o[e];
-    }
+    for (int e = 0; e < kPerC; ++e)
+      if (e * kRole < nt) dst[e * kRole] = o[e];
+    if (do_prep) { prep_consume(3); prep_end(j); }
+    m_in = m_mid; m_mid = m_prep;
+    AUG_T(c3);
+    AUG_ACC(6, c2, c3);
   }
 }
 
@@ -806,8 +920,20 @@ static int launch_augment_t(ww_ctx* c, const AugKParams& p, cudaStream_t st) {
   const size_t smem = ((size_t)2 * (NP + 2 * kPad) + NP + 2 * kTblWords) * 4;
   WW_CHECK(c, cudaFuncSetAttribute(augment_pipe_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(c, WW_STAGE_AUGMENT, st);
-  augment_pipe_kernel<TIn><<<grid, 2 * kRole, smem, st>>>(p);
+  augment_pipe_kernel<TIn><<<grid, kPipeThreads, smem, st>>>(p);
   WW_LAUNCH_CHECK(c);
+#ifdef WW_AUG_TRACE
+  {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, aug_trace, sizeof(h));
+    const int K = (p.B + grid - 1) / grid;
+    fprintf(stderr, "[aug trace] CTA 0, %d clips, cycles per clip: G wait src %llu, wait res_empty %llu, gather %llu | C prep %llu, wait res_full %llu, finish %llu (res load %llu, reduce3 %llu, mix %llu, max reduce %llu)\n",
+            K, h[0] / K, h[1] / K, h[2] / K, h[4] / K, h[5] / K, h[6] / K, h[8] / K, h[9] / K, h[10] / K, h[11] / K);
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(aug_trace, h, sizeof(h));
+  }
+#endif
   return WW_OK;
 }
 
