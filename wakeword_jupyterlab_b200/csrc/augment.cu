@@ -614,14 +614,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
         const bool in_smem = tbl_words <= kTblWords;
         const int out_len = (d.n * N + d.o - 1) / d.o;                               // ceil(n*N/o), < 2^31
         const int crop = (out_len > N) ? q.crop : 0;
-        const bool fixed = in_smem && d.n <= kRoleG && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
+        // Lanes of a warp take consecutive outputs, whose sources are o / n words apart: when the clip is being shortened
+        // (o > n) the 32 loads of a tap would span more than 32 words = two wavefronts each.  Then only the first L lanes of
+        // every warp work (30 o / n + 2 <= 32 words, the jitter of the first-tap table included): one wavefront per load,
+        // and for n = 100 the idle lanes are the ones that S = n floor(threads / n) leaves idle anyway.
+        const int L = d.o > d.n ? min(32, (30 * d.n) / d.o + 1) : 32;
+        const int lanes = (kRoleG / 32) * L;
+        const bool fixed = in_smem && d.n <= lanes && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
         if (fixed) {
-          const int S = d.n * (kRoleG / d.n);
-          if (t < S) {
+          const int S = d.n * (lanes / d.n);
+          const int u = (t >> 5) * L + (t & 31);
+          if ((t & 31) < L && u < S) {
             switch (d.nz >> 2) {
-              case 4: gather_role<4>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
-              case 5: gather_role<5>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
-              default: gather_role<6>(cur, tbl, pitch, d, crop, out_len, N, S, t, res); break;
+              case 4: gather_role<4>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+              case 5: gather_role<5>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+              default: gather_role<6>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
             }
           }
         } else {
