@@ -280,6 +280,39 @@ def test_forward_golden_seeded(ww, golden_dir, mode):
     assert _rel(out.cpu().numpy(), g["logits_f64"]) < _tol(mode)
 
 
+def test_tensor_core_head_matches_fp32_head(ww, golden_dir, monkeypatch):
+    """head_tc.cu (the two LSTM layers as tcgen05 TF32 GEMMs, both operands split hi + lo: three products) against the fp32
+    CUDA-core kernels of head.cu (WW_HEAD_KERNEL=fp32) on the same pooled features: logits within 5e-6 of their scale (measured 1.5e-6: the tensor core accumulates with fewer guard bits than an FMA chain),
+    identical decisions, at batch sizes that are not multiples of the 128-row tile; trained weights (large gate
+    pre-activations) and the float64 golden logits as the outside reference."""
+    g = np.load(os.path.join(golden_dir, "model_trained.npz"))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    net = _load(ww, sd, mode="fp32")                     # exact conv stack: any difference is the head's
+    base = R.make_clips(int(g["n"]), seed=int(g["clip_seed"]))
+    for n in (int(g["n"]), 1, 129, 300):
+        clips = np.tile(base, ((n + len(base) - 1) // len(base), 1))[:n]
+        x = torch.from_numpy(clips).cuda()
+        lt, pt, dt = ww.score_clips(x, net, normalize=True)
+        monkeypatch.setenv("WW_HEAD_KERNEL", "fp32")
+        lf, pf, df = ww.score_clips(x, net, normalize=True)
+        monkeypatch.delenv("WW_HEAD_KERNEL")
+        assert _rel(lt.cpu().numpy(), lf.cpu().numpy()) < 5e-6, n
+        assert torch.equal(dt, df) and float((pt - pf).abs().max()) < 1e-6
+        if n == int(g["n"]):
+            assert _rel(lt.cpu().numpy(), g["logits_reference"]) < LOGIT_REL_TOL
+    # the README preset (hidden 128: two column tiles, K = 128 in both layers)
+    g2 = np.load(os.path.join(golden_dir, "model_readme.npz"))
+    clips = _norm(R.make_clips(24, seed=int(g2["clip_seed"])))[:int(g2["n"])]
+    feats = torch.from_numpy(LM.audio_to_mel_batch(clips, hop=100)[:, None]).cuda()
+    net2 = _load(ww, R.seeded_state_dict(128, seed=1), ww.ReadmeModelConfig, ww.ReadmeAudioConfig, mode="fp32")
+    with torch.no_grad():
+        a = net2(feats).cpu().numpy()
+        monkeypatch.setenv("WW_HEAD_KERNEL", "fp32")
+        b = net2(feats).cpu().numpy()
+        monkeypatch.delenv("WW_HEAD_KERNEL")
+    assert _rel(a, b) < 5e-6 and _rel(a, g2["logits_reference"]) < LOGIT_REL_TOL
+
+
 @pytest.mark.parametrize("mode", _conv_modes())
 def test_forward_golden_trained_and_decisions(ww, golden_dir, mode):
     g = np.load(os.path.join(golden_dir, "model_trained.npz"))

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwakeword_b200.so")
-SOURCES = ["c_api.cu", "logmel.cu", "logmel_tc.cu", "augment.cu", "conv_fp32.cu", "conv12_tc.cu", "conv3_tc.cu", "head.cu", "train.cu", "train_tc.cu", "pvoc.cu"]
+SOURCES = ["c_api.cu", "logmel.cu", "logmel_tc.cu", "augment.cu", "conv_fp32.cu", "conv12_tc.cu", "conv3_tc.cu", "head.cu", "head_tc.cu", "train.cu", "train_tc.cu", "pvoc.cu"]
 NVCC_FLAGS = (["-DWW_AUG_TRACE"] if os.environ.get("WW_AUG_TRACE_BUILD") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 

@@ -144,7 +144,7 @@ int free_all(ww_ctx* c) {
   cudaFree(c->d_tc_f32); cudaFree(c->d_tc_f64hi); cudaFree(c->d_tc_f64lo); cudaFree(c->d_tc_tw); cudaFree(c->d_tc_rot); cudaFree(c->d_tc_tasks);
   for (auto& kv : c->w) cudaFree(kv.second);
   for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
-  for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); cudaFree(c->d_bias_sum[i]); }
+  for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); cudaFree(c->d_bias_sum[i]); cudaFree(c->d_head_tc[i]); }
   {
     TrainState& t = c->train;
     float* bufs[] = {t.grad, t.m, t.v, t.wflip3, t.wflip2, t.part, t.loss, t.act1, t.act2, t.act3, t.dact2, t.dact1, t.pooled,

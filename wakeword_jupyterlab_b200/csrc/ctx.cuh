@@ -121,6 +121,8 @@ struct ww_ctx {
   float* d_head_wt[8] = {};                            // per LSTM layer: [K][3H] gate-interleaved (i,g,o), fp32
   float* d_head_b[8] = {};                             // per layer: [3H] b_ih + b_hh (i,g,o)
   float* d_bias_sum[8] = {};                           // per layer: [4H] b_ih + b_hh in reference row order (training)
+  float* d_head_tc[8] = {};                            // per layer: TF32 hi | lo operand of the tensor-core head (head_tc.cu)
+  uint64_t head_tc_version[8] = {};                    // weights_version each was packed from
   TrainState train;
   cudaEvent_t apply_event = nullptr;                    // recorded after the Adam kernels of ww_train_apply
   __half* d_w2_split = nullptr;                        // conv2 weights * 2^k, fp16 hi/lo, UMMA canonical layout
@@ -213,6 +215,7 @@ int ww_launch_pad_logmel(ww_ctx* c, const float* logmel, float* in_pad, int B, c
 LogmelOut ww_conv_tc_logmel_out(const ww_ctx* c, float* in_pad);
 size_t ww_conv_tc_inpad_floats_per_clip(const ww_ctx* c);
 int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decision, cudaStream_t st);
+int ww_launch_gated_dense_tc(ww_ctx* c, int l, const float* x, float* out, int B, cudaStream_t st);   // 1: shape not handled
 int ww_prepare_weights(ww_ctx* c, cudaStream_t st);
 int ww_conv_tc_prepare(ww_ctx* c, cudaStream_t st);
 size_t ww_conv_tc_act2_bytes_per_clip(const ww_ctx* c);

@@ -297,9 +297,14 @@ int ww_launch_head(ww_ctx* c, int B, float* logits, float* prob1, uint8_t* decis
     p.wt = c->d_head_wt[l]; p.bias = c->d_head_b[l];
     p.out = c->ws_h[l & 1]; p.B = B; p.K = (l == 0) ? 128 : H; p.H = H;
     dim3 grid((B + TM - 1) / TM, (H + TN - 1) / TN);
-    if (pipe) gated_dense_pipe_kernel<<<grid, kThreads, kPipeSmem, st>>>(p);
-    else gated_dense_kernel<<<grid, kThreads, 0, st>>>(p);
-    WW_LAUNCH_CHECK(c);
+    // the tensor-core kernel (head_tc.cu) where its tile shape applies, else the fp32 kernels of this file
+    const int rc = pipe ? ww_launch_gated_dense_tc(c, l, p.x, p.out, B, st) : 1;
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      if (pipe) gated_dense_pipe_kernel<<<grid, kThreads, kPipeSmem, st>>>(p);
+      else gated_dense_kernel<<<grid, kThreads, 0, st>>>(p);
+      WW_LAUNCH_CHECK(c);
+    }
     x = p.out;
   }
   FcParams f;
