@@ -10,7 +10,7 @@ python bench.py --workload train --no-cpu-baseline > $O/${T}_bench_train_1gpu.js
 python bench.py --conv-mode fp16 --no-cpu-baseline > $O/${T}_bench_score_fp16mode_1gpu.json 2>/dev/null
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_reference_arm.json 2>/dev/null
 CMD="python bench.py --clips 8192 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-K='regex:augment_pipe_kernel|augment_kernel|logmel_kernel|conv12_kernel|conv3_kernel|pool_finish|gated_dense|fc_softmax'
+K='regex:augment_pipe_kernel|augment_kernel|logmel_kernel|conv12_kernel|conv3_kernel|pool_finish|gated_dense|fc_softmax|head_tc_pack'
 $CMD > $O/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 24 -c 8 --csv --log-file $O/${T}_ncu_launches.csv $CMD > $O/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k "$K" -s 24 -c 8 -f -o $O/${T}_full $CMD > $O/ncu2.log 2>&1
 tail -2 $O/ncu2.log
