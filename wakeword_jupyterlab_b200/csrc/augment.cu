@@ -469,18 +469,22 @@ __global__ void __launch_bounds__(kThreads, 1) augment_kernel(const AugKParams p
 // ---------------------------------------------------------------------------------------------------------------------
 // Pipelined form (default).  The lock-step kernel above keeps every warp in the same phase between block barriers: the
 // gather saturates the shared-memory port while the issue slots idle, the element-wise passes do the opposite (ncu: LSU
-// data pipe 54 %, issue 47 %).  Here the CTA is two ROLES of 512 threads that work on DIFFERENT clips:
-//   C (conditioning, warps 0-15): loads clip k + 1 from HBM, peak-normalises it, stores it ROLLED into src[(k + 1) & 1]
-//     with the zero pads of the fixed-phase gather around it, copies its polyphase table; then takes the gathered clip k out
-//     of `res` into registers (32 samples per thread) and runs noise mix / gain / peak normalise / store on it;
-//   G (gather, warps 16-31): res[i] = sum_k taps[ph][k] * src[k & 1][x0(i) + k] for clip k, nothing else: one LDS + one FMA
-//     per tap, its tap row in registers (fixed-phase ownership as above, S = n * floor(512 / n)).
-// so the port-bound gather of one clip runs under the issue-bound passes of its neighbours.  The roles meet at named
-// barriers in producer / consumer form (bar.arrive by the producer, bar.sync by the consumer, 1024 = both roles):
-// src_full[2], src_empty[2], res_full, res_empty.  Arithmetic per element is the lock-step kernel's (same normalise,
-// same tap order, same mix); the block sums are taken over 16 warps instead of 32 (1e-7 relative on the noise scalars).
-// The RMS values "re-measured after scaling" (audiolib.py:60,65) are taken as scale^2 x the sums already known instead of a
-// second pass over registers (mathematically equal; 1e-7 relative).
+// data pipe 54 %, issue 47 %).  Here the CTA is two ROLES that work on DIFFERENT clips:
+//   C (conditioning, warps 0-15): in iteration k it takes the gathered clip k out of `res` into registers (32 samples per
+//     thread), releases `res` at once and finishes the clip: peak normalise (the gather is linear, so the peak of the raw
+//     clip is applied behind it: one rounding of difference, none for clips that are only rolled), noise mix, gain, peak
+//     normalise, store.  Threaded through that pass in four batches of 8 samples per thread, it loads clip k + 2 from HBM
+//     and stores it ROLLED into src[k & 1] -- which the gather of clip k has just released -- with the zero pads of the
+//     fixed-phase gather around it, and copies its polyphase table;
+//   G (gather, warps 16-23): res[i] = sum_k taps[ph][k] * src[k & 1][x0(i) + k] for clip k, nothing else: two adjacent
+//     outputs per thread off one window fetched with 64-bit loads, both tap rows in registers (gather_role_pairs).
+// so the port-bound gather of one clip runs under the latency-bound passes of its neighbours.  The roles meet at named
+// barriers in producer / consumer form (bar.arrive by the producer, bar.sync by the consumer, count = both roles):
+// src_full[2], res_full, res_empty (res_full(k) also says that src[k & 1] is free again).  The per-clip scalars live in a
+// 4-entry ring that warp 0 fills three clips ahead.  The peak of the raw clip, the energy of the gathered clip and the
+// energy of the noise segment share ONE reduction; the RMS values "re-measured after scaling" (audiolib.py:60,65) are
+// scale^2 x the sums already known (mathematically equal; 1e-7 relative); the block sums are taken over 16 warps instead
+// of 32 (1e-7 relative on the noise scalars).  Per element the arithmetic is the lock-step kernel's up to summation order.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kRole = 512;            // threads of the conditioning role
 constexpr int kRoleG = 256;           // threads of the gather role (port-bound: a few warps saturate it, and a short queue in front of
@@ -524,39 +528,55 @@ __device__ __forceinline__ void role_reduce3(float& m, float& a, float& b, float
   a = ra; b = rb;
 }
 
-// gather role, fixed phase: thread t < S owns the outputs t + m S (see gather_fixed_phase)
-template <int NZ4>
-__device__ __forceinline__ void gather_role(const float* __restrict__ xr, const float* __restrict__ tbl, int pitch,
-                                            const RsDesc& d, int crop, int out_len, int N, int S, int t,
-                                            float* __restrict__ res) {
+// Gather role, two adjacent outputs per thread.  Outputs j and j + 1 read windows that start 0-2 samples apart, so ONE window
+// of NW = nz + 4 samples serves both: it is fetched as 64-bit loads from an even start (the parity of the first tap's
+// position and the offset of the second output's window are constants of the thread -- its two phases are fixed and the
+// window advances by an even step -- and are folded into two tap rows shifted into place once per clip), which turns the
+// gather's nz loads per output into (nz + 4) / 4: the LSU pipe, which paces this kernel, sees 3.4x fewer instructions.
+// Thread u < S / 2 owns the outputs 2 u + e + m S (S = n c, c even).  Returns false (nothing written) when a tap row does not
+// fit its shifted window; the caller then runs the one-output form for this thread's outputs.
+template <int NW>
+__device__ __forceinline__ bool gather_role_pairs(const float* __restrict__ xr, const float* __restrict__ tbl, int pitch,
+                                                  const RsDesc& d, int crop, int out_len, int N, int S, int u,
+                                                  float* __restrict__ res) {
   const int* lo_t = reinterpret_cast<const int*>(tbl + d.n * pitch);
-  const int j0 = t + crop;
-  const int qq0 = j0 / d.n, ph = j0 - qq0 * d.n;
-  float w[4 * NZ4];
-  const float4* kr4 = reinterpret_cast<const float4*>(tbl + ph * pitch);
+  const int* cnt_t = lo_t + d.n;
+  const int j0 = 2 * u + crop, j1 = j0 + 1;
+  const int q0 = j0 / d.n, p0 = j0 - q0 * d.n;
+  const int q1 = j1 / d.n, p1 = j1 - q1 * d.n;
+  const int x0 = q0 * d.o - d.width + lo_t[p0], x1 = q1 * d.o - d.width + lo_t[p1];
+  const int wb = min(x0, x1) & ~1;                      // even window start (two's complement: also for negative positions)
+  const int s0 = x0 - wb, s1 = x1 - wb, c0 = cnt_t[p0], c1 = cnt_t[p1];
+  if (s0 + c0 > NW || s1 + c1 > NW) return false;
+  float w0[NW], w1[NW];
+  const float* r0 = tbl + p0 * pitch - s0;
+  const float* r1 = tbl + p1 * pitch - s1;
 #pragma unroll
-  for (int k4 = 0; k4 < NZ4; ++k4) {
-    const float4 v = kr4[k4];
-    w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+  for (int k = 0; k < NW; ++k) {
+    w0[k] = (k >= s0 && k < s0 + c0) ? r0[k] : 0.0f;
+    w1[k] = (k >= s1 && k < s1 + c1) ? r1[k] : 0.0f;
   }
-  const float* sp = xr + (qq0 * d.o - d.width + lo_t[ph]);
-  const int xstep = (S / d.n) * d.o;
-  // outputs past the resampled length read the leading zero pad instead (4 NZ4 <= 24 < kPad): no branch
-  const int i_end = min(N, out_len - crop);             // first output that has no source
-#pragma unroll 2
-  for (int i = t; i < N; i += S) {
-    const float* sq = (i < i_end) ? sp : xr - kPad;
-    float acc0 = 0.0f, acc1 = 0.0f;
+  const float* wp = xr + wb;
+  const int xstep = (S / d.n) * d.o;                     // even
+  const int i_end = min(N, out_len - crop);              // first output that has no source
+#pragma unroll 1
+  for (int i0 = 2 * u; i0 < N; i0 += S, wp += xstep) {
+    // outputs past the resampled length read the leading zero pad instead: no branch
+    const float2* w2 = reinterpret_cast<const float2*>(i0 < i_end ? wp : xr - kPad);
+    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
 #pragma unroll
-    for (int k4 = 0; k4 < NZ4; ++k4) {
-      acc0 = fmaf(w[4 * k4], sq[4 * k4], acc0);
-      acc1 = fmaf(w[4 * k4 + 1], sq[4 * k4 + 1], acc1);
-      acc0 = fmaf(w[4 * k4 + 2], sq[4 * k4 + 2], acc0);
-      acc1 = fmaf(w[4 * k4 + 3], sq[4 * k4 + 3], acc1);
+    for (int k2 = 0; k2 < NW / 2; ++k2) {
+      const float2 x = w2[k2];
+      a0 = fmaf(w0[2 * k2], x.x, a0);
+      a1 = fmaf(w0[2 * k2 + 1], x.y, a1);
+      b0 = fmaf(w1[2 * k2], x.x, b0);
+      b1 = fmaf(w1[2 * k2 + 1], x.y, b1);
     }
-    res[i] = acc0 + acc1;
-    sp += xstep;
+    const float v0 = a0 + a1, v1 = (i0 + 1 < i_end) ? b0 + b1 : 0.0f;
+    if (i0 + 1 < N) *reinterpret_cast<float2*>(res + i0) = make_float2(v0, v1);
+    else res[i0] = v0;
   }
+  return true;
 }
 
 #ifdef WW_AUG_TRACE
@@ -614,21 +634,40 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
         const bool in_smem = tbl_words <= kTblWords;
         const int out_len = (d.n * N + d.o - 1) / d.o;                               // ceil(n*N/o), < 2^31
         const int crop = (out_len > N) ? q.crop : 0;
-        // Lanes of a warp take consecutive outputs, whose sources are o / n words apart: when the clip is being shortened
-        // (o > n) the 32 loads of a tap would span more than 32 words = two wavefronts each.  Then only the first L lanes of
-        // every warp work (30 o / n + 2 <= 32 words, the jitter of the first-tap table included): one wavefront per load,
-        // and for n = 100 the idle lanes are the ones that S = n floor(threads / n) leaves idle anyway.
-        const int L = d.o > d.n ? min(32, (30 * d.n) / d.o + 1) : 32;
-        const int lanes = (kRoleG / 32) * L;
-        const bool fixed = in_smem && d.n <= lanes && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
+        // Two adjacent outputs per thread (gather_role_pairs).  A half-warp's 64-bit loads are conflict-free while its
+        // windows span <= 32 words: lanes are 2 o / n words apart, so when the clip is being shortened (o > n) only the first
+        // Lh lanes of every half-warp work (for n = 100 the idle lanes are the ones S = n c leaves idle anyway).
+        const int Lh = d.o > d.n ? min(16, (15 * d.n) / d.o + 1) : 16;
+        const int lanes = (kRoleG / 16) * Lh;                                     // threads that may own a pair
+        const int cmul = ((2 * lanes) / d.n) & ~1;                                // periods per sweep (even: the window step stays even)
+        const bool fixed = in_smem && cmul >= 2 && d.nz >= 16 && d.nz <= 24 && d.width <= kPad - 8;
         if (fixed) {
-          const int S = d.n * (lanes / d.n);
-          const int u = (t >> 5) * L + (t & 31);
-          if ((t & 31) < L && u < S) {
+          const int S = d.n * cmul;
+          const int u = (t >> 4) * Lh + (t & 15);
+          if ((t & 15) < Lh && 2 * u < S) {
+            bool done;
             switch (d.nz >> 2) {
-              case 4: gather_role<4>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
-              case 5: gather_role<5>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
-              default: gather_role<6>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+              case 4: done = gather_role_pairs<20>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+              case 5: done = gather_role_pairs<24>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+              default: done = gather_role_pairs<28>(cur, tbl, pitch, d, crop, out_len, N, S, u, res); break;
+            }
+            if (!done) {
+              // a tap row that does not fit its shifted window (irregular first-tap table): this thread's outputs one by one
+              const int* lo_t = reinterpret_cast<const int*>(tbl + d.n * pitch);
+              const int* cnt_t = lo_t + d.n;
+              for (int i = 2 * u; i < N; i += S)
+                for (int e = 0; e < 2 && i + e < N; ++e) {
+                  const int j = i + e + crop;
+                  float acc = 0.0f;
+                  if (j < out_len) {
+                    const int qq = j / d.n, ph = j - qq * d.n;
+                    const int x0 = qq * d.o - d.width + lo_t[ph];
+                    const float* kr = tbl + ph * pitch;
+                    const int k0 = x0 < 0 ? -x0 : 0, k1 = min(cnt_t[ph], N - x0);
+                    for (int kk = k0; kk < k1; ++kk) acc = fmaf(kr[kk], cur[x0 + kk], acc);
+                  }
+                  res[i + e] = acc;
+                }
             }
           }
         } else {
