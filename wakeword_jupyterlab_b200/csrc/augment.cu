@@ -761,6 +761,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
     pbw = pa - N;
     lim = nt - sh;
     m_prep = 0.0f;
+    // the clip's polyphase table travels by cp.async (no registers, no exposed latency): waited for in prep_end
+    if ((qn.flags & WW_AUG_SPEED) && qn.rs >= 0) {
+      const int pitch = qn.d.nz + ((qn.d.nz & 4) ? 0 : 4);
+      const int tbl_words = qn.d.n * pitch + 2 * qn.d.n;
+      if (tbl_words <= kTblWords) {
+        const float* g = p.rs_kern + qn.d.offset;                                        // offset and size are whole float4s
+        float* dst = tbl0 + (j & 1) * kTblWords;
+        for (int i = t * 4; i < ((tbl_words + 3) & ~3); i += kRole * 4) cp_async16(dst + i, g + i);
+      }
+    }
+    cp_commit();
   };
   auto prep_issue = [&](int bi) {
 #pragma unroll
@@ -778,16 +789,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
     }
   };
   auto prep_end = [&](int j) {
-    const ClipPrm& qn = prm[j & 3];
-    if ((qn.flags & WW_AUG_SPEED) && qn.rs >= 0) {
-      const int pitch = qn.d.nz + ((qn.d.nz & 4) ? 0 : 4);
-      const int tbl_words = qn.d.n * pitch + 2 * qn.d.n;
-      if (tbl_words <= kTblWords) {
-        const float4* g4 = reinterpret_cast<const float4*>(p.rs_kern + qn.d.offset);    // offset and size are whole float4s
-        float4* t4 = reinterpret_cast<float4*>(tbl0 + (j & 1) * kTblWords);
-        for (int i = t; i < (tbl_words + 3) >> 2; i += kRole) t4[i] = __ldg(g4 + i);
-      }
-    }
+    cp_wait<0>();
     bar_arrive(BAR_SRC_FULL + (j & 1), kPipeThreads);
     if (j + 1 < K) prefetch_clip(j + 1);
     if (t < 32 && j + 1 < K && j >= 2) fetch_scalars(j + 1);     // published by the role-wide barriers before it is read
