@@ -47,6 +47,7 @@ struct AugKParams {
   const RsDesc* rs_desc;
   int n_rs;
   const float* rs_kern;
+  const double* bank_prefix;          // [bank_rows][bank_len + 1] running sums of squares of the bank, or null
 };
 
 // per-clip scalars, fetched one iteration ahead into shared memory
@@ -54,6 +55,7 @@ struct ClipPrm {
   uint32_t flags;
   int shift, crop, noise_idx, noise_off;
   float snr, gain;
+  float noise_energy;                 // sum of squares of the clip's noise segment (pipelined kernel, from bank_prefix)
   int rs;                             // index into rs_desc, -1 = ratio not prepared
   RsDesc d;
 };
@@ -528,6 +530,19 @@ __device__ __forceinline__ void role_reduce3(float& m, float& a, float& b, float
   a = ra; b = rb;
 }
 
+// max of a non-negative value and one sum in one barrier
+__device__ __forceinline__ void role_reduce_max_sum(float& m, float& a, float* red, int t) {
+  const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  a = warp_sum(a);
+  if ((t & 31) == 0) { red[t >> 5] = a; red[32 + (t >> 5)] = __uint_as_float(w); }
+  bar_sync(BAR_C, kRole);
+  float ra = red[t & 15];
+  m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(red[32 + (t & 15)])));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ra += __shfl_xor_sync(0xffffffffu, ra, o);
+  a = ra;
+}
+
 // Gather role, two adjacent outputs per thread.  Outputs j and j + 1 read windows that start 0-2 samples apart, so ONE window
 // of NW = nz + 4 samples serves both: it is fetched as 64-bit loads from an even start (the parity of the first tap's
 // position and the offset of the second output's window are constants of the thread -- its two phases are fixed and the
@@ -711,6 +726,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
     if (t == 0) {
       q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
       q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
+      if (p.bank_prefix && (flags & WW_AUG_NOISE)) {
+        const double* pp = p.bank_prefix + (int64_t)q.noise_idx * (p.bank_len + 1) + q.noise_off;
+        q.noise_energy = (float)(pp[N] - pp[0]);
+      }
     }
     __syncwarp();
     if (flags & WW_AUG_SPEED) {
@@ -816,7 +835,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
     const uint32_t flags = q.flags;
     AUG_T(c0);
     // the noise energy of clip k does not depend on the gather: taken while the gather role is still busy with the clip
-    float sn = (flags & WW_AUG_NOISE) ? noise_sumsq(q) : 0.0f;
+    const bool have_energy = p.bank_prefix != nullptr;
+    float sn = ((flags & WW_AUG_NOISE) && !have_energy) ? noise_sumsq(q) : 0.0f;
     AUG_T(c1);
     bar_sync(BAR_RES_FULL, kPipeThreads);
     AUG_T(c2);
@@ -842,7 +862,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
         for (int e = 0; e < kPerC; ++e) sc = fmaf(o[e], o[e], sc);
       }
       mred = m_in;
-      role_reduce3(mred, sc, sn, red3[1], t);
+      if (have_energy) { role_reduce_max_sum(mred, sc, red3[1], t); sn = q.noise_energy; }
+      else role_reduce3(mred, sc, sn, red3[1], t);
     }
     AUG_T(c2b); AUG_ACC(9, c2a, c2b);
     if (do_prep) { prep_consume(0); prep_issue(1); }
@@ -936,6 +957,47 @@ __global__ void divide_kernel(const float* __restrict__ x, float* __restrict__ y
 
 }  // namespace
 
+namespace {
+// running sums of squares of one bank row per CTA (double): P[0] = 0, P[i + 1] = P[i] + x[i]^2
+__global__ void __launch_bounds__(1024) bank_prefix_kernel(const float* __restrict__ bank, int64_t len, double* __restrict__ out) {
+  __shared__ double part[1024];
+  const float* x = bank + (int64_t)blockIdx.x * len;
+  double* P = out + (int64_t)blockIdx.x * (len + 1);
+  const int tid = threadIdx.x;
+  const int64_t chunk = (len + blockDim.x - 1) / blockDim.x;
+  const int64_t lo = min((int64_t)tid * chunk, len), hi = min(lo + chunk, len);
+  double s = 0.0;
+  for (int64_t i = lo; i < hi; ++i) s += (double)x[i] * (double)x[i];
+  part[tid] = s;
+  __syncthreads();
+  for (int o = 1; o < (int)blockDim.x; o <<= 1) {       // inclusive scan of the per-thread totals
+    const double v = tid >= o ? part[tid - o] : 0.0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  double run = part[tid] - s;
+  if (tid == 0) P[0] = 0.0;
+  for (int64_t i = lo; i < hi; ++i) { run += (double)x[i] * (double)x[i]; P[i + 1] = run; }
+}
+}  // namespace
+
+// Called once by every API entry that augments with `bank`, on the stream its augment launches follow.
+int ww_prepare_bank_energy(ww_ctx* c, const float* bank, int bank_rows, int64_t bank_len, cudaStream_t st) {
+  c->bank_prefix_src = nullptr;
+  if (!bank || bank_rows <= 0 || bank_len <= 0) return WW_OK;
+  const size_t need = (size_t)bank_rows * (size_t)(bank_len + 1);
+  if (need > c->bank_prefix_cap) {
+    if (c->d_bank_prefix) { WW_CHECK(c, cudaDeviceSynchronize()); cudaFree(c->d_bank_prefix); c->d_bank_prefix = nullptr; }
+    WW_CHECK(c, cudaMalloc((void**)&c->d_bank_prefix, need * sizeof(double)));
+    c->bank_prefix_cap = need;
+  }
+  bank_prefix_kernel<<<bank_rows, 1024, 0, st>>>(bank, bank_len, c->d_bank_prefix);
+  WW_LAUNCH_CHECK(c);
+  c->bank_prefix_src = bank; c->bank_prefix_rows = bank_rows; c->bank_prefix_len = bank_len;
+  return WW_OK;
+}
+
 int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st) {
   if (n <= 0) return WW_OK;
   if (!c->d_scalar) WW_CHECK(c, cudaMalloc((void**)&c->d_scalar, sizeof(unsigned int)));
@@ -992,6 +1054,8 @@ int ww_launch_augment(ww_ctx* c, const void* clips, int pcm16, const float* bank
   p.clips = clips; p.bank = bank; p.bank_rows = bank_rows; p.bank_len = bank_len;
   p.a = *a; p.out = out; p.B = B; p.N = c->cfg.n_samples;
   p.rs_desc = c->d_rs_desc; p.n_rs = (int)c->rs_tables.size(); p.rs_kern = c->d_rs_kern;
+  p.bank_prefix = (bank && c->bank_prefix_src == bank && c->bank_prefix_rows == bank_rows && c->bank_prefix_len == bank_len)
+                      ? c->d_bank_prefix : nullptr;
   if (p.N > kThreads * kMaxPerThread) {
     c->set_error("ww_augment: n_samples too large (max 16384 samples per clip)");
     return WW_ERR_INVALID;

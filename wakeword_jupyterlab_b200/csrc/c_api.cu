@@ -145,6 +145,7 @@ int free_all(ww_ctx* c) {
   for (auto& kv : c->w) cudaFree(kv.second);
   for (int i = 0; i < 3; ++i) cudaFree(c->d_convw_t[i]);
   for (int i = 0; i < 8; ++i) { cudaFree(c->d_head_wt[i]); cudaFree(c->d_head_b[i]); cudaFree(c->d_bias_sum[i]); cudaFree(c->d_head_tc[i]); }
+  cudaFree(c->d_bank_prefix);
   {
     TrainState& t = c->train;
     float* bufs[] = {t.grad, t.m, t.v, t.wflip3, t.wflip2, t.part, t.loss, t.act1, t.act2, t.act3, t.dact2, t.dact1, t.pooled,
@@ -490,6 +491,7 @@ int ww_augment(ww_ctx* c, const float* clips, const float* bank, int bank_rows, 
                const ww_aug* p, float* out, int B, void* stream) {
   if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
   DeviceGuard dev_guard(c->device);
+  if (int rc = ww_prepare_bank_energy(c, bank, bank_rows, bank_len, (cudaStream_t)stream)) return rc;
   return ww_launch_augment(c, clips, 0, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
 }
 
@@ -497,6 +499,7 @@ int ww_augment_pcm16(ww_ctx* c, const int16_t* clips, const float* bank, int ban
                      const ww_aug* p, float* out, int B, void* stream) {
   if (!c || !clips || !p || !out || B < 0) return WW_ERR_INVALID;
   DeviceGuard dev_guard(c->device);
+  if (int rc = ww_prepare_bank_energy(c, bank, bank_rows, bank_len, (cudaStream_t)stream)) return rc;
   return ww_launch_augment(c, clips, 1, bank, bank_rows, bank_len, p, out, B, (cudaStream_t)stream);
 }
 
@@ -595,6 +598,8 @@ static int score_entry(ww_ctx* c, const void* clips, int pcm16, const float* ban
     return WW_ERR_INVALID;
   }
   DeviceGuard dev_guard(c->device);
+  if (aug)
+    if (int rc = ww_prepare_bank_energy(c, bank, bank_rows, bank_len, (cudaStream_t)stream)) return rc;
   return score_impl(c, clips, pcm16, c->cfg.n_samples, bank, bank_rows, bank_len, aug, normalize, logits, prob1,
                     decision, B, (cudaStream_t)stream);
 }
@@ -698,6 +703,7 @@ static int score_host_impl(ww_ctx* c, const void* clips_host, int pcm16, const f
     a_dev.snr_db = (float*)(base + (size_t)7 * B); a_dev.gain = (float*)(base + (size_t)8 * B);
   }
   if ((rc = ww_prepare_weights(c, st))) return rc;
+  if (aug_host && (rc = ww_prepare_bank_energy(c, bank_dev, bank_rows, bank_len, st))) return rc;
   // the conv partials of every piece stay live until the head runs with the last one: size the pool for the whole
   // batch now (growing it between pieces would drop the earlier pieces' partials)
   if ((rc = ensure_pool(c, B))) return rc;

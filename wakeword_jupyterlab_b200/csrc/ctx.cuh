@@ -109,6 +109,13 @@ struct ww_ctx {
   std::vector<ResampleTable> rs_tables;
   float* d_rs_kern = nullptr;    // packed [n phases][taps] tables
   RsDesc* d_rs_desc = nullptr;
+  // running sums of squares of the noise bank (double, [rows][len + 1]), rebuilt by every API call that augments with it:
+  // the energy of a clip's noise segment is then two loads instead of a pass over the segment (augment.cu)
+  double* d_bank_prefix = nullptr;
+  size_t bank_prefix_cap = 0;
+  const float* bank_prefix_src = nullptr;
+  int bank_prefix_rows = 0;
+  int64_t bank_prefix_len = 0;
   int rs_kern_floats = 0, rs_kern_cap = 0, rs_desc_cap = 0;
 
   // ---- weights (fp32 masters, reference layouts)
@@ -207,6 +214,7 @@ int ww_launch_logmel_tc(ww_ctx* c, const void* clips, int pcm16, int64_t clip_st
 int ww_launch_blockmax(ww_ctx* c, const void* x, int pcm16, int64_t n, int block, float* out, int64_t n_blocks,
                        cudaStream_t st);
 int ww_launch_normalize(ww_ctx* c, const float* in, float* out, int64_t n, cudaStream_t st);
+int ww_prepare_bank_energy(ww_ctx* c, const float* bank, int bank_rows, int64_t bank_len, cudaStream_t st);
 int ww_launch_augment(ww_ctx* c, const void* clips, int pcm16, const float* bank, int bank_rows, int64_t bank_len,
                       const ww_aug* p, float* out, int B, cudaStream_t st);
 int ww_launch_conv_fp32(ww_ctx* c, const float* logmel, int B, cudaStream_t st);   // -> ws_pool_part
