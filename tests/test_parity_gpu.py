@@ -205,6 +205,11 @@ def test_augment_pipelined_roles_match_lockstep_kernel(ww, monkeypatch):
     monkeypatch.delenv("WW_AUGMENT_KERNEL")
     assert np.isfinite(got).all()
     assert np.abs(got - old).max() < 1e-6
+    # the noise energy out of the bank's running sums of squares against a pass over the segment (WW_AUG_BANK_SUMS=0)
+    monkeypatch.setenv("WW_AUG_BANK_SUMS", "0")
+    direct = eng.augment(clips, _aug_to_ww(ww, p), noise_bank=bank).cpu().numpy()
+    monkeypatch.delenv("WW_AUG_BANK_SUMS")
+    assert np.abs(got - direct).max() < 1e-6
     exact = (flags & (A.F_SPEED | A.F_NOISE)) == 0
     assert exact.any() and np.array_equal(got[exact], old[exact])
     ref = A.augment_batch(clips[:56], bank, A.AugParams(*[getattr(p, f)[:56] for f in (

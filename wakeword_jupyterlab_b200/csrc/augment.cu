@@ -986,6 +986,8 @@ __global__ void __launch_bounds__(1024) bank_prefix_kernel(const float* __restri
 int ww_prepare_bank_energy(ww_ctx* c, const float* bank, int bank_rows, int64_t bank_len, cudaStream_t st) {
   c->bank_prefix_src = nullptr;
   if (!bank || bank_rows <= 0 || bank_len <= 0) return WW_OK;
+  const char* env = getenv("WW_AUG_BANK_SUMS");          // "0": every clip measures its noise segment itself (tests); read per call
+  if (env && env[0] == '0') return WW_OK;
   const size_t need = (size_t)bank_rows * (size_t)(bank_len + 1);
   if (need > c->bank_prefix_cap) {
     if (c->d_bank_prefix) { WW_CHECK(c, cudaDeviceSynchronize()); cudaFree(c->d_bank_prefix); c->d_bank_prefix = nullptr; }
