@@ -603,6 +603,26 @@ __device__ unsigned long long aug_trace[16];
 #define AUG_ACC(slot, a, b)
 #endif
 
+// scalars of clip b -> one slot of the per-clip ring, by one warp (lane 0 the plain fields, the warp the search of the
+// prepared resample ratios): a two-level chain of global loads
+__device__ __forceinline__ void fetch_clip_scalars(const AugKParams& p, ClipPrm& q, int b, int lane) {
+  const uint32_t flags = __ldg(p.a.flags + b);
+  if (lane == 0) {
+    q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
+    q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
+    if (p.bank_prefix && (flags & WW_AUG_NOISE)) {
+      const double* pp = p.bank_prefix + (int64_t)q.noise_idx * (p.bank_len + 1) + q.noise_off;
+      q.noise_energy = (float)(pp[p.N] - pp[0]);
+    }
+  }
+  __syncwarp();
+  if (flags & WW_AUG_SPEED) {
+    const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
+    for (int i = lane; i < p.n_rs; i += 32)
+      if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const AugKParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -633,6 +653,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
       AUG_T(g1);
       if (k >= 1) bar_sync(BAR_RES_EMPTY, kPipeThreads);
       AUG_T(g2);
+      // The scalars of clip k + 2 (a two-level chain of global loads) are fetched HERE, by the first warp of the role that has
+      // slack: the conditioning role has finished clip k - 2, whose ring slot this is, and reads the new entry after
+      // res_full(k), which this warp arrives at after the gather below.
+      if (t < 32 && k + 2 < K) fetch_clip_scalars(p, prm[(k + 2) & 3], (int)blockIdx.x + (k + 2) * (int)gridDim.x, t);
       AUG_ACC(0, g0, g1); AUG_ACC(1, g1, g2);
       const ClipPrm& q = prm[k & 3];
       const uint32_t flags = q.flags;
@@ -717,27 +741,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
   const int t = tid;
   const int nt = N - t;                                  // sample t + off exists  <=>  off < nt
   const int esz = (int)sizeof(TIn);
-  // scalars of clip j -> prm[j & 3] (warp 0: lane 0 the plain fields, the warp the search of the prepared resample ratios).
-  // Fetched ONE CLIP AHEAD of prep(j), so nobody ever waits for this two-level chain of global loads.
-  auto fetch_scalars = [&](int j) {
-    const int b = (int)blockIdx.x + j * (int)gridDim.x;
-    ClipPrm& q = prm[j & 3];
-    const uint32_t flags = __ldg(p.a.flags + b);
-    if (t == 0) {
-      q.flags = flags; q.shift = p.a.shift[b]; q.crop = p.a.crop_off[b]; q.noise_idx = p.a.noise_idx[b];
-      q.noise_off = p.a.noise_off[b]; q.snr = p.a.snr_db[b]; q.gain = p.a.gain[b]; q.rs = -1;
-      if (p.bank_prefix && (flags & WW_AUG_NOISE)) {
-        const double* pp = p.bank_prefix + (int64_t)q.noise_idx * (p.bank_len + 1) + q.noise_off;
-        q.noise_energy = (float)(pp[N] - pp[0]);
-      }
-    }
-    __syncwarp();
-    if (flags & WW_AUG_SPEED) {
-      const int orig = p.a.rs_orig[b], neu = p.a.rs_new[b];
-      for (int i = t; i < p.n_rs; i += 32)
-        if (p.rs_desc[i].orig == orig && p.rs_desc[i].neu == neu) { q.rs = i; q.d = p.rs_desc[i]; }
-    }
-  };
   auto clip_ptr = [&](int j) {
     return static_cast<const TIn*>(p.clips) + (int64_t)((int)blockIdx.x + j * (int)gridDim.x) * N;
   };
@@ -811,11 +814,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) augment_pipe_kernel(const Aug
     cp_wait<0>();
     bar_arrive(BAR_SRC_FULL + (j & 1), kPipeThreads);
     if (j + 1 < K) prefetch_clip(j + 1);
-    if (t < 32 && j + 1 < K && j >= 2) fetch_scalars(j + 1);     // published by the role-wide barriers before it is read
   };
   static_assert(kPerC == 4 * kPB, "four conditioning batches per clip");
 
-  if (t < 32) { fetch_scalars(0); if (K > 1) fetch_scalars(1); if (K > 2) fetch_scalars(2); }
+  if (t < 32)
+    for (int j = 0; j < 2 && j < K; ++j) fetch_clip_scalars(p, prm[j], (int)blockIdx.x + j * (int)gridDim.x, t);
   bar_sync(BAR_C, kRole);
   float m_in = 0.0f, m_mid = 0.0f;                       // thread-partial peaks of clip k (being finished) and clip k + 1
   for (int j = 0; j < 2 && j < K; ++j) {                 // the first two clips: nothing to hide behind yet
